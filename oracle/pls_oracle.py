@@ -1,0 +1,632 @@
+# -*- coding: utf-8 -*-
+"""
+CPU oracle for the PLS resampling hot path -- TEST INFRASTRUCTURE ONLY.
+
+This module is a NumPy restatement of the per-resample algorithm of
+netneurolab/pypyls (reference checked out at /root/reference, commit e0ff056).
+It exists so that the CUDA engine in ``pypyls_b200`` can be checked against the
+reference's arithmetic on a box where the reference itself is not present.
+
+Rules (enforced by tests/test_no_oracle_in_product.py):
+  * only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+    ``cpu_baseline`` / ``--impl reference`` legs may import this module;
+  * the product package ``pypyls_b200`` never imports it and has no CPU
+    fallback.
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` (run in the build
+container, where /root/reference is importable with three shims) stores the
+reference's own outputs for several small analyses plus the in-tree Matlab
+fixtures; ``tests/test_oracle_golden.py`` checks every function here against
+them.  The exception is SIMPLS resampling (``pls_regression``): the reference's
+tests only pin shapes for it, so the oracle is pinned against the shimmed
+reference run only ("parity unpinned by the reference's tests").
+
+Third-party arithmetic the reference calls and this oracle calls identically
+(not vendored by the reference; versions in this image are the de-facto pin):
+``sklearn.utils.extmath.randomized_svd`` (scikit-learn 1.9.0),
+``scipy.stats.zscore`` (scipy 1.18.1), ``numpy.percentile`` (numpy 2.3.5).
+
+Every function cites the reference file:line it follows.
+"""
+
+import warnings
+
+import numpy as np
+from scipy.stats import zscore
+from sklearn.utils.extmath import randomized_svd
+from sklearn.utils.validation import check_random_state
+
+
+# --------------------------------------------------------------------------
+# layout helpers
+# --------------------------------------------------------------------------
+
+def cell_labels(groups, n_cond=1):
+    """Cell label (1-based) of every row; rows are ordered group -> condition
+    -> subject.  Follows pyls/utils.py:178-197 (dummy_label)."""
+    groups = [int(g) for g in groups]
+    n_cells = len(groups) * n_cond
+    return np.repeat(np.arange(1, n_cells + 1), np.repeat(groups, n_cond))
+
+
+def dummy_code(groups, n_cond=1):
+    """(S, J) 0/1 cell-membership matrix.  Follows pyls/utils.py:155-175."""
+    lab = cell_labels(groups, n_cond)
+    return (lab[:, None] == np.unique(lab)[None, :]).astype(int)
+
+
+def permute_cols(x, rs):
+    """Shuffle the rows of every column independently by arg-sorting uniform
+    draws.  Follows pyls/utils.py:200-224."""
+    x = np.asarray(x)
+    order = rs.random_sample(x.shape).argsort(axis=0)
+    return x[order, np.arange(x.shape[1])[None, :]]
+
+
+# --------------------------------------------------------------------------
+# index generators (integer work -> bit-exact with the reference for a seed)
+# --------------------------------------------------------------------------
+
+def _cond_index_blocks(groups, n_cond):
+    """Per group, the (n_cond, n_subj) array of row ids (row c = condition c).
+    Restates the np.where/np.split construction of pyls/base.py:42-45."""
+    blocks, start = [], 0
+    for g in groups:
+        blocks.append(start + np.arange(n_cond * g).reshape(n_cond, g))
+        start += n_cond * g
+    return blocks
+
+
+def _stack_by_group(table, perm, groups):
+    """Take subject columns ``perm`` of the (n_cond, n_subj_total) ``table``,
+    cut them into the groups' sizes and lay every group out condition-major.
+    Restates pyls/base.py:64-65 and :142-143."""
+    picked = table[:, perm].T
+    out, start = [], 0
+    for g in groups:
+        out.append(picked[start:start + g].flatten('F'))
+        start += g
+    return np.hstack(out)
+
+
+def gen_permsamp(groups, n_cond, n_perm, seed=None):
+    """Permutation index table (S, n_perm).  Follows pyls/base.py:10-79:
+    per-subject condition shuffle, cross-group subject permutation, rejection
+    when a group keeps its own subject set or the column repeats an earlier
+    one, give up (warn once) after 500 tries."""
+    groups = [int(g) for g in groups]
+    n_rows = sum(groups) * n_cond
+    n_subj = sum(groups)
+    rs = check_random_state(seed)
+    blocks = _cond_index_blocks(groups, n_cond)
+    bounds = np.concatenate([[0], np.cumsum(groups)])
+    out = np.zeros((n_rows, n_perm), dtype=int)
+    subj = np.arange(n_subj)
+    warned = False
+    for i in range(n_perm):
+        tries, bad = 0, True
+        while bad and tries < 500:
+            tries, bad = tries + 1, False
+            table = np.hstack([permute_cols(b, rs) for b in blocks])
+            perm = rs.permutation(subj)
+            if len(groups) > 1:
+                for a, b in zip(bounds[:-1], bounds[1:]):
+                    if np.array_equal(np.sort(perm[a:b]), subj[a:b]):
+                        bad = True
+            col = _stack_by_group(table, perm, groups)
+            if i and (col[:, None] == out[:, :i]).all(axis=0).any():
+                bad = True
+        if tries == 500 and not warned:
+            warnings.warn('WARNING: Duplicate permutations used.')
+            warned = True
+        out[:, i] = col
+    return out
+
+
+def gen_bootsamp(groups, n_cond, n_boot, seed=None):
+    """Bootstrap index table (S, n_boot).  Follows pyls/base.py:82-159: sorted
+    within-group sampling with replacement, at least ceil(min_cell/2) distinct
+    subjects per group, conditions follow their subject, per-group duplicate
+    rejection (the reference compares rows indexed by SUBJECT id, :145-149 --
+    reproduced as is), give up after 500 tries."""
+    groups = [int(g) for g in groups]
+    n_rows = sum(groups) * n_cond
+    n_subj = sum(groups)
+    rs = check_random_state(seed)
+    min_subj = int(np.ceil(min(groups) * 0.5))
+    table = np.hstack(_cond_index_blocks(groups, n_cond))
+    bounds = np.concatenate([[0], np.cumsum(groups)])
+    out = np.zeros((n_rows, n_boot), dtype=int)
+    warned = False
+    for i in range(n_boot):
+        tries, bad = 0, True
+        while bad and tries < 500:
+            tries, bad = tries + 1, False
+            boot = np.zeros(n_subj, dtype=int)
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                pool = np.arange(a, b)
+                while True:
+                    boot[a:b] = np.sort(rs.choice(pool, size=b - a,
+                                                  replace=True))
+                    if np.unique(boot[a:b]).size >= min_subj:
+                        break
+            col = _stack_by_group(table, boot, groups)
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                if i and (col[a:b, None] == out[a:b, :i]).all(axis=0).any():
+                    bad = True
+        if tries == 500 and not warned:
+            warnings.warn('WARNING: Duplicate bootstraps used.')
+            warned = True
+        out[:, i] = col
+    return out
+
+
+# --------------------------------------------------------------------------
+# numeric primitives (pyls/compute.py)
+# --------------------------------------------------------------------------
+
+def svd(crosscov, n_components=None, seed=None):
+    """Randomized SVD on the tall orientation; returns (U (B,L), diag(d), V).
+    Follows pyls/compute.py:10-52."""
+    rs = check_random_state(seed)
+    crosscov = np.asanyarray(crosscov)
+    if n_components is None:
+        n_components = min(crosscov.shape)
+    if crosscov.shape[0] <= crosscov.shape[1]:
+        U, d, Vt = randomized_svd(crosscov.T, n_components=n_components,
+                                  random_state=rs, transpose=False)
+        V = Vt.T
+    else:
+        V, d, Ut = randomized_svd(crosscov, n_components=n_components,
+                                  random_state=rs, transpose=False)
+        U = Ut.T
+    return U, np.diag(d), V
+
+
+def xcorr(X, Y, covariance=False):
+    """(T, B) cross-correlation (z-scored, ddof=1) or cross-covariance of the
+    rows given.  Follows pyls/compute.py:55-94 (norm=False branch)."""
+    if not covariance:
+        Xn = (X - X.mean(axis=0)) / X.std(axis=0, ddof=1)
+        Yn = (Y - Y.mean(axis=0)) / Y.std(axis=0, ddof=1)
+    else:
+        Xn = X - X.mean(0, keepdims=True)
+        Yn = Y - Y.mean(0, keepdims=True)
+    return (Yn.T @ Xn) / (len(Xn) - 1)
+
+
+def normalize(X, axis=0):
+    """Unit-norm columns, zero-safe.  Follows pyls/compute.py:97-126."""
+    out = np.array(X, dtype=float)
+    nrm = np.linalg.norm(out, axis=axis, keepdims=True)
+    zero = nrm == 0
+    nrm[zero] = 1
+    out = out / nrm
+    out[np.broadcast_to(zero, out.shape)] = 0
+    return out
+
+
+def perm_sig(orig, perm):
+    """(#[perm > orig] + 1) / (P + 1), strict '>'.  pyls/compute.py:154-181."""
+    count = np.sum(perm > np.diag(orig)[:, None], axis=1) + 1
+    return count / (perm.shape[-1] + 1)
+
+
+def boot_ci(boot, ci=95):
+    """Percentile CI along the last axis.  pyls/compute.py:184-209."""
+    low = (100 - ci) / 2
+    lower, upper = np.percentile(boot, [low, 100 - low], axis=-1)
+    return lower, upper
+
+
+def boot_rel(orig, u_sum, u_square, n_boot):
+    """Bootstrap ratio and standard error.  pyls/compute.py:212-237."""
+    u_sum2 = (u_sum ** 2) / n_boot
+    u_se = np.sqrt(np.abs(u_square - u_sum2) / (n_boot - 1))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        bsr = orig / u_se
+    return bsr, u_se
+
+
+def procrustes(original, permuted, singular):
+    """Rotate ``permuted @ singular`` onto ``original``: polar factor of
+    original.T @ permuted.  Follows pyls/compute.py:240-264 (the reference
+    calls randomized_svd with the global RNG; full-rank so any seed gives the
+    same factor up to rounding -- a fixed seed is used here)."""
+    temp = original.T @ permuted
+    N, _, P = randomized_svd(temp, n_components=min(temp.shape),
+                             random_state=0)
+    return permuted @ singular @ (P.T @ N.T)
+
+
+def get_group_mean(X, dummy, n_cond=1, mean_centering=0):
+    """(J, B) mean to remove from every cell.  pyls/compute.py:267-317."""
+    J = dummy.shape[-1]
+    if mean_centering == 0:
+        sizes = dummy[:, 0:J:n_cond].sum(axis=0).astype(int) * n_cond
+        member = dummy_code(sizes)
+    elif mean_centering == 1:
+        member = dummy.copy()
+    elif mean_centering == 2:
+        member = np.ones((len(X), 1))
+    else:
+        raise ValueError("Mean centering type must be in [0, 1, 2].")
+    means = np.vstack([X[m].mean(axis=0)[None]
+                       for m in member.T.astype(bool)])
+    if mean_centering == 0:
+        means = np.repeat(means, n_cond, axis=0)
+    elif mean_centering == 1:
+        means = means.reshape(-1, n_cond, X.shape[-1]).mean(axis=0)
+        means = np.tile(means.T, int(J / n_cond)).T
+    else:
+        means = np.repeat(means, J, axis=0)
+    return means
+
+
+def get_mean_center(X, dummy, n_cond=1, mean_centering=0, means=True):
+    """Cell means minus the centering mean ((J, B), means=True) or de-meaned
+    rows ((S, B)).  Follows pyls/compute.py:320-357."""
+    mc = get_group_mean(X, dummy, n_cond=n_cond, mean_centering=mean_centering)
+    cells = dummy.T.astype(bool)
+    if means:
+        return np.vstack([X[c].mean(axis=0) - mc[n]
+                          for n, c in enumerate(cells)])
+    return np.vstack([X[c] - mc[n][None] for n, c in enumerate(cells)])
+
+
+def efficient_corr(x, y):
+    """Column-wise Pearson r, clipped.  pyls/compute.py:360-391."""
+    x, y = np.vstack(x), np.vstack(y)
+    corr = np.sum(zscore(x, ddof=1) * zscore(y, ddof=1), axis=0) / (len(x) - 1)
+    return np.clip(corr, -1, 1)
+
+
+def varexp(singular):
+    """Squared singular values normalised to 1.  pyls/compute.py:394-414."""
+    sq = np.diag(singular) ** 2
+    return np.diag(sq / np.sum(sq))
+
+
+# --------------------------------------------------------------------------
+# type-specific cross-covariance / distribution builders
+# --------------------------------------------------------------------------
+
+class _Spec:
+    """What kind of analysis is running (replaces the reference's subclasses
+    of BasePLS)."""
+
+    def __init__(self, kind, groups, n_cond, covariance=False,
+                 mean_centering=0, rotate=True, n_components=None):
+        self.kind = kind                    # 'behavioral' | 'meancentered' | 'regression'
+        self.groups = [int(g) for g in groups]
+        self.n_cond = int(n_cond)
+        self.covariance = covariance
+        self.mean_centering = mean_centering
+        self.rotate = rotate
+        self.n_components = n_components
+        self.dummy = dummy_code(self.groups, self.n_cond)
+
+
+def gen_covcorr(spec, X, Y, dummy=None):
+    """Matrix that is decomposed.  behavioral: row-stack of per-cell xcorr
+    (pyls/types/behavioral.py:27-52); mean-centered: cell means minus
+    centering mean (pyls/types/meancentered.py:50-73)."""
+    dummy = spec.dummy if dummy is None else dummy
+    if spec.kind == 'behavioral':
+        return np.vstack([xcorr(X[c], Y[c], covariance=spec.covariance)
+                          for c in dummy.T.astype(bool)])
+    return get_mean_center(X, dummy, spec.n_cond, spec.mean_centering,
+                           means=True)
+
+
+def gen_distrib(spec, X, Y, original, dummy=None):
+    """Bootstrap distribution entry.  behavioral: per-cell xcorr of the scores
+    X @ normalize(U_orig) with Y (pyls/types/behavioral.py:54-80);
+    mean-centered: cell means of the de-meaned rows projected on
+    normalize(U_orig) (pyls/types/meancentered.py:75-102)."""
+    dummy = spec.dummy if dummy is None else dummy
+    if spec.kind == 'behavioral':
+        return gen_covcorr(spec, X @ normalize(original), Y, dummy)
+    usc = get_mean_center(X, dummy, spec.n_cond, spec.mean_centering,
+                          means=False)
+    usc = usc @ normalize(original)
+    return np.vstack([usc[c].mean(axis=0) for c in dummy.T.astype(bool)])
+
+
+def decompose(spec, X, Y, seed=None):
+    """gen_covcorr followed by the SVD.  pyls/base.py:401-437; regression:
+    pyls/types/regression.py:248-277."""
+    if spec.kind == 'regression':
+        mask = get_mask(X, Y)
+        out = simpls(X[mask], Y[mask], spec.n_components, seed=seed)
+        return out['x_weights'], np.diag(out['pctvar'][1]), None
+    return svd(gen_covcorr(spec, X, Y), seed=seed)
+
+
+# --------------------------------------------------------------------------
+# per-resample bodies (pyls/base.py)
+# --------------------------------------------------------------------------
+
+def single_perm(spec, X, Y, perminds, original_v, seed=None):
+    """One permutation -> (L,) permuted singular values.  Follows
+    pyls/base.py:654-712 with use_permind=True and n_split=None; the permuted
+    operand is Y for behavioral (base.py:599) and X for mean-centered
+    (pyls/types/meancentered.py:125)."""
+    if spec.kind == 'regression':
+        return _regression_single_perm(spec, X, Y, perminds, seed)
+    if spec.kind == 'meancentered':
+        Xp, Yp = X[perminds], Y
+    else:
+        Xp, Yp = X, Y[perminds]
+    U, d, V = decompose(spec, Xp, Yp, seed=seed)
+    if spec.rotate:
+        rot = procrustes(original_v, V, d)
+        return np.sqrt(np.sum(rot ** 2, axis=0))
+    return np.diag(d)
+
+
+def single_boot(spec, X, Y, inds, original_u, seed=None):
+    """One bootstrap -> (distrib (K, L), U_boot (B, L)).  Follows
+    pyls/base.py:530-576."""
+    if spec.kind == 'regression':
+        return _regression_single_boot(spec, X, Y, inds, original_u, seed)
+    Xb, Yb = X[inds], Y[inds]
+    U, d = decompose(spec, Xb, Yb, seed=seed)[:-1]
+    U_boot = procrustes(original_u, U, d)
+    distrib = gen_distrib(spec, Xb, Yb, original_u)
+    return distrib, U_boot
+
+
+def run_perms(spec, X, Y, permsamp, original_v, first=0, count=None):
+    """d_perm (L, count) over columns [first, first+count) of ``permsamp``;
+    resample i uses seed=i exactly like pyls/base.py:644-650."""
+    count = permsamp.shape[-1] - first if count is None else count
+    cols = [single_perm(spec, X, Y, permsamp[:, i], original_v, seed=i)
+            for i in range(first, first + count)]
+    return np.stack(cols, axis=-1)
+
+
+def run_boots(spec, X, Y, bootsamp, original_u, first=0, count=None):
+    """(distrib (K, L, count), u_sum, u_square) as pyls/base.py:439-528."""
+    count = bootsamp.shape[-1] - first if count is None else count
+    u_sum = np.zeros_like(original_u)
+    u_square = np.zeros_like(original_u)
+    distrib = []
+    for i in range(first, first + count):
+        d, u = single_boot(spec, X, Y, bootsamp[:, i], original_u, seed=i)
+        u_sum += u
+        u_square += u ** 2
+        distrib.append(d)
+    return np.stack(distrib, axis=-1), u_sum, u_square
+
+
+# --------------------------------------------------------------------------
+# SIMPLS (pyls/types/regression.py)
+# --------------------------------------------------------------------------
+
+def get_mask(X, Y):
+    """Rows where neither X nor Y is all-NaN.  regression.py:48-53."""
+    return ~(np.all(np.isnan(X), axis=1) | np.all(np.isnan(Y), axis=1))
+
+
+def simpls(X, Y, n_components=None, seed=1234):
+    """SIMPLS with the reference's randomized top-1 SVD per component, double
+    modified Gram-Schmidt and deflation.  Follows
+    pyls/types/regression.py:56-186; only the outputs the resampling path
+    consumes (x_weights, pctvar, loadings, scores) are produced -- the
+    reference's mse / t2 / residual reconstructions (:159-172) are unused by
+    the permutation and bootstrap loops and are omitted."""
+    X, Y = np.asanyarray(X), np.asanyarray(Y)
+    if n_components is None:
+        n_components = min(len(X) - 1, X.shape[1])
+    X0 = X - X.mean(axis=0, keepdims=True)
+    Y0 = Y - Y.mean(axis=0, keepdims=True)
+    Cov = X0.T @ Y0
+    B, T, S = X.shape[1], Y.shape[1], X.shape[0]
+    x_loadings = np.zeros((B, n_components))
+    y_loadings = np.zeros((T, n_components))
+    x_scores = np.zeros((S, n_components))
+    x_weights = np.zeros((B, n_components))
+    basis = np.zeros((B, n_components))
+    for comp in range(n_components):
+        ci, si, ri = svd(Cov, n_components=1, seed=seed)
+        ti = X0 @ ri
+        nt = np.linalg.norm(ti)
+        x_weights[:, [comp]] = ri / nt
+        ti /= nt
+        x_scores[:, [comp]] = ti
+        x_loadings[:, [comp]] = X0.T @ ti
+        y_loadings[:, [comp]] = Y0.T @ ti
+        vi = x_loadings[:, [comp]]
+        for _ in range(2):
+            for j in range(comp):
+                vj = basis[:, [j]]
+                vi = vi - ((vj.T @ vi) * vj)
+        vi /= np.linalg.norm(vi)
+        basis[:, [comp]] = vi
+        Cov = Cov - (vi @ (vi.T @ Cov))
+        Vi = basis[:, :comp]
+        Cov = Cov - (Vi @ (Vi.T @ Cov))
+    pctvar = [np.sum(x_loadings ** 2, axis=0) / np.sum(X0 ** 2),
+              np.sum(y_loadings ** 2, axis=0) / np.sum(Y0 ** 2)]
+    return dict(x_weights=x_weights, x_loadings=x_loadings,
+                y_loadings=y_loadings, x_scores=x_scores, pctvar=pctvar)
+
+
+def resid_yscores(x_scores, y_scores):
+    """Orthogonalise y_scores against preceding x_scores (double MGS).
+    regression.py:9-45."""
+    x_scores = np.array(x_scores)
+    y_scores = np.array(y_scores, copy=True)
+    for comp in range(x_scores.shape[1]):
+        ui = y_scores[:, [comp]]
+        for _ in range(2):
+            for j in range(comp):
+                tj = x_scores[:, [j]]
+                ui = ui - ((tj.T @ ui) * tj)
+        y_scores[:, [comp]] = ui
+    return y_scores
+
+
+def _regression_single_perm(spec, X, Y, inds, seed):
+    """regression.py:329-373 -- y_weights is None in the caller so the rotate
+    branch (:359) never runs; returns pctvar in Y per component."""
+    x_weights, vexp, _ = decompose(spec, X, Y[inds], seed=seed)
+    return np.diag(vexp)
+
+
+def _regression_single_boot(spec, X, Y, inds, original, seed):
+    """regression.py:279-327 (2-D Y): sign-align against the original weights
+    through efficient_corr, y_loadings = Yi.T @ (Xi @ w)."""
+    Xi, Yi = X[inds], Y[inds]
+    x_weights = decompose(spec, Xi, Yi, seed=seed)[0]
+    if original is not None:
+        x_weights = x_weights * np.sign(efficient_corr(x_weights, original))
+    mask = get_mask(Xi, Yi)
+    y_loadings = Yi[mask].T @ (Xi @ x_weights)[mask]
+    return y_loadings, x_weights
+
+
+# --------------------------------------------------------------------------
+# whole analyses (what the reference's front-end functions return, restricted
+# to the keys the hot path feeds).  test_split / n_split are always off.
+# --------------------------------------------------------------------------
+
+def _finish_boot(res, orig_bs, distrib, u_sum, u_square, n, ci, add_orig):
+    if add_orig:
+        u_sum, u_square = u_sum + orig_bs, u_square + orig_bs ** 2
+    bsr, se = boot_rel(orig_bs, u_sum, u_square, n)
+    res['x_weights_normed'] = bsr
+    res['x_weights_stderr'] = se
+    res['distrib'] = distrib
+    res['distrib_ci'] = np.stack(boot_ci(distrib, ci=ci), -1)
+
+
+def behavioral_pls(X, Y, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
+                   covariance=False, rotate=True, ci=95, permsamples=None,
+                   bootsamples=None, seed=None):
+    """pyls.behavioral_pls with test_split=0, n_split=0, permindices=True.
+    Follows pyls/base.py:341-399 and pyls/types/behavioral.py:172-227,
+    including the order in which the seeded RandomState is consumed
+    (original SVD -> gen_permsamp -> gen_bootsamp)."""
+    X, Y = np.asarray(X), np.asarray(Y)
+    groups = [len(X) // n_cond] if groups is None else list(np.atleast_1d(groups))
+    spec = _Spec('behavioral', groups, n_cond, covariance=covariance,
+                 rotate=rotate)
+    rs = check_random_state(seed)
+    res = {}
+    U, d, V = decompose(spec, X, Y, seed=rs)
+    res['x_weights'], res['singvals_diag'], res['y_weights'] = U, d, V
+    res['x_scores'] = X @ U
+    if n_perm > 0:
+        if permsamples is None:
+            permsamples = gen_permsamp(groups, n_cond, n_perm, seed=rs)
+        d_perm = run_perms(spec, X, Y, permsamples, V)
+        res['pvals'] = perm_sig(d, d_perm)
+        res['permsamples'] = permsamples
+        res['perm_singval'] = d_perm
+    cells = np.repeat(groups, n_cond)
+    res['y_scores'] = np.vstack([
+        y @ v for y, v in zip(np.split(Y, np.cumsum(cells)[:-1]),
+                              np.split(V, len(cells)))])
+    res['y_loadings'] = gen_covcorr(spec, res['x_scores'], Y)
+    if n_boot > 0:
+        if bootsamples is None:
+            bootsamples = gen_bootsamp(groups, n_cond, n_boot, seed=rs)
+        distrib, u_sum, u_square = run_boots(spec, X, Y, bootsamples, U)
+        res['bootsamples'] = bootsamples
+        _finish_boot(res, U @ d, distrib, u_sum, u_square, n_boot + 1, ci,
+                     add_orig=True)
+    res['varexp'] = np.diag(varexp(d))
+    res['singvals'] = np.diag(d)
+    return res
+
+
+def meancentered_pls(X, groups=None, n_cond=1, mean_centering=0, n_perm=5000,
+                     n_boot=5000, rotate=True, ci=95, permsamples=None,
+                     bootsamples=None, seed=None):
+    """pyls.meancentered_pls with n_split=0, permindices=True.  Follows
+    pyls/types/meancentered.py:11-48 (argument fix-ups) and :127-179."""
+    X = np.asarray(X)
+    groups = [len(X) // n_cond] if groups is None else list(np.atleast_1d(groups))
+    if n_cond == 1 and len(groups) == 1:
+        raise ValueError('Cannot perform PLS with only one group and one '
+                         'condition. Please confirm inputs are correct.')
+    if n_cond == 1 and mean_centering == 0:
+        mean_centering = 1
+    elif len(groups) == 1 and mean_centering == 1:
+        mean_centering = 0
+    spec = _Spec('meancentered', groups, n_cond,
+                 mean_centering=mean_centering, rotate=rotate)
+    Y = spec.dummy
+    rs = check_random_state(seed)
+    res = {}
+    U, d, V = decompose(spec, X, Y, seed=rs)
+    res['x_weights'], res['singvals_diag'], res['y_weights'] = U, d, V
+    res['x_scores'] = X @ U
+    if n_perm > 0:
+        if permsamples is None:
+            permsamples = gen_permsamp(groups, n_cond, n_perm, seed=rs)
+        d_perm = run_perms(spec, X, Y, permsamples, V)
+        res['pvals'] = perm_sig(d, d_perm)
+        res['permsamples'] = permsamples
+        res['perm_singval'] = d_perm
+    res['y_scores'] = Y @ V
+    dm = get_mean_center(X, Y, n_cond, mean_centering, False) @ U
+    res['contrast'] = np.vstack([dm[c].mean(axis=0)
+                                 for c in Y.T.astype(bool)])
+    if n_boot > 0:
+        if bootsamples is None:
+            bootsamples = gen_bootsamp(groups, n_cond, n_boot, seed=rs)
+        distrib, u_sum, u_square = run_boots(spec, X, Y, bootsamples, U)
+        res['bootsamples'] = bootsamples
+        _finish_boot(res, U @ d, distrib, u_sum, u_square, n_boot, ci,
+                     add_orig=False)
+    res['varexp'] = np.diag(varexp(d))
+    res['singvals'] = np.diag(d)
+    return res
+
+
+def pls_regression(X, Y, n_components=None, n_perm=5000, n_boot=5000,
+                   rotate=True, ci=95, permsamples=None, bootsamples=None,
+                   seed=None):
+    """pyls.pls_regression for 2-D Y.  Follows
+    pyls/types/regression.py:190-246 and :375-428.  Unlike the reference the
+    caller's arrays are not centred in place (the oracle works on copies)."""
+    X, Y = np.array(X, dtype=float), np.array(Y, dtype=float)
+    max_comp = min(len(X) - 1, X.shape[1])
+    n_components = max_comp if n_components is None else int(n_components)
+    if n_components > max_comp:
+        raise ValueError('Provided `n_components` cannot be greater '
+                         'than {}'.format(max_comp))
+    groups = [len(X)]
+    spec = _Spec('regression', groups, 1, rotate=rotate,
+                 n_components=n_components)
+    rs = check_random_state(seed)
+    X -= np.nanmean(X, axis=0, keepdims=True)
+    Y -= np.nanmean(Y, axis=0, keepdims=True)
+    mask = get_mask(X, Y)
+    res = {}
+    W, vexp, _ = decompose(spec, X, Y, seed=rs)
+    res['x_weights'] = W
+    res['x_scores'] = X @ W
+    if n_perm > 0:
+        if permsamples is None:
+            permsamples = gen_permsamp(groups, 1, n_perm, seed=rs)
+        d_perm = run_perms(spec, X, Y, permsamples, None)
+        res['pvals'] = perm_sig(vexp, d_perm)
+        res['permsamples'] = permsamples
+        res['perm_singval'] = d_perm
+    res['y_loadings'] = Y[mask].T @ res['x_scores'][mask]
+    res['y_scores'] = np.full((len(Y), n_components), np.nan)
+    res['y_scores'][mask] = resid_yscores(res['x_scores'][mask],
+                                          Y[mask] @ res['y_loadings'])
+    if n_boot > 0:
+        if bootsamples is None:
+            bootsamples = gen_bootsamp(groups, 1, n_boot, seed=rs)
+        distrib, u_sum, u_square = run_boots(spec, X, Y, bootsamples, W)
+        res['bootsamples'] = bootsamples
+        _finish_boot(res, W, distrib, u_sum, u_square, n_boot + 1, ci,
+                     add_orig=True)
+    res['varexp'] = np.diag(vexp)
+    return res
