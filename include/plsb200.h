@@ -1,0 +1,199 @@
+/*
+ * plsb200.h -- C ABI of libplsb200.so, the B200 (sm_100a) PLS resampling engine.
+ *
+ * The reference (netneurolab/pypyls) has no FFI: its seam for this path is the
+ * Python methods BasePLS.permutation() / BasePLS.bootstrap() and the numeric
+ * primitives they call.  Each entry point below names the reference interface
+ * it replaces (file:line into the reference tree).  The Python binding a
+ * maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative plsb_status otherwise;
+ *     plsb_last_error() returns the message of the last failure on the
+ *     calling thread;
+ *   - all `d_` pointers are DEVICE pointers owned by the caller (e.g. torch
+ *     tensors); the library never frees or keeps them beyond the call except
+ *     where stated (plsb_set_data keeps no reference: it copies);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
+ *     work is enqueued on it and the call does not synchronise unless stated;
+ *   - matrices are row-major fp64; index tables are int32, RESAMPLE-MAJOR:
+ *     idx[r * S + s] = source row of destination row s in resample r (the
+ *     reference stores the transpose, (S, n) int64, pyls/base.py:35,107);
+ *   - a handle is used by one host thread at a time.
+ *
+ * Sizes:  S rows, B features, T behaviours, J = n_groups * n_cond cells,
+ *         K = J*T (behavioural) or J (mean-centred), L = K (requires K <= B).
+ */
+#ifndef PLSB200_H
+#define PLSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct plsb_ctx *plsb_handle_t;
+
+enum plsb_status {
+  PLSB_OK = 0,
+  PLSB_ERR_ARG = -1,      /* bad argument / unsupported shape            */
+  PLSB_ERR_CUDA = -2,     /* a CUDA runtime call or kernel failed         */
+  PLSB_ERR_STATE = -3,    /* call order violated (e.g. no data set yet)   */
+  PLSB_ERR_NOMEM = -4     /* workspace does not fit the configured limit  */
+};
+
+enum plsb_mode {
+  PLSB_BEHAVIORAL_CORR = 0, /* behavioral_pls(covariance=False)            */
+  PLSB_BEHAVIORAL_COV = 1,  /* behavioral_pls(covariance=True)             */
+  PLSB_MEANCENTERED = 2,    /* meancentered_pls (mean_centering 0/1/2)     */
+  PLSB_SIMPLS = 3           /* pls_regression                              */
+};
+
+/* Library version (major*10000 + minor*100 + patch). */
+int plsb_version(void);
+const char *plsb_last_error(void);
+
+/* Handle life cycle.  `device` is the CUDA ordinal. */
+int plsb_create(plsb_handle_t *out, int device);
+int plsb_destroy(plsb_handle_t h);
+/* Upper bound (bytes) for the per-chunk resample workspace (default 12 GiB). */
+int plsb_set_workspace_limit(plsb_handle_t h, uint64_t bytes);
+
+/*
+ * Analysis layout.  Replaces BasePLS.__init__ validation + utils.dummy_code
+ * (pyls/base.py:254-283, pyls/utils.py:155-197): rows are ordered
+ * group -> condition -> subject.  `T` is ignored for PLSB_MEANCENTERED.
+ * `n_components` is used by PLSB_SIMPLS only.
+ */
+int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T,
+                   int n_groups, const int *groups, int n_cond,
+                   int mean_centering, int n_components);
+
+/*
+ * Copies X (S,B) and Y (S,T) into padded internal buffers and precomputes the
+ * per-cell statistics every resample shares (per-cell centred / z-scored X;
+ * pyls/compute.py:84-87).  d_Y may be NULL for PLSB_MEANCENTERED.
+ */
+int plsb_set_data(plsb_handle_t h, const double *d_X, const double *d_Y,
+                  void *stream);
+
+/*
+ * Original decomposition on the device.  Replaces BasePLS.svd on the
+ * un-resampled data (pyls/base.py:362-363, 401-437; pyls/compute.py:10-52)
+ * including sklearn's svd_flip sign convention on the B-side factor.
+ *   d_U (B,L)  d_d (L)  d_V (K,L).  The result is also installed as the
+ * "original" used by plsb_run_perms / plsb_run_boots.
+ */
+int plsb_decompose(plsb_handle_t h, double *d_U, double *d_d, double *d_V,
+                   void *stream);
+/* Install a caller-provided original decomposition instead. */
+int plsb_set_original(plsb_handle_t h, const double *d_U, const double *d_d,
+                      const double *d_V, void *stream);
+/* x_scores = X @ U for the raw X (pyls/base.py:364).  d_out (S,L). */
+int plsb_project_scores(plsb_handle_t h, const double *d_U, int L,
+                        double *d_out, void *stream);
+
+/*
+ * On-device resample tables (counter-based RNG keyed by (seed, kind, resample
+ * id, attempt) so any rank can generate any id).  Replace gen_permsamp /
+ * gen_bootsamp (pyls/base.py:10-79, 82-159) with the same validity rules:
+ * conditions stay with their subject, subjects must mix across groups, each
+ * group keeps >= ceil(min_group/2) distinct subjects, duplicate columns are
+ * re-drawn at most 500 times.  `first` is the global id of the first column;
+ * duplicates are checked over [0, first+count) so the table is the same for
+ * any sharding.  *h_n_exhausted (host) = columns that hit the 500-try cap.
+ * d_idx is (count, S) int32.  These two calls synchronise the stream.
+ */
+int plsb_gen_perm_indices(plsb_handle_t h, uint64_t seed, int64_t first,
+                          int count, int32_t *d_idx, int *h_n_exhausted,
+                          void *stream);
+int plsb_gen_boot_indices(plsb_handle_t h, uint64_t seed, int64_t first,
+                          int count, int32_t *d_idx, int *h_n_exhausted,
+                          void *stream);
+
+/*
+ * Permutation loop.  Replaces BasePLS.permutation + _single_perm with
+ * use_permind=True, n_split=None (pyls/base.py:601-712) and
+ * MeanCenteredPLS.make_permutation (pyls/types/meancentered.py:104-125).
+ *   d_idx (count,S) int32;  d_dperm (count,L): permuted singular values
+ *   (rotate != 0: Procrustes-rotated, base.py:696-700; else diag(d), :702).
+ */
+int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count,
+                   int rotate, double *d_dperm, void *stream);
+
+/*
+ * Bootstrap loop.  Replaces BasePLS.bootstrap + _single_boot
+ * (pyls/base.py:439-576), gen_distrib (pyls/types/behavioral.py:54-80,
+ * pyls/types/meancentered.py:75-102) and compute.procrustes
+ * (pyls/compute.py:240-264).
+ *   d_distrib (count,K,L);  d_usum / d_usquare (B,L) are ACCUMULATED into
+ *   (zero them first; base.py:475-476, 510-511).
+ */
+int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count,
+                   double *d_distrib, double *d_usum, double *d_usquare,
+                   void *stream);
+
+/* compute.perm_sig (pyls/compute.py:154-181): strict '>' count.
+ * d_dperm (count,L), d_dorig (L) -> d_pvals (L). */
+int plsb_perm_pvals(plsb_handle_t h, const double *d_dperm, int count, int L,
+                    const double *d_dorig, double *d_pvals, void *stream);
+
+/* compute.boot_ci (pyls/compute.py:184-209): numpy 'linear' percentiles over
+ * the resample axis.  d_distrib (count, n_series) -> d_lo, d_hi (n_series). */
+int plsb_percentile(plsb_handle_t h, const double *d_distrib, int count,
+                    int n_series, double q_lo, double q_hi, double *d_lo,
+                    double *d_hi, void *stream);
+
+/* compute.boot_rel (pyls/compute.py:212-237) incl. the "add the original
+ * sample" step of behavioral.py:202-207 when add_orig != 0.
+ * d_bs (B,L) = U @ diag(d) flattened to n_elem values; outputs d_bsr, d_se. */
+int plsb_boot_ratio(plsb_handle_t h, const double *d_bs, const double *d_usum,
+                    const double *d_usquare, int64_t n_elem, int n_boot,
+                    int add_orig, double *d_bsr, double *d_se, void *stream);
+
+/* ---- primitives (exposed for unit tests and for callers that want the
+ *      compute.py-level operations; pyls/compute.py:55-94, 10-52, 240-264) -- */
+
+/* C (M,N) = A (M,Kd) @ X (Kd,N), fp64 DMMA; all three dense row-major without
+ * padding (the call pads internally).  The contraction of compute.xcorr
+ * (pyls/compute.py:92) as the resampling drivers use it: A = stacked
+ * per-resample left operands, X = shared data matrix. */
+int plsb_dgemm(plsb_handle_t h, const double *d_A, const double *d_X, int M,
+               int N, int Kd, double *d_C, void *stream);
+/* Cross-covariance / cross-correlation matrices of `count` resamples.
+ * Replaces BasePLS.gen_covcorr on resampled data (pyls/base.py:401-437 ->
+ * pyls/types/behavioral.py:27-52, pyls/types/meancentered.py:50-73).
+ * bootstrap != 0: both X and Y follow d_idx (base.py:569-570); otherwise the
+ * permutation rule of the analysis type applies (Y rows for behavioural,
+ * base.py:599; X rows for mean-centred, meancentered.py:125).  d_idx may be
+ * NULL with count == 1 for the un-resampled matrix.  d_R is (count, K, B). */
+int plsb_crosscov(plsb_handle_t h, const int32_t *d_idx, int count,
+                  int bootstrap, double *d_R, void *stream);
+/* Batched small decomposition (replaces the per-resample compute.svd +
+ * compute.procrustes, pyls/compute.py:36-49, 240-264): for each of `count`
+ * matrices G (K,K) = R R^T and H (K,L) = R U_orig, M = V Q with
+ * G = V diag(lam) V^T and Q the transposed polar factor of H^T V lam^-1/2, so
+ * that R^T M = U_boot d Q.  d_dorig (L) are the original singular values
+ * (NULL = all non-null): null original latent variables are left out of the
+ * rotation.  d_lam (count,K), optional, receives lam sorted descending. */
+int plsb_small_decomp(plsb_handle_t h, const double *d_G, const double *d_H,
+                      int count, int K, int L, const double *d_dorig,
+                      double *d_M, double *d_lam, void *stream);
+
+/* Counters for bench / tests: kernels launched by this handle so far. */
+int64_t plsb_launch_count(plsb_handle_t h);
+
+/* Optional per-launch CUDA-event timing, grouped by kernel class (the bench's
+ * roofline uses it).  plsb_timing_read synchronises the recorded events, writes
+ * the milliseconds and launch counts accumulated since the previous read into
+ * arrays of plsb_timing_classes() entries and resets them. */
+int plsb_timing_enable(plsb_handle_t h, int on);
+int plsb_timing_classes(void);
+const char *plsb_timing_class_name(int cls);
+int plsb_timing_read(plsb_handle_t h, double *ms, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLSB200_H */

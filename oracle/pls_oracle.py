@@ -377,6 +377,42 @@ def single_boot(spec, X, Y, inds, original_u, seed=None):
     return distrib, U_boot
 
 
+def single_boot_nullsafe(spec, X, Y, inds, original_u, d_orig):
+    """One bootstrap with numerically null latent variables LEFT OUT of the
+    Procrustes rotation -- the documented deviation of the CUDA engine from
+    pyls/base.py:530-576 for rank-deficient cross-covariances (mean-centred
+    PLS: rank J-1).  The reference rotates with the arbitrary unit vectors its
+    randomized SVD returns for the null directions (rounding noise, different
+    for every BLAS), which perturbs the non-null latent variables by
+    O(sqrt(K/B)); here the rotation is the Procrustes solution restricted to
+    the non-null subspaces and the null columns of U_boot are 0.  Uses an
+    exact LAPACK SVD.  For full-rank problems this equals single_boot."""
+    Xb, Yb = X[inds], Y[inds]
+    R = gen_covcorr(spec, Xb, Yb)
+    U, d, _ = np.linalg.svd(R.T, full_matrices=False)
+    keep_b = d > 1e-7 * d.max()
+    keep_o = d_orig > 1e-10 * d_orig.max()
+    temp = original_u[:, keep_o].T @ U[:, keep_b]
+    N, _, P = np.linalg.svd(temp, full_matrices=False)
+    U_boot = np.zeros_like(original_u)
+    U_boot[:, keep_o] = (U[:, keep_b] * d[keep_b]) @ (P.T @ N.T)
+    return gen_distrib(spec, Xb, Yb, original_u), U_boot
+
+
+def run_boots_nullsafe(spec, X, Y, bootsamp, original_u, d_orig):
+    """run_boots over single_boot_nullsafe."""
+    u_sum = np.zeros_like(original_u)
+    u_square = np.zeros_like(original_u)
+    distrib = []
+    for i in range(bootsamp.shape[-1]):
+        d, u = single_boot_nullsafe(spec, X, Y, bootsamp[:, i], original_u,
+                                    d_orig)
+        u_sum += u
+        u_square += u ** 2
+        distrib.append(d)
+    return np.stack(distrib, axis=-1), u_sum, u_square
+
+
 def run_perms(spec, X, Y, permsamp, original_v, first=0, count=None):
     """d_perm (L, count) over columns [first, first+count) of ``permsamp``;
     resample i uses seed=i exactly like pyls/base.py:644-650."""

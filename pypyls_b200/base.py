@@ -1,0 +1,228 @@
+# -*- coding: utf-8 -*-
+"""
+Resampling driver with the interface of the reference's ``BasePLS``
+(pyls/base.py:232-770): ``run_pls`` -> ``permutation()`` / ``bootstrap()``.
+
+Where the reference maps ``_single_perm`` / ``_single_boot`` over resamples in
+Python (optionally in joblib worker processes), this class hands the whole
+batch to the CUDA engine: ONE host -> C-ABI -> device crossing per analysis
+step.  With ``torch.distributed`` initialised (one process per GPU) every rank
+runs a contiguous block of resample ids and the results are all-gathered /
+all-reduced (see :mod:`pypyls_b200.dist`).
+"""
+
+import warnings
+
+import numpy as np
+import torch
+
+from . import dist as pdist
+from . import structures
+from .engine import ResamplingEngine
+from .resample import check_random_state, gen_bootsamp, gen_permsamp
+
+
+def _device_seed(rs):
+    """64-bit key for the on-device generator, drawn from the analysis'
+    RandomState so that an integer ``seed`` makes runs repeatable."""
+    hi, lo = rs.randint(0, 2 ** 31 - 1, size=2)
+    return (int(hi) << 32) | int(lo)
+
+
+class BasePLS():
+    """
+    Base class of the PLS types.
+
+    Parameters
+    ----------
+    X : (S, B) array_like
+    Y : (S, T) array_like, optional
+    groups : (G,) list of int, optional
+    n_cond : int, optional
+    **kwargs : see :obj:`pypyls_b200.structures.PLSInputs`.  Additions to the
+        reference's keys: ``index_backend`` ('device' -- counter-based
+        generator on the GPU, default; 'reference' -- host tables replaying
+        the reference's NumPy stream for the given seed), ``device`` (CUDA
+        ordinal) and ``workspace_bytes``.
+    """
+
+    engine_mode = None
+
+    def __init__(self, X, Y=None, groups=None, n_cond=1, **kwargs):
+        if groups is None:
+            groups = [len(X) // n_cond]
+        elif not isinstance(groups, (list, np.ndarray)):
+            groups = [groups]
+        groups = [int(g) for g in groups]
+
+        n_samples = sum([g * n_cond for g in groups])
+        if len(X) != n_samples:
+            raise ValueError('Number of samples specified by `groups` and '
+                             '`n_cond` does not match number of samples in '
+                             'input array(s).\n'
+                             '    EXPECTED: {}\n'
+                             '    ACTUAL:   {} (groups: {} * n_cond: {})'
+                             .format(len(X), n_samples, groups, n_cond))
+        if Y is not None and len(X) != len(Y):
+            raise ValueError('Provided `X` and `Y` matrices must have the '
+                             'same number of samples. Provided matrices '
+                             'differed: X: {}, Y: {}'.format(len(X), len(Y)))
+
+        self.inputs = structures.PLSInputs(X=X, Y=Y, groups=groups,
+                                           n_cond=n_cond, **kwargs)
+        self.rs = check_random_state(self.inputs.get('seed'))
+        backend = self.inputs.get('index_backend')
+        if backend is None:
+            self.inputs['index_backend'] = backend = 'device'
+        if backend not in ('device', 'reference'):
+            raise ValueError("index_backend must be 'device' or 'reference'")
+        if self.inputs.get('n_split') is not None:
+            raise NotImplementedError(
+                'Split-half resampling (n_split) is not part of the '
+                'accelerated path yet; pass n_split=0.')
+        if self.inputs.get('permsamples') is not None and \
+                self.inputs.get('permindices') is False:
+            raise NotImplementedError(
+                'Pre-permuted Y arrays (permindices=False) are not part of '
+                'the accelerated path yet; pass index tables.')
+        self.engine = None
+
+    # -- engine ------------------------------------------------------------
+    def _make_engine(self, X, Y):
+        S, B = X.shape
+        T = 1 if Y is None else Y.shape[1]
+        device = self.inputs.get('device')
+        if device is None:
+            device = torch.cuda.current_device() \
+                if torch.cuda.is_available() else 0
+        eng = ResamplingEngine(self.engine_mode(), S, B, T,
+                               self.inputs.groups, self.inputs.n_cond,
+                               mean_centering=self.inputs.get(
+                                   'mean_centering') or 0,
+                               device=device,
+                               workspace_bytes=self.inputs.get(
+                                   'workspace_bytes'))
+        eng.set_data(X, Y)
+        return eng
+
+    def engine_mode(self):
+        raise NotImplementedError
+
+    def _engine_y(self, Y):
+        return Y
+
+    def _replay_svd_draws(self):
+        """The reference's original decomposition draws a (K, K+10) normal
+        matrix from the analysis' RandomState inside sklearn's randomized_svd
+        (pyls/base.py:362-363 -> pyls/compute.py:44-45) before any resampling
+        table is generated; consume the same draws so that
+        index_backend='reference' reproduces the reference's tables."""
+        K = self.engine.K
+        self.rs.normal(size=(K, K + 10))
+
+    # -- analysis ------------------------------------------------------------
+    def run_pls(self, X, Y):
+        """
+        Original decomposition + permutation test
+        (pyls/base.py:341-399).  Returns the results object; device copies of
+        the decomposition stay in ``self._dev``.
+        """
+        self.res = res = structures.PLSResults(inputs=self.inputs)
+        X = np.asarray(X) if not isinstance(X, torch.Tensor) else X
+        self.engine = eng = self._make_engine(X, self._engine_y(Y))
+        U, d, V = eng.decompose()
+        self._replay_svd_draws()
+        self._dev = dict(U=U, d=d, V=V)
+        res['x_weights'] = U.cpu().numpy()
+        res['singvals'] = np.diag(d.cpu().numpy())
+        res['y_weights'] = V.cpu().numpy()
+        res['x_scores'] = eng.project_scores(U).cpu().numpy()
+
+        if self.inputs.n_perm > 0:
+            d_perm, _, _ = self.permutation(X, Y, seed=self.rs)
+            res['permres']['pvals'] = eng.perm_pvals(
+                self._dev['d_perm'], d).cpu().numpy()
+            res['permres']['permsamples'] = self.permsamp
+            res['permres']['perm_singval'] = d_perm
+        return res
+
+    def _table(self, kind, n, seed):
+        """Resampling table for this analysis: user-provided, replayed on the
+        host, or generated on the device.  Returns (host (S, n) int array,
+        device (n_local, S) int32 block of this rank, first id of the block).
+        """
+        eng = self.engine
+        key = 'permsamples' if kind == 'perm' else 'bootsamples'
+        first, count = pdist.my_block(n)
+        given = self.inputs.get(key)
+        if given is None and self.inputs.index_backend == 'reference':
+            gen = gen_permsamp if kind == 'perm' else gen_bootsamp
+            given = gen(self.inputs.groups, self.inputs.n_cond, n, seed=seed,
+                        verbose=self.inputs.get('verbose'))
+        if given is not None:
+            given = np.asarray(given)
+            if given.ndim != 2 or given.shape[-1] != n:
+                raise ValueError('Provided `{}` must have shape ({}, {}); got '
+                                 '{}'.format(key, eng.S, n, given.shape))
+            block = eng.to_device_indices(given[:, first:first + count])
+            return given, block, first
+        gen = eng.gen_perm_indices if kind == 'perm' else eng.gen_boot_indices
+        block, exhausted = gen(_device_seed(check_random_state(seed)), count,
+                               first=first)
+        if exhausted:
+            warnings.warn('WARNING: Duplicate {} used.'.format(
+                'permutations' if kind == 'perm' else 'bootstraps'))
+        full = pdist.gather_resamples(block, n)
+        return full.cpu().numpy().T.astype(int), block, first
+
+    def permutation(self, X, Y, seed=None):
+        """
+        Permutation test on the device (replaces pyls/base.py:601-712).
+
+        Returns
+        -------
+        d_perm : (L, P) numpy.ndarray
+        ucorrs, vcorrs : None
+            Split-half correlations are not computed by this engine.
+        """
+        n = self.inputs.n_perm
+        self.permsamp, block, _ = self._table('perm', n, seed)
+        rotate = self.inputs.get('rotate')
+        rotate = True if rotate is None else bool(rotate)
+        local = self.engine.run_perms(block, rotate=rotate)
+        d_perm = pdist.gather_resamples(local, n)
+        self._dev['d_perm'] = d_perm
+        return d_perm.cpu().numpy().T.copy(), None, None
+
+    def bootstrap(self, X, Y, seed=None):
+        """
+        Bootstrap resampling on the device (replaces pyls/base.py:439-576).
+
+        Returns
+        -------
+        distrib : (K, L, R) numpy.ndarray
+        u_sum, u_square : (B, L) numpy.ndarray
+        """
+        n = self.inputs.n_boot
+        self.bootsamp, block, _ = self._table('boot', n, seed)
+        distrib, u_sum, u_square = self.engine.run_boots(block)
+        distrib = pdist.gather_resamples(distrib, n)
+        pdist.reduce_sum(u_sum, u_square)
+        self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
+        return (distrib.permute(1, 2, 0).contiguous().cpu().numpy(),
+                u_sum.cpu().numpy(), u_square.cpu().numpy())
+
+    def _boot_stats(self, add_orig):
+        """Bootstrap ratios, standard errors and percentile intervals from the
+        device-resident accumulators (compute.boot_rel / boot_ci,
+        pyls/compute.py:184-237)."""
+        eng, dev = self.engine, self._dev
+        bs = dev['U'] * dev['d'][None, :]
+        bsr, se = eng.boot_ratio(bs, dev['u_sum'], dev['u_square'],
+                                 self.inputs.n_boot, add_orig)
+        ci = self.inputs.get('ci')
+        ci = 95 if ci is None else ci
+        low = (100 - ci) / 2
+        lo, hi = eng.percentile(dev['distrib'], low, 100 - low)
+        return (bsr.cpu().numpy(), se.cpu().numpy(),
+                torch.stack([lo, hi], dim=-1).cpu().numpy())

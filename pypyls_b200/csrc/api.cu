@@ -1,0 +1,562 @@
+// C ABI of libplsb200.so (include/plsb200.h): handle life cycle, the one-time
+// data preparation, the original decomposition and the two resampling drivers
+// that replace BasePLS.permutation / BasePLS.bootstrap (pyls/base.py:439-528,
+// 601-652).  Everything here only sequences kernels on the caller's stream.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace plsb {
+
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+namespace {
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define PLSB_HANDLE(h)                                                                 \
+  PLSB_CHECK((h) != nullptr, PLSB_ERR_ARG, "null handle");                            \
+  PLSB_CUDA(cudaSetDevice((h)->device))
+
+// data matrix the contraction runs against
+const double *perm_data(const plsb_ctx *h) {
+  return h->lay.behavioral() ? h->Xcell.as<double>() : h->Xglob.as<double>();
+}
+
+// zero the operand rows [rows, rows_pad)
+int zero_tail(double *A, long long rows, long long rows_pad, int lda, cudaStream_t st) {
+  if (rows_pad > rows)
+    PLSB_CUDA(cudaMemsetAsync(A + rows * lda, 0, sizeof(double) * (size_t)(rows_pad - rows) * lda,
+                              st));
+  return PLSB_OK;
+}
+
+// R (n*K rows, ldx) for resamples idx[0..n): operands + GEMM (+ column scaling)
+int crosscov_chunk(plsb_ctx *h, const int32_t *idx, int n, bool boot, double *distrib,
+                   cudaStream_t st) {
+  const Layout &l = h->lay;
+  const long long Mw = (long long)n * l.K, Mw_pad = round_up_ll(Mw, GEMM_BM);
+  PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)Mw_pad * l.S_pad));
+  PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)Mw_pad * l.ldx));
+  PLSB_TRY(zero_tail(h->A.as<double>(), Mw, Mw_pad, l.S_pad, st));
+  const bool scaled = boot && l.corr();
+  long long Mc = (long long)n * l.J, Mc_pad = round_up_ll(Mc, GEMM_BM);
+  if (scaled) {
+    PLSB_TRY(h->Ac.ensure(sizeof(double) * (size_t)Mc_pad * l.S_pad));
+    PLSB_TRY(h->S1.ensure(sizeof(double) * (size_t)Mc_pad * l.ldx));
+    PLSB_TRY(h->S2.ensure(sizeof(double) * (size_t)Mc_pad * l.ldx));
+    PLSB_TRY(zero_tail(h->Ac.as<double>(), Mc, Mc_pad, l.S_pad, st));
+  }
+  PLSB_TRY(launch_build(h, boot ? BUILD_BOOT : BUILD_PLAIN, idx, n, h->A.as<double>(),
+                        scaled ? h->Ac.as<double>() : nullptr, distrib, st));
+  GemmArgs g;
+  g.lda = l.S_pad;
+  g.ldx = l.ldx;
+  g.N_pad = l.ldx;
+  g.Kd = l.S_pad;
+  g.ldc = l.ldx;
+  if (scaled) {
+    g.A = h->Ac.as<double>();
+    g.X = h->Xglob.as<double>();
+    g.M_pad = (int)Mc_pad;
+    g.C = h->S1.as<double>();
+    PLSB_TRY(launch_gemm(h, g, st));
+    g.C = h->S2.as<double>();
+    g.square_b = true;
+    PLSB_TRY(launch_gemm(h, g, st));
+    g.square_b = false;
+    PLSB_TRY(launch_colscale(h, h->S1.as<double>(), h->S2.as<double>(), (int)Mc, l.ldx, st));
+    g.scale = h->S1.as<double>();
+    g.scale_div = l.T;
+    g.lds = l.ldx;
+  }
+  g.A = h->A.as<double>();
+  g.X = boot ? h->Xglob.as<double>() : perm_data(h);
+  g.M_pad = (int)Mw_pad;
+  g.C = h->R.as<double>();
+  PLSB_TRY(launch_gemm(h, g, st));
+  return PLSB_OK;
+}
+
+// resamples per chunk so that the stored matrices fit the workspace limit
+int chunk_size(const plsb_ctx *h, bool boot, int count) {
+  const Layout &l = h->lay;
+  size_t per = sizeof(double) * ((size_t)l.K * l.ldx + (size_t)l.K * l.S_pad);
+  if (boot && l.corr()) per += sizeof(double) * (2 * (size_t)l.J * l.ldx + (size_t)l.J * l.S_pad);
+  per += sizeof(double) * 4 * (size_t)l.K * l.K;
+  long long n = (long long)(h->ws_limit / per);
+  // operand row counts are ints
+  const long long cap = (long long)((1u << 31) - 1024) / std::max(l.K, 1);
+  n = std::min(n, cap);
+  if (n < 1) n = 1;
+  return (int)std::min<long long>(n, count);
+}
+
+}  // namespace
+}  // namespace plsb
+
+using namespace plsb;
+
+extern "C" {
+
+int plsb_version(void) { return 100; }
+
+const char *plsb_last_error(void) { return g_err.c_str(); }
+
+int plsb_create(plsb_handle_t *out, int device) {
+  PLSB_CHECK(out != nullptr, PLSB_ERR_ARG, "plsb_create: null output");
+  int n_dev = 0;
+  PLSB_CUDA(cudaGetDeviceCount(&n_dev));
+  PLSB_CHECK(device >= 0 && device < n_dev, PLSB_ERR_ARG, "plsb_create: device %d of %d", device,
+             n_dev);
+  PLSB_CUDA(cudaSetDevice(device));
+  plsb_ctx *h = new plsb_ctx();
+  h->device = device;
+  cudaDeviceProp prop;
+  PLSB_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  *out = h;
+  return PLSB_OK;
+}
+
+int plsb_destroy(plsb_handle_t h) {
+  if (!h) return PLSB_OK;
+  cudaSetDevice(h->device);
+  DevBuf *bufs[] = {&h->tables, &h->Xraw, &h->Xcell, &h->Xglob, &h->Y,    &h->Cmat,  &h->Uo,
+                    &h->Vo,     &h->dorig, &h->Sx,   &h->norms, &h->A,    &h->Ac,    &h->R,
+                    &h->S1,     &h->S2,   &h->G,     &h->H,     &h->M,    &h->lam,   &h->rowsq,
+                    &h->part,   &h->misc, &h->idxall, &h->flags};
+  for (DevBuf *b : bufs) b->release();
+  delete h;
+  return PLSB_OK;
+}
+
+int plsb_set_workspace_limit(plsb_handle_t h, uint64_t bytes) {
+  PLSB_CHECK(h != nullptr, PLSB_ERR_ARG, "null handle");
+  PLSB_CHECK(bytes >= (1ull << 20), PLSB_ERR_ARG, "workspace limit below 1 MiB");
+  h->ws_limit = bytes;
+  return PLSB_OK;
+}
+
+int64_t plsb_launch_count(plsb_handle_t h) { return h ? h->launches : 0; }
+
+int plsb_timing_enable(plsb_handle_t h, int on) {
+  PLSB_CHECK(h != nullptr, PLSB_ERR_ARG, "null handle");
+  h->timing = on != 0;
+  return PLSB_OK;
+}
+
+int plsb_timing_classes(void) { return KC_COUNT; }
+
+const char *plsb_timing_class_name(int cls) {
+  static const char *names[KC_COUNT] = {"xcov_gemm", "build_operands", "gram_proj", "small_decomp",
+                                        "accum_u",   "stats",          "indexgen",  "prep"};
+  return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "";
+}
+
+int plsb_timing_read(plsb_handle_t h, double *ms, int64_t *launches) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(ms && launches, PLSB_ERR_ARG, "plsb_timing_read: null output");
+  for (int c = 0; c < KC_COUNT; ++c) {
+    ms[c] = 0.0;
+    launches[c] = 0;
+  }
+  for (auto &t : h->timed) {
+    PLSB_CUDA(cudaEventSynchronize(t.b));
+    float v = 0.f;
+    PLSB_CUDA(cudaEventElapsedTime(&v, t.a, t.b));
+    ms[t.cls] += v;
+    launches[t.cls] += 1;
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  h->timed.clear();
+  return PLSB_OK;
+}
+
+int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups, const int *groups,
+                   int n_cond, int mean_centering, int n_components) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(mode >= PLSB_BEHAVIORAL_CORR && mode <= PLSB_MEANCENTERED, PLSB_ERR_ARG,
+             "plsb_configure: mode %d is not supported by this build", mode);
+  PLSB_CHECK(S >= 2 && B >= 1 && n_groups >= 1 && n_cond >= 1 && groups != nullptr, PLSB_ERR_ARG,
+             "plsb_configure: bad sizes S=%d B=%d n_groups=%d n_cond=%d", S, B, n_groups, n_cond);
+  Layout l;
+  l.mode = mode;
+  l.S = S;
+  l.B = B;
+  l.n_groups = n_groups;
+  l.n_cond = n_cond;
+  l.mean_centering = mean_centering;
+  l.n_components = n_components;
+  int n_subj = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    PLSB_CHECK(groups[g] >= 1, PLSB_ERR_ARG, "plsb_configure: empty group %d", g);
+    l.groups.push_back(groups[g]);
+    n_subj += groups[g];
+  }
+  l.n_subj = n_subj;
+  PLSB_CHECK(n_subj * n_cond == S, PLSB_ERR_ARG,
+             "plsb_configure: sum(groups) * n_cond = %d does not match the %d rows of X",
+             n_subj * n_cond, S);
+  l.J = n_groups * n_cond;
+  if (l.behavioral()) {
+    PLSB_CHECK(T >= 1, PLSB_ERR_ARG, "plsb_configure: T=%d", T);
+    l.T = T;
+    l.K = l.J * T;
+    for (int g = 0; g < n_groups; ++g)
+      PLSB_CHECK(groups[g] >= 2, PLSB_ERR_ARG,
+                 "plsb_configure: group %d has a single subject (no variance)", g);
+  } else {
+    PLSB_CHECK(mean_centering >= 0 && mean_centering <= 2, PLSB_ERR_ARG,
+               "Mean centering type must be in [0, 1, 2].");
+    l.T = 1;
+    l.K = l.J;
+  }
+  l.L = l.K;
+  PLSB_CHECK(l.K <= B, PLSB_ERR_ARG,
+             "plsb_configure: K=%d latent variables exceed the %d features (K <= B required)", l.K,
+             B);
+  PLSB_CHECK(l.K <= MAX_K, PLSB_ERR_ARG, "plsb_configure: K=%d exceeds the supported maximum %d",
+             l.K, MAX_K);
+  l.S_pad = round_up(S, GEMM_BK);
+  l.ldx = round_up(B, GEMM_BN);
+
+  // layout tables
+  std::vector<int> tab;
+  int row = 0;
+  for (int g = 0; g < n_groups; ++g)
+    for (int c = 0; c < n_cond; ++c) {
+      l.cell_start.push_back(row);
+      row += groups[g];
+    }
+  l.cell_start.push_back(row);
+  tab.insert(tab.end(), l.cell_start.begin(), l.cell_start.end());   // J+1
+  for (int j = 0; j < l.J; ++j)
+    for (int s = l.cell_start[j]; s < l.cell_start[j + 1]; ++s) tab.push_back(j);   // S
+  for (int j = 0; j < l.J; ++j) tab.push_back(l.cell_start[j + 1] - l.cell_start[j]);   // J
+  int acc = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    tab.push_back(acc);
+    acc += groups[g];
+  }
+  tab.push_back(acc);   // n_groups + 1
+  PLSB_TRY(h->tables.ensure(sizeof(int) * tab.size()));
+  PLSB_CUDA(cudaMemcpy(h->tables.p, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
+  h->d_cell_start = h->tables.as<int>();
+  h->d_cell_of_row = h->d_cell_start + (l.J + 1);
+  h->d_cell_n = h->d_cell_of_row + S;
+  h->d_group_start = h->d_cell_n + l.J;
+
+  if (!l.behavioral()) {
+    // C (J,S): "cell mean minus centring mean" as a row operator
+    // (pyls/compute.py:267-357)
+    std::vector<double> C((size_t)l.J * S, 0.0);
+    for (int j = 0; j < l.J; ++j) {
+      const int g = j / n_cond, c = j % n_cond;
+      const int nj = l.cell_start[j + 1] - l.cell_start[j];
+      for (int s = l.cell_start[j]; s < l.cell_start[j + 1]; ++s) C[(size_t)j * S + s] += 1.0 / nj;
+      if (mean_centering == 0) {
+        const int r0 = l.cell_start[g * n_cond], r1 = l.cell_start[(g + 1) * n_cond];
+        for (int s = r0; s < r1; ++s) C[(size_t)j * S + s] -= 1.0 / (r1 - r0);
+      } else if (mean_centering == 1) {
+        for (int g2 = 0; g2 < n_groups; ++g2) {
+          const int j2 = g2 * n_cond + c;
+          const int n2 = l.cell_start[j2 + 1] - l.cell_start[j2];
+          for (int s = l.cell_start[j2]; s < l.cell_start[j2 + 1]; ++s)
+            C[(size_t)j * S + s] -= 1.0 / ((double)n_groups * n2);
+        }
+      } else {
+        for (int s = 0; s < S; ++s) C[(size_t)j * S + s] -= 1.0 / S;
+      }
+    }
+    PLSB_TRY(h->Cmat.ensure(sizeof(double) * C.size()));
+    PLSB_CUDA(cudaMemcpy(h->Cmat.p, C.data(), sizeof(double) * C.size(), cudaMemcpyHostToDevice));
+  }
+  h->lay = l;
+  h->configured = true;
+  h->has_data = h->has_original = false;
+  return PLSB_OK;
+}
+
+int plsb_set_data(plsb_handle_t h, const double *d_X, const double *d_Y, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->configured, PLSB_ERR_STATE, "plsb_set_data before plsb_configure");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  PLSB_CHECK(d_X != nullptr, PLSB_ERR_ARG, "plsb_set_data: null X");
+  PLSB_CHECK(!l.behavioral() || d_Y != nullptr, PLSB_ERR_ARG, "plsb_set_data: null Y");
+  const size_t bytes = sizeof(double) * (size_t)l.S_pad * l.ldx;
+  PLSB_TRY(h->Xraw.ensure(bytes));
+  PLSB_TRY(h->Xglob.ensure(bytes));
+  PLSB_TRY(launch_pad_copy(h, d_X, l.S, l.B, h->Xraw.as<double>(), l.S_pad, l.ldx, st));
+  PLSB_CUDA(cudaMemsetAsync(h->Xglob.p, 0, bytes, st));
+  double *xcell = nullptr;
+  if (l.behavioral()) {
+    PLSB_TRY(h->Xcell.ensure(bytes));
+    PLSB_CUDA(cudaMemsetAsync(h->Xcell.p, 0, bytes, st));
+    xcell = h->Xcell.as<double>();
+    PLSB_TRY(h->Y.ensure(sizeof(double) * (size_t)l.S * l.T));
+    PLSB_CUDA(cudaMemcpyAsync(h->Y.p, d_Y, sizeof(double) * (size_t)l.S * l.T,
+                              cudaMemcpyDeviceToDevice, st));
+  }
+  PLSB_TRY(launch_prep_cells(h, h->Xraw.as<double>(), xcell, h->Xglob.as<double>(), st));
+  h->has_data = true;
+  h->has_original = false;
+  return PLSB_OK;
+}
+
+int plsb_set_original(plsb_handle_t h, const double *d_U, const double *d_d, const double *d_V,
+                      void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data, PLSB_ERR_STATE, "plsb_set_original before plsb_set_data");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  PLSB_CHECK(d_U && d_d && d_V, PLSB_ERR_ARG, "plsb_set_original: null argument");
+  PLSB_TRY(h->Uo.ensure(sizeof(double) * (size_t)l.B * l.L));
+  PLSB_TRY(h->Vo.ensure(sizeof(double) * (size_t)l.K * l.L));
+  PLSB_TRY(h->dorig.ensure(sizeof(double) * l.L));
+  PLSB_TRY(h->Sx.ensure(sizeof(double) * (size_t)l.S * l.L));
+  PLSB_TRY(h->norms.ensure(sizeof(double) * l.L));
+  if (d_U != h->Uo.p)
+    PLSB_CUDA(cudaMemcpyAsync(h->Uo.p, d_U, sizeof(double) * (size_t)l.B * l.L,
+                              cudaMemcpyDeviceToDevice, st));
+  if (d_V != h->Vo.p)
+    PLSB_CUDA(cudaMemcpyAsync(h->Vo.p, d_V, sizeof(double) * (size_t)l.K * l.L,
+                              cudaMemcpyDeviceToDevice, st));
+  if (d_d != h->dorig.p)
+    PLSB_CUDA(cudaMemcpyAsync(h->dorig.p, d_d, sizeof(double) * l.L, cudaMemcpyDeviceToDevice, st));
+  // Sx = X @ normalize(U_orig)   (pyls/types/behavioral.py:78, meancentered.py:98)
+  PLSB_TRY(launch_colnorm(h, h->Uo.as<double>(), l.B, l.L, h->norms.as<double>(), st));
+  PLSB_TRY(launch_xproj(h, h->Xraw.as<double>(), l.ldx, l.S, l.B, h->Uo.as<double>(), l.L,
+                        h->norms.as<double>(), h->Sx.as<double>(), st));
+  h->has_original = true;
+  return PLSB_OK;
+}
+
+int plsb_decompose(plsb_handle_t h, double *d_U, double *d_d, double *d_V, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data, PLSB_ERR_STATE, "plsb_decompose before plsb_set_data");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  PLSB_CHECK(d_U && d_d && d_V, PLSB_ERR_ARG, "plsb_decompose: null output");
+  PLSB_TRY(crosscov_chunk(h, nullptr, 1, false, nullptr, st));
+  const size_t kk = (size_t)l.K * l.K, bl = (size_t)l.B * l.L;
+  PLSB_TRY(h->G.ensure(sizeof(double) * 4 * kk));
+  PLSB_TRY(h->lam.ensure(sizeof(double) * 2 * l.K));
+  PLSB_TRY(h->misc.ensure(sizeof(double) * 2 * bl));
+  double *G1 = h->G.as<double>(), *V1 = G1 + kk, *G2 = V1 + kk, *V2 = G2 + kk;
+  double *lam1 = h->lam.as<double>(), *lam2 = lam1 + l.K;
+  double *uraw = h->misc.as<double>(), *usq = uraw + bl;
+  // pass 1: eigenvectors of the Gram matrix R R^T (accurate to eps * cond(R)^2)
+  PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, 1, l.K, l.B, nullptr, 0, G1, nullptr, st));
+  PLSB_TRY(launch_sym_eig(h, G1, 1, l.K, V1, lam1, 0, st));
+  // pass 2 (refinement): W = R^T V1 is computed from R itself, its Gram matrix
+  // W^T W is diagonal up to pass 1's error and graded, so a second Jacobi
+  // recovers the small singular directions to working precision
+  PLSB_CUDA(cudaMemsetAsync(uraw, 0, sizeof(double) * 2 * bl, st));
+  PLSB_TRY(launch_accum_u(h, h->R.as<double>(), l.ldx, 1, l.K, l.B, V1, l.L, uraw, usq, st));
+  PLSB_TRY(launch_colgram(h, uraw, l.B, l.K, G2, st));
+  PLSB_TRY(launch_sym_eig(h, G2, 1, l.K, V2, lam2, 0, st));
+  PLSB_TRY(launch_matmul_small(h, V1, V2, l.K, d_V, st));
+  // U d = R^T V, then column norms / signs (sklearn svd_flip on the B-side factor)
+  PLSB_CUDA(cudaMemsetAsync(uraw, 0, sizeof(double) * 2 * bl, st));
+  PLSB_TRY(launch_accum_u(h, h->R.as<double>(), l.ldx, 1, l.K, l.B, d_V, l.L, uraw, usq, st));
+  PLSB_TRY(launch_normalize_flip(h, uraw, l.B, l.L, lam2, d_U, d_V, l.K, d_d, st));
+  return plsb_set_original(h, d_U, d_d, d_V, stream);
+}
+
+int plsb_project_scores(plsb_handle_t h, const double *d_U, int L, double *d_out, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data, PLSB_ERR_STATE, "plsb_project_scores before plsb_set_data");
+  PLSB_CHECK(d_U && d_out && L >= 1, PLSB_ERR_ARG, "plsb_project_scores: bad argument");
+  const Layout &l = h->lay;
+  return launch_xproj(h, h->Xraw.as<double>(), l.ldx, l.S, l.B, d_U, L, nullptr, d_out,
+                      as_stream(stream));
+}
+
+int plsb_gen_perm_indices(plsb_handle_t h, uint64_t seed, int64_t first, int count, int32_t *d_idx,
+                          int *h_n_exhausted, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->configured, PLSB_ERR_STATE, "index generation before plsb_configure");
+  return gen_indices(h, false, seed, first, count, d_idx, h_n_exhausted, as_stream(stream));
+}
+
+int plsb_gen_boot_indices(plsb_handle_t h, uint64_t seed, int64_t first, int count, int32_t *d_idx,
+                          int *h_n_exhausted, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->configured, PLSB_ERR_STATE, "index generation before plsb_configure");
+  return gen_indices(h, true, seed, first, count, d_idx, h_n_exhausted, as_stream(stream));
+}
+
+int plsb_crosscov(plsb_handle_t h, const int32_t *d_idx, int count, int bootstrap, double *d_R,
+                  void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data, PLSB_ERR_STATE, "plsb_crosscov before plsb_set_data");
+  PLSB_CHECK(d_R != nullptr && count >= 0, PLSB_ERR_ARG, "plsb_crosscov: bad argument");
+  PLSB_CHECK(d_idx != nullptr || count == 1, PLSB_ERR_ARG, "plsb_crosscov: null index table");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  const int chunk = chunk_size(h, bootstrap != 0, count);
+  for (int off = 0; off < count; off += chunk) {
+    const int n = std::min(chunk, count - off);
+    PLSB_TRY(crosscov_chunk(h, d_idx ? d_idx + (size_t)off * l.S : nullptr, n, bootstrap != 0,
+                            nullptr, st));
+    PLSB_TRY(launch_unpad_copy(h, h->R.as<double>(), l.ldx, n * l.K, l.B,
+                               d_R + (size_t)off * l.K * l.B, st));
+  }
+  return PLSB_OK;
+}
+
+int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, int rotate, double *d_dperm,
+                   void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data, PLSB_ERR_STATE, "plsb_run_perms before plsb_set_data");
+  PLSB_CHECK(!rotate || h->has_original, PLSB_ERR_STATE,
+             "plsb_run_perms(rotate) before the original decomposition is set");
+  PLSB_CHECK(d_idx && d_dperm && count >= 0, PLSB_ERR_ARG, "plsb_run_perms: bad argument");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  if (rotate) {
+    // |R^T v_j| for every original y-weight v_j: A = V^T-weighted operand, row sums of squares
+    const size_t per = sizeof(double) * (size_t)l.L * l.S_pad;
+    int chunk = (int)std::min<long long>(
+        count, std::max<long long>(1, (long long)(h->ws_limit / per)));
+    chunk = (int)std::min<long long>(chunk, ((1ll << 31) - 1024) / l.L);
+    const int n_ntiles = l.ldx / GEMM_BN;
+    for (int off = 0; off < count; off += chunk) {
+      const int n = std::min(chunk, count - off);
+      const long long M = (long long)n * l.L, M_pad = round_up_ll(M, GEMM_BM);
+      PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)M_pad * l.S_pad));
+      PLSB_TRY(zero_tail(h->A.as<double>(), M, M_pad, l.S_pad, st));
+      PLSB_TRY(launch_build(h, BUILD_ROT, d_idx + (size_t)off * l.S, n, h->A.as<double>(), nullptr,
+                            nullptr, st));
+      const int n_mtiles = (int)(M_pad / GEMM_BM);
+      const int n_splits = gemm_pick_splits(h, n_mtiles, n_ntiles);
+      PLSB_TRY(h->rowsq.ensure(sizeof(double) * (size_t)n_splits * M_pad));
+      GemmArgs g;
+      g.A = h->A.as<double>();
+      g.lda = l.S_pad;
+      g.X = perm_data(h);
+      g.ldx = l.ldx;
+      g.M_pad = (int)M_pad;
+      g.N_pad = l.ldx;
+      g.Kd = l.S_pad;
+      g.rowsq = h->rowsq.as<double>();
+      g.n_splits = n_splits;
+      PLSB_TRY(launch_gemm(h, g, st));
+      PLSB_TRY(launch_finish_rowsq(h, h->rowsq.as<double>(), n_splits, (int)M_pad, (int)M,
+                                   d_dperm + (size_t)off * l.L, st));
+    }
+    return PLSB_OK;
+  }
+  // un-rotated: singular values of every R from the eigenvalues of R R^T
+  const int chunk = chunk_size(h, false, count);
+  for (int off = 0; off < count; off += chunk) {
+    const int n = std::min(chunk, count - off);
+    PLSB_TRY(crosscov_chunk(h, d_idx + (size_t)off * l.S, n, false, nullptr, st));
+    PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * l.K * l.K));
+    PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, n, l.K, l.B, nullptr, 0,
+                              h->G.as<double>(), nullptr, st));
+    PLSB_TRY(launch_sym_eig(h, h->G.as<double>(), n, l.K, nullptr, d_dperm + (size_t)off * l.L, 1,
+                            st));
+  }
+  return PLSB_OK;
+}
+
+int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, double *d_distrib,
+                   double *d_usum, double *d_usquare, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->has_original, PLSB_ERR_STATE,
+             "plsb_run_boots before data and original decomposition are set");
+  PLSB_CHECK(d_idx && d_distrib && d_usum && d_usquare && count >= 0, PLSB_ERR_ARG,
+             "plsb_run_boots: bad argument");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  const int chunk = chunk_size(h, true, count);
+  for (int off = 0; off < count; off += chunk) {
+    const int n = std::min(chunk, count - off);
+    PLSB_TRY(crosscov_chunk(h, d_idx + (size_t)off * l.S, n, true,
+                            d_distrib + (size_t)off * l.K * l.L, st));
+    PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * l.K * l.K));
+    PLSB_TRY(h->H.ensure(sizeof(double) * (size_t)n * l.K * l.L));
+    PLSB_TRY(h->M.ensure(sizeof(double) * (size_t)n * l.K * l.L));
+    PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, n, l.K, l.B, h->Uo.as<double>(), l.L,
+                              h->G.as<double>(), h->H.as<double>(), st));
+    PLSB_TRY(launch_small_decomp(h, h->G.as<double>(), h->H.as<double>(), n, l.K, l.L,
+                                 h->dorig.as<double>(), h->M.as<double>(), nullptr, st));
+    PLSB_TRY(launch_accum_u(h, h->R.as<double>(), l.ldx, n, l.K, l.B, h->M.as<double>(), l.L,
+                            d_usum, d_usquare, st));
+  }
+  return PLSB_OK;
+}
+
+int plsb_perm_pvals(plsb_handle_t h, const double *d_dperm, int count, int L, const double *d_dorig,
+                    double *d_pvals, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_dperm && d_dorig && d_pvals && count >= 0 && L >= 1, PLSB_ERR_ARG,
+             "plsb_perm_pvals: bad argument");
+  return launch_pvals(h, d_dperm, count, L, d_dorig, d_pvals, as_stream(stream));
+}
+
+int plsb_percentile(plsb_handle_t h, const double *d_distrib, int count, int n_series, double q_lo,
+                    double q_hi, double *d_lo, double *d_hi, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_distrib && d_lo && d_hi, PLSB_ERR_ARG, "plsb_percentile: null argument");
+  return launch_percentile(h, d_distrib, count, n_series, q_lo, q_hi, d_lo, d_hi,
+                           as_stream(stream));
+}
+
+int plsb_boot_ratio(plsb_handle_t h, const double *d_bs, const double *d_usum,
+                    const double *d_usquare, int64_t n_elem, int n_boot, int add_orig,
+                    double *d_bsr, double *d_se, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_bs && d_usum && d_usquare && d_bsr && d_se, PLSB_ERR_ARG,
+             "plsb_boot_ratio: null argument");
+  return launch_boot_ratio(h, d_bs, d_usum, d_usquare, n_elem, n_boot, add_orig, d_bsr, d_se,
+                           as_stream(stream));
+}
+
+int plsb_dgemm(plsb_handle_t h, const double *d_A, const double *d_X, int M, int N, int Kd,
+               double *d_C, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_A && d_X && d_C && M >= 1 && N >= 1 && Kd >= 1, PLSB_ERR_ARG,
+             "plsb_dgemm: bad argument");
+  cudaStream_t st = as_stream(stream);
+  const int M_pad = round_up(M, GEMM_BM), N_pad = round_up(N, GEMM_BN), K_pad = round_up(Kd, GEMM_BK);
+  PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)M_pad * K_pad));
+  PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)K_pad * N_pad));
+  PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)M_pad * N_pad));
+  PLSB_TRY(launch_pad_copy(h, d_A, M, Kd, h->A.as<double>(), M_pad, K_pad, st));
+  PLSB_TRY(launch_pad_copy(h, d_X, Kd, N, h->misc.as<double>(), K_pad, N_pad, st));
+  GemmArgs g;
+  g.A = h->A.as<double>();
+  g.lda = K_pad;
+  g.X = h->misc.as<double>();
+  g.ldx = N_pad;
+  g.M_pad = M_pad;
+  g.N_pad = N_pad;
+  g.Kd = K_pad;
+  g.C = h->R.as<double>();
+  g.ldc = N_pad;
+  PLSB_TRY(launch_gemm(h, g, st));
+  return launch_unpad_copy(h, h->R.as<double>(), N_pad, M, N, d_C, st);
+}
+
+int plsb_small_decomp(plsb_handle_t h, const double *d_G, const double *d_H, int count, int K,
+                      int L, const double *d_dorig, double *d_M, double *d_lam, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_G && d_H && d_M && count >= 0, PLSB_ERR_ARG, "plsb_small_decomp: bad argument");
+  return launch_small_decomp(h, d_G, d_H, count, K, L, d_dorig, d_M, d_lam, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// Internal declarations shared by the translation units of libplsb200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/plsb200.h"
+
+namespace plsb {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char *fmt, ...);
+
+#define PLSB_CUDA(expr)                                                      \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) {                                                 \
+      plsb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,          \
+                      cudaGetErrorString(_e));                               \
+      return PLSB_ERR_CUDA;                                                  \
+    }                                                                        \
+  } while (0)
+
+#define PLSB_CHECK(cond, code, ...)                                          \
+  do {                                                                       \
+    if (!(cond)) {                                                           \
+      plsb::set_error(__VA_ARGS__);                                          \
+      return (code);                                                         \
+    }                                                                        \
+  } while (0)
+
+#define PLSB_TRY(expr)                                                       \
+  do {                                                                       \
+    int _s = (expr);                                                         \
+    if (_s != PLSB_OK) return _s;                                            \
+  } while (0)
+
+// kernel launch check (no sync); every wrapper bumps the handle's counter
+#define PLSB_LAUNCHED(h)                                                     \
+  do {                                                                       \
+    PLSB_CUDA(cudaGetLastError());                                           \
+    (h)->launches++;                                                         \
+  } while (0)
+
+// ---- tiny device buffer that grows on demand -------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return PLSB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return PLSB_ERR_NOMEM;
+    }
+    bytes = need;
+    return PLSB_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline long long round_up_ll(long long x, long long m) { return (x + m - 1) / m * m; }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- GEMM tile geometry (gemm_dmma.cu) --------------------------------------
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 128;
+constexpr int GEMM_BK = 16;
+
+// kernel classes for the optional per-launch event timing (bench / profiling)
+enum KernelClass {
+  KC_GEMM = 0,   // xcov_gemm_kernel (DMMA cross-covariance contraction)
+  KC_BUILD,      // operand builders + distrib
+  KC_GRAM,       // gram_proj
+  KC_SMALL,      // small_decomp (Jacobi / Procrustes)
+  KC_ACCUM,      // accum_u + partial reduction
+  KC_STATS,      // colscale, finish_rowsq, pvals, percentile, boot_ratio
+  KC_INDEX,      // index generation
+  KC_PREP,       // pad / prep / projections
+  KC_COUNT
+};
+
+constexpr int MAX_K = 80;     // small-matrix kernels keep four K x K tiles in shared memory
+constexpr int MAX_COND = 32;  // index generator: conditions per subject
+
+// ---- analysis layout --------------------------------------------------------
+struct Layout {
+  int mode = -1;
+  int S = 0, B = 0, T = 0, J = 0, K = 0, L = 0;
+  int n_groups = 0, n_cond = 1, mean_centering = 0, n_components = 0;
+  int n_subj = 0;
+  std::vector<int> groups;      // subjects per group
+  std::vector<int> cell_start;  // first row of each cell (J+1 entries)
+  int S_pad = 0;                // rows of the padded data matrices == lda of operands
+  int ldx = 0;                  // leading dimension (elements) of padded (., B) matrices
+  bool behavioral() const { return mode == PLSB_BEHAVIORAL_CORR || mode == PLSB_BEHAVIORAL_COV; }
+  bool corr() const { return mode == PLSB_BEHAVIORAL_CORR; }
+};
+
+}  // namespace plsb
+
+// The opaque handle of the C ABI.
+struct plsb_ctx {
+  int device = 0;
+  plsb::Layout lay;
+  bool configured = false, has_data = false, has_original = false;
+  uint64_t ws_limit = 12ull << 30;
+  int64_t launches = 0;
+  int sm_count = 148;
+  // optional event timing: (class, start, stop) per launch since the last read
+  bool timing = false;
+  struct TimedLaunch { int cls; cudaEvent_t a, b; };
+  std::vector<TimedLaunch> timed;
+
+  // layout tables on the device: int cell_start[J+1], cell_of_row[S], cell_n[J],
+  // group_start[n_groups+1] (subject units)
+  plsb::DevBuf tables;
+  const int *d_cell_start = nullptr, *d_cell_of_row = nullptr, *d_cell_n = nullptr,
+            *d_group_start = nullptr;
+
+  // data-dependent state (set_data); all (S_pad, ldx) zero padded
+  plsb::DevBuf Xraw;   // raw X
+  plsb::DevBuf Xcell;  // behavioural: X z-scored (corr) / centred (cov) within each cell
+  plsb::DevBuf Xglob;  // X centred (and for corr scaled) with whole-column statistics
+  plsb::DevBuf Y;      // Y (S, T)
+  plsb::DevBuf Cmat;   // mean-centred: operator C (J, S)
+  // original decomposition
+  plsb::DevBuf Uo;     // (B, L)
+  plsb::DevBuf Vo;     // (K, L)
+  plsb::DevBuf dorig;  // (L)
+  plsb::DevBuf Sx;     // Xraw @ normalize(Uo)   (S, L)
+  plsb::DevBuf norms;  // (L)
+  // per-chunk workspaces
+  plsb::DevBuf A, Ac, R, S1, S2, G, H, M, lam, rowsq, part, misc, idxall, flags;
+};
+
+namespace plsb {
+
+// Brackets the launches of one wrapper with events when timing is enabled.
+struct KernelTimer {
+  plsb_ctx *h;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int cls;
+  KernelTimer(plsb_ctx *h_, int cls_, cudaStream_t st_) : h(h_), st(st_), cls(cls_) {
+    if (!h->timing) return;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+      a = b = nullptr;
+      return;
+    }
+    cudaEventRecord(a, st);
+  }
+  ~KernelTimer() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    h->timed.push_back({cls, a, b});
+  }
+};
+
+// ---- kernel launch wrappers (each returns plsb_status) ----------------------
+
+// C = A @ X (+ epilogues).  See gemm_dmma.cu.
+struct GemmArgs {
+  const double *A = nullptr;   // (M_pad, lda), rows beyond M zero
+  int lda = 0;
+  const double *X = nullptr;   // (Kd, ldx)
+  int ldx = 0;
+  int M_pad = 0;               // multiple of GEMM_BM
+  int N_pad = 0;               // multiple of GEMM_BN (<= ldx)
+  int Kd = 0;                  // contraction length, multiple of GEMM_BK (padding zero)
+  const int2 *kranges = nullptr;  // optional per-M-tile [kbeg,kend), kbeg even
+  bool square_b = false;       // use X*X elementwise as the right operand
+  // STORE epilogue
+  double *C = nullptr;
+  long long ldc = 0;
+  const int *row_map = nullptr;   // optional: output row of operand row m, <0 = skip
+  const double *scale = nullptr;  // optional: C[m,n] *= scale[(m / scale_div) * lds + n]
+  int scale_div = 1;
+  long long lds = 0;
+  // ROWSUMSQ epilogue: rowsq[split * M_pad + m] = sum_n C[m,n]^2 over the split
+  double *rowsq = nullptr;
+  int n_splits = 1;
+};
+int launch_gemm(plsb_ctx *h, const GemmArgs &a, cudaStream_t st);
+int gemm_pick_splits(const plsb_ctx *h, int n_mtiles, int n_ntiles);
+
+// data preparation (prep.cu)
+int launch_pad_copy(plsb_ctx *h, const double *X, int S, int B, double *out, int S_pad, int ldx,
+                    cudaStream_t st);
+int launch_unpad_copy(plsb_ctx *h, const double *in, long long ld_in, int rows, int cols,
+                      double *out, cudaStream_t st);
+int launch_prep_cells(plsb_ctx *h, const double *Xraw, double *Xcell, double *Xglob,
+                      cudaStream_t st);
+int launch_colnorm(plsb_ctx *h, const double *U, int B, int L, double *norms, cudaStream_t st);
+int launch_xproj(plsb_ctx *h, const double *Xmat, int ldx_, int S, int B, const double *U, int L,
+                 const double *norms, double *out, cudaStream_t st);
+int launch_normalize_flip(plsb_ctx *h, const double *Uraw, int B, int L, const double *lam,
+                          double *U, double *V, int K, double *d, cudaStream_t st);
+int launch_colgram(plsb_ctx *h, const double *W, int B, int K, double *G, cudaStream_t st);
+int launch_matmul_small(plsb_ctx *h, const double *A, const double *Bm, int n, double *C,
+                        cudaStream_t st);
+
+// operand builders / distrib (operands.cu)
+enum BuildKind { BUILD_ROT = 0, BUILD_PLAIN = 1, BUILD_BOOT = 2 };
+int launch_build(plsb_ctx *h, int kind, const int32_t *idx, int count, double *A, double *Ac,
+                 double *distrib, cudaStream_t st);
+
+// streaming kernels over stored R (stream_kernels.cu)
+int launch_finish_rowsq(plsb_ctx *h, const double *rowsq, int n_splits, int M_pad, int n_rows,
+                        double *out, cudaStream_t st);
+int launch_colscale(plsb_ctx *h, double *S1, const double *S2, int n_rows, long long ld,
+                    cudaStream_t st);
+int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
+                     const double *Uo, int L, double *G, double *H, cudaStream_t st);
+int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
+                   const double *M, int L, double *usum, double *usq, cudaStream_t st);
+
+// small matrices (small_matrix.cu)
+int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count, int K, int L,
+                        const double *dorig, double *M, double *lam, cudaStream_t st);
+int launch_sym_eig(plsb_ctx *h, const double *G, int count, int K, double *V, double *lam,
+                   int sqrt_lam, cudaStream_t st);
+
+// index generation (indexgen.cu), statistics (stats.cu)
+int gen_indices(plsb_ctx *h, bool boot, uint64_t seed, int64_t first, int count, int32_t *d_idx,
+                int *h_n_exhausted, cudaStream_t st);
+int launch_pvals(plsb_ctx *h, const double *dperm, int count, int L, const double *dorig,
+                 double *pvals, cudaStream_t st);
+int launch_percentile(plsb_ctx *h, const double *distrib, int count, int n_series, double qlo,
+                      double qhi, double *lo, double *hi, cudaStream_t st);
+int launch_boot_ratio(plsb_ctx *h, const double *bs, const double *usum, const double *usq,
+                      long long n, int n_boot, int add_orig, double *bsr, double *se,
+                      cudaStream_t st);
+
+}  // namespace plsb

@@ -1,0 +1,261 @@
+// FP64 tensor-core (DMMA) cross-covariance GEMM for sm_100a.
+//
+//   C (M, N) = A (M, Kd) @ X (Kd, N)
+//
+// A is the stack of per-resample left operands (a few rows per resample, built
+// by operands.cu), X is the data matrix shared by every resample.  This is the
+// contraction of compute.xcorr (pyls/compute.py:92, `Yn.T @ Xn`) for thousands
+// of resamples at once.  tcgen05 has no f64 kind, so the tensor path for fp64
+// on sm_100a is mma.sync.m8n8k4 (SASS DMMA.8x8x4).
+//
+// Tiling: CTA 128x128, 8 warps as 2 (M) x 4 (N), warp tile 64x32 = 8 x 4
+// fragments, BK = 16 per pipeline stage, 4-stage cp.async ring.  The (N tile,
+// k chunk) loops are flattened into one sequence so the ring never drains
+// between N tiles.  Shared-memory leading dimensions are == 4 (mod 16) doubles,
+// which makes every fragment load (8 rows x 4 k) bank-conflict free.
+//
+// Epilogues:
+//   STORE     write C (optionally through a row map: operand row -> output row)
+//   ROWSUMSQ  rowsq[split][m] = sum_n C[m,n]^2  (rotated permutation singular
+//             values, pyls/base.py:699-700, without materialising C)
+// Optional per-M-tile contraction ranges skip the structural zeros of
+// block-diagonal operands (one block per group x condition cell).
+#include "common.cuh"
+
+namespace plsb {
+
+namespace {
+
+constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
+constexpr int STAGES = 4;
+constexpr int LDA_S = BK + 4;           // 20
+constexpr int LDB_S = BN + 4;           // 132
+constexpr int A_STAGE = BM * LDA_S;     // doubles
+constexpr int B_STAGE = BK * LDB_S;     // doubles
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+constexpr int NTHREADS = 256;
+constexpr int MF = 8, NF = 4;           // fragments per warp tile
+
+enum { EPI_STORE = 0, EPI_ROWSUMSQ = 1 };
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+template <int EPI, bool SQB>
+__global__ void __launch_bounds__(NTHREADS, 1)
+xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict__ X, int ldx,
+                 int n_mtiles, int n_ntiles, int nt_per_split, const int2 *__restrict__ kranges,
+                 int Kd, double *__restrict__ C, long long ldc, const int *__restrict__ row_map,
+                 const double *__restrict__ scale, int scale_div, long long lds,
+                 double *__restrict__ rowsq, int M_pad) {
+  extern __shared__ __align__(16) double smem[];
+  double *As = smem;
+  double *Bs = smem + STAGES * A_STAGE;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+
+  const int split = blockIdx.x / n_mtiles;
+  const int mtile = blockIdx.x - split * n_mtiles;
+  const int nt0 = split * nt_per_split;
+  const int nt1 = min(nt0 + nt_per_split, n_ntiles);
+  if (nt0 >= nt1) return;
+
+  int kbeg = 0, kend = Kd;
+  if (kranges) {
+    int2 kr = kranges[mtile];
+    kbeg = kr.x;
+    kend = kr.y;
+  }
+  const int nkc = (kend - kbeg + BK - 1) / BK;     // k chunks per N tile
+  const int total = (nt1 - nt0) * nkc;             // flattened pipeline steps
+
+  const double *Ablk = A + (size_t)mtile * BM * lda;
+
+  // producer: issue the loads of flattened step `s` into ring slot s % STAGES
+  auto issue = [&](int s) {
+    if (s < total) {
+      const int nt = nt0 + s / nkc;
+      const int kc = s - (s / nkc) * nkc;
+      const int k0 = kbeg + kc * BK;
+      double *as = As + (s % STAGES) * A_STAGE;
+      double *bs = Bs + (s % STAGES) * B_STAGE;
+      // A: 128 rows x 16 doubles = 1024 x 16 B, 4 per thread
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        int c = tid + it * NTHREADS;
+        int row = c >> 3, seg = c & 7;
+        cp_async16(as + row * LDA_S + seg * 2, Ablk + (size_t)row * lda + k0 + seg * 2);
+      }
+      // X: 16 rows x 128 doubles = 1024 x 16 B, 4 per thread
+      const double *xg = X + (size_t)k0 * ldx + (size_t)nt * BN;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        int c = tid + it * NTHREADS;
+        int row = c >> 6, seg = c & 63;
+        cp_async16(bs + row * LDB_S + seg * 2, xg + (size_t)row * ldx + seg * 2);
+      }
+    }
+    cp_async_commit();
+  };
+
+  double acc[MF][NF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i)
+#pragma unroll
+    for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double rsq[MF];
+#pragma unroll
+  for (int i = 0; i < MF; ++i) rsq[i] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) issue(s);
+
+  int kc = 0, nt = nt0;
+  for (int s = 0; s < total; ++s) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    // refill the slot consumed in the previous iteration
+    issue(s + STAGES - 1);
+
+    const double *as = As + (s % STAGES) * A_STAGE + (wm * 64 + g) * LDA_S + q;
+    const double *bs = Bs + (s % STAGES) * B_STAGE + q * LDB_S + wn * 32 + g;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double af[MF], bf[NF];
+#pragma unroll
+      for (int i = 0; i < MF; ++i) af[i] = as[i * 8 * LDA_S + kk * 4];
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        double v = bs[kk * 4 * LDB_S + j * 8];
+        bf[j] = SQB ? v * v : v;
+      }
+#pragma unroll
+      for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+
+    if (++kc == nkc) {
+      // ---- epilogue of N tile `nt` ----
+      if (EPI == EPI_STORE) {
+#pragma unroll
+        for (int i = 0; i < MF; ++i) {
+          const int m = mtile * BM + wm * 64 + i * 8 + g;
+          const int orow = row_map ? row_map[m] : m;
+          if (orow >= 0) {
+            const size_t col = (size_t)nt * BN + wn * 32 + 2 * q;
+            double *crow = C + (size_t)orow * ldc + col;
+            if (scale) {
+              const double *srow = scale + (size_t)(m / scale_div) * lds + col;
+#pragma unroll
+              for (int j = 0; j < NF; ++j) {
+                const double2 sc = *reinterpret_cast<const double2 *>(srow + j * 8);
+                *reinterpret_cast<double2 *>(crow + j * 8) =
+                    make_double2(acc[i][j][0] * sc.x, acc[i][j][1] * sc.y);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < NF; ++j)
+                *reinterpret_cast<double2 *>(crow + j * 8) =
+                    make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < MF; ++i)
+#pragma unroll
+          for (int j = 0; j < NF; ++j)
+            rsq[i] += acc[i][j][0] * acc[i][j][0] + acc[i][j][1] * acc[i][j][1];
+      }
+#pragma unroll
+      for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      kc = 0;
+      ++nt;
+    }
+  }
+
+  if (EPI == EPI_ROWSUMSQ) {
+    // reduce over the 4 lanes of a quad, then over the 4 N-warps through smem
+    cp_async_wait<0>();
+    __syncthreads();
+    double *red = smem;  // [4 wn][128 rows]
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+      double v = rsq[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (q == 0) red[wn * BM + wm * 64 + i * 8 + g] = v;
+    }
+    __syncthreads();
+    if (tid < BM) {
+      double v = red[tid] + red[BM + tid] + red[2 * BM + tid] + red[3 * BM + tid];
+      rowsq[(size_t)split * M_pad + (size_t)mtile * BM + tid] = v;
+    }
+  }
+}
+
+template <int EPI, bool SQB>
+int launch_variant(plsb_ctx *h, const GemmArgs &a, int n_mtiles, int n_ntiles, int n_splits,
+                   cudaStream_t st) {
+  KernelTimer kt(h, KC_GEMM, st);
+  auto kern = xcov_gemm_kernel<EPI, SQB>;
+  PLSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int nt_per_split = (n_ntiles + n_splits - 1) / n_splits;
+  dim3 grid((unsigned)(n_mtiles * n_splits));
+  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(a.A, a.lda, a.X, a.ldx, n_mtiles, n_ntiles, nt_per_split,
+                                           a.kranges, a.Kd, a.C, a.ldc, a.row_map, a.scale,
+                                           a.scale_div, a.lds, a.rowsq, a.M_pad);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
+}  // namespace
+
+// Splits of the N range per M tile: enough CTAs for >= ~6 waves over the SMs,
+// never more than the N tiles there are.
+int gemm_pick_splits(const plsb_ctx *h, int n_mtiles, int n_ntiles) {
+  int want = (6 * h->sm_count + n_mtiles - 1) / n_mtiles;
+  if (want < 1) want = 1;
+  if (want > n_ntiles) want = n_ntiles;
+  return want;
+}
+
+int launch_gemm(plsb_ctx *h, const GemmArgs &a, cudaStream_t st) {
+  PLSB_CHECK(a.M_pad % BM == 0 && a.N_pad % BN == 0 && a.Kd % BK == 0, PLSB_ERR_ARG,
+             "gemm: M_pad=%d N_pad=%d Kd=%d must be multiples of %d/%d/%d", a.M_pad, a.N_pad, a.Kd,
+             BM, BN, BK);
+  PLSB_CHECK(a.lda % 2 == 0 && a.ldx % 2 == 0, PLSB_ERR_ARG, "gemm: odd leading dimension");
+  if (a.M_pad == 0 || a.N_pad == 0) return PLSB_OK;
+  const int n_mtiles = a.M_pad / BM, n_ntiles = a.N_pad / BN;
+  const bool rowsq = a.rowsq != nullptr;
+  int n_splits = rowsq ? a.n_splits : gemm_pick_splits(h, n_mtiles, n_ntiles);
+  if (rowsq) {
+    PLSB_CHECK(a.n_splits >= 1, PLSB_ERR_ARG, "gemm: n_splits");
+    if (a.square_b) return launch_variant<EPI_ROWSUMSQ, true>(h, a, n_mtiles, n_ntiles, n_splits, st);
+    return launch_variant<EPI_ROWSUMSQ, false>(h, a, n_mtiles, n_ntiles, n_splits, st);
+  }
+  PLSB_CHECK(a.C != nullptr && a.ldc % 2 == 0, PLSB_ERR_ARG, "gemm: bad output");
+  if (a.square_b) return launch_variant<EPI_STORE, true>(h, a, n_mtiles, n_ntiles, n_splits, st);
+  return launch_variant<EPI_STORE, false>(h, a, n_mtiles, n_ntiles, n_splits, st);
+}
+
+}  // namespace plsb

@@ -1,0 +1,289 @@
+// On-device resample tables.  Replaces gen_permsamp / gen_bootsamp
+// (pyls/base.py:10-79, 82-159) with a counter-based generator: the stream of
+// resample `id` is Philox4x32-10 keyed by the user's seed with counter
+// (block, id, attempt, kind), so any rank can produce any column and the table
+// does not depend on how resamples are sharded.  Validity rules are the
+// reference's:
+//   permutation  every subject keeps its conditions together, in an
+//                independently shuffled order (utils.permute_cols,
+//                pyls/utils.py:200-224); subjects are permuted across groups and
+//                a draw in which some group keeps its own subject set is
+//                rejected (base.py:59-62); a column equal to an earlier one is
+//                re-drawn (base.py:67-69)
+//   bootstrap    sorted sampling with replacement inside each group, at least
+//                ceil(min(groups)/2) distinct subjects per group (base.py:111,
+//                134-139), conditions follow their subject (:142-143); a column
+//                whose rows [a,b) equal an earlier column's for some group
+//                bounds (a,b) is re-drawn (:145-149, bounds in SUBJECT units
+//                as in the reference)
+//   at most 500 draws per column (base.py:51,125); columns that hit the cap are
+//   kept and counted.
+// One thread generates one column; duplicate detection compares 64-bit hashes
+// first and full columns on a hash match.
+#include "common.cuh"
+
+namespace plsb {
+namespace {
+
+constexpr int MAX_TRIES = 500;
+
+struct Philox {
+  uint32_t k0, k1, c1, c2, c3, n;
+  uint32_t out[4];
+  int have;
+  __device__ Philox(uint64_t seed, uint32_t id, uint32_t attempt, uint32_t kind)
+      : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), c1(id), c2(attempt), c3(kind), n(0),
+        have(0) {}
+  __device__ void refill() {
+    uint32_t a = n++, b = c1, c = c2, d = c3, key0 = k0, key1 = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, a), lo0 = 0xD2511F53u * a;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c), lo1 = 0xCD9E8D57u * c;
+      a = hi1 ^ b ^ key0;
+      b = lo1;
+      c = hi0 ^ d ^ key1;
+      d = lo0;
+      key0 += 0x9E3779B9u;
+      key1 += 0xBB67AE85u;
+    }
+    out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+    have = 4;
+  }
+  __device__ uint32_t next() {
+    if (!have) refill();
+    return out[--have];
+  }
+  // uniform integer in [0, bound)
+  __device__ uint32_t below(uint32_t bound) { return __umulhi(next(), bound); }
+};
+
+struct GenParams {
+  uint64_t seed;
+  int total, S, n_subj, n_groups, n_cond, min_subj;
+  const int *group_start;  // subject units, n_groups + 1
+  int *flags;              // 1 = (re)generate this column
+  int *attempts;           // draws used so far per column
+  int *scratch;            // total x n_subj
+  int32_t *idx;            // total x S
+};
+
+__device__ __forceinline__ int group_of(const int *gs, int n_groups, int subj) {
+  int g = 0;
+  while (g + 1 < n_groups && subj >= gs[g + 1]) ++g;
+  return g;
+}
+
+__global__ void gen_perm_kernel(GenParams p) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= p.total || !p.flags[id]) return;
+  int *perm = p.scratch + (size_t)id * p.n_subj;
+  int32_t *col = p.idx + (size_t)id * p.S;
+  int att = p.attempts[id];
+  for (;;) {
+    Philox rng(p.seed, (uint32_t)id, (uint32_t)att, 0u);
+    ++att;
+    for (int i = 0; i < p.n_subj; ++i) perm[i] = i;
+    for (int i = p.n_subj - 1; i > 0; --i) {
+      const int j = (int)rng.below((uint32_t)i + 1u);
+      const int t = perm[i];
+      perm[i] = perm[j];
+      perm[j] = t;
+    }
+    bool bad = false;
+    if (p.n_groups > 1) {
+      for (int g = 0; g < p.n_groups && !bad; ++g) {
+        const int a = p.group_start[g], b = p.group_start[g + 1];
+        bool kept = true;
+        for (int k = a; k < b && kept; ++k) kept = (perm[k] >= a && perm[k] < b);
+        bad = kept;
+      }
+    }
+    if (bad && att < MAX_TRIES) continue;
+    // lay the column out: destination (group g, condition c, slot k)
+    for (int g = 0; g < p.n_groups; ++g) {
+      const int a = p.group_start[g], b = p.group_start[g + 1], ng = b - a;
+      for (int k = a; k < b; ++k) {
+        const int subj = perm[k];
+        const int gs = group_of(p.group_start, p.n_groups, subj);
+        const int sa = p.group_start[gs], sn = p.group_start[gs + 1] - sa;
+        int order[MAX_COND];
+        for (int c = 0; c < p.n_cond; ++c) order[c] = c;
+        for (int c = p.n_cond - 1; c > 0; --c) {
+          const int j = (int)rng.below((uint32_t)c + 1u);
+          const int t = order[c];
+          order[c] = order[j];
+          order[j] = t;
+        }
+        for (int c = 0; c < p.n_cond; ++c)
+          col[p.n_cond * a + c * ng + (k - a)] = p.n_cond * sa + order[c] * sn + (subj - sa);
+      }
+    }
+    break;
+  }
+  p.attempts[id] = att;
+}
+
+__global__ void gen_boot_kernel(GenParams p) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= p.total || !p.flags[id]) return;
+  int *cnt = p.scratch + (size_t)id * p.n_subj;
+  int32_t *col = p.idx + (size_t)id * p.S;
+  const int att = p.attempts[id];
+  Philox rng(p.seed, (uint32_t)id, (uint32_t)att, 1u);
+  for (int g = 0; g < p.n_groups; ++g) {
+    const int a = p.group_start[g], b = p.group_start[g + 1], ng = b - a;
+    for (int redo = 0; redo < 100000; ++redo) {
+      for (int k = a; k < b; ++k) cnt[k] = 0;
+      for (int i = 0; i < ng; ++i) cnt[a + (int)rng.below((uint32_t)ng)]++;
+      int uniq = 0;
+      for (int k = a; k < b; ++k) uniq += cnt[k] > 0;
+      if (uniq >= p.min_subj) break;
+    }
+    int slot = 0;
+    for (int subj = a; subj < b; ++subj)
+      for (int m = 0; m < cnt[subj]; ++m, ++slot)
+        for (int c = 0; c < p.n_cond; ++c)
+          col[p.n_cond * a + c * ng + slot] = p.n_cond * a + c * ng + (subj - a);
+  }
+  p.attempts[id] = att + 1;
+}
+
+// FNV-1a style 64-bit hash of rows [a,b) of every column, one per (column, segment)
+__global__ void hash_kernel(const int32_t *__restrict__ idx, int total, int S, int n_seg,
+                            const int *__restrict__ seg_bounds, uint64_t *__restrict__ hashes) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total * n_seg) return;
+  const int id = e / n_seg, sg = e - id * n_seg;
+  const int a = seg_bounds[sg], b = seg_bounds[sg + 1];
+  uint64_t hsh = 1469598103934665603ull;
+  for (int s = a; s < b; ++s) {
+    hsh ^= (uint64_t)(uint32_t)idx[(size_t)id * S + s];
+    hsh *= 1099511628211ull;
+  }
+  hashes[e] = hsh;
+}
+
+// flags[i] = 1 when column i repeats an earlier column (in any segment) and may
+// still be re-drawn; counters[0] = columns to re-draw, counters[1] = exhausted
+__global__ void dup_kernel(const int32_t *__restrict__ idx, int total, int S, int n_seg,
+                           const int *__restrict__ seg_bounds,
+                           const uint64_t *__restrict__ hashes, const int *__restrict__ attempts,
+                           int *__restrict__ flags, int *__restrict__ counters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  bool dup = false;
+  for (int sg = 0; sg < n_seg && !dup; ++sg) {
+    const uint64_t mine = hashes[(size_t)i * n_seg + sg];
+    const int a = seg_bounds[sg], b = seg_bounds[sg + 1];
+    for (int j = 0; j < i && !dup; ++j) {
+      if (hashes[(size_t)j * n_seg + sg] != mine) continue;
+      bool same = true;
+      for (int s = a; s < b && same; ++s)
+        same = idx[(size_t)i * S + s] == idx[(size_t)j * S + s];
+      dup = same;
+    }
+  }
+  int f = 0;
+  if (dup) {
+    if (attempts[i] < MAX_TRIES) {
+      f = 1;
+      atomicAdd(&counters[0], 1);
+    } else {
+      atomicAdd(&counters[1], 1);
+    }
+  }
+  flags[i] = f;
+}
+
+__global__ void fill_int_kernel(int *p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+int gen_indices(plsb_ctx *h, bool boot, uint64_t seed, int64_t first, int count, int32_t *d_idx,
+                int *h_n_exhausted, cudaStream_t st) {
+  KernelTimer kt(h, KC_INDEX, st);
+  const Layout &l = h->lay;
+  PLSB_CHECK(first >= 0 && count >= 0 && first + count < (1ll << 30), PLSB_ERR_ARG,
+             "index generation: bad range first=%lld count=%d", (long long)first, count);
+  PLSB_CHECK(l.n_cond <= MAX_COND, PLSB_ERR_ARG, "index generation: n_cond=%d > %d", l.n_cond,
+             MAX_COND);
+  if (h_n_exhausted) *h_n_exhausted = 0;
+  if (count == 0) return PLSB_OK;
+  const int total = (int)(first + count);
+  const int n_seg = boot ? l.n_groups : 1;
+  // segments whose equality defines a duplicate (rows; the bootstrap bounds are
+  // the reference's subject-unit bounds used as row bounds)
+  std::vector<int> seg(n_seg + 1);
+  if (boot) {
+    int acc = 0;
+    for (int g = 0; g < l.n_groups; ++g) {
+      seg[g] = acc;
+      acc += l.groups[g];
+    }
+    seg[l.n_groups] = acc;
+  } else {
+    seg[0] = 0;
+    seg[1] = l.S;
+  }
+  PLSB_TRY(h->idxall.ensure(sizeof(int32_t) * (size_t)total * l.S));
+  const size_t n_int = (size_t)total * 2 + (size_t)total * l.n_subj + 2 + (n_seg + 1);
+  PLSB_TRY(h->flags.ensure(sizeof(int) * n_int + sizeof(uint64_t) * ((size_t)total * n_seg + 1)));
+  uint64_t *hashes = h->flags.as<uint64_t>();
+  int *flags = reinterpret_cast<int *>(hashes + (size_t)total * n_seg + 1);
+  int *attempts = flags + total;
+  int *scratch = attempts + total;
+  int *counters = scratch + (size_t)total * l.n_subj;
+  int *d_seg = counters + 2;
+  PLSB_CUDA(cudaMemcpyAsync(d_seg, seg.data(), sizeof(int) * (n_seg + 1), cudaMemcpyHostToDevice,
+                            st));
+  const int tb = 128, nb = cdiv(total, tb);
+  fill_int_kernel<<<nb, tb, 0, st>>>(flags, total, 1);
+  PLSB_LAUNCHED(h);
+  PLSB_CUDA(cudaMemsetAsync(attempts, 0, sizeof(int) * total, st));
+
+  GenParams p;
+  p.seed = seed;
+  p.total = total;
+  p.S = l.S;
+  p.n_subj = l.n_subj;
+  p.n_groups = l.n_groups;
+  p.n_cond = l.n_cond;
+  int min_group = l.groups[0];
+  for (int g : l.groups) min_group = std::min(min_group, g);
+  p.min_subj = (min_group + 1) / 2;
+  p.group_start = h->d_group_start;
+  p.flags = flags;
+  p.attempts = attempts;
+  p.scratch = scratch;
+  p.idx = h->idxall.as<int32_t>();
+
+  int host_counters[2] = {0, 0};
+  for (int round = 0; round <= MAX_TRIES; ++round) {
+    if (boot)
+      gen_boot_kernel<<<nb, tb, 0, st>>>(p);
+    else
+      gen_perm_kernel<<<nb, tb, 0, st>>>(p);
+    PLSB_LAUNCHED(h);
+    hash_kernel<<<cdiv(total * n_seg, tb), tb, 0, st>>>(p.idx, total, l.S, n_seg, d_seg, hashes);
+    PLSB_LAUNCHED(h);
+    PLSB_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(int), st));
+    dup_kernel<<<nb, tb, 0, st>>>(p.idx, total, l.S, n_seg, d_seg, hashes, attempts, flags,
+                                  counters);
+    PLSB_LAUNCHED(h);
+    PLSB_CUDA(cudaMemcpyAsync(host_counters, counters, 2 * sizeof(int), cudaMemcpyDeviceToHost,
+                              st));
+    PLSB_CUDA(cudaStreamSynchronize(st));
+    if (host_counters[0] == 0) break;
+  }
+  if (h_n_exhausted) *h_n_exhausted = host_counters[1];
+  PLSB_CUDA(cudaMemcpyAsync(d_idx, h->idxall.as<int32_t>() + (size_t)first * l.S,
+                            sizeof(int32_t) * (size_t)count * l.S, cudaMemcpyDeviceToDevice, st));
+  PLSB_CUDA(cudaStreamSynchronize(st));
+  return PLSB_OK;
+}
+
+}  // namespace plsb

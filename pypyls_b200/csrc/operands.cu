@@ -1,0 +1,246 @@
+// Per-resample left operands of the cross-covariance contraction.
+//
+// The reference gathers rows of X and Y for every resample and then forms
+// `Yn.T @ Xn` (pyls/base.py:569,599; pyls/compute.py:84-92).  Here the row
+// gather is moved to the small operand: for a resample with source rows
+// src[s], X[src]^T Z = X^T W with W[u,:] = sum_{s: src[s]=u} Z[s,:], so every
+// resample is a few rows of a tall matrix A that multiplies the SAME data
+// matrix.  One CTA builds the rows of one resample.
+//
+//   behavioural (pyls/types/behavioral.py:27-52)
+//     ROT    A[r*L+j, u] = sum_t zy[u,t] V[(cell(u),t), j] / (n-1)   (rotated perms:
+//            |R^T v_j| = |Xcell^T a_j|, pyls/base.py:696-700)
+//     PLAIN  A[r*K+(g,t), u] = [u in g] zy[u,t] / (n-1)              (R itself)
+//     BOOT   A[r*K+(g,t), u] = sum_{s in g, src[s]=u} zy[s,t]        (x 1/(n-1) for covariance)
+//            Ac[r*J+g, u]    = #{s in g : src[s]=u}                  (column statistics)
+//            distrib[r]      = per-cell xcorr(Sx[src], Y[src])       (behavioral.py:54-80)
+//     zy = Y[src] z-scored (ddof=1) or centred within each cell.
+//   mean-centred (pyls/types/meancentered.py:50-125, pyls/compute.py:267-357)
+//     AR[j,u] = sum_{s: src[s]=u} C[j,s];  ROT: A = V^T AR;  PLAIN/BOOT: A = AR;
+//     distrib[r] = AR @ Sx.
+#include "common.cuh"
+
+namespace plsb {
+namespace {
+
+struct BuildParams {
+  const int32_t *idx;
+  int S, T, J, K, L, lda, corr, kind;
+  const double *Y;
+  const int *cell_start, *cell_of_row;
+  const double *Vo, *Sx, *Cmat;
+  double *A, *Ac, *distrib;
+};
+
+__global__ void build_behavioral_kernel(BuildParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int S = p.S, T = p.T, J = p.J, K = p.K, L = p.L, lda = p.lda;
+  double *Yp = sm;                 // S*T
+  double *ymean = Yp + S * T;      // J*T
+  double *yistd = ymean + J * T;   // J*T
+  double *sxm = yistd + J * T;     // J*L
+  double *sxi = sxm + J * L;       // J*L
+  int *src = reinterpret_cast<int *>(sxi + J * L);  // S
+  const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+
+  for (int s = tid; s < S; s += nt) src[s] = p.idx ? p.idx[(size_t)r * S + s] : s;
+  __syncthreads();
+  for (int e = tid; e < S * T; e += nt) {
+    const int s = e / T, t = e - s * T;
+    Yp[e] = p.Y[(size_t)src[s] * T + t];
+  }
+  __syncthreads();
+  for (int c = tid; c < J * T; c += nt) {
+    const int g = c / T, t = c - g * T;
+    const int r0 = p.cell_start[g], r1 = p.cell_start[g + 1], n = r1 - r0;
+    double m = 0.0;
+    for (int s = r0; s < r1; ++s) m += Yp[s * T + t];
+    m /= n;
+    double v = 0.0;
+    for (int s = r0; s < r1; ++s) {
+      const double d = Yp[s * T + t] - m;
+      v += d * d;
+    }
+    ymean[c] = m;
+    yistd[c] = p.corr ? 1.0 / sqrt(v / (n - 1)) : 1.0;
+  }
+  __syncthreads();
+  for (int e = tid; e < S * T; e += nt) {
+    const int s = e / T, t = e - s * T;
+    const int c = p.cell_of_row[s] * T + t;
+    Yp[e] = (Yp[e] - ymean[c]) * yistd[c];
+  }
+  __syncthreads();
+
+  if (p.kind == BUILD_ROT) {
+    double *Ar = p.A + (size_t)r * L * lda;
+    for (int e = tid; e < L * lda; e += nt) {
+      const int j = e / lda, u = e - j * lda;
+      double val = 0.0;
+      if (u < S) {
+        const int g = p.cell_of_row[u];
+        const int n = p.cell_start[g + 1] - p.cell_start[g];
+        for (int t = 0; t < T; ++t) val += Yp[u * T + t] * p.Vo[(size_t)(g * T + t) * L + j];
+        val /= (n - 1);
+      }
+      Ar[e] = val;
+    }
+    return;
+  }
+  if (p.kind == BUILD_PLAIN) {
+    double *Ar = p.A + (size_t)r * K * lda;
+    for (int e = tid; e < K * lda; e += nt) {
+      const int row = e / lda, u = e - row * lda;
+      const int g = row / T, t = row - g * T;
+      double val = 0.0;
+      if (u < S && p.cell_of_row[u] == g) {
+        const int n = p.cell_start[g + 1] - p.cell_start[g];
+        val = Yp[u * T + t] / (n - 1);
+      }
+      Ar[e] = val;
+    }
+    return;
+  }
+
+  // ---- BUILD_BOOT ----
+  {
+    double *Ar = p.A + (size_t)r * K * lda;
+    for (int e = tid; e < K * lda; e += nt) {
+      const int row = e / lda, u = e - row * lda;
+      const int g = row / T, t = row - g * T;
+      const int r0 = p.cell_start[g], r1 = p.cell_start[g + 1];
+      double val = 0.0;
+      if (u < S)
+        for (int s = r0; s < r1; ++s)
+          if (src[s] == u) val += Yp[s * T + t];
+      if (!p.corr) val /= (r1 - r0 - 1);
+      Ar[e] = val;
+    }
+    if (p.Ac) {
+      double *Cr = p.Ac + (size_t)r * J * lda;
+      for (int e = tid; e < J * lda; e += nt) {
+        const int g = e / lda, u = e - g * lda;
+        const int r0 = p.cell_start[g], r1 = p.cell_start[g + 1];
+        int cnt = 0;
+        if (u < S)
+          for (int s = r0; s < r1; ++s) cnt += (src[s] == u);
+        Cr[e] = (double)cnt;
+      }
+    }
+  }
+  if (!p.distrib) return;
+  // per-cell statistics of the gathered scores Sx[src]
+  for (int c = tid; c < J * L; c += nt) {
+    const int g = c / L, l = c - g * L;
+    const int r0 = p.cell_start[g], r1 = p.cell_start[g + 1], n = r1 - r0;
+    double m = 0.0;
+    for (int s = r0; s < r1; ++s) m += p.Sx[(size_t)src[s] * L + l];
+    m /= n;
+    double v = 0.0;
+    for (int s = r0; s < r1; ++s) {
+      const double d = p.Sx[(size_t)src[s] * L + l] - m;
+      v += d * d;
+    }
+    sxm[c] = m;
+    sxi[c] = p.corr ? 1.0 / sqrt(v / (n - 1)) : 1.0;
+  }
+  __syncthreads();
+  double *Dr = p.distrib + (size_t)r * K * L;
+  for (int e = tid; e < K * L; e += nt) {
+    const int row = e / L, l = e - row * L;
+    const int g = row / T, t = row - g * T;
+    const int r0 = p.cell_start[g], r1 = p.cell_start[g + 1], n = r1 - r0;
+    const double m = sxm[g * L + l], is = sxi[g * L + l];
+    double acc = 0.0;
+    for (int s = r0; s < r1; ++s)
+      acc += Yp[s * T + t] * ((p.Sx[(size_t)src[s] * L + l] - m) * is);
+    Dr[e] = acc / (n - 1);
+  }
+}
+
+__global__ void build_meancentered_kernel(BuildParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int S = p.S, J = p.J, L = p.L, lda = p.lda;
+  double *AR = sm;                                   // J*S
+  int *src = reinterpret_cast<int *>(AR + J * S);    // S
+  const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  for (int s = tid; s < S; s += nt) src[s] = p.idx ? p.idx[(size_t)r * S + s] : s;
+  __syncthreads();
+  for (int e = tid; e < J * S; e += nt) {
+    const int j = e / S, u = e - j * S;
+    double val = 0.0;
+    for (int s = 0; s < S; ++s)
+      if (src[s] == u) val += p.Cmat[(size_t)j * S + s];
+    AR[e] = val;
+  }
+  __syncthreads();
+  if (p.kind == BUILD_ROT) {
+    double *Ar = p.A + (size_t)r * L * lda;
+    for (int e = tid; e < L * lda; e += nt) {
+      const int l = e / lda, u = e - l * lda;
+      double val = 0.0;
+      if (u < S)
+        for (int j = 0; j < J; ++j) val += p.Vo[(size_t)j * L + l] * AR[j * S + u];
+      Ar[e] = val;
+    }
+    return;
+  }
+  double *Ar = p.A + (size_t)r * J * lda;
+  for (int e = tid; e < J * lda; e += nt) {
+    const int j = e / lda, u = e - j * lda;
+    Ar[e] = u < S ? AR[j * S + u] : 0.0;
+  }
+  if (p.kind == BUILD_BOOT && p.distrib) {
+    double *Dr = p.distrib + (size_t)r * J * L;
+    for (int e = tid; e < J * L; e += nt) {
+      const int j = e / L, l = e - j * L;
+      double acc = 0.0;
+      for (int u = 0; u < S; ++u) acc += AR[j * S + u] * p.Sx[(size_t)u * L + l];
+      Dr[e] = acc;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_build(plsb_ctx *h, int kind, const int32_t *idx, int count, double *A, double *Ac,
+                 double *distrib, cudaStream_t st) {
+  KernelTimer kt(h, KC_BUILD, st);
+  const Layout &l = h->lay;
+  if (count <= 0) return PLSB_OK;
+  BuildParams p;
+  p.idx = idx;
+  p.S = l.S; p.T = l.T; p.J = l.J; p.K = l.K; p.L = l.L; p.lda = l.S_pad;
+  p.corr = l.corr() ? 1 : 0;
+  p.kind = kind;
+  p.Y = h->Y.as<double>();
+  p.cell_start = h->d_cell_start;
+  p.cell_of_row = h->d_cell_of_row;
+  p.Vo = h->Vo.as<double>();
+  p.Sx = h->Sx.as<double>();
+  p.Cmat = h->Cmat.as<double>();
+  p.A = A; p.Ac = Ac; p.distrib = distrib;
+  if (kind == BUILD_ROT || (kind == BUILD_BOOT && distrib))
+    PLSB_CHECK(h->has_original, PLSB_ERR_STATE, "operand builder needs the original decomposition");
+  size_t smem;
+  if (l.behavioral()) {
+    smem = sizeof(double) * ((size_t)l.S * l.T + 2 * (size_t)l.J * l.T + 2 * (size_t)l.J * l.L) +
+           sizeof(int) * (size_t)l.S;
+    PLSB_CHECK(smem <= 200 * 1024, PLSB_ERR_ARG,
+               "behavioural operand builder needs %zu bytes of shared memory (S*T too large)", smem);
+    PLSB_CUDA(cudaFuncSetAttribute(build_behavioral_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    build_behavioral_kernel<<<count, 256, smem, st>>>(p);
+  } else {
+    smem = sizeof(double) * (size_t)l.J * l.S + sizeof(int) * (size_t)l.S;
+    PLSB_CHECK(smem <= 200 * 1024, PLSB_ERR_ARG,
+               "mean-centred operand builder needs %zu bytes of shared memory (J*S too large)", smem);
+    PLSB_CUDA(cudaFuncSetAttribute(build_meancentered_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    build_meancentered_kernel<<<count, 256, smem, st>>>(p);
+  }
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
+}  // namespace plsb

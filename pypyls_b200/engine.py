@@ -1,0 +1,288 @@
+# -*- coding: utf-8 -*-
+"""
+Thin object wrapper over the C ABI of ``libplsb200.so``.
+
+PyTorch is used for device memory and streams only: every tensor handed to the
+library is a plain device pointer, all arithmetic happens in the hand-written
+sm_100a kernels of ``csrc/``.  There is no CPU path -- constructing an engine
+without a CUDA device or without the compiled library raises.
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+MODES = {
+    'behavioral': _cabi.PLSB_BEHAVIORAL_CORR,
+    'behavioral_cov': _cabi.PLSB_BEHAVIORAL_COV,
+    'meancentered': _cabi.PLSB_MEANCENTERED,
+}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class ResamplingEngine:
+    """
+    One analysis layout + data set resident on one GPU.
+
+    Parameters
+    ----------
+    mode : {'behavioral', 'behavioral_cov', 'meancentered'}
+    S, B, T : int
+        Rows, features, behaviours (``T`` ignored for mean-centred PLS)
+    groups : list of int
+        Subjects per group; rows are ordered group -> condition -> subject
+        (pyls/structures.py:37-44)
+    n_cond : int
+    mean_centering : {0, 1, 2}
+    device : int
+        CUDA ordinal
+    """
+
+    def __init__(self, mode, S, B, T, groups, n_cond=1, mean_centering=0,
+                 device=0, workspace_bytes=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('pypyls_b200 needs a CUDA device (B200, '
+                               'sm_100a); there is no CPU fallback.')
+        self._lib = _cabi.lib()
+        self.device = torch.device('cuda', int(device))
+        self.mode = mode
+        groups = [int(g) for g in groups]
+        self.S, self.B, self.T = int(S), int(B), int(T)
+        self.groups, self.n_cond = groups, int(n_cond)
+        self.J = len(groups) * self.n_cond
+        self.K = self.J * self.T if mode != 'meancentered' else self.J
+        self.L = self.K
+        self._h = C.c_void_p(0)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.plsb_create(C.byref(self._h),
+                                              self.device.index))
+        if workspace_bytes is not None:
+            _cabi.check(self._lib.plsb_set_workspace_limit(
+                self._h, int(workspace_bytes)))
+        garr = (C.c_int * len(groups))(*groups)
+        _cabi.check(self._lib.plsb_configure(
+            self._h, MODES[mode], self.S, self.B, self.T, len(groups), garr,
+            self.n_cond, int(mean_centering), 0))
+
+    # -- plumbing ----------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            torch.cuda.synchronize(self.device)
+            self._lib.plsb_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f64(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=self.device)
+
+    def to_device(self, a, dtype=torch.float64):
+        """Host array (NumPy or tensor) or device tensor -> contiguous device
+        tensor of `dtype`."""
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype,
+                        non_blocking=True).contiguous()
+        a = np.ascontiguousarray(a)
+        return torch.from_numpy(a).to(device=self.device, dtype=dtype,
+                                      non_blocking=True).contiguous()
+
+    def to_device_indices(self, samples):
+        """Resampling table as the reference stores it, (S, n) integers
+        (pyls/base.py:35,107), -> (n, S) int32 on the device."""
+        if isinstance(samples, torch.Tensor) and samples.is_cuda:
+            if samples.dtype != torch.int32 or samples.shape[-1] != self.S:
+                raise ValueError('device index tables must be (n, S) int32')
+            return samples.contiguous()
+        samples = np.asarray(samples)
+        if samples.ndim == 1:
+            samples = samples[:, None]
+        if samples.ndim != 2 or samples.shape[0] != self.S:
+            raise ValueError('Resampling array must have shape ({}, n); got '
+                             '{}'.format(self.S, samples.shape))
+        if samples.size and (samples.min() < 0 or samples.max() >= self.S):
+            raise ValueError('Resampling array has indices outside '
+                             '[0, {})'.format(self.S))
+        host = np.ascontiguousarray(samples.T.astype(np.int32))
+        return torch.from_numpy(host).to(self.device)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.plsb_launch_count(self._h))
+
+    # -- data / original decomposition ---------------------------------------
+    def set_data(self, X, Y=None):
+        X = self.to_device(X)
+        if tuple(X.shape) != (self.S, self.B):
+            raise ValueError('X must have shape ({}, {})'.format(self.S, self.B))
+        if self.mode != 'meancentered':
+            Y = self.to_device(Y)
+            if tuple(Y.shape) != (self.S, self.T):
+                raise ValueError('Y must have shape ({}, {})'
+                                 .format(self.S, self.T))
+        else:
+            Y = None
+        _cabi.check(self._lib.plsb_set_data(self._h, _ptr(X), _ptr(Y),
+                                            self._stream()))
+        return self
+
+    def decompose(self):
+        """Original decomposition -> (U (B,L), d (L,), V (K,L)) on the device;
+        also installs it as the original for the resampling drivers."""
+        U, d, V = self._f64(self.B, self.L), self._f64(self.L), \
+            self._f64(self.K, self.L)
+        _cabi.check(self._lib.plsb_decompose(self._h, _ptr(U), _ptr(d),
+                                             _ptr(V), self._stream()))
+        return U, d, V
+
+    def set_original(self, U, d, V):
+        U, d, V = self.to_device(U), self.to_device(d), self.to_device(V)
+        if d.ndim == 2:
+            d = torch.diagonal(d).contiguous()
+        if tuple(U.shape) != (self.B, self.L) or \
+                tuple(V.shape) != (self.K, self.L) or d.numel() != self.L:
+            raise ValueError('original decomposition has the wrong shape')
+        _cabi.check(self._lib.plsb_set_original(self._h, _ptr(U), _ptr(d),
+                                                _ptr(V), self._stream()))
+        return self
+
+    def project_scores(self, U):
+        U = self.to_device(U)
+        out = self._f64(self.S, U.shape[1])
+        _cabi.check(self._lib.plsb_project_scores(
+            self._h, _ptr(U), int(U.shape[1]), _ptr(out), self._stream()))
+        return out
+
+    # -- index generation -----------------------------------------------------
+    def _gen(self, fn, seed, first, count):
+        idx = torch.empty((count, self.S), dtype=torch.int32,
+                          device=self.device)
+        n_ex = C.c_int(0)
+        _cabi.check(fn(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)),
+                       int(first), int(count), _ptr(idx), C.byref(n_ex),
+                       self._stream()))
+        return idx, int(n_ex.value)
+
+    def gen_perm_indices(self, seed, count, first=0):
+        """(count, S) int32 permutation table for resample ids
+        [first, first+count) and the number of columns that hit the 500-draw
+        cap (pyls/base.py:10-79)."""
+        return self._gen(self._lib.plsb_gen_perm_indices, seed, first, count)
+
+    def gen_boot_indices(self, seed, count, first=0):
+        """Bootstrap table (pyls/base.py:82-159); see gen_perm_indices."""
+        return self._gen(self._lib.plsb_gen_boot_indices, seed, first, count)
+
+    # -- resampling drivers ---------------------------------------------------
+    def run_perms(self, idx, rotate=True):
+        """Permuted singular values, (count, L) on the device
+        (BasePLS.permutation, pyls/base.py:601-712)."""
+        idx = self.to_device_indices(idx)
+        out = self._f64(idx.shape[0], self.L)
+        _cabi.check(self._lib.plsb_run_perms(
+            self._h, _ptr(idx), int(idx.shape[0]), int(bool(rotate)),
+            _ptr(out), self._stream()))
+        return out
+
+    def run_boots(self, idx, u_sum=None, u_square=None):
+        """(distrib (count,K,L), u_sum (B,L), u_square (B,L)) on the device
+        (BasePLS.bootstrap, pyls/base.py:439-576)."""
+        idx = self.to_device_indices(idx)
+        n = int(idx.shape[0])
+        distrib = self._f64(n, self.K, self.L)
+        if u_sum is None:
+            u_sum = torch.zeros((self.B, self.L), dtype=torch.float64,
+                                device=self.device)
+            u_square = torch.zeros_like(u_sum)
+        _cabi.check(self._lib.plsb_run_boots(
+            self._h, _ptr(idx), n, _ptr(distrib), _ptr(u_sum), _ptr(u_square),
+            self._stream()))
+        return distrib, u_sum, u_square
+
+    def crosscov(self, idx=None, bootstrap=False):
+        """Cross-covariance matrices (count, K, B) of the given resamples;
+        ``idx=None`` gives the un-resampled matrix."""
+        if idx is None:
+            n, p = 1, C.c_void_p(0)
+        else:
+            idx = self.to_device_indices(idx)
+            n, p = int(idx.shape[0]), _ptr(idx)
+        out = self._f64(n, self.K, self.B)
+        _cabi.check(self._lib.plsb_crosscov(self._h, p, n, int(bool(bootstrap)),
+                                            _ptr(out), self._stream()))
+        return out
+
+    # -- statistics -----------------------------------------------------------
+    def perm_pvals(self, d_perm, d_orig):
+        d_perm, d_orig = self.to_device(d_perm), self.to_device(d_orig)
+        out = self._f64(d_perm.shape[1])
+        _cabi.check(self._lib.plsb_perm_pvals(
+            self._h, _ptr(d_perm), int(d_perm.shape[0]), int(d_perm.shape[1]),
+            _ptr(d_orig), _ptr(out), self._stream()))
+        return out
+
+    def percentile(self, distrib, q_lo, q_hi):
+        """numpy-'linear' percentiles over axis 0 of a (count, ...) tensor."""
+        distrib = self.to_device(distrib)
+        n = int(distrib.shape[0])
+        series = int(distrib.numel() // max(n, 1))
+        lo, hi = self._f64(*distrib.shape[1:]), self._f64(*distrib.shape[1:])
+        _cabi.check(self._lib.plsb_percentile(
+            self._h, _ptr(distrib), n, series, float(q_lo), float(q_hi),
+            _ptr(lo), _ptr(hi), self._stream()))
+        return lo, hi
+
+    def boot_ratio(self, bs, u_sum, u_square, n_boot, add_orig):
+        bs = self.to_device(bs)
+        bsr, se = torch.empty_like(bs), torch.empty_like(bs)
+        _cabi.check(self._lib.plsb_boot_ratio(
+            self._h, _ptr(bs), _ptr(u_sum), _ptr(u_square), int(bs.numel()),
+            int(n_boot), int(bool(add_orig)), _ptr(bsr), _ptr(se),
+            self._stream()))
+        return bsr, se
+
+    # -- primitives (unit tests) ----------------------------------------------
+    def dgemm(self, A, X):
+        A, X = self.to_device(A), self.to_device(X)
+        M, Kd = A.shape
+        N = X.shape[1]
+        out = self._f64(M, N)
+        _cabi.check(self._lib.plsb_dgemm(self._h, _ptr(A), _ptr(X), int(M),
+                                         int(N), int(Kd), _ptr(out),
+                                         self._stream()))
+        return out
+
+    def small_decomp(self, G, H, d_orig=None):
+        G, H = self.to_device(G), self.to_device(H)
+        d_orig = None if d_orig is None else self.to_device(d_orig)
+        n, K = int(G.shape[0]), int(G.shape[1])
+        L = int(H.shape[2])
+        M, lam = self._f64(n, K, L), self._f64(n, K)
+        _cabi.check(self._lib.plsb_small_decomp(
+            self._h, _ptr(G), _ptr(H), n, K, L, _ptr(d_orig), _ptr(M),
+            _ptr(lam), self._stream()))
+        return M, lam
+
+    # -- per-kernel-class timing (bench) ---------------------------------------
+    def timing_enable(self, on=True):
+        _cabi.check(self._lib.plsb_timing_enable(self._h, int(bool(on))))
+
+    def timing_read(self):
+        """{class name: (milliseconds, launches)} since the previous read."""
+        n = int(self._lib.plsb_timing_classes())
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        _cabi.check(self._lib.plsb_timing_read(self._h, ms, cnt))
+        return {self._lib.plsb_timing_class_name(i).decode(): (ms[i], cnt[i])
+                for i in range(n)}

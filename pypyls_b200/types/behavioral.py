@@ -1,0 +1,98 @@
+# -*- coding: utf-8 -*-
+"""
+Behavioral PLS front-end (interface of pyls/types/behavioral.py:10-242) on the
+CUDA resampling engine.
+"""
+
+import numpy as np
+
+from .. import structures
+from ..base import BasePLS
+
+
+class BehavioralPLS(BasePLS):
+    def __init__(self, X, Y, *, groups=None, n_cond=1, n_perm=5000,
+                 n_boot=5000, n_split=0, test_size=0.25, test_split=0,
+                 covariance=False, rotate=True, ci=95, permsamples=None,
+                 bootsamples=None, seed=None, verbose=True, n_proc=None,
+                 **kwargs):
+        if test_split:
+            raise NotImplementedError(
+                'Cross-validation (test_split) is not part of the accelerated '
+                'path yet; pass test_split=0.')
+        X, Y = np.asarray(X), np.asarray(Y)
+        if X.ndim != 2 or Y.ndim != 2:
+            raise ValueError('`X` and `Y` must be two-dimensional arrays.')
+        super().__init__(X=X, Y=Y, groups=groups, n_cond=n_cond,
+                         n_perm=n_perm, n_boot=n_boot, n_split=n_split,
+                         test_size=test_size, test_split=test_split,
+                         covariance=covariance, rotate=rotate, ci=ci,
+                         permsamples=permsamples, bootsamples=bootsamples,
+                         seed=seed, verbose=verbose, n_proc=n_proc, **kwargs)
+        self.results = self.run_pls(self.inputs.X, self.inputs.Y)
+
+    def engine_mode(self):
+        return 'behavioral_cov' if self.inputs.get('covariance') \
+            else 'behavioral'
+
+    def run_pls(self, X, Y):
+        """Follows pyls/types/behavioral.py:172-227 (cross-validation
+        excluded)."""
+        res = super().run_pls(X, Y)
+        eng = self.engine
+
+        # y_scores: every cell's rows of Y times that cell's block of V
+        cells = np.repeat(res['inputs']['groups'], res['inputs']['n_cond'])
+        T = Y.shape[1]
+        res['y_scores'] = np.vstack([
+            y @ res['y_weights'][j * T:(j + 1) * T]
+            for j, y in enumerate(np.split(Y, np.cumsum(cells)[:-1]))])
+
+        # y_loadings = per-cell xcorr(x_scores, Y): the bootstrap distribution
+        # kernel evaluated on the identity resample (X @ U has unit-norm U)
+        ident = np.arange(eng.S)[:, None]
+        y_load, _, _ = eng.run_boots(ident)
+        res['y_loadings'] = y_load[0].cpu().numpy()
+
+        if self.inputs.n_boot > 0:
+            distrib, u_sum, u_square = self.bootstrap(X, Y, self.rs)
+            bsrs, uboot_se, corrci = self._boot_stats(add_orig=True)
+            res['bootres'].update(dict(x_weights_normed=bsrs,
+                                       x_weights_stderr=uboot_se,
+                                       y_loadings=res['y_loadings'].copy(),
+                                       y_loadings_boot=distrib,
+                                       y_loadings_ci=corrci,
+                                       bootsamples=self.bootsamp))
+
+        sq = np.diag(res['singvals']) ** 2
+        res['varexp'] = sq / np.sum(sq)
+        res['singvals'] = np.diag(res['singvals'])
+        return res
+
+
+def behavioral_pls(X, Y, *, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
+                   n_split=0, test_size=0.25, test_split=0,
+                   covariance=False, rotate=True, ci=95, permsamples=None,
+                   bootsamples=None, seed=None, verbose=True, n_proc=None,
+                   **kwargs):
+    """
+    Behavioral PLS of `X` (S, B) and `Y` (S, T); same call as
+    ``pyls.behavioral_pls`` (pyls/types/behavioral.py:231-242) with the
+    permutation test and bootstrap executed on the GPU.
+
+    Differences from the reference front-end: ``test_split`` defaults to 0
+    (cross-validation is not accelerated), ``n_split`` must be 0, and
+    ``n_proc`` is accepted but unused (resamples run as one batched launch).
+    Extra keywords: ``index_backend``, ``device``, ``workspace_bytes``.
+
+    Returns
+    -------
+    results : :obj:`pypyls_b200.structures.PLSResults`
+    """
+    pls = BehavioralPLS(X=X, Y=Y, groups=groups, n_cond=n_cond,
+                        n_perm=n_perm, n_boot=n_boot, n_split=n_split,
+                        test_size=test_size, test_split=test_split,
+                        covariance=covariance, rotate=rotate, ci=ci,
+                        permsamples=permsamples, bootsamples=bootsamples,
+                        seed=seed, verbose=verbose, n_proc=n_proc, **kwargs)
+    return pls.results

@@ -1,0 +1,113 @@
+# -*- coding: utf-8 -*-
+"""
+Mean-centered PLS front-end (interface of pyls/types/meancentered.py:10-195)
+on the CUDA resampling engine.
+"""
+
+import warnings
+
+import numpy as np
+
+from ..base import BasePLS
+
+
+def dummy_code(groups, n_cond=1):
+    """(S, J) 0/1 membership of every row in its group x condition cell
+    (pyls/utils.py:155-175)."""
+    sizes = np.repeat([int(g) for g in groups], n_cond)
+    labels = np.repeat(np.arange(len(sizes)), sizes)
+    return (labels[:, None] == np.arange(len(sizes))[None, :]).astype(int)
+
+
+class MeanCenteredPLS(BasePLS):
+    def __init__(self, X, groups=None, n_cond=1, mean_centering=0, n_perm=5000,
+                 n_boot=5000, n_split=0, rotate=True, ci=95,
+                 permsamples=None, bootsamples=None, seed=None,
+                 verbose=True, n_proc=None, **kwargs):
+        X = np.asarray(X)
+        if groups is None:
+            if len(X) // n_cond != len(X) / n_cond:
+                raise ValueError('Provided `X` matrix with {} samples is not '
+                                 'evenly divisible into {} conditions. Please '
+                                 'confirm inputs are correct and try again. '
+                                 .format(len(X), n_cond))
+            groups = [len(X) // n_cond]
+        elif not isinstance(groups, (list, np.ndarray)):
+            groups = [groups]
+
+        if n_cond == 1 and len(groups) == 1:
+            raise ValueError('Cannot perform PLS with only one group and one '
+                             'condition. Please confirm inputs are correct.')
+        if n_cond == 1 and mean_centering == 0:
+            warnings.warn('Cannot set mean_centering to 0 when there is only '
+                          'one condition. Resetting mean_centering to 1.')
+            mean_centering = 1
+        elif len(groups) == 1 and mean_centering == 1:
+            warnings.warn('Cannot set mean_centering to 1 when there is only '
+                          'one group. Resetting mean_centering to 0.')
+            mean_centering = 0
+        if mean_centering not in (0, 1, 2):
+            raise ValueError("Mean centering type must be in [0, 1, 2].")
+
+        super().__init__(X=X, groups=groups, n_cond=n_cond,
+                         mean_centering=mean_centering, n_perm=n_perm,
+                         n_boot=n_boot, n_split=n_split, rotate=rotate, ci=ci,
+                         permsamples=permsamples, bootsamples=bootsamples,
+                         seed=seed, verbose=verbose, n_proc=n_proc, **kwargs)
+        self.inputs.Y = dummy_code(self.inputs.groups, self.inputs.n_cond)
+        self.results = self.run_pls(self.inputs.X, self.inputs.Y)
+
+    def engine_mode(self):
+        return 'meancentered'
+
+    def _engine_y(self, Y):
+        return None
+
+    def run_pls(self, X, Y):
+        """Follows pyls/types/meancentered.py:127-179."""
+        res = super().run_pls(X, Y)
+        eng = self.engine
+        res['y_scores'] = Y @ res['y_weights']
+
+        # contrast = cell means of the de-meaned rows projected on U: the
+        # bootstrap distribution kernel evaluated on the identity resample
+        ident = np.arange(eng.S)[:, None]
+        contrast = eng.run_boots(ident)[0][0].cpu().numpy()
+
+        if self.inputs.n_boot > 0:
+            distrib, u_sum, u_square = self.bootstrap(X, Y, self.rs)
+            bsrs, uboot_se, corrci = self._boot_stats(add_orig=False)
+            res['bootres'].update(dict(x_weights_normed=bsrs,
+                                       x_weights_stderr=uboot_se,
+                                       bootsamples=self.bootsamp,
+                                       contrast=contrast,
+                                       contrast_boot=distrib,
+                                       contrast_ci=corrci))
+
+        sq = np.diag(res['singvals']) ** 2
+        res['varexp'] = sq / np.sum(sq)
+        res['singvals'] = np.diag(res['singvals'])
+        return res
+
+
+def meancentered_pls(X, *, groups=None, n_cond=1, mean_centering=0,
+                     n_perm=5000, n_boot=5000, n_split=0, rotate=True, ci=95,
+                     permsamples=None, bootsamples=None, seed=None,
+                     verbose=True, n_proc=None, **kwargs):
+    """
+    Mean-centered PLS of `X` (S, B) sorted into `groups` and conditions; same
+    call as ``pyls.meancentered_pls`` (pyls/types/meancentered.py:182-195)
+    with the permutation test and bootstrap executed on the GPU.
+    ``n_split`` must be 0; ``n_proc`` is accepted but unused.
+
+    Returns
+    -------
+    results : :obj:`pypyls_b200.structures.PLSResults`
+    """
+    pls = MeanCenteredPLS(X=X, groups=groups, n_cond=n_cond,
+                          mean_centering=mean_centering,
+                          n_perm=n_perm, n_boot=n_boot, n_split=n_split,
+                          rotate=rotate, ci=ci, permsamples=permsamples,
+                          bootsamples=bootsamples, seed=seed, verbose=verbose,
+                          n_proc=n_proc, **kwargs)
+    return pls.results

@@ -1,0 +1,152 @@
+# -*- coding: utf-8 -*-
+"""
+CPU tests of the host side: resampling-table replay, result containers, and
+that the C-ABI library loads and exports every symbol include/plsb200.h
+declares (no compute calls -- there is no GPU here).
+"""
+
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, load_golden
+from oracle import pls_oracle as po
+
+
+def test_index_tables_bit_exact_with_reference():
+    from pypyls_b200.resample import gen_bootsamp, gen_permsamp
+    z = np.load(os.path.join(GOLDEN, 'index_tables.npz'))
+    n = 0
+    while 'spec%d' % n in z.files:
+        spec = [int(v) for v in z['spec%d' % n]]
+        groups, (n_cond, seed, cnt) = spec[:-3], spec[-3:]
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            assert np.array_equal(gen_permsamp(groups, n_cond, cnt, seed=seed),
+                                  z['perm%d' % n])
+            assert np.array_equal(gen_bootsamp(groups, n_cond, cnt, seed=seed),
+                                  z['boot%d' % n])
+        n += 1
+    assert n == 5
+
+
+@pytest.mark.parametrize('groups,n_cond', [([6, 5], 2), ([9], 3), ([3, 3, 4], 1)])
+def test_index_tables_match_oracle_stream(groups, n_cond):
+    from pypyls_b200.resample import gen_bootsamp, gen_permsamp
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        a = gen_permsamp(groups, n_cond, 40, seed=np.random.RandomState(5))
+        b = po.gen_permsamp(groups, n_cond, 40, seed=np.random.RandomState(5))
+        assert np.array_equal(a, b)
+        a = gen_bootsamp(groups, n_cond, 40, seed=np.random.RandomState(6))
+        b = po.gen_bootsamp(groups, n_cond, 40, seed=np.random.RandomState(6))
+        assert np.array_equal(a, b)
+
+
+def test_duplicate_warning_on_tiny_layout():
+    """pyls/tests/test_base.py: tiny inputs exhaust the distinct resamples."""
+    from pypyls_b200.resample import gen_bootsamp, gen_permsamp
+    with pytest.warns(UserWarning, match='Duplicate permutations'):
+        gen_permsamp([2], 1, 5, seed=1)
+    with pytest.warns(UserWarning, match='Duplicate bootstraps'):
+        gen_bootsamp([3], 1, 30, seed=1)
+
+
+@pytest.mark.parametrize('name', ['bpls_2g2c_rot', 'mpls_3g2c_mc0_rot'])
+def test_seed_replay_reproduces_reference_tables(name):
+    """The analysis' RandomState is consumed by the original decomposition
+    (a (K, K+10) normal draw inside sklearn's randomized_svd) before the
+    tables are made (pyls/base.py:362-368, 466-470)."""
+    from pypyls_b200.resample import (check_random_state, gen_bootsamp,
+                                      gen_permsamp)
+    ins, ref = load_golden(name)
+    J = len(ins['groups']) * ins['n_cond']
+    K = J * ins['Y'].shape[1] if 'Y' in ins else J
+    rs = check_random_state(ins['seed'])
+    rs.normal(size=(K, K + 10))
+    perm = gen_permsamp(ins['groups'], ins['n_cond'], ins['n_perm'], seed=rs)
+    boot = gen_bootsamp(ins['groups'], ins['n_cond'], ins['n_boot'], seed=rs)
+    assert np.array_equal(perm, ref['permsamples'])
+    assert np.array_equal(boot, ref['bootsamples'])
+
+
+def test_shard_range_partitions():
+    from pypyls_b200.resample import shard_range
+    for n in (0, 1, 7, 5000, 10001):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0
+            for (f0, c0), (f1, _) in zip(blocks[:-1], blocks[1:]):
+                assert f0 + c0 == f1
+            assert blocks[-1][0] + blocks[-1][1] == n
+            sizes = [c for _, c in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_structures_behave_like_reference():
+    """pyls/tests/test_structures.py: whitelist, n_split/test_split/n_proc
+    normalisation, test_size validation, tolerant equality."""
+    from pypyls_b200.structures import PLSInputs, PLSResults
+    inp = PLSInputs(X=1, n_split=0, test_split=0, n_proc='max', bogus=3)
+    assert 'bogus' not in inp and inp.n_split is None
+    assert inp.test_split is None and inp.n_proc == os.cpu_count()
+    assert PLSInputs(n_proc=-2).n_proc == os.cpu_count() - 1
+    with pytest.raises(ValueError):
+        PLSInputs(test_size=1)
+    with pytest.raises(ValueError):
+        PLSInputs(test_size=-0.5)
+    a = PLSResults(x_weights=np.ones(3), n_perm=5)
+    b = PLSResults(x_weights=np.ones(3) + 1e-7, n_perm=5)
+    c = PLSResults(x_weights=np.ones(3) + 1e-5, n_perm=5)
+    assert a == b and a != c
+    assert a.inputs.n_perm == 5 and 'x_weights' in str(a)
+    a.not_allowed = 4
+    assert 'not_allowed' not in a
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'plsb200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(plsb_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    """Builds (if needed) and loads libplsb200.so; every function declared in
+    include/plsb200.h must be exported and bound by the ctypes layer."""
+    from pypyls_b200 import _build, _cabi
+    _build.build()
+    lib = _cabi.load()
+    names = _header_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), name
+        assert name in _cabi.PROTOTYPES, name
+    assert set(_cabi.PROTOTYPES) == set(names)
+    assert lib.plsb_version() >= 100
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from pypyls_b200.engine import ResamplingEngine
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ResamplingEngine('behavioral', 8, 16, 2, [8])
+    import pypyls_b200 as pyls
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        pyls.behavioral_pls(np.random.rand(8, 16), np.random.rand(8, 2),
+                            n_perm=2, n_boot=2)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'pypyls_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', text,
+                                     flags=re.M), f
+                assert 'pls_oracle' not in text, f
