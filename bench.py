@@ -1,0 +1,450 @@
+# -*- coding: utf-8 -*-
+"""
+Benchmark of the PLS resampling hot path (BASELINE.json: resamples/sec,
+permutations + bootstraps combined).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+        --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: n_perm permutations and
+n_boot bootstraps of the workload (per GPU; weak scaling), including the
+p-value / bootstrap-ratio / percentile reductions and, for N > 1, the closing
+all-gather + all-reduce.  `value` is timed with CUDA events with X, Y and the
+resampling tables resident in HBM; `e2e` times the public front-end call
+(pypyls_b200.behavioral_pls) from pinned host arrays to host results, host<->
+device copies and on-device index generation included.
+
+`--impl reference` times the CPU implementation of the same path (the NumPy
+oracle port of the reference, oracle/pls_oracle.py -- the reference itself is
+a Python package that is not present on the GPU box) on all host cores, one
+process per core with single-threaded BLAS, which is the reference's own
+parallel mode (pyls/utils.py:252-279, .travis.yml:22-23).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    'cfg2': dict(kind='behavioral', S=80, B=10000, T=10, groups=[20, 20],
+                 n_cond=2, n_perm=5000, n_boot=5000,
+                 name='behavioral_pls X(80x10000) Y(80x10) groups=[20,20] '
+                      'n_cond=2 n_perm=5000 n_boot=5000'),
+    # BASELINE.json configs[4] (per GPU share is set by --gpus in a real run)
+    'cfg5': dict(kind='behavioral', S=200, B=100000, T=10, groups=[200],
+                 n_cond=1, n_perm=10000, n_boot=10000,
+                 name='behavioral_pls X(200x100000) Y(200x10) n_perm=10000 '
+                      'n_boot=10000'),
+}
+
+
+def make_data(w):
+    rs = np.random.RandomState(1234)
+    X = rs.rand(w['S'], w['B'])
+    Y = rs.rand(w['S'], w['T'])
+    return X, Y
+
+
+# ---------------------------------------------------------------------------
+# CPU arm (oracle port): one process per core, BLAS pinned to one thread
+# ---------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(wname):
+    os.environ['OPENBLAS_NUM_THREADS'] = '1'
+    os.environ['OMP_NUM_THREADS'] = '1'
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU['limit'] = threadpool_limits(1)
+    except Exception:
+        pass
+    import warnings
+    warnings.filterwarnings('ignore')
+    from oracle import pls_oracle as po
+    w = WORKLOADS[wname]
+    X, Y = make_data(w)
+    spec = po._Spec('behavioral', w['groups'], w['n_cond'])
+    U, d, V = po.decompose(spec, X, Y, seed=1234)
+    _CPU.update(po=po, X=X, Y=Y, spec=spec, U=U, V=V)
+
+
+def _cpu_task(args):
+    kind, cols = args
+    po, c = _CPU['po'], _CPU
+    if kind == 'perm':
+        po.run_perms(c['spec'], c['X'], c['Y'], cols, c['V'])
+    else:
+        po.run_boots(c['spec'], c['X'], c['Y'], cols, c['U'])
+    return cols.shape[1]
+
+
+class CpuArm:
+    """Times the oracle's permutation + bootstrap loops on `cores` worker
+    processes over a bounded sample of the workload's resamples."""
+
+    def __init__(self, wname, cores=None):
+        import multiprocessing as mp
+        self.w = WORKLOADS[wname]
+        self.cores = cores or len(os.sched_getaffinity(0))
+        from oracle import pls_oracle as po
+        import warnings
+        warnings.filterwarnings('ignore')
+        n = max(4 * self.cores, 32)
+        self.perm = po.gen_permsamp(self.w['groups'], self.w['n_cond'], n,
+                                    seed=1)
+        self.boot = po.gen_bootsamp(self.w['groups'], self.w['n_cond'], n,
+                                    seed=2)
+        self.pool = mp.get_context('spawn').Pool(
+            self.cores, initializer=_cpu_init, initargs=(wname,))
+        # make sure every worker is up and has its data before timing
+        self.pool.map(_cpu_task, [('perm', self.perm[:, :1])] * self.cores)
+
+    def step(self, n_each):
+        """Runs n_each permutations and n_each bootstraps; returns seconds."""
+        per = max(1, n_each // (2 * self.cores))
+        tasks = []
+        for kind, tab in (('perm', self.perm), ('boot', self.boot)):
+            for a in range(0, n_each, per):
+                cols = tab[:, [i % tab.shape[1] for i in
+                               range(a, min(a + per, n_each))]]
+                tasks.append((kind, cols))
+        t0 = time.perf_counter()
+        done = sum(self.pool.map(_cpu_task, tasks, chunksize=1))
+        dt = time.perf_counter() - t0
+        assert done == 2 * n_each
+        return dt
+
+    def calibrate(self, target_s):
+        """Resamples of each kind per step so that a step takes ~target_s."""
+        n0 = 2 * self.cores
+        dt = self.step(n0)
+        rate = 2 * n0 / dt
+        n = int(max(n0, min(rate * target_s / 2, 20000)))
+        return n
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+# ---------------------------------------------------------------------------
+def sample_clocks(stop, out, device_index):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region
+    runs (B200_PROFILING.md's clocks line)."""
+    q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+    while not stop.is_set():
+        try:
+            r = subprocess.run(
+                ['nvidia-smi', '-i', str(device_index), '--query-gpu=' + q,
+                 '--format=csv,noheader,nounits'], capture_output=True,
+                text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(',')]
+            if len(f) >= 8:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.1)
+
+
+def summarise_clocks(samples):
+    if not samples:
+        return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
+    sm = sorted(float(s[0]) for s in samples)
+    reasons = set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap']
+    for s in samples:
+        for name, v in zip(names, s[4:8]):
+            if v.lower().startswith('active'):
+                reasons.add(name)
+    return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(samples[0][1]),
+            'reasons': sorted(reasons), 'samples': len(samples)}
+
+
+def measure_fp64_peak(torch, device):
+    """cuBLAS DGEMM 8192^3, best of 5 (burst) -- MEASURED_PEAKS.json carries no
+    FP64 figure, so the roofline denominator is measured in the same run."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    torch.cuda.synchronize(device)
+    best = float('inf')
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize(device)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def algorithmic_work(w, n_perm, n_boot):
+    """Algorithmic flop / bytes per step and per kernel class."""
+    S, B, T = w['S'], w['B'], w['T']
+    J = len(w['groups']) * w['n_cond']
+    K = J * T
+    xcov = 2.0 * S * B * T * (n_perm + n_boot)       # 2*S*B*T_eff
+    return {
+        'xcov_gemm': ('tensor', xcov),
+        'gram_proj': ('tensor', 2.0 * K * (2 * K) * B * n_boot),
+        'accum_u': ('tensor', 2.0 * K * K * B * n_boot),
+        'small_decomp': ('tensor', None),
+        'build_operands': ('hbm', None),
+        'stats': ('hbm', None),
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    wname = args.workload
+    w = WORKLOADS[wname]
+    arm = CpuArm(wname)
+    n_each = arm.calibrate(target_s=min(20.0, 150.0 / max(1, args.steps +
+                                                          args.warmup)))
+    for _ in range(args.warmup):
+        arm.step(max(2 * arm.cores, n_each // 4))
+    times = [arm.step(n_each) for _ in range(args.steps)]
+    arm.close()
+    total = sum(times)
+    value = 2 * n_each * args.steps / total
+    sample = ('%d permutations + %d bootstraps of the workload per step '
+              '(first columns of seeded tables), %d worker processes, BLAS 1 '
+              'thread each' % (n_each, n_each, arm.cores))
+    line = {
+        'impl': 'reference', 'metric': 'resamples/sec (perm+boot)',
+        'value': value, 'unit': 'resamples/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic (RandomState(1234).rand)',
+        'config': {'workload': w['name'], 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'resamples/s',
+                         'cores': arm.cores, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': 'resamples/s',
+                'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == 'reference':
+        run_reference_arm(args)
+        return
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    w = WORKLOADS[args.workload]
+
+    # CPU baseline first (rank 0, N = 1 only), before CUDA is initialised
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm(args.workload)
+        n_each = arm.calibrate(target_s=12.0)
+        dt = arm.step(n_each)
+        arm.close()
+        cpu_baseline = {
+            'value': 2 * n_each / dt, 'unit': 'resamples/s',
+            'cores': arm.cores, 'kind': 'port',
+            'sample': '%d permutations + %d bootstraps of the workload, %d '
+                      'worker processes with single-threaded BLAS (the '
+                      'reference\'s n_proc mode)' % (n_each, n_each,
+                                                     arm.cores)}
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device'
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    import pypyls_b200 as pyls
+    from pypyls_b200 import dist as pdist
+    from pypyls_b200.engine import ResamplingEngine
+
+    X, Y = make_data(w)
+    Xh = torch.from_numpy(X).pin_memory()
+    Yh = torch.from_numpy(Y).pin_memory()
+    n_perm, n_boot = w['n_perm'], w['n_boot']          # per GPU (weak scaling)
+    P, R = n_perm * world, n_boot * world               # whole job
+
+    eng = ResamplingEngine('behavioral', w['S'], w['B'], w['T'], w['groups'],
+                           w['n_cond'], device=local_rank)
+    eng.set_data(Xh, Yh)
+    U, d, V = eng.decompose()
+    idx_p, _ = eng.gen_perm_indices(1234, n_perm, first=rank * n_perm)
+    idx_b, _ = eng.gen_boot_indices(1234, n_boot, first=rank * n_boot)
+    bs = (U * d[None, :]).contiguous()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def step():
+        d_perm = eng.run_perms(idx_p, rotate=True)
+        distrib, us, uq = eng.run_boots(idx_b)
+        if world > 1:
+            d_perm = pdist.gather_resamples(d_perm, P)
+            distrib = pdist.gather_resamples(distrib, R)
+            pdist.reduce_sum(us, uq)
+        pv = eng.perm_pvals(d_perm, d)
+        bsr, se = eng.boot_ratio(bs, us, uq, R, True)
+        lo, hi = eng.percentile(distrib, 2.5, 97.5)
+        return pv, bsr, lo, hi
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    stop, samples = threading.Event(), []
+    sampler = threading.Thread(target=sample_clocks,
+                               args=(stop, samples, local_rank), daemon=True)
+    sampler.start()
+    eng.timing_enable(True)
+    eng.timing_read()
+    launches0 = eng.launch_count
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)                      # evict L2 between timed iterations
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = eng.launch_count - launches0
+    classes = eng.timing_read()
+    eng.timing_enable(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = (P + R) * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public front-end ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        def call(seed):
+            return pyls.behavioral_pls(
+                Xh, Yh, groups=w['groups'], n_cond=w['n_cond'], n_perm=P,
+                n_boot=R, seed=seed, verbose=False, device=local_rank)
+        for i in range(2):
+            call(100 + i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            out = call(i)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        d2h = 0
+        for res in (out, out.permres, out.bootres):
+            for k, v in res.items():
+                if isinstance(v, np.ndarray) and k not in ('X', 'Y'):
+                    d2h += v.nbytes // (2 if v.dtype == np.int64 else 1)
+        e2e = {'value': (P + R) * args.steps / dt, 'unit': 'resamples/s',
+               'h2d_bytes_per_step': int(X.nbytes + Y.nbytes),
+               'd2h_bytes_per_step': int(d2h),
+               'ms_per_step': 1e3 * dt / args.steps}
+    stop.set()
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class -------------------------------
+    work = algorithmic_work(w, n_perm, n_boot)
+    top = max(classes, key=lambda k: classes[k][0])
+    top_ms, top_n = classes[top]
+    bound, flops = work.get(top, ('hbm', None))
+    peak_tf = measure_fp64_peak(torch, device)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    roofline = {'kernel': top, 'bound': bound, 'achieved': None,
+                'peak': None, 'unit': None, 'frac': None, 'traffic': None,
+                'kernel_ms_per_step': top_ms / args.steps,
+                'launches_per_step': top_n / args.steps}
+    if bound == 'tensor' and flops:
+        ach = flops * args.steps / (top_ms * 1e-3) / 1e12
+        roofline.update(achieved=ach, peak=peak_tf, unit='TFLOP/s',
+                        frac=ach / peak_tf,
+                        peak_source='cuBLAS DGEMM 8192^3 measured in this run '
+                                    '(FP64; MEASURED_PEAKS.json has no FP64 '
+                                    'figure)')
+    else:
+        roofline.update(peak=peaks.get('hbm_gbs', 6650.0), unit='GB/s',
+                        peak_source='MEASURED_PEAKS.json hbm_gbs'
+                        if peaks else 'fallback 6.65 TB/s')
+    line = {
+        'metric': 'resamples/sec (perm+boot)', 'value': value,
+        'unit': 'resamples/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic (RandomState(1234).rand)',
+        'config': {'workload': w['name'] + ' per GPU, 1xB200 each',
+                   'parallelism': 'resamples sharded over %d GPU(s); '
+                                  'all-gather + all-reduce at the end' % world,
+                   'l2': 'flushed between timed steps (256 MiB fill); every '
+                         'step also streams a multi-GB cross-covariance '
+                         'workspace'},
+        'e2e': e2e, 'gpu_launches': int(launches),
+        'clocks': summarise_clocks(samples), 'roofline': roofline,
+        'cpu_baseline': cpu_baseline,
+        'kernel_ms_per_step': {k: v[0] / args.steps
+                               for k, v in classes.items() if v[1]},
+        'fp64_dgemm_tflops_measured': peak_tf,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
