@@ -1,14 +1,21 @@
-// Small dense decompositions, one CTA per resample, one WARP per column pair.
+// Small dense decompositions, one CTA per resample.
 //
 // The reference runs sklearn's randomized_svd on the (K, B) cross-covariance
 // of every resample (pyls/compute.py:36-49) and a second SVD inside
 // compute.procrustes (pyls/compute.py:260-262).  Both collapse onto K x K
-// problems once G = R R^T and H = R U_orig are known:
+// symmetric eigenproblems once G = R R^T and H = R U_orig are known:
 //
-//   G = V diag(lam) V^T                      one-sided Jacobi on the columns of G
+//   G = V diag(lam) V^T                      Jacobi on G
 //   d = sqrt(lam);  temp = H^T V d^-1        (= U_orig^T U_boot)
-//   temp = N s Vr^T                          one-sided Jacobi on the columns of temp
-//   Q = Vr N^T  (= P^T N^T of compute.py:262);   M = V Q
+//   temp^T temp = W diag(mu) W^T             Jacobi on temp^T temp
+//   N s = temp W;  Q = W N^T                 (= P^T N^T of compute.py:262)
+//   M = V Q                                  so that U_boot d Q = R^T M
+//
+// The eigen-solver is the cyclic two-sided Jacobi method with a round-robin
+// (tournament) ordering: the n/2 plane rotations of one round act on disjoint
+// index pairs, so their parameters come from three matrix entries each and
+// the column / row updates of all pairs run concurrently across the CTA with
+// three barriers per round and no reductions.
 //
 // Numerically null directions (mean-centred PLS always has one: the cell
 // means minus their mean have rank J-1) are removed from the rotation: their
@@ -16,43 +23,31 @@
 // are zeroed, so Q is the Procrustes rotation of the non-null subspace and the
 // null columns of R^T M are 0.  (The reference rotates with whatever unit
 // vectors its randomized SVD returns for the null directions, which perturbs
-// the other latent variables by O(sqrt(K/B)); see DESIGN.md.)
-//
-// so that U_boot d Q = R^T M.  A column pair (p, q) is handled by one warp:
-// lanes stride over the rows, the three inner products are reduced with warp
-// shuffles, and the pairs of one round-robin round are independent, so the
-// warps of a CTA rotate them concurrently.
+// the other latent variables; see DESIGN.md.)
 #include "common.cuh"
 
 namespace plsb {
 namespace {
 
 constexpr int SM_THREADS = 256;
-constexpr int SM_WARPS = SM_THREADS / 32;
-constexpr int MAX_SWEEPS = 40;
-constexpr double JACOBI_TOL = 1e-14;
+constexpr int MAX_SWEEPS = 30;
+constexpr double JACOBI_TOL = 1e-15;
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// Orthogonalises the n columns of W (column j at W + j*ld) by plane rotations
-// applied from the right; the same rotations are accumulated into Vacc.
-// Called by every thread of the CTA.
-__device__ void jacobi_onesided(double *W, double *Vacc, int n, int ld, int *s_flag) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+// Diagonalises the symmetric n x n matrix A (row-major, leading dimension ld,
+// both triangles stored) in place: A <- J^T A J, V <- V J over all rotations.
+// pq[2*half] and cs[2*half] are scratch.  Called by every thread of the CTA.
+__device__ void jacobi_sym(double *A, double *V, int n, int ld, int *pq, double *cs, int *s_flag) {
+  const int tid = threadIdx.x;
   const int ne = n + (n & 1);       // even number of players (last may be a dummy)
   const int half = ne / 2;
   __syncthreads();
   if (n < 2) return;
   for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
-    __syncthreads();
     if (tid == 0) *s_flag = 0;
     __syncthreads();
     for (int round = 0; round < ne - 1; ++round) {
-      for (int pi = warp; pi < half; pi += SM_WARPS) {
+      // phase 0: rotation parameters of the pairs of this round
+      for (int pi = tid; pi < half; pi += SM_THREADS) {
         int a, b;
         if (pi == 0) {
           a = ne - 1;
@@ -62,51 +57,55 @@ __device__ void jacobi_onesided(double *W, double *Vacc, int n, int ld, int *s_f
           b = (round - pi + (ne - 1)) % (ne - 1);
         }
         const int p = min(a, b), q = max(a, b);
-        if (q >= n) continue;
-        double *wp = W + p * ld, *wq = W + q * ld;
-        double alpha = 0.0, beta = 0.0, gamma = 0.0;
-        for (int i = lane; i < n; i += 32) {
-          const double x = wp[i], y = wq[i];
-          alpha += x * x;
-          beta += y * y;
-          gamma += x * y;
+        double c = 1.0, s = 0.0;
+        int active = 0;
+        if (q < n) {
+          const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
+          if (apq != 0.0 && fabs(apq) > JACOBI_TOL * sqrt(fabs(app * aqq))) {
+            const double zeta = (aqq - app) / (2.0 * apq);
+            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = c * t;
+            active = 1;
+          }
         }
-        alpha = warp_sum(alpha);
-        beta = warp_sum(beta);
-        gamma = warp_sum(gamma);
-        if (alpha == 0.0 || beta == 0.0) continue;
-        if (fabs(gamma) <= JACOBI_TOL * sqrt(alpha * beta)) continue;
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-        for (int i = lane; i < n; i += 32) {
-          const double x = wp[i], y = wq[i];
-          wp[i] = c * x - s * y;
-          wq[i] = s * x + c * y;
-        }
-        double *vp = Vacc + p * ld, *vq = Vacc + q * ld;
-        for (int i = lane; i < n; i += 32) {
-          const double x = vp[i], y = vq[i];
-          vp[i] = c * x - s * y;
-          vq[i] = s * x + c * y;
-        }
-        if (lane == 0) *s_flag = 1;
+        pq[2 * pi] = active ? p : -1;
+        pq[2 * pi + 1] = q;
+        cs[2 * pi] = c;
+        cs[2 * pi + 1] = s;
+        if (active) *s_flag = 1;
+      }
+      __syncthreads();
+      // phase 1: column rotations  A <- A J,  V <- V J
+      for (int e = tid; e < half * n; e += SM_THREADS) {
+        const int pi = e / n, i = e - pi * n;
+        const int p = pq[2 * pi];
+        if (p < 0) continue;
+        const int q = pq[2 * pi + 1];
+        const double c = cs[2 * pi], s = cs[2 * pi + 1];
+        const double x = A[i * ld + p], y = A[i * ld + q];
+        A[i * ld + p] = c * x - s * y;
+        A[i * ld + q] = s * x + c * y;
+        const double vx = V[i * ld + p], vy = V[i * ld + q];
+        V[i * ld + p] = c * vx - s * vy;
+        V[i * ld + q] = s * vx + c * vy;
+      }
+      __syncthreads();
+      // phase 2: row rotations  A <- J^T A
+      for (int e = tid; e < half * n; e += SM_THREADS) {
+        const int pi = e / n, j = e - pi * n;
+        const int p = pq[2 * pi];
+        if (p < 0) continue;
+        const int q = pq[2 * pi + 1];
+        const double c = cs[2 * pi], s = cs[2 * pi + 1];
+        const double x = A[p * ld + j], y = A[q * ld + j];
+        A[p * ld + j] = c * x - s * y;
+        A[q * ld + j] = s * x + c * y;
       }
       __syncthreads();
     }
     if (*s_flag == 0) break;
-  }
-  __syncthreads();
-}
-
-// column norms of W into nrm[0..n), by warps
-__device__ void col_norms(const double *W, int n, int ld, double *nrm) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < n; j += SM_WARPS) {
-    double v = 0.0;
-    for (int i = lane; i < n; i += 32) v += W[j * ld + i] * W[j * ld + i];
-    v = warp_sum(v);
-    if (lane == 0) nrm[j] = sqrt(v);
+    __syncthreads();
   }
   __syncthreads();
 }
@@ -121,24 +120,28 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
                     double *__restrict__ lam_out) {
   extern __shared__ __align__(16) double sm[];
   const int ld = K | 1;
-  double *bufA = sm;
-  double *bufV = bufA + K * ld;
-  double *bufT = bufV + K * ld;
-  double *bufZ = bufT + K * ld;
-  double *lam = bufZ + K * ld;   // K
-  double *aux = lam + K;         // K
-  int *rank = reinterpret_cast<int *>(aux + K);  // K
+  double *bufA = sm;                 // G, later temp^T temp, later N s
+  double *bufV = bufA + K * ld;      // V
+  double *bufT = bufV + K * ld;      // temp, later Q
+  double *bufW = bufT + K * ld;      // H, later W
+  double *lam = bufW + K * ld;       // K
+  double *aux = lam + K;             // K
+  double *cs = aux + K;              // K + 2
+  int *rank = reinterpret_cast<int *>(cs + K + 2);  // K
+  int *pq = rank + K;                // K + 2
   __shared__ int s_flag;
   const int r = blockIdx.x, tid = threadIdx.x;
   const double *Gr = G + (size_t)r * K * K;
 
   for (int e = tid; e < K * K; e += SM_THREADS) {
-    const int j = e / K, i = e - j * K;
-    bufA[j * ld + i] = Gr[(size_t)i * K + j];
-    bufV[j * ld + i] = (i == j) ? 1.0 : 0.0;
+    const int i = e / K, j = e - i * K;
+    // symmetrise: both triangles must agree exactly for the two-sided updates
+    bufA[i * ld + j] = 0.5 * (Gr[(size_t)i * K + j] + Gr[(size_t)j * K + i]);
+    bufV[i * ld + j] = (i == j) ? 1.0 : 0.0;
   }
-  jacobi_onesided(bufA, bufV, K, ld, &s_flag);   // bufA = V diag(lam), bufV = V
-  col_norms(bufA, K, ld, lam);
+  jacobi_sym(bufA, bufV, K, ld, pq, cs, &s_flag);   // diag(bufA) = lam, bufV = V
+  for (int j = tid; j < K; j += SM_THREADS) lam[j] = fmax(bufA[j * ld + j], 0.0);
+  __syncthreads();
   // descending rank of every eigenvalue (ties broken by index)
   for (int j = tid; j < K; j += SM_THREADS) {
     int rk = 0;
@@ -152,67 +155,84 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
   if (mode == 1) {
     if (V_out)
       for (int e = tid; e < K * K; e += SM_THREADS) {
-        const int j = e / K, i = e - j * K;
-        V_out[(size_t)r * K * K + (size_t)i * K + rank[j]] = bufV[j * ld + i];
+        const int i = e / K, j = e - i * K;
+        V_out[(size_t)r * K * K + (size_t)i * K + rank[j]] = bufV[i * ld + j];
       }
     return;
   }
 
   // d^-1 with a guard for numerically null directions
-  {
-    double lmax = 0.0;
-    for (int i = 0; i < K; ++i) lmax = fmax(lmax, lam[i]);
-    __syncthreads();
-    for (int j = tid; j < K; j += SM_THREADS)
-      aux[j] = (lam[j] > 1e-14 * lmax && lam[j] > 0.0) ? 1.0 / sqrt(lam[j]) : 0.0;
-  }
-  // bufA <- H^T (bufA[i*ld + k] = H[k][i]);  bufZ <- I
-  const double *Hr = H + (size_t)r * K * L;
-  __syncthreads();
-  for (int e = tid; e < K * L; e += SM_THREADS) {
-    const int k = e / L, i = e - k * L;
-    bufA[i * ld + k] = Hr[e];
-  }
-  for (int e = tid; e < L * L; e += SM_THREADS) {
-    const int j = e / L, i = e - j * L;
-    bufZ[j * ld + i] = (i == j) ? 1.0 : 0.0;
-  }
-  __syncthreads();
+  double lmax = 0.0;
+  for (int i = 0; i < K; ++i) lmax = fmax(lmax, lam[i]);
   double dorig_max = 0.0;
   if (dorig)
     for (int i = 0; i < L; ++i) dorig_max = fmax(dorig_max, dorig[i]);
-  // temp[i][j] = sum_k H[k][i] V[k][j] / d_j, stored column-major in bufT
-  for (int e = tid; e < L * L; e += SM_THREADS) {
-    const int j = e / L, i = e - j * L;
-    double v = 0.0;
-    for (int k = 0; k < K; ++k) v += bufA[i * ld + k] * bufV[j * ld + k];
-    // a numerically null ORIGINAL latent variable has no direction to rotate onto
-    if (dorig && !(dorig[i] > 1e-10 * dorig_max)) v = 0.0;
-    bufT[j * ld + i] = v * aux[j];
-  }
-  jacobi_onesided(bufT, bufZ, L, ld, &s_flag);   // bufT = N diag(s), bufZ = Vr
-  col_norms(bufT, L, ld, lam);                   // lam <- s
-  {
-    double smax = 0.0;
-    for (int i = 0; i < L; ++i) smax = fmax(smax, lam[i]);
-    __syncthreads();
-    for (int j = tid; j < L; j += SM_THREADS)
-      aux[j] = (lam[j] > 1e-12 * smax && lam[j] > 0.0) ? 1.0 / lam[j] : 0.0;
+  __syncthreads();
+  for (int j = tid; j < K; j += SM_THREADS)
+    aux[j] = (lam[j] > 1e-14 * lmax && lam[j] > 0.0) ? 1.0 / sqrt(lam[j]) : 0.0;
+  // bufW <- H (K x L)
+  const double *Hr = H + (size_t)r * K * L;
+  for (int e = tid; e < K * L; e += SM_THREADS) {
+    const int k = e / L, i = e - k * L;
+    bufW[k * ld + i] = Hr[e];
   }
   __syncthreads();
-  // Q[i][j] = sum_k Vr[i][k] N[j][k]  -> bufA[j*ld + i]
+  // temp[i][j] = sum_k H[k][i] V[k][j] / d_j   (L x L)
   for (int e = tid; e < L * L; e += SM_THREADS) {
-    const int j = e / L, i = e - j * L;
+    const int i = e / L, j = e - i * L;
     double v = 0.0;
-    for (int k = 0; k < L; ++k) v += bufZ[k * ld + i] * bufT[k * ld + j] * aux[k];
-    bufA[j * ld + i] = v;
+    for (int k = 0; k < K; ++k) v += bufW[k * ld + i] * bufV[k * ld + j];
+    // a numerically null ORIGINAL latent variable has no direction to rotate onto
+    if (dorig && !(dorig[i] > 1e-10 * dorig_max)) v = 0.0;
+    bufT[i * ld + j] = v * aux[j];
+  }
+  __syncthreads();
+  // S = temp^T temp -> bufA;  W <- I
+  for (int e = tid; e < L * L; e += SM_THREADS) {
+    const int i = e / L, j = e - i * L;
+    if (j >= i) {
+      double v = 0.0;
+      for (int k = 0; k < L; ++k) v += bufT[k * ld + i] * bufT[k * ld + j];
+      bufA[i * ld + j] = v;
+      bufA[j * ld + i] = v;
+    }
+    bufW[i * ld + j] = (i == j) ? 1.0 : 0.0;
+  }
+  jacobi_sym(bufA, bufW, L, ld, pq, cs, &s_flag);   // bufW = W (right singular vectors)
+  // N s = temp W -> bufA
+  for (int e = tid; e < L * L; e += SM_THREADS) {
+    const int i = e / L, k = e - i * L;
+    double v = 0.0;
+    for (int j = 0; j < L; ++j) v += bufT[i * ld + j] * bufW[j * ld + k];
+    bufA[i * ld + k] = v;
+  }
+  __syncthreads();
+  // singular values = column norms of temp W
+  for (int k = tid; k < L; k += SM_THREADS) {
+    double v = 0.0;
+    for (int i = 0; i < L; ++i) v += bufA[i * ld + k] * bufA[i * ld + k];
+    lam[k] = sqrt(v);
+  }
+  __syncthreads();
+  double smax = 0.0;
+  for (int i = 0; i < L; ++i) smax = fmax(smax, lam[i]);
+  __syncthreads();
+  for (int k = tid; k < L; k += SM_THREADS)
+    aux[k] = (lam[k] > 1e-12 * smax && lam[k] > 0.0) ? 1.0 / lam[k] : 0.0;
+  __syncthreads();
+  // Q[i][j] = sum_k W[i][k] N[j][k]  -> bufT
+  for (int e = tid; e < L * L; e += SM_THREADS) {
+    const int i = e / L, j = e - i * L;
+    double v = 0.0;
+    for (int k = 0; k < L; ++k) v += bufW[i * ld + k] * bufA[j * ld + k] * aux[k];
+    bufT[i * ld + j] = v;
   }
   __syncthreads();
   // M[a][j] = sum_i V[a][i] Q[i][j]
   for (int e = tid; e < K * L; e += SM_THREADS) {
     const int a = e / L, j = e - a * L;
     double v = 0.0;
-    for (int i = 0; i < K; ++i) v += bufV[i * ld + a] * bufA[j * ld + i];
+    for (int i = 0; i < K; ++i) v += bufV[a * ld + i] * bufT[i * ld + j];
     M_out[(size_t)r * K * L + e] = v;
   }
 }
@@ -226,7 +246,8 @@ int launch_small(plsb_ctx *h, const double *G, const double *H, int count, int K
              MAX_K);
   PLSB_CHECK(mode == 1 || L == K, PLSB_ERR_ARG, "small decomposition: L=%d must equal K=%d", L, K);
   const int ld = K | 1;
-  const size_t smem = sizeof(double) * (4 * (size_t)K * ld + 2 * K) + sizeof(int) * K;
+  const size_t smem =
+      sizeof(double) * (4 * (size_t)K * ld + 3 * K + 2) + sizeof(int) * (2 * K + 2);
   PLSB_CUDA(cudaFuncSetAttribute(small_decomp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   small_decomp_kernel<<<count, SM_THREADS, smem, st>>>(G, H, K, L, mode, sqrt_lam, dorig, M, V,

@@ -232,6 +232,14 @@ __global__ void reduce_partials_kernel(const double *__restrict__ P, int n_split
 
 }  // namespace
 
+int launch_reduce_partials(plsb_ctx *h, const double *P, int n_splits, size_t stride, size_t n,
+                           double *out, cudaStream_t st) {
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+  reduce_partials_kernel<<<blocks, 256, 0, st>>>(P, n_splits, stride, n, out);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
 int launch_finish_rowsq(plsb_ctx *h, const double *rowsq, int n_splits, int M_pad, int n_rows,
                         double *out, cudaStream_t st) {
   KernelTimer kt(h, KC_STATS, st);
@@ -252,7 +260,7 @@ int launch_colscale(plsb_ctx *h, double *S1, const double *S2, int n_rows, long 
   return PLSB_OK;
 }
 
-int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
+int launch_gram_proj_fma(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
                      const double *Uo, int L, double *G, double *H, cudaStream_t st) {
   KernelTimer kt(h, KC_GRAM, st);
   if (count <= 0) return PLSB_OK;
@@ -274,7 +282,7 @@ int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int
   return PLSB_OK;
 }
 
-int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
+int launch_accum_u_fma(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
                    const double *M, int L, double *usum, double *usq, cudaStream_t st) {
   KernelTimer kt(h, KC_ACCUM, st);
   if (count <= 0) return PLSB_OK;

@@ -29,31 +29,45 @@ def close(a, b, rtol=RTOL, atol=1e-11):
     np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
 
 
-def check_meancentered_bsr(out, X, kw, ref_bsr, keep):
-    """Bootstrap ratios of a rank-deficient (mean-centred) analysis.
+def check_rank_deficient_bsr(out, X, Y, ref_bsr, keep, min_corr=0.999,
+                             max_dev=0.05):
+    """Bootstrap ratios when some resampled cross-covariance is rank deficient
+    (always for mean-centred PLS; for behavioural PLS when K is close to the
+    number of distinct subjects in a bootstrap sample).
 
     The reference rotates every bootstrap with the arbitrary unit vectors its
-    randomized SVD returns for the null latent variable, so its own ratios
-    move by ~1e-3 when only the seed of the original decomposition changes
-    ("null latent variables").  The CUDA path leaves null
-    directions out of the rotation; it must (a) equal the oracle's
-    restatement of exactly that rule tightly and (b) stay within the
-    reference's noise of the reference: the reference's own harness asks for a
-    column correlation >= 0.975 (pyls/tests/matlab.py:181-188).
+    randomized SVD returns for the null directions, so its own ratios move by
+    ~1e-3 when only the seed of the original decomposition changes (DESIGN.md,
+    "null latent variables").  The CUDA path leaves null directions out of the
+    rotation; it must (a) equal the oracle's restatement of exactly that rule
+    tightly and (b) stay within the reference's noise of the reference: the
+    reference's own harness asks for a column correlation >= 0.975
+    (pyls/tests/matlab.py:181-188).
     """
-    spec = po._Spec('meancentered', kw['groups'], kw['n_cond'],
-                    mean_centering=out.inputs.mean_centering)
+    inp = out.inputs
+    if Y is None:
+        spec = po._Spec('meancentered', inp.groups, inp.n_cond,
+                        mean_centering=inp.mean_centering)
+        Y, n, add = spec.dummy, inp.n_boot, False
+    else:
+        spec = po._Spec('behavioral', inp.groups, inp.n_cond,
+                        covariance=bool(inp.get('covariance')))
+        n, add = inp.n_boot + 1, True
     U, d = out.x_weights, out.singvals
-    _, us, uq = po.run_boots_nullsafe(spec, X, spec.dummy,
-                                      out.bootres.bootsamples, U, d)
-    want, want_se = po.boot_rel(U * d[None], us, uq, kw['n_boot'])
+    _, us, uq = po.run_boots_nullsafe(spec, X, Y, out.bootres.bootsamples,
+                                      U, d)
+    bs = U * d[None]
+    if add:
+        us, uq = us + bs, uq + bs ** 2
+    want, want_se = po.boot_rel(bs, us, uq, n)
     got = out.bootres.x_weights_normed
     close(got[:, keep], want[:, keep], rtol=1e-6, atol=1e-9)
     close(out.bootres.x_weights_stderr[:, keep], want_se[:, keep], rtol=1e-6,
           atol=1e-12)
-    assert np.all(po.efficient_corr(got[:, keep], ref_bsr[:, keep]) >= 0.999)
+    assert np.all(po.efficient_corr(got[:, keep], ref_bsr[:, keep])
+                  >= min_corr)
     scale = np.abs(ref_bsr[:, keep]).max()
-    assert np.abs(got[:, keep] - ref_bsr[:, keep]).max() <= 0.05 * scale
+    assert np.abs(got[:, keep] - ref_bsr[:, keep]).max() <= max_dev * scale
 
 
 BPLS = ['bpls_linnerud', 'bpls_2g2c_rot', 'bpls_2g2c_norot', 'bpls_2g2c_cov',
@@ -102,7 +116,7 @@ def test_meancentered_matches_reference_golden(name):
     close(out.bootres.contrast[:, keep], ref['boot_contrast'][:, keep])
     close(out.bootres.contrast_boot[:, keep], ref['contrast_boot'][:, keep])
     close(out.bootres.contrast_ci[:, keep], ref['contrast_ci'][:, keep])
-    check_meancentered_bsr(out, X, ins, ref['x_weights_normed'], keep)
+    check_rank_deficient_bsr(out, X, None, ref['x_weights_normed'], keep)
 
 
 @pytest.mark.parametrize('name', ['matlab_bpls_onegroup_onecond_nosplit',
@@ -143,11 +157,11 @@ def test_matlab_golden_vectors(name):
     close(out.permres.perm_singval[keep], ref['py_perm_singval'][keep],
           rtol=tol)
     assert np.array_equal(out.permres.pvals[keep], ref['py_pvals'][keep])
-    if 'bpls' in name:
-        close(out.bootres.x_weights_normed[:, keep],
-              ref['py_x_weights_normed'][:, keep], rtol=1e-4, atol=1e-6)
-    else:
-        check_meancentered_bsr(out, X, kw, ref['py_x_weights_normed'], keep)
+    # bpls: K = 25 latent variables but a bootstrap of 40 subjects has ~25
+    # distinct ones, so many resampled matrices have rank < K
+    check_rank_deficient_bsr(out, X, ins['Y'].astype(float) if 'bpls' in name
+                             else None, ref['py_x_weights_normed'], keep,
+                             min_corr=0.975, max_dev=0.2)
 
 
 @pytest.mark.parametrize('groups,n_cond,T,cov,rotate', [
@@ -207,7 +221,7 @@ def test_meancentered_matches_oracle(groups, n_cond, mc, rotate):
     close(out.bootres.contrast[:, keep], ref['contrast'][:, keep])
     close(out.bootres.contrast_boot[:, keep], ref['distrib'][:, keep])
     close(out.bootres.contrast_ci[:, keep], ref['distrib_ci'][:, keep])
-    check_meancentered_bsr(out, X, kw, ref['x_weights_normed'], keep)
+    check_rank_deficient_bsr(out, X, None, ref['x_weights_normed'], keep)
 
 
 def test_config2_properties_full_size():
