@@ -27,7 +27,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -141,26 +140,41 @@ class CpuArm:
 
 
 # ---------------------------------------------------------------------------
-def sample_clocks(stop, out, device_index):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region
-    runs (B200_PROFILING.md's clocks line)."""
-    q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-         'clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
-    while not stop.is_set():
+class ClockSampler:
+    """One long-running `nvidia-smi -lms 200` that logs clocks / throttle
+    reasons while the timed regions run (B200_PROFILING.md's clocks line)."""
+
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device_index):
+        import tempfile
+        self.log = tempfile.NamedTemporaryFile('w+', suffix='.csv')
         try:
-            r = subprocess.run(
-                ['nvidia-smi', '-i', str(device_index), '--query-gpu=' + q,
-                 '--format=csv,noheader,nounits'], capture_output=True,
-                text=True, timeout=5)
-            f = [x.strip() for x in r.stdout.strip().split(',')]
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(device_index),
+                 '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits',
+                 '-lms', '200'], stdout=self.log, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        self.log.seek(0)
+        out = []
+        for line in self.log.read().splitlines():
+            f = [x.strip() for x in line.split(',')]
             if len(f) >= 8:
                 out.append(f)
-        except Exception:
-            pass
-        stop.wait(0.1)
+        return out
 
 
 def summarise_clocks(samples):
@@ -333,10 +347,7 @@ def main():
         step()
     barrier()
 
-    stop, samples = threading.Event(), []
-    sampler = threading.Thread(target=sample_clocks,
-                               args=(stop, samples, local_rank), daemon=True)
-    sampler.start()
+    sampler = ClockSampler(local_rank)
     eng.timing_enable(True)
     eng.timing_read()
     launches0 = eng.launch_count
@@ -388,8 +399,7 @@ def main():
                'h2d_bytes_per_step': int(X.nbytes + Y.nbytes),
                'd2h_bytes_per_step': int(d2h),
                'ms_per_step': 1e3 * dt / args.steps}
-    stop.set()
-    sampler.join(timeout=2)
+    samples = sampler.stop()
 
     if rank != 0:
         if world > 1:

@@ -7,11 +7,11 @@ loops run as batched CUDA launches through ``libplsb200.so``.
 """
 
 __all__ = ['behavioral_pls', 'meancentered_pls', 'PLSResults', 'PLSInputs',
-           'ResamplingEngine', 'gen_permsamp', 'gen_bootsamp', '__version__']
+           'ResamplingEngine', 'release_workspaces', 'gen_permsamp', 'gen_bootsamp', '__version__']
 
 __version__ = '0.1.0'
 
 from .structures import PLSInputs, PLSResults
 from .resample import gen_bootsamp, gen_permsamp
-from .engine import ResamplingEngine
+from .engine import ResamplingEngine, release_workspaces
 from .types import behavioral_pls, meancentered_pls

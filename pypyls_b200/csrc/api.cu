@@ -40,24 +40,53 @@ int zero_tail(double *A, long long rows, long long rows_pad, int lda, cudaStream
   return PLSB_OK;
 }
 
-// R (n*K rows, ldx) for resamples idx[0..n): operands + GEMM (+ column scaling)
+// R (n*K rows, ldx) for resamples idx[0..n): operands + GEMM (+ column scaling).
+// Behavioural operands are block structured -- the rows of cell g only touch
+// that cell's rows of the data matrix -- so they are laid out grouped by cell
+// (every 128-row GEMM tile inside one cell), the GEMM contracts each tile over
+// its cell's rows only and a row map puts the result back in resample order.
 int crosscov_chunk(plsb_ctx *h, const int32_t *idx, int n, bool boot, double *distrib,
                    cudaStream_t st) {
   const Layout &l = h->lay;
-  const long long Mw = (long long)n * l.K, Mw_pad = round_up_ll(Mw, GEMM_BM);
-  PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)Mw_pad * l.S_pad));
-  PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)Mw_pad * l.ldx));
-  PLSB_TRY(zero_tail(h->A.as<double>(), Mw, Mw_pad, l.S_pad, st));
+  const bool grouped = l.behavioral() && l.J > 1;
   const bool scaled = boot && l.corr();
-  long long Mc = (long long)n * l.J, Mc_pad = round_up_ll(Mc, GEMM_BM);
+  const long long Mw = (long long)n * l.K, Mc = (long long)n * l.J;
+  const long long cellpad_w = grouped ? round_up_ll((long long)n * l.T, GEMM_BM) : 0;
+  const long long cellpad_c = grouped ? round_up_ll(n, GEMM_BM) : 0;
+  const long long Mw_op = grouped ? cellpad_w * l.J : round_up_ll(Mw, GEMM_BM);
+  const long long Mc_op = grouped ? cellpad_c * l.J : round_up_ll(Mc, GEMM_BM);
+  const long long Mw_pad = round_up_ll(Mw, GEMM_BM), Mc_pad = round_up_ll(Mc, GEMM_BM);
+  PLSB_CHECK(Mw_op < (1ll << 31) - 1, PLSB_ERR_ARG, "chunk of %d resamples is too large", n);
+  PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)Mw_op * l.S_pad));
+  PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)Mw_pad * l.ldx));
+  int *map_w = nullptr, *map_c = nullptr;
+  int2 *kr_w = nullptr, *kr_c = nullptr;
+  if (grouped) {
+    const size_t n_int = (size_t)Mw_op + (size_t)Mc_op;
+    const size_t n_kr = (size_t)(Mw_op + Mc_op) / GEMM_BM;
+    PLSB_TRY(h->maps.ensure(sizeof(int2) * n_kr + sizeof(int) * n_int));
+    kr_w = h->maps.as<int2>();
+    kr_c = kr_w + Mw_op / GEMM_BM;
+    map_w = reinterpret_cast<int *>(kr_c + Mc_op / GEMM_BM);
+    map_c = map_w + Mw_op;
+    PLSB_CUDA(cudaMemsetAsync(h->A.p, 0, sizeof(double) * (size_t)Mw_op * l.S_pad, st));
+    PLSB_TRY(launch_build_maps(h, n, l.T, l.K, cellpad_w, map_w, kr_w, st));
+  } else {
+    PLSB_TRY(zero_tail(h->A.as<double>(), Mw, Mw_op, l.S_pad, st));
+  }
   if (scaled) {
-    PLSB_TRY(h->Ac.ensure(sizeof(double) * (size_t)Mc_pad * l.S_pad));
+    PLSB_TRY(h->Ac.ensure(sizeof(double) * (size_t)Mc_op * l.S_pad));
     PLSB_TRY(h->S1.ensure(sizeof(double) * (size_t)Mc_pad * l.ldx));
     PLSB_TRY(h->S2.ensure(sizeof(double) * (size_t)Mc_pad * l.ldx));
-    PLSB_TRY(zero_tail(h->Ac.as<double>(), Mc, Mc_pad, l.S_pad, st));
+    if (grouped) {
+      PLSB_CUDA(cudaMemsetAsync(h->Ac.p, 0, sizeof(double) * (size_t)Mc_op * l.S_pad, st));
+      PLSB_TRY(launch_build_maps(h, n, 1, l.J, cellpad_c, map_c, kr_c, st));
+    } else {
+      PLSB_TRY(zero_tail(h->Ac.as<double>(), Mc, Mc_op, l.S_pad, st));
+    }
   }
   PLSB_TRY(launch_build(h, boot ? BUILD_BOOT : BUILD_PLAIN, idx, n, h->A.as<double>(),
-                        scaled ? h->Ac.as<double>() : nullptr, distrib, st));
+                        scaled ? h->Ac.as<double>() : nullptr, distrib, cellpad_w, cellpad_c, st));
   GemmArgs g;
   g.lda = l.S_pad;
   g.ldx = l.ldx;
@@ -67,7 +96,9 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, int n, bool boot, double *di
   if (scaled) {
     g.A = h->Ac.as<double>();
     g.X = h->Xglob.as<double>();
-    g.M_pad = (int)Mc_pad;
+    g.M_pad = (int)Mc_op;
+    g.row_map = map_c;
+    g.kranges = kr_c;
     g.C = h->S1.as<double>();
     PLSB_TRY(launch_gemm(h, g, st));
     g.C = h->S2.as<double>();
@@ -81,7 +112,9 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, int n, bool boot, double *di
   }
   g.A = h->A.as<double>();
   g.X = boot ? h->Xglob.as<double>() : perm_data(h);
-  g.M_pad = (int)Mw_pad;
+  g.M_pad = (int)Mw_op;
+  g.row_map = map_w;
+  g.kranges = kr_w;
   g.C = h->R.as<double>();
   PLSB_TRY(launch_gemm(h, g, st));
   return PLSB_OK;
@@ -134,7 +167,7 @@ int plsb_destroy(plsb_handle_t h) {
   DevBuf *bufs[] = {&h->tables, &h->Xraw, &h->Xcell, &h->Xglob, &h->Y,    &h->Cmat,  &h->Uo,
                     &h->Vo,     &h->dorig, &h->Sx,   &h->norms, &h->A,    &h->Ac,    &h->R,
                     &h->S1,     &h->S2,   &h->G,     &h->H,     &h->M,    &h->lam,   &h->rowsq,
-                    &h->part,   &h->misc, &h->idxall, &h->flags};
+                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps};
   for (DevBuf *b : bufs) b->release();
   delete h;
   return PLSB_OK;
@@ -250,12 +283,23 @@ int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups,
     acc += groups[g];
   }
   tab.push_back(acc);   // n_groups + 1
+  if (tab.size() % 2) tab.push_back(0);   // keep the int2 table 8-byte aligned
+  const size_t kr_off = tab.size();
+  for (int j = 0; j < l.J; ++j) {
+    // contraction range of cell j: even start, whole GEMM_BK chunks, inside [0, S_pad)
+    int kb = l.cell_start[j] & ~1;
+    const int nkc = cdiv(l.cell_start[j + 1] - kb, GEMM_BK);
+    if (kb + nkc * GEMM_BK > l.S_pad) kb = l.S_pad - nkc * GEMM_BK;
+    tab.push_back(kb);
+    tab.push_back(kb + nkc * GEMM_BK);
+  }
   PLSB_TRY(h->tables.ensure(sizeof(int) * tab.size()));
   PLSB_CUDA(cudaMemcpy(h->tables.p, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
   h->d_cell_start = h->tables.as<int>();
   h->d_cell_of_row = h->d_cell_start + (l.J + 1);
   h->d_cell_n = h->d_cell_of_row + S;
   h->d_group_start = h->d_cell_n + l.J;
+  h->d_cell_kr = reinterpret_cast<const int2 *>(h->tables.as<int>() + kr_off);
 
   if (!l.behavioral()) {
     // C (J,S): "cell mean minus centring mean" as a row operator
@@ -439,7 +483,7 @@ int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, int rotate,
       PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)M_pad * l.S_pad));
       PLSB_TRY(zero_tail(h->A.as<double>(), M, M_pad, l.S_pad, st));
       PLSB_TRY(launch_build(h, BUILD_ROT, d_idx + (size_t)off * l.S, n, h->A.as<double>(), nullptr,
-                            nullptr, st));
+                            nullptr, 0, 0, st));
       const int n_mtiles = (int)(M_pad / GEMM_BM);
       const int n_splits = gemm_pick_splits(h, n_mtiles, n_ntiles);
       PLSB_TRY(h->rowsq.ensure(sizeof(double) * (size_t)n_splits * M_pad));

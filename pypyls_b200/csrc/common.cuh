@@ -131,6 +131,7 @@ struct plsb_ctx {
   plsb::DevBuf tables;
   const int *d_cell_start = nullptr, *d_cell_of_row = nullptr, *d_cell_n = nullptr,
             *d_group_start = nullptr;
+  const int2 *d_cell_kr = nullptr;   // per cell: contraction range [kbeg, kend) of its rows
 
   // data-dependent state (set_data); all (S_pad, ldx) zero padded
   plsb::DevBuf Xraw;   // raw X
@@ -145,7 +146,7 @@ struct plsb_ctx {
   plsb::DevBuf Sx;     // Xraw @ normalize(Uo)   (S, L)
   plsb::DevBuf norms;  // (L)
   // per-chunk workspaces
-  plsb::DevBuf A, Ac, R, S1, S2, G, H, M, lam, rowsq, part, misc, idxall, flags;
+  plsb::DevBuf A, Ac, R, S1, S2, G, H, M, lam, rowsq, part, misc, idxall, flags, maps;
 };
 
 namespace plsb {
@@ -217,7 +218,9 @@ int launch_matmul_small(plsb_ctx *h, const double *A, const double *Bm, int n, d
 // operand builders / distrib (operands.cu)
 enum BuildKind { BUILD_ROT = 0, BUILD_PLAIN = 1, BUILD_BOOT = 2 };
 int launch_build(plsb_ctx *h, int kind, const int32_t *idx, int count, double *A, double *Ac,
-                 double *distrib, cudaStream_t st);
+                 double *distrib, long long cellpad_w, long long cellpad_c, cudaStream_t st);
+int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long cellpad,
+                      int *row_map, int2 *kranges, cudaStream_t st);
 
 // streaming kernels over stored R (stream_kernels.cu)
 int launch_finish_rowsq(plsb_ctx *h, const double *rowsq, int n_splits, int M_pad, int n_rows,

@@ -162,7 +162,7 @@ xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict
             const size_t col = (size_t)nt * BN + wn * 32 + 2 * q;
             double *crow = C + (size_t)orow * ldc + col;
             if (scale) {
-              const double *srow = scale + (size_t)(m / scale_div) * lds + col;
+              const double *srow = scale + (size_t)(orow / scale_div) * lds + col;
 #pragma unroll
               for (int j = 0; j < NF; ++j) {
                 const double2 sc = *reinterpret_cast<const double2 *>(srow + j * 8);
@@ -236,7 +236,9 @@ int gemm_pick_splits(const plsb_ctx *h, int n_mtiles, int n_ntiles) {
   int want = (6 * h->sm_count + n_mtiles - 1) / n_mtiles;
   if (want < 1) want = 1;
   if (want > n_ntiles) want = n_ntiles;
-  return want;
+  // every split must own at least one N tile (a CTA without tiles writes nothing)
+  const int per = (n_ntiles + want - 1) / want;
+  return (n_ntiles + per - 1) / per;
 }
 
 int launch_gemm(plsb_ctx *h, const GemmArgs &a, cudaStream_t st) {

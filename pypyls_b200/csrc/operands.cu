@@ -26,6 +26,7 @@ namespace {
 struct BuildParams {
   const int32_t *idx;
   int S, T, J, K, L, lda, corr, kind;
+  long long cellpad_w, cellpad_c;   // > 0: rows grouped by cell, cell g starts at g * cellpad
   const double *Y;
   const int *cell_start, *cell_of_row;
   const double *Vo, *Sx, *Cmat;
@@ -88,7 +89,6 @@ __global__ void build_behavioral_kernel(BuildParams p) {
     return;
   }
   if (p.kind == BUILD_PLAIN) {
-    double *Ar = p.A + (size_t)r * K * lda;
     for (int e = tid; e < K * lda; e += nt) {
       const int row = e / lda, u = e - row * lda;
       const int g = row / T, t = row - g * T;
@@ -97,14 +97,15 @@ __global__ void build_behavioral_kernel(BuildParams p) {
         const int n = p.cell_start[g + 1] - p.cell_start[g];
         val = Yp[u * T + t] / (n - 1);
       }
-      Ar[e] = val;
+      const size_t orow = p.cellpad_w ? (size_t)g * p.cellpad_w + (size_t)r * T + t
+                                      : (size_t)r * K + row;
+      p.A[orow * lda + u] = val;
     }
     return;
   }
 
   // ---- BUILD_BOOT ----
   {
-    double *Ar = p.A + (size_t)r * K * lda;
     for (int e = tid; e < K * lda; e += nt) {
       const int row = e / lda, u = e - row * lda;
       const int g = row / T, t = row - g * T;
@@ -114,17 +115,19 @@ __global__ void build_behavioral_kernel(BuildParams p) {
         for (int s = r0; s < r1; ++s)
           if (src[s] == u) val += Yp[s * T + t];
       if (!p.corr) val /= (r1 - r0 - 1);
-      Ar[e] = val;
+      const size_t orow = p.cellpad_w ? (size_t)g * p.cellpad_w + (size_t)r * T + t
+                                      : (size_t)r * K + row;
+      p.A[orow * lda + u] = val;
     }
     if (p.Ac) {
-      double *Cr = p.Ac + (size_t)r * J * lda;
       for (int e = tid; e < J * lda; e += nt) {
         const int g = e / lda, u = e - g * lda;
         const int r0 = p.cell_start[g], r1 = p.cell_start[g + 1];
         int cnt = 0;
         if (u < S)
           for (int s = r0; s < r1; ++s) cnt += (src[s] == u);
-        Cr[e] = (double)cnt;
+        const size_t orow = p.cellpad_c ? (size_t)g * p.cellpad_c + r : (size_t)r * J + g;
+        p.Ac[orow * lda + u] = (double)cnt;
       }
     }
   }
@@ -201,10 +204,43 @@ __global__ void build_meancentered_kernel(BuildParams p) {
   }
 }
 
+// row_map / kranges of a cell-grouped operand: operand row g*cellpad + i (i =
+// r*rows_pc + t) is output row r*stride_r + g*rows_pc + t; rows i >= n*rows_pc
+// are padding (-1).  Every 128-row tile lies inside one cell and contracts
+// only over that cell's rows of the data matrix.
+__global__ void build_maps_kernel(int n, int rows_pc, int stride_r, int J, long long cellpad,
+                                  const int2 *__restrict__ cell_kr, int *__restrict__ row_map,
+                                  int2 *__restrict__ kranges) {
+  const long long total = (long long)J * cellpad;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < total;
+       m += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(m / cellpad);
+    const long long i = m - g * cellpad;
+    int out = -1;
+    if (i < (long long)n * rows_pc) {
+      const int r = (int)(i / rows_pc), t = (int)(i - (long long)r * rows_pc);
+      out = r * stride_r + g * rows_pc + t;
+    }
+    row_map[m] = out;
+    if (m % GEMM_BM == 0) kranges[m / GEMM_BM] = cell_kr[g];
+  }
+}
+
 }  // namespace
 
+int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long cellpad,
+                      int *row_map, int2 *kranges, cudaStream_t st) {
+  KernelTimer kt(h, KC_BUILD, st);
+  const long long total = (long long)h->lay.J * cellpad;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
+  build_maps_kernel<<<blocks, 256, 0, st>>>(n, rows_pc, stride_r, h->lay.J, cellpad, h->d_cell_kr,
+                                            row_map, kranges);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
 int launch_build(plsb_ctx *h, int kind, const int32_t *idx, int count, double *A, double *Ac,
-                 double *distrib, cudaStream_t st) {
+                 double *distrib, long long cellpad_w, long long cellpad_c, cudaStream_t st) {
   KernelTimer kt(h, KC_BUILD, st);
   const Layout &l = h->lay;
   if (count <= 0) return PLSB_OK;
@@ -220,6 +256,7 @@ int launch_build(plsb_ctx *h, int kind, const int32_t *idx, int count, double *A
   p.Sx = h->Sx.as<double>();
   p.Cmat = h->Cmat.as<double>();
   p.A = A; p.Ac = Ac; p.distrib = distrib;
+  p.cellpad_w = cellpad_w; p.cellpad_c = cellpad_c;
   if (kind == BUILD_ROT || (kind == BUILD_BOOT && distrib))
     PLSB_CHECK(h->has_original, PLSB_ERR_STATE, "operand builder needs the original decomposition");
   size_t smem;

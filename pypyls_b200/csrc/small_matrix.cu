@@ -31,83 +31,105 @@ namespace {
 
 constexpr int SM_THREADS = 256;
 constexpr int MAX_SWEEPS = 30;
-constexpr double JACOBI_TOL = 1e-15;
+constexpr double JACOBI_TOL = 1e-14;
+constexpr double JACOBI_EPS = 1e-15;
 
 // Diagonalises the symmetric n x n matrix A (row-major, leading dimension ld,
 // both triangles stored) in place: A <- J^T A J, V <- V J over all rotations.
-// pq[2*half] and cs[2*half] are scratch.  Called by every thread of the CTA.
-__device__ void jacobi_sym(double *A, double *V, int n, int ld, int *pq, double *cs, int *s_flag) {
-  const int tid = threadIdx.x;
+// Called by every thread of the CTA.
+//
+// One round = the n/2 disjoint pairs of the tournament schedule.  Every warp
+// owns up to NPW pairs of the round: lane j derives the rotation of the warp's
+// j-th pair from (a_pp, a_qq, a_pq) -- entries no other pair's column update
+// touches -- the parameters are broadcast with shuffles, then the warp rotates
+// the columns of its pairs (lanes stride over the rows) and, after one barrier,
+// the rows (lanes stride over the columns).  Two barriers per round.
+constexpr int SM_WARPS = SM_THREADS / 32;
+constexpr int NPW = (MAX_K / 2 + SM_WARPS - 1) / SM_WARPS;   // pairs per warp per round
+
+__device__ void jacobi_sym(double *A, double *V, int n, int ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ne = n + (n & 1);       // even number of players (last may be a dummy)
   const int half = ne / 2;
   __syncthreads();
   if (n < 2) return;
   for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
-    if (tid == 0) *s_flag = 0;
-    __syncthreads();
+    int any = 0;
     for (int round = 0; round < ne - 1; ++round) {
-      // phase 0: rotation parameters of the pairs of this round
-      for (int pi = tid; pi < half; pi += SM_THREADS) {
+      // rotation of pair (warp + lane * SM_WARPS), lanes < NPW
+      int my_p = -1, my_q = 0;
+      double my_c = 1.0, my_s = 0.0;
+      const int my_pi = warp + lane * SM_WARPS;
+      if (lane < NPW && my_pi < half) {
         int a, b;
-        if (pi == 0) {
+        if (my_pi == 0) {
           a = ne - 1;
           b = round;
         } else {
-          a = (round + pi) % (ne - 1);
-          b = (round - pi + (ne - 1)) % (ne - 1);
+          a = (round + my_pi) % (ne - 1);
+          b = (round - my_pi + (ne - 1)) % (ne - 1);
         }
         const int p = min(a, b), q = max(a, b);
-        double c = 1.0, s = 0.0;
-        int active = 0;
         if (q < n) {
           const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
-          if (apq != 0.0 && fabs(apq) > JACOBI_TOL * sqrt(fabs(app * aqq))) {
+          // rotate while the off-diagonal entry is above both the relative
+          // (graded-matrix) threshold and the rounding level of the larger
+          // diagonal entry -- below that a rotation only shuffles noise
+          const double thr = fmax(JACOBI_TOL * sqrt(fabs(app * aqq)),
+                                  JACOBI_EPS * fmax(fabs(app), fabs(aqq)));
+          if (fabs(apq) > thr) {
             const double zeta = (aqq - app) / (2.0 * apq);
             const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            c = 1.0 / sqrt(1.0 + t * t);
-            s = c * t;
-            active = 1;
+            my_c = rsqrt(1.0 + t * t);
+            my_s = my_c * t;
+            my_p = p;
+            my_q = q;
           }
         }
-        pq[2 * pi] = active ? p : -1;
-        pq[2 * pi + 1] = q;
-        cs[2 * pi] = c;
-        cs[2 * pi + 1] = s;
-        if (active) *s_flag = 1;
       }
-      __syncthreads();
-      // phase 1: column rotations  A <- A J,  V <- V J
-      for (int e = tid; e < half * n; e += SM_THREADS) {
-        const int pi = e / n, i = e - pi * n;
-        const int p = pq[2 * pi];
-        if (p < 0) continue;
-        const int q = pq[2 * pi + 1];
-        const double c = cs[2 * pi], s = cs[2 * pi + 1];
-        const double x = A[i * ld + p], y = A[i * ld + q];
-        A[i * ld + p] = c * x - s * y;
-        A[i * ld + q] = s * x + c * y;
-        const double vx = V[i * ld + p], vy = V[i * ld + q];
-        V[i * ld + p] = c * vx - s * vy;
-        V[i * ld + q] = s * vx + c * vy;
+      int pp[NPW], qq[NPW];
+      double cc[NPW], ss[NPW];
+#pragma unroll
+      for (int j = 0; j < NPW; ++j) {
+        pp[j] = __shfl_sync(0xffffffffu, my_p, j);
+        qq[j] = __shfl_sync(0xffffffffu, my_q, j);
+        cc[j] = __shfl_sync(0xffffffffu, my_c, j);
+        ss[j] = __shfl_sync(0xffffffffu, my_s, j);
       }
-      __syncthreads();
-      // phase 2: row rotations  A <- J^T A
-      for (int e = tid; e < half * n; e += SM_THREADS) {
-        const int pi = e / n, j = e - pi * n;
-        const int p = pq[2 * pi];
-        if (p < 0) continue;
-        const int q = pq[2 * pi + 1];
-        const double c = cs[2 * pi], s = cs[2 * pi + 1];
-        const double x = A[p * ld + j], y = A[q * ld + j];
-        A[p * ld + j] = c * x - s * y;
-        A[q * ld + j] = s * x + c * y;
+      // column rotations  A <- A J,  V <- V J
+      int rotated = 0;
+#pragma unroll
+      for (int j = 0; j < NPW; ++j) {
+        if (pp[j] < 0) continue;
+        rotated = 1;
+        const int p = pp[j], q = qq[j];
+        const double c = cc[j], s = ss[j];
+        for (int i = lane; i < n; i += 32) {
+          const double x = A[i * ld + p], y = A[i * ld + q];
+          A[i * ld + p] = c * x - s * y;
+          A[i * ld + q] = s * x + c * y;
+          const double vx = V[i * ld + p], vy = V[i * ld + q];
+          V[i * ld + p] = c * vx - s * vy;
+          V[i * ld + q] = s * vx + c * vy;
+        }
+      }
+      any |= __syncthreads_or(rotated);
+      // row rotations  A <- J^T A
+#pragma unroll
+      for (int j = 0; j < NPW; ++j) {
+        if (pp[j] < 0) continue;
+        const int p = pp[j], q = qq[j];
+        const double c = cc[j], s = ss[j];
+        for (int i = lane; i < n; i += 32) {
+          const double x = A[p * ld + i], y = A[q * ld + i];
+          A[p * ld + i] = c * x - s * y;
+          A[q * ld + i] = s * x + c * y;
+        }
       }
       __syncthreads();
     }
-    if (*s_flag == 0) break;
-    __syncthreads();
+    if (!any) break;
   }
-  __syncthreads();
 }
 
 // mode 0: full decomposition -> M (K,L) [+ lam sorted descending if lam_out]
@@ -126,10 +148,7 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
   double *bufW = bufT + K * ld;      // H, later W
   double *lam = bufW + K * ld;       // K
   double *aux = lam + K;             // K
-  double *cs = aux + K;              // K + 2
-  int *rank = reinterpret_cast<int *>(cs + K + 2);  // K
-  int *pq = rank + K;                // K + 2
-  __shared__ int s_flag;
+  int *rank = reinterpret_cast<int *>(aux + K);  // K
   const int r = blockIdx.x, tid = threadIdx.x;
   const double *Gr = G + (size_t)r * K * K;
 
@@ -139,7 +158,7 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
     bufA[i * ld + j] = 0.5 * (Gr[(size_t)i * K + j] + Gr[(size_t)j * K + i]);
     bufV[i * ld + j] = (i == j) ? 1.0 : 0.0;
   }
-  jacobi_sym(bufA, bufV, K, ld, pq, cs, &s_flag);   // diag(bufA) = lam, bufV = V
+  jacobi_sym(bufA, bufV, K, ld);   // diag(bufA) = lam, bufV = V
   for (int j = tid; j < K; j += SM_THREADS) lam[j] = fmax(bufA[j * ld + j], 0.0);
   __syncthreads();
   // descending rank of every eigenvalue (ties broken by index)
@@ -198,7 +217,7 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
     }
     bufW[i * ld + j] = (i == j) ? 1.0 : 0.0;
   }
-  jacobi_sym(bufA, bufW, L, ld, pq, cs, &s_flag);   // bufW = W (right singular vectors)
+  jacobi_sym(bufA, bufW, L, ld);   // bufW = W (right singular vectors)
   // N s = temp W -> bufA
   for (int e = tid; e < L * L; e += SM_THREADS) {
     const int i = e / L, k = e - i * L;
@@ -246,8 +265,7 @@ int launch_small(plsb_ctx *h, const double *G, const double *H, int count, int K
              MAX_K);
   PLSB_CHECK(mode == 1 || L == K, PLSB_ERR_ARG, "small decomposition: L=%d must equal K=%d", L, K);
   const int ld = K | 1;
-  const size_t smem =
-      sizeof(double) * (4 * (size_t)K * ld + 3 * K + 2) + sizeof(int) * (2 * K + 2);
+  const size_t smem = sizeof(double) * (4 * (size_t)K * ld + 2 * K) + sizeof(int) * K;
   PLSB_CUDA(cudaFuncSetAttribute(small_decomp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   small_decomp_kernel<<<count, SM_THREADS, smem, st>>>(G, H, K, L, mode, sqrt_lam, dorig, M, V,

@@ -15,6 +15,8 @@ import torch
 
 from . import _cabi
 
+DEFAULT_WORKSPACE = 2 << 30      # bytes per chunk of stored cross-covariances
+
 MODES = {
     'behavioral': _cabi.PLSB_BEHAVIORAL_CORR,
     'behavioral_cov': _cabi.PLSB_BEHAVIORAL_COV,
@@ -24,6 +26,21 @@ MODES = {
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+# Library handles (and the device workspaces they own) are pooled per device:
+# an engine borrows a free handle and gives it back when closed, so repeated
+# analyses do not pay cudaMalloc / cudaFree of the workspaces again.
+_FREE_HANDLES = {}
+
+
+def release_workspaces():
+    """Destroys every pooled library handle (frees their device memory)."""
+    lib = _cabi.lib()
+    for handles in _FREE_HANDLES.values():
+        for h in handles:
+            lib.plsb_destroy(h)
+    _FREE_HANDLES.clear()
 
 
 class ResamplingEngine:
@@ -58,13 +75,18 @@ class ResamplingEngine:
         self.J = len(groups) * self.n_cond
         self.K = self.J * self.T if mode != 'meancentered' else self.J
         self.L = self.K
-        self._h = C.c_void_p(0)
-        with torch.cuda.device(self.device):
-            _cabi.check(self._lib.plsb_create(C.byref(self._h),
-                                              self.device.index))
-        if workspace_bytes is not None:
-            _cabi.check(self._lib.plsb_set_workspace_limit(
-                self._h, int(workspace_bytes)))
+        pool = _FREE_HANDLES.setdefault(self.device.index, [])
+        if pool:
+            self._h = pool.pop()
+        else:
+            self._h = C.c_void_p(0)
+            with torch.cuda.device(self.device):
+                _cabi.check(self._lib.plsb_create(C.byref(self._h),
+                                                  self.device.index))
+        # pooled handles keep their settings: always (re)set them
+        _cabi.check(self._lib.plsb_set_workspace_limit(
+            self._h, int(workspace_bytes or DEFAULT_WORKSPACE)))
+        _cabi.check(self._lib.plsb_timing_enable(self._h, 0))
         garr = (C.c_int * len(groups))(*groups)
         _cabi.check(self._lib.plsb_configure(
             self._h, MODES[mode], self.S, self.B, self.T, len(groups), garr,
@@ -73,8 +95,9 @@ class ResamplingEngine:
     # -- plumbing ----------------------------------------------------------
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:
-            torch.cuda.synchronize(self.device)
-            self._lib.plsb_destroy(self._h)
+            # stream-ordered reuse: the next borrower enqueues on the same
+            # (current) stream, so no synchronisation is needed here
+            _FREE_HANDLES.setdefault(self.device.index, []).append(self._h)
             self._h = C.c_void_p(0)
 
     def __del__(self):
