@@ -12,10 +12,13 @@
 //   M = V Q                                  so that U_boot d Q = R^T M
 //
 // The eigen-solver is the cyclic two-sided Jacobi method with a round-robin
-// (tournament) ordering: the n/2 plane rotations of one round act on disjoint
-// index pairs, so their parameters come from three matrix entries each and
-// the column / row updates of all pairs run concurrently across the CTA with
-// three barriers per round and no reductions.
+// (tournament) ordering.  The n/2 plane rotations of one round act on disjoint
+// index pairs, so the update A <- J^T A J decomposes into independent 2 x 2
+// blocks, one per (pair a, pair b): a thread reads the four entries of its
+// block, applies pair b's rotation from the right and pair a's from the left,
+// and writes the block and its mirror image.  Only blocks with a <= b are
+// computed (symmetry), the parameters of a rotation come from the diagonal
+// block of its pair, and a round needs two barriers.
 //
 // Numerically null directions (mean-centred PLS always has one: the cell
 // means minus their mean have rank J-1) are removed from the rotation: their
@@ -30,100 +33,108 @@ namespace plsb {
 namespace {
 
 constexpr int SM_THREADS = 256;
+constexpr int SM_WARPS = SM_THREADS / 32;
 constexpr int MAX_SWEEPS = 30;
 constexpr double JACOBI_TOL = 1e-14;
 constexpr double JACOBI_EPS = 1e-15;
 
-// Diagonalises the symmetric n x n matrix A (row-major, leading dimension ld,
-// both triangles stored) in place: A <- J^T A J, V <- V J over all rotations.
-// Called by every thread of the CTA.
-//
-// One round = the n/2 disjoint pairs of the tournament schedule.  Every warp
-// owns up to NPW pairs of the round: lane j derives the rotation of the warp's
-// j-th pair from (a_pp, a_qq, a_pq) -- entries no other pair's column update
-// touches -- the parameters are broadcast with shuffles, then the warp rotates
-// the columns of its pairs (lanes stride over the rows) and, after one barrier,
-// the rows (lanes stride over the columns).  Two barriers per round.
-constexpr int SM_WARPS = SM_THREADS / 32;
-constexpr int NPW = (MAX_K / 2 + SM_WARPS - 1) / SM_WARPS;   // pairs per warp per round
+struct JacobiScratch {
+  short2 *blk;   // (a, b) of every upper-triangular block, a <= b   [half*(half+1)/2]
+  int *pq;       // (p, q) of every pair of the current round         [2*half]
+  double *cst;   // (c, s, t) of every pair of the current round      [3*half]
+};
 
-__device__ void jacobi_sym(double *A, double *V, int n, int ld) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ne = n + (n & 1);       // even number of players (last may be a dummy)
+// Diagonalises the symmetric matrix A in place: A <- J^T A J, V <- V J over
+// all rotations.  A and V are row-major with leading dimension ld; n is the
+// order, ne = n rounded up to even.  For odd n the extra index n is a dummy
+// player: row / column n of A and column n of V must be zero on entry (they
+// stay zero).  Called by every thread of the CTA.
+__device__ void jacobi_sym(double *A, double *V, int n, int ld, const JacobiScratch &sc) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ne = n + (n & 1);
   const int half = ne / 2;
+  const int nb = half * (half + 1) / 2;
   __syncthreads();
   if (n < 2) return;
   for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
     int any = 0;
     for (int round = 0; round < ne - 1; ++round) {
-      // rotation of pair (warp + lane * SM_WARPS), lanes < NPW
-      int my_p = -1, my_q = 0;
-      double my_c = 1.0, my_s = 0.0;
-      const int my_pi = warp + lane * SM_WARPS;
-      if (lane < NPW && my_pi < half) {
+      // phase 0: rotation of every pair from its diagonal block
+      int active = 0;
+      for (int pi = tid; pi < half; pi += SM_THREADS) {
         int a, b;
-        if (my_pi == 0) {
+        if (pi == 0) {
           a = ne - 1;
           b = round;
         } else {
-          a = (round + my_pi) % (ne - 1);
-          b = (round - my_pi + (ne - 1)) % (ne - 1);
+          a = (round + pi) % (ne - 1);
+          b = (round - pi + (ne - 1)) % (ne - 1);
         }
         const int p = min(a, b), q = max(a, b);
-        if (q < n) {
-          const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
-          // rotate while the off-diagonal entry is above both the relative
-          // (graded-matrix) threshold and the rounding level of the larger
-          // diagonal entry -- below that a rotation only shuffles noise
-          const double thr = fmax(JACOBI_TOL * sqrt(fabs(app * aqq)),
-                                  JACOBI_EPS * fmax(fabs(app), fabs(aqq)));
-          if (fabs(apq) > thr) {
-            const double zeta = (aqq - app) / (2.0 * apq);
-            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            my_c = rsqrt(1.0 + t * t);
-            my_s = my_c * t;
-            my_p = p;
-            my_q = q;
-          }
+        const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
+        double c = 1.0, s = 0.0, t = 0.0;
+        // rotate while the off-diagonal entry is above both the relative
+        // (graded-matrix) threshold and the rounding level of the larger
+        // diagonal entry -- below that a rotation only shuffles noise
+        const double thr = fmax(JACOBI_TOL * sqrt(fabs(app * aqq)),
+                                JACOBI_EPS * fmax(fabs(app), fabs(aqq)));
+        if (fabs(apq) > thr) {
+          const double zeta = (aqq - app) / (2.0 * apq);
+          t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = rsqrt(1.0 + t * t);
+          s = c * t;
+          active = 1;
         }
+        sc.pq[2 * pi] = p;
+        sc.pq[2 * pi + 1] = q;
+        sc.cst[3 * pi] = c;
+        sc.cst[3 * pi + 1] = s;
+        sc.cst[3 * pi + 2] = t;
       }
-      int pp[NPW], qq[NPW];
-      double cc[NPW], ss[NPW];
-#pragma unroll
-      for (int j = 0; j < NPW; ++j) {
-        pp[j] = __shfl_sync(0xffffffffu, my_p, j);
-        qq[j] = __shfl_sync(0xffffffffu, my_q, j);
-        cc[j] = __shfl_sync(0xffffffffu, my_c, j);
-        ss[j] = __shfl_sync(0xffffffffu, my_s, j);
+      any |= __syncthreads_or(active);
+      // phase 1a: the 2 x 2 blocks of A
+      for (int bi = tid; bi < nb; bi += SM_THREADS) {
+        const int a = sc.blk[bi].x, b = sc.blk[bi].y;
+        const int pa = sc.pq[2 * a], qa = sc.pq[2 * a + 1];
+        const double ca = sc.cst[3 * a], sa = sc.cst[3 * a + 1];
+        if (a == b) {
+          if (sa != 0.0) {
+            const double t = sc.cst[3 * a + 2], apq = A[pa * ld + qa];
+            A[pa * ld + pa] -= t * apq;
+            A[qa * ld + qa] += t * apq;
+            A[pa * ld + qa] = 0.0;
+            A[qa * ld + pa] = 0.0;
+          }
+          continue;
+        }
+        const int pb = sc.pq[2 * b], qb = sc.pq[2 * b + 1];
+        const double cb = sc.cst[3 * b], sb = sc.cst[3 * b + 1];
+        if (sa == 0.0 && sb == 0.0) continue;
+        const double x00 = A[pa * ld + pb], x01 = A[pa * ld + qb];
+        const double x10 = A[qa * ld + pb], x11 = A[qa * ld + qb];
+        const double y00 = cb * x00 - sb * x01, y01 = sb * x00 + cb * x01;
+        const double y10 = cb * x10 - sb * x11, y11 = sb * x10 + cb * x11;
+        const double z00 = ca * y00 - sa * y10, z01 = ca * y01 - sa * y11;
+        const double z10 = sa * y00 + ca * y10, z11 = sa * y01 + ca * y11;
+        A[pa * ld + pb] = z00;
+        A[pa * ld + qb] = z01;
+        A[qa * ld + pb] = z10;
+        A[qa * ld + qb] = z11;
+        A[pb * ld + pa] = z00;
+        A[qb * ld + pa] = z01;
+        A[pb * ld + qa] = z10;
+        A[qb * ld + qa] = z11;
       }
-      // column rotations  A <- A J,  V <- V J
-      int rotated = 0;
-#pragma unroll
-      for (int j = 0; j < NPW; ++j) {
-        if (pp[j] < 0) continue;
-        rotated = 1;
-        const int p = pp[j], q = qq[j];
-        const double c = cc[j], s = ss[j];
+      // phase 1b: V <- V J (a warp per pair, lanes over the rows)
+      for (int pi = warp; pi < half; pi += SM_WARPS) {
+        const double s = sc.cst[3 * pi + 1];
+        if (s == 0.0) continue;
+        const double c = sc.cst[3 * pi];
+        const int p = sc.pq[2 * pi], q = sc.pq[2 * pi + 1];
         for (int i = lane; i < n; i += 32) {
-          const double x = A[i * ld + p], y = A[i * ld + q];
-          A[i * ld + p] = c * x - s * y;
-          A[i * ld + q] = s * x + c * y;
           const double vx = V[i * ld + p], vy = V[i * ld + q];
           V[i * ld + p] = c * vx - s * vy;
           V[i * ld + q] = s * vx + c * vy;
-        }
-      }
-      any |= __syncthreads_or(rotated);
-      // row rotations  A <- J^T A
-#pragma unroll
-      for (int j = 0; j < NPW; ++j) {
-        if (pp[j] < 0) continue;
-        const int p = pp[j], q = qq[j];
-        const double c = cc[j], s = ss[j];
-        for (int i = lane; i < n; i += 32) {
-          const double x = A[p * ld + i], y = A[q * ld + i];
-          A[p * ld + i] = c * x - s * y;
-          A[q * ld + i] = s * x + c * y;
         }
       }
       __syncthreads();
@@ -141,24 +152,36 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
                     double *__restrict__ M_out, double *__restrict__ V_out,
                     double *__restrict__ lam_out) {
   extern __shared__ __align__(16) double sm[];
-  const int ld = K | 1;
+  const int ne = K + (K & 1), ld = ne | 1, half = ne / 2;
+  const int nb = half * (half + 1) / 2;
   double *bufA = sm;                 // G, later temp^T temp, later N s
-  double *bufV = bufA + K * ld;      // V
-  double *bufT = bufV + K * ld;      // temp, later Q
-  double *bufW = bufT + K * ld;      // H, later W
-  double *lam = bufW + K * ld;       // K
-  double *aux = lam + K;             // K
-  int *rank = reinterpret_cast<int *>(aux + K);  // K
+  double *bufV = bufA + ne * ld;     // V
+  double *bufT = bufV + ne * ld;     // temp, later Q
+  double *bufW = bufT + ne * ld;     // H, later W
+  double *lam = bufW + ne * ld;      // ne
+  double *aux = lam + ne;            // ne
+  JacobiScratch sc;
+  sc.cst = aux + ne;                                   // 3*half
+  sc.pq = reinterpret_cast<int *>(sc.cst + 3 * half);  // 2*half
+  int *rank = sc.pq + 2 * half;                        // ne
+  sc.blk = reinterpret_cast<short2 *>(rank + ne);      // nb
   const int r = blockIdx.x, tid = threadIdx.x;
   const double *Gr = G + (size_t)r * K * K;
 
-  for (int e = tid; e < K * K; e += SM_THREADS) {
-    const int i = e / K, j = e - i * K;
-    // symmetrise: both triangles must agree exactly for the two-sided updates
-    bufA[i * ld + j] = 0.5 * (Gr[(size_t)i * K + j] + Gr[(size_t)j * K + i]);
-    bufV[i * ld + j] = (i == j) ? 1.0 : 0.0;
+  // block table: bi -> (a, b), a <= b
+  for (int a = tid; a < half; a += SM_THREADS) {
+    int bi = a * half - a * (a - 1) / 2;   // blocks of the rows before a
+    for (int b = a; b < half; ++b) sc.blk[bi++] = make_short2((short)a, (short)b);
   }
-  jacobi_sym(bufA, bufV, K, ld);   // diag(bufA) = lam, bufV = V
+  for (int e = tid; e < ne * ne; e += SM_THREADS) {
+    const int i = e / ne, j = e - i * ne;
+    double g = 0.0;
+    // symmetrise: both triangles must agree exactly for the two-sided updates
+    if (i < K && j < K) g = 0.5 * (Gr[(size_t)i * K + j] + Gr[(size_t)j * K + i]);
+    bufA[i * ld + j] = g;
+    bufV[i * ld + j] = (i == j && i < K) ? 1.0 : 0.0;
+  }
+  jacobi_sym(bufA, bufV, K, ld, sc);   // diag(bufA) = lam, bufV = V
   for (int j = tid; j < K; j += SM_THREADS) lam[j] = fmax(bufA[j * ld + j], 0.0);
   __syncthreads();
   // descending rank of every eigenvalue (ties broken by index)
@@ -206,18 +229,17 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
     bufT[i * ld + j] = v * aux[j];
   }
   __syncthreads();
-  // S = temp^T temp -> bufA;  W <- I
-  for (int e = tid; e < L * L; e += SM_THREADS) {
-    const int i = e / L, j = e - i * L;
-    if (j >= i) {
-      double v = 0.0;
+  // S = temp^T temp -> bufA (zero padded to ne);  W <- I
+  for (int e = tid; e < ne * ne; e += SM_THREADS) {
+    const int i = e / ne, j = e - i * ne;
+    double v = 0.0;
+    if (i < L && j < L)
       for (int k = 0; k < L; ++k) v += bufT[k * ld + i] * bufT[k * ld + j];
-      bufA[i * ld + j] = v;
-      bufA[j * ld + i] = v;
-    }
-    bufW[i * ld + j] = (i == j) ? 1.0 : 0.0;
+    bufA[i * ld + j] = v;
+    bufW[i * ld + j] = (i == j && i < L) ? 1.0 : 0.0;
   }
-  jacobi_sym(bufA, bufW, L, ld);   // bufW = W (right singular vectors)
+  // (S[i][j] and S[j][i] are the same sum in the same order: exactly symmetric)
+  jacobi_sym(bufA, bufW, L, ld, sc);   // bufW = W (right singular vectors)
   // N s = temp W -> bufA
   for (int e = tid; e < L * L; e += SM_THREADS) {
     const int i = e / L, k = e - i * L;
@@ -264,8 +286,10 @@ int launch_small(plsb_ctx *h, const double *G, const double *H, int count, int K
   PLSB_CHECK(K >= 1 && K <= MAX_K, PLSB_ERR_ARG, "small decomposition: K=%d outside [1,%d]", K,
              MAX_K);
   PLSB_CHECK(mode == 1 || L == K, PLSB_ERR_ARG, "small decomposition: L=%d must equal K=%d", L, K);
-  const int ld = K | 1;
-  const size_t smem = sizeof(double) * (4 * (size_t)K * ld + 2 * K) + sizeof(int) * K;
+  const int ne = K + (K & 1), ld = ne | 1, half = ne / 2;
+  const int nb = half * (half + 1) / 2;
+  const size_t smem = sizeof(double) * (4 * (size_t)ne * ld + 2 * ne + 3 * half) +
+                      sizeof(int) * (2 * half + ne) + sizeof(short2) * nb + 16;
   PLSB_CUDA(cudaFuncSetAttribute(small_decomp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   small_decomp_kernel<<<count, SM_THREADS, smem, st>>>(G, H, K, L, mode, sqrt_lam, dorig, M, V,
