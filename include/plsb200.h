@@ -181,6 +181,38 @@ int plsb_small_decomp(plsb_handle_t h, const double *d_G, const double *d_H,
                       int count, int K, int L, const double *d_dorig,
                       double *d_M, double *d_lam, void *stream);
 
+/* ---- SIMPLS (pls_regression; mode PLSB_SIMPLS, n_groups = 1, n_cond = 1) -------
+ * plsb_set_data takes X (S,B) and Y (S,T) already column-centred
+ * (pyls/types/regression.py:395-396).  `d_omega` tables hold the Gaussian test
+ * matrices sklearn's randomized_svd would draw, (T, 11) row-major each
+ * (compute.svd(Cov, n_components=1, seed) at pyls/types/regression.py:103); they
+ * may be NULL when T <= 11 (the probes then span the whole space).
+ *
+ * plsb_simpls_decompose: original decomposition; replaces PLSRegression.svd ->
+ *   simpls on the un-resampled data (pyls/types/regression.py:248-277, 56-186).
+ *   d_omega (L,T,11): one table per component (the reference draws them in turn
+ *   from the analysis' RandomState).  Outputs x_weights (B,L) with sklearn's
+ *   svd_flip signs and pctvar in Y (L); installs the weights as the original.
+ * plsb_simpls_run_perms: replaces PLSRegression._single_perm over a batch
+ *   (regression.py:329-373): Y rows follow d_idx (count,S), X fixed;
+ *   d_omega (count,T,11) (resample i uses RandomState(i)); d_pctvar (count,L).
+ * plsb_simpls_run_boots: replaces PLSRegression._single_boot over a batch
+ *   (regression.py:279-327): X and Y rows follow d_idx; x_weights are sign
+ *   aligned with the original (efficient_corr, :317-320) and ACCUMULATED into
+ *   d_usum / d_usquare (B,L); d_distrib (count,T,L) = Yi^T (Xi x_weights)
+ *   (:323-325); d_pctvar (count,L). */
+int plsb_simpls_set_original(plsb_handle_t h, const double *d_xweights,
+                             void *stream);
+int plsb_simpls_decompose(plsb_handle_t h, const double *d_omega,
+                          double *d_xweights, double *d_pctvar, void *stream);
+int plsb_simpls_run_perms(plsb_handle_t h, const int32_t *d_idx, int count,
+                          const double *d_omega, double *d_pctvar,
+                          void *stream);
+int plsb_simpls_run_boots(plsb_handle_t h, const int32_t *d_idx, int count,
+                          const double *d_omega, double *d_pctvar,
+                          double *d_distrib, double *d_usum, double *d_usquare,
+                          void *stream);
+
 /* Counters for bench / tests: kernels launched by this handle so far. */
 int64_t plsb_launch_count(plsb_handle_t h);
 

@@ -6,7 +6,7 @@ behind the front-end of netneurolab/pypyls: ``behavioral_pls`` and
 loops run as batched CUDA launches through ``libplsb200.so``.
 """
 
-__all__ = ['behavioral_pls', 'meancentered_pls', 'PLSResults', 'PLSInputs',
+__all__ = ['behavioral_pls', 'meancentered_pls', 'pls_regression', 'PLSResults', 'PLSInputs',
            'ResamplingEngine', 'release_workspaces', 'gen_permsamp', 'gen_bootsamp', '__version__']
 
 __version__ = '0.1.0'
@@ -14,4 +14,4 @@ __version__ = '0.1.0'
 from .structures import PLSInputs, PLSResults
 from .resample import gen_bootsamp, gen_permsamp
 from .engine import ResamplingEngine, release_workspaces
-from .types import behavioral_pls, meancentered_pls
+from .types import behavioral_pls, meancentered_pls, pls_regression

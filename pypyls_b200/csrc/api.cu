@@ -120,6 +120,29 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, int n, bool boot, double *di
   return PLSB_OK;
 }
 
+// C (M,N) = A (M,Kd) @ X (Kd,N), all dense row-major without padding
+int dense_gemm(plsb_ctx *h, const double *d_A, const double *d_X, int M, int N, int Kd,
+               double *d_C, cudaStream_t st) {
+  const int M_pad = round_up(M, GEMM_BM), N_pad = round_up(N, GEMM_BN), K_pad = round_up(Kd, GEMM_BK);
+  PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)M_pad * K_pad));
+  PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)K_pad * N_pad));
+  PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)M_pad * N_pad));
+  PLSB_TRY(launch_pad_copy(h, d_A, M, Kd, h->A.as<double>(), M_pad, K_pad, st));
+  PLSB_TRY(launch_pad_copy(h, d_X, Kd, N, h->misc.as<double>(), K_pad, N_pad, st));
+  GemmArgs g;
+  g.A = h->A.as<double>();
+  g.lda = K_pad;
+  g.X = h->misc.as<double>();
+  g.ldx = N_pad;
+  g.M_pad = M_pad;
+  g.N_pad = N_pad;
+  g.Kd = K_pad;
+  g.C = h->R.as<double>();
+  g.ldc = N_pad;
+  PLSB_TRY(launch_gemm(h, g, st));
+  return launch_unpad_copy(h, h->R.as<double>(), N_pad, M, N, d_C, st);
+}
+
 // resamples per chunk so that the stored matrices fit the workspace limit
 int chunk_size(const plsb_ctx *h, bool boot, int count) {
   const Layout &l = h->lay;
@@ -219,8 +242,8 @@ int plsb_timing_read(plsb_handle_t h, double *ms, int64_t *launches) {
 int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups, const int *groups,
                    int n_cond, int mean_centering, int n_components) {
   PLSB_HANDLE(h);
-  PLSB_CHECK(mode >= PLSB_BEHAVIORAL_CORR && mode <= PLSB_MEANCENTERED, PLSB_ERR_ARG,
-             "plsb_configure: mode %d is not supported by this build", mode);
+  PLSB_CHECK(mode >= PLSB_BEHAVIORAL_CORR && mode <= PLSB_SIMPLS, PLSB_ERR_ARG,
+             "plsb_configure: unknown mode %d", mode);
   PLSB_CHECK(S >= 2 && B >= 1 && n_groups >= 1 && n_cond >= 1 && groups != nullptr, PLSB_ERR_ARG,
              "plsb_configure: bad sizes S=%d B=%d n_groups=%d n_cond=%d", S, B, n_groups, n_cond);
   Layout l;
@@ -249,6 +272,13 @@ int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups,
     for (int g = 0; g < n_groups; ++g)
       PLSB_CHECK(groups[g] >= 2, PLSB_ERR_ARG,
                  "plsb_configure: group %d has a single subject (no variance)", g);
+  } else if (l.simpls()) {
+    PLSB_CHECK(T >= 1 && n_groups == 1 && n_cond == 1, PLSB_ERR_ARG,
+               "plsb_configure: SIMPLS takes one group, one condition and T >= 1");
+    PLSB_CHECK(n_components >= 1 && n_components <= std::min(S - 1, B), PLSB_ERR_ARG,
+               "Provided `n_components` cannot be greater than %d", std::min(S - 1, B));
+    l.T = T;
+    l.K = n_components;
   } else {
     PLSB_CHECK(mean_centering >= 0 && mean_centering <= 2, PLSB_ERR_ARG,
                "Mean centering type must be in [0, 1, 2].");
@@ -301,7 +331,7 @@ int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups,
   h->d_group_start = h->d_cell_n + l.J;
   h->d_cell_kr = reinterpret_cast<const int2 *>(h->tables.as<int>() + kr_off);
 
-  if (!l.behavioral()) {
+  if (l.mode == PLSB_MEANCENTERED) {
     // C (J,S): "cell mean minus centring mean" as a row operator
     // (pyls/compute.py:267-357)
     std::vector<double> C((size_t)l.J * S, 0.0);
@@ -338,8 +368,25 @@ int plsb_set_data(plsb_handle_t h, const double *d_X, const double *d_Y, void *s
   const Layout &l = h->lay;
   cudaStream_t st = as_stream(stream);
   PLSB_CHECK(d_X != nullptr, PLSB_ERR_ARG, "plsb_set_data: null X");
-  PLSB_CHECK(!l.behavioral() || d_Y != nullptr, PLSB_ERR_ARG, "plsb_set_data: null Y");
+  PLSB_CHECK(!(l.behavioral() || l.simpls()) || d_Y != nullptr, PLSB_ERR_ARG,
+             "plsb_set_data: null Y");
   const size_t bytes = sizeof(double) * (size_t)l.S_pad * l.ldx;
+  if (l.simpls()) {
+    // X and Y arrive column-centred (pyls/types/regression.py:395-396).  Kraw = X X^T (S,S)
+    // is the only B-sized object the component loops need.
+    PLSB_TRY(h->Xraw.ensure(bytes));
+    PLSB_TRY(launch_pad_copy(h, d_X, l.S, l.B, h->Xraw.as<double>(), l.S_pad, l.ldx, st));
+    PLSB_TRY(h->Y.ensure(sizeof(double) * (size_t)l.S * l.T));
+    PLSB_CUDA(cudaMemcpyAsync(h->Y.p, d_Y, sizeof(double) * (size_t)l.S * l.T,
+                              cudaMemcpyDeviceToDevice, st));
+    PLSB_TRY(h->Xglob.ensure(sizeof(double) * (size_t)l.S * l.B));
+    PLSB_TRY(launch_transpose(h, d_X, l.S, l.B, l.B, h->Xglob.as<double>(), st));
+    PLSB_TRY(h->Cmat.ensure(sizeof(double) * (size_t)l.S * l.S));
+    PLSB_TRY(dense_gemm(h, d_X, h->Xglob.as<double>(), l.S, l.S, l.B, h->Cmat.as<double>(), st));
+    h->has_data = true;
+    h->has_original = false;
+    return PLSB_OK;
+  }
   PLSB_TRY(h->Xraw.ensure(bytes));
   PLSB_TRY(h->Xglob.ensure(bytes));
   PLSB_TRY(launch_pad_copy(h, d_X, l.S, l.B, h->Xraw.as<double>(), l.S_pad, l.ldx, st));
@@ -575,25 +622,120 @@ int plsb_dgemm(plsb_handle_t h, const double *d_A, const double *d_X, int M, int
   PLSB_HANDLE(h);
   PLSB_CHECK(d_A && d_X && d_C && M >= 1 && N >= 1 && Kd >= 1, PLSB_ERR_ARG,
              "plsb_dgemm: bad argument");
-  cudaStream_t st = as_stream(stream);
-  const int M_pad = round_up(M, GEMM_BM), N_pad = round_up(N, GEMM_BN), K_pad = round_up(Kd, GEMM_BK);
-  PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)M_pad * K_pad));
-  PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)K_pad * N_pad));
-  PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)M_pad * N_pad));
-  PLSB_TRY(launch_pad_copy(h, d_A, M, Kd, h->A.as<double>(), M_pad, K_pad, st));
-  PLSB_TRY(launch_pad_copy(h, d_X, Kd, N, h->misc.as<double>(), K_pad, N_pad, st));
+  return dense_gemm(h, d_A, d_X, M, N, Kd, d_C, as_stream(stream));
+}
+
+// ---- SIMPLS (pls_regression) ---------------------------------------------------
+
+// x_weights operand rows D (n*L, S_pad) in h->A  ->  R (n*L, ldx) = D @ X
+static int simpls_weights_gemm(plsb_ctx *h, int n, cudaStream_t st) {
+  const Layout &l = h->lay;
+  const long long M = (long long)n * l.L, M_pad = round_up_ll(M, GEMM_BM);
+  PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)M_pad * l.ldx));
+  PLSB_TRY(zero_tail(h->A.as<double>(), M, M_pad, l.S_pad, st));
   GemmArgs g;
   g.A = h->A.as<double>();
-  g.lda = K_pad;
-  g.X = h->misc.as<double>();
-  g.ldx = N_pad;
-  g.M_pad = M_pad;
-  g.N_pad = N_pad;
-  g.Kd = K_pad;
+  g.lda = l.S_pad;
+  g.X = h->Xraw.as<double>();
+  g.ldx = l.ldx;
+  g.M_pad = (int)M_pad;
+  g.N_pad = l.ldx;
+  g.Kd = l.S_pad;
   g.C = h->R.as<double>();
-  g.ldc = N_pad;
-  PLSB_TRY(launch_gemm(h, g, st));
-  return launch_unpad_copy(h, h->R.as<double>(), N_pad, M, N, d_C, st);
+  g.ldc = l.ldx;
+  return launch_gemm(h, g, st);
+}
+
+static int simpls_chunk(const plsb_ctx *h, int count, bool boot) {
+  const Layout &l = h->lay;
+  size_t per = sizeof(double) * 4 * (size_t)l.S * l.L;
+  if (boot) per += sizeof(double) * ((size_t)l.L * l.S_pad + (size_t)l.L * l.ldx + (size_t)l.L * l.L);
+  long long n = std::max<long long>(1, (long long)(h->ws_limit / per));
+  n = std::min<long long>(n, ((1ll << 31) - 1024) / std::max(l.L, 1));
+  return (int)std::min<long long>(n, count);
+}
+
+int plsb_simpls_set_original(plsb_handle_t h, const double *d_xweights, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->lay.simpls(), PLSB_ERR_STATE,
+             "plsb_simpls_set_original needs a SIMPLS handle with data");
+  PLSB_CHECK(d_xweights != nullptr, PLSB_ERR_ARG, "plsb_simpls_set_original: null argument");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  PLSB_TRY(h->Uo.ensure(sizeof(double) * (size_t)l.B * l.L));
+  PLSB_TRY(h->Sx.ensure(sizeof(double) * (size_t)l.S * l.L));
+  // So = X (orig - colmean(orig)): sign(efficient_corr(x_weights_boot, orig)) in sample space
+  PLSB_TRY(launch_colcenter(h, d_xweights, l.B, l.L, h->Uo.as<double>(), st));
+  PLSB_TRY(launch_xproj(h, h->Xraw.as<double>(), l.ldx, l.S, l.B, h->Uo.as<double>(), l.L, nullptr,
+                        h->Sx.as<double>(), st));
+  h->has_original = true;
+  return PLSB_OK;
+}
+
+int plsb_simpls_decompose(plsb_handle_t h, const double *d_omega, double *d_xweights,
+                          double *d_pctvar, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->lay.simpls(), PLSB_ERR_STATE,
+             "plsb_simpls_decompose needs a SIMPLS handle with data");
+  PLSB_CHECK(d_xweights && d_pctvar, PLSB_ERR_ARG, "plsb_simpls_decompose: null output");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  h->has_original = false;
+  PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)GEMM_BM * l.S_pad));
+  PLSB_TRY(launch_simpls(h, nullptr, 1, 0, 1, d_omega, 0, (long long)l.T * 11, d_pctvar, nullptr,
+                         st));
+  PLSB_TRY(simpls_weights_gemm(h, 1, st));
+  PLSB_TRY(launch_xweights_flip(h, h->R.as<double>(), l.ldx, l.B, l.L, d_xweights, st));
+  return plsb_simpls_set_original(h, d_xweights, stream);
+}
+
+int plsb_simpls_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, const double *d_omega,
+                          double *d_pctvar, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->lay.simpls(), PLSB_ERR_STATE,
+             "plsb_simpls_run_perms needs a SIMPLS handle with data");
+  PLSB_CHECK(d_idx && d_pctvar && count >= 0, PLSB_ERR_ARG, "plsb_simpls_run_perms: bad argument");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  const int chunk = simpls_chunk(h, count, false);
+  const long long om = (long long)l.T * 11;
+  for (int off = 0; off < count; off += chunk) {
+    const int n = std::min(chunk, count - off);
+    PLSB_TRY(launch_simpls(h, d_idx + (size_t)off * l.S, n, 0, 0,
+                           d_omega ? d_omega + (size_t)off * om : nullptr, om, 0,
+                           d_pctvar + (size_t)off * l.L, nullptr, st));
+  }
+  return PLSB_OK;
+}
+
+int plsb_simpls_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, const double *d_omega,
+                          double *d_pctvar, double *d_distrib, double *d_usum, double *d_usquare,
+                          void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->has_original && h->lay.simpls(), PLSB_ERR_STATE,
+             "plsb_simpls_run_boots needs a SIMPLS handle with data and the original weights");
+  PLSB_CHECK(d_idx && d_pctvar && d_distrib && d_usum && d_usquare && count >= 0, PLSB_ERR_ARG,
+             "plsb_simpls_run_boots: bad argument");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  const int chunk = simpls_chunk(h, count, true);
+  const long long om = (long long)l.T * 11;
+  for (int off = 0; off < count; off += chunk) {
+    const int n = std::min(chunk, count - off);
+    const long long M_pad = round_up_ll((long long)n * l.L, GEMM_BM);
+    PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)M_pad * l.S_pad));
+    PLSB_TRY(launch_simpls(h, d_idx + (size_t)off * l.S, n, 1, 1,
+                           d_omega ? d_omega + (size_t)off * om : nullptr, om, 0,
+                           d_pctvar + (size_t)off * l.L, d_distrib + (size_t)off * l.T * l.L, st));
+    PLSB_TRY(simpls_weights_gemm(h, n, st));
+    // u_sum += x_weights_r, u_square += x_weights_r^2 (pyls/base.py:510-511): the shared
+    // accumulation kernel with identity rotations
+    PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)n * l.L * l.L));
+    PLSB_TRY(launch_identity_blocks(h, h->misc.as<double>(), n, l.L, st));
+    PLSB_TRY(launch_accum_u(h, h->R.as<double>(), l.ldx, n, l.L, l.B, h->misc.as<double>(), l.L,
+                            d_usum, d_usquare, st));
+  }
+  return PLSB_OK;
 }
 
 int plsb_small_decomp(plsb_handle_t h, const double *d_G, const double *d_H, int count, int K,

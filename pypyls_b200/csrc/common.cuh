@@ -109,6 +109,7 @@ struct Layout {
   int ldx = 0;                  // leading dimension (elements) of padded (., B) matrices
   bool behavioral() const { return mode == PLSB_BEHAVIORAL_CORR || mode == PLSB_BEHAVIORAL_COV; }
   bool corr() const { return mode == PLSB_BEHAVIORAL_CORR; }
+  bool simpls() const { return mode == PLSB_SIMPLS; }
 };
 
 }  // namespace plsb
@@ -237,6 +238,17 @@ int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count
                         const double *dorig, double *M, double *lam, cudaStream_t st);
 int launch_sym_eig(plsb_ctx *h, const double *G, int count, int K, double *V, double *lam,
                    int sqrt_lam, cudaStream_t st);
+
+// SIMPLS (simpls.cu)
+int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit_ops,
+                  const double *omega, long long om_stride_r, long long om_stride_c, double *pct,
+                  double *distrib, cudaStream_t st);
+int launch_transpose(plsb_ctx *h, const double *in, int rows, int cols, int ld_in, double *out,
+                     cudaStream_t st);
+int launch_identity_blocks(plsb_ctx *h, double *M, int n, int L, cudaStream_t st);
+int launch_xweights_flip(plsb_ctx *h, const double *Rw, long long ldr, int B, int L, double *xw,
+                         cudaStream_t st);
+int launch_colcenter(plsb_ctx *h, const double *U, int B, int L, double *out, cudaStream_t st);
 
 // index generation (indexgen.cu), statistics (stats.cu)
 int gen_indices(plsb_ctx *h, bool boot, uint64_t seed, int64_t first, int count, int32_t *d_idx,

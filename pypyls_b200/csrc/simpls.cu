@@ -1,0 +1,618 @@
+// SIMPLS resampling (pls_regression) in sample space, one CTA per resample.
+//
+// The reference (pyls/types/regression.py:56-186, 279-373) recomputes for every
+// resample Cov = X0^T Y0 (B x T) and runs, per component, a randomized top-1
+// SVD of Cov (sklearn randomized_svd: Omega = RandomState(seed).normal((T,11)),
+// 7 or 4 power iterations), the score t = X0 r, loadings and a deflation of Cov.
+// Every B-vector that algorithm touches is X0^T (S-vector), so with the S x S
+// matrix Kx = X0 X0^T (for a resample: a gather of the fixed Kraw = X X^T,
+// centred on both sides) the whole component loop runs on S x T, T x T and
+// 11 x 11 objects:
+//
+//   A = Y0 (deflated in place);   KA = Kx A;   C = A^T KA            (= Cov^T Cov)
+//   W = orth(C^n_iter Omega)  (T x p, p = min(T, 11); the randomized range finder)
+//   Gz = W^T C W = E diag(lz) E^T;   Bm = lz^-1/2 E^T W^T C;   uh = top left singular vector
+//   wt = W E lz^-1/2 uh;   a = A wt;   t = KA wt;   x_weights column = X0^T a / |t|
+//   pctvar_y = |Yp^T t|^2 / |Y0|^2;   b = MGS(t) in the Kx inner product;   A -= b (Kx b)^T A ...
+//
+// (the eigen form of the 11-dimensional step replaces the reference's QR of a
+// possibly rank-deficient B x 11 matrix; it selects the same vector).  Only the
+// final x_weights = X0^T Wcoef of a bootstrap needs a B-sized product; it goes
+// through the shared DMMA GEMM as L operand rows per resample.
+// The tests check this against the direct B-space restatement of the reference.
+#include "common.cuh"
+#include "jacobi.cuh"
+
+namespace plsb {
+namespace {
+
+constexpr int SP_THREADS = 512;
+constexpr int SP_WARPS = SP_THREADS / 32;
+constexpr int SP_PROBES = 11;   // n_components (1) + n_oversamples (10) of randomized_svd
+
+struct SimplsParams {
+  int S, T, L, p, n_iter, boot, emit_ops, lda;
+  const double *Kraw, *Yc, *omega, *So;
+  const int32_t *idx;
+  long long om_stride_r, om_stride_c;
+  double *Wcoef, *Bs, *Gs, *Tm;   // (n, S, L) each
+  double *pct, *D, *distrib;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum over the CTA; every thread gets the result.  red: >= SP_WARPS doubles
+__device__ double block_sum(double v, double *red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < SP_WARPS; ++w) t += red[w];
+  return t;
+}
+
+// out[t] = sum_i x[i] * M[i*T + t]  (t < T), a warp per column; then barrier
+__device__ void colvec(const double *x, const double *M, int S, int T, double *out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < T; t += SP_WARPS) {
+    double v = 0.0;
+    for (int i = lane; i < S; i += 32) v += x[i] * M[i * T + t];
+    v = warp_sum(v);
+    if (lane == 0) out[t] = v;
+  }
+  __syncthreads();
+}
+
+template <int TT>
+__device__ void gram_apply(const SimplsParams &p, const int *pix, const double *A, double *KA,
+                           double *csum) {
+  // KA = H (Kpi A):  row i of Kpi is a gather of row pix[i] of Kraw
+  const int S = p.S, T = p.T;
+  for (int i = threadIdx.x; i < S; i += SP_THREADS) {
+    double acc[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) acc[t] = 0.0;
+    const double *krow = p.Kraw + (size_t)pix[i] * S;
+    for (int j = 0; j < S; ++j) {
+      const double k = krow[pix[j]];
+      const double *aj = A + j * T;
+#pragma unroll
+      for (int t = 0; t < TT; ++t)
+        if (t < T) acc[t] += k * aj[t];
+    }
+#pragma unroll
+    for (int t = 0; t < TT; ++t)
+      if (t < T) KA[i * T + t] = acc[t];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < T; t += SP_WARPS) {
+    double v = 0.0;
+    for (int i = lane; i < S; i += 32) v += KA[i * T + t];
+    v = warp_sum(v);
+    if (lane == 0) csum[t] = v / S;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < S * T; e += SP_THREADS) KA[e] -= csum[e % T];
+  __syncthreads();
+}
+
+template <int TT>
+__global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int S = p.S, T = p.T, L = p.L, P = p.p;
+  const int pe = P + (P & 1), ldz = pe | 1, halfz = pe / 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = blockIdx.x;
+  // ---- shared memory carve-up ----
+  double *A = sm;                  // S*T
+  double *KA = A + S * T;          // S*T
+  double *tv = KA + S * T;         // S
+  double *bv = tv + S;             // S
+  double *gv = bv + S;             // S
+  double *C = gv + S;              // T*T
+  double *W = C + T * T;           // T*P
+  double *CW = W + T * P;          // T*P
+  double *F = CW + T * P;          // P*T
+  double *Bm = F + P * T;          // P*T
+  double *Gz = Bm + P * T;         // pe*ldz
+  double *Ez = Gz + pe * ldz;      // pe*ldz
+  double *E2 = Ez + pe * ldz;      // pe*ldz
+  double *Z = E2 + pe * ldz;       // max(L*T, 2L): deflation coefficients, later signs
+  double *lamz = Z + max(L * T, 2 * L);   // pe
+  double *inv = lamz + pe;         // pe
+  double *yv = inv + pe;           // pe
+  double *wt = yv + pe;            // T
+  double *qv = wt + T;             // T
+  double *ysum = qv + T;           // T
+  double *csum = ysum + T;         // T
+  double *red = csum + T;          // SP_WARPS + 2
+  JacobiScratch sc;
+  sc.cst = red + SP_WARPS + 2;                                  // 3*halfz
+  sc.pq = reinterpret_cast<int *>(sc.cst + 3 * halfz);          // 2*halfz
+  int *pix = sc.pq + 2 * halfz;                                 // S
+  int *piy = pix + S;                                           // S
+  sc.blk = reinterpret_cast<short2 *>(piy + S);                 // halfz*(halfz+1)/2
+
+  double *Wc = p.Wcoef + (size_t)r * S * L;
+  double *Bs = p.Bs + (size_t)r * S * L;
+  double *Gs = p.Gs + (size_t)r * S * L;
+  double *Tm = p.Tm + (size_t)r * S * L;
+
+  for (int a = tid; a < halfz; a += SP_THREADS) {
+    int bi = a * halfz - a * (a - 1) / 2;
+    for (int b = a; b < halfz; ++b) sc.blk[bi++] = make_short2((short)a, (short)b);
+  }
+  for (int i = tid; i < S; i += SP_THREADS) {
+    const int src = p.idx ? p.idx[(size_t)r * S + i] : i;
+    piy[i] = src;
+    pix[i] = p.boot ? src : i;
+  }
+  __syncthreads();
+  // A = Y0 = Yp - column means;  ysum = column sums of Yp
+  for (int e = tid; e < S * T; e += SP_THREADS) {
+    const int i = e / T, t = e - i * T;
+    A[e] = p.Yc[(size_t)piy[i] * T + t];
+  }
+  __syncthreads();
+  for (int t = warp; t < T; t += SP_WARPS) {
+    double v = 0.0;
+    for (int i = lane; i < S; i += 32) v += A[i * T + t];
+    v = warp_sum(v);
+    if (lane == 0) ysum[t] = v;
+  }
+  __syncthreads();
+  double ssy = 0.0;
+  for (int e = tid; e < S * T; e += SP_THREADS) {
+    const double v = A[e] - ysum[e % T] / S;
+    A[e] = v;
+    ssy += v * v;
+  }
+  ssy = block_sum(ssy, red);
+
+  for (int comp = 0; comp < L; ++comp) {
+    gram_apply<TT>(p, pix, A, KA, csum);
+    // C = A^T KA (upper triangle, mirrored)
+    for (int e = tid; e < T * T; e += SP_THREADS) {
+      const int t1 = e / T, t2 = e - t1 * T;
+      if (t2 < t1) continue;
+      double v = 0.0;
+      for (int s = 0; s < S; ++s) v += A[s * T + t1] * KA[s * T + t2];
+      C[t1 * T + t2] = v;
+      C[t2 * T + t1] = v;
+    }
+    __syncthreads();
+    // ---- randomized range finder: W = orth(C^n_iter Omega) ----
+    if (T <= SP_PROBES) {
+      for (int e = tid; e < T * P; e += SP_THREADS) W[e] = (e / P == e % P) ? 1.0 : 0.0;
+      __syncthreads();
+    } else {
+      const double *om = p.omega + (size_t)r * p.om_stride_r + (size_t)comp * p.om_stride_c;
+      for (int e = tid; e < T * P; e += SP_THREADS) W[e] = om[e];
+      __syncthreads();
+      for (int it = 0; it < p.n_iter; ++it) {
+        for (int e = tid; e < T * P; e += SP_THREADS) {
+          const int t = e / P, a = e - t * P;
+          double v = 0.0;
+          for (int u = 0; u < T; ++u) v += C[t * T + u] * W[u * P + a];
+          CW[e] = v;
+        }
+        __syncthreads();
+        // modified Gram-Schmidt (two passes), warp 0: lanes over the T rows
+        if (warp == 0) {
+          for (int k = 0; k < P; ++k) {
+            for (int pass = 0; pass < 2; ++pass)
+              for (int j = 0; j < k; ++j) {
+                double d = 0.0;
+                for (int t = lane; t < T; t += 32) d += CW[t * P + j] * CW[t * P + k];
+                d = warp_sum(d);
+                for (int t = lane; t < T; t += 32) CW[t * P + k] -= d * CW[t * P + j];
+                __syncwarp();
+              }
+            double n2 = 0.0;
+            for (int t = lane; t < T; t += 32) n2 += CW[t * P + k] * CW[t * P + k];
+            n2 = warp_sum(n2);
+            const double sc_ = n2 > 0.0 ? rsqrt(n2) : 0.0;
+            for (int t = lane; t < T; t += 32) CW[t * P + k] *= sc_;
+            __syncwarp();
+          }
+        }
+        __syncthreads();
+        for (int e = tid; e < T * P; e += SP_THREADS) W[e] = CW[e];
+        __syncthreads();
+      }
+    }
+    // F = W^T C (P x T);  Gz = F W (P x P, padded to pe)
+    for (int e = tid; e < P * T; e += SP_THREADS) {
+      const int a = e / T, t = e - a * T;
+      double v = 0.0;
+      for (int u = 0; u < T; ++u) v += W[u * P + a] * C[u * T + t];
+      F[e] = v;
+    }
+    __syncthreads();
+    for (int e = tid; e < pe * pe; e += SP_THREADS) {
+      const int a = e / pe, b = e - a * pe;
+      double v = 0.0;
+      if (a < P && b < P) {
+        const int lo = min(a, b), hi = max(a, b);   // one summation order for both triangles
+        for (int t = 0; t < T; ++t) v += F[lo * T + t] * W[t * P + hi];
+      }
+      Gz[a * ldz + b] = v;
+      Ez[a * ldz + b] = (a == b && a < P) ? 1.0 : 0.0;
+    }
+    jacobi_sym(Gz, Ez, P, ldz, sc);
+    if (tid == 0) {
+      double lmax = 0.0;
+      for (int k = 0; k < P; ++k) lmax = fmax(lmax, Gz[k * ldz + k]);
+      for (int k = 0; k < P; ++k) {
+        const double l = Gz[k * ldz + k];
+        inv[k] = (l > 1e-12 * lmax && l > 0.0) ? rsqrt(l) : 0.0;
+      }
+    }
+    __syncthreads();
+    // Bm = diag(inv) Ez^T F (P x T);  BB = Bm Bm^T -> Gz;  E2 = I
+    for (int e = tid; e < P * T; e += SP_THREADS) {
+      const int k = e / T, t = e - k * T;
+      double v = 0.0;
+      for (int a = 0; a < P; ++a) v += Ez[a * ldz + k] * F[a * T + t];
+      Bm[e] = v * inv[k];
+    }
+    __syncthreads();
+    for (int e = tid; e < pe * pe; e += SP_THREADS) {
+      const int a = e / pe, b = e - a * pe;
+      double v = 0.0;
+      if (a < P && b < P) {
+        const int lo = min(a, b), hi = max(a, b);
+        for (int t = 0; t < T; ++t) v += Bm[lo * T + t] * Bm[hi * T + t];
+      }
+      Gz[a * ldz + b] = v;
+      E2[a * ldz + b] = (a == b && a < P) ? 1.0 : 0.0;
+    }
+    jacobi_sym(Gz, E2, P, ldz, sc);
+    if (tid == 0) {
+      int kmax = 0;
+      for (int k = 1; k < P; ++k)
+        if (Gz[k * ldz + k] > Gz[kmax * ldz + kmax]) kmax = k;
+      // yv = Ez (inv o uh)
+      for (int a = 0; a < P; ++a) {
+        double v = 0.0;
+        for (int k = 0; k < P; ++k) v += Ez[a * ldz + k] * inv[k] * E2[k * ldz + kmax];
+        yv[a] = v;
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += SP_THREADS) {
+      double v = 0.0;
+      for (int a = 0; a < P; ++a) v += W[t * P + a] * yv[a];
+      wt[t] = v;
+    }
+    __syncthreads();
+    // a = A wt, t = KA wt, normalise by |t|
+    double nt2 = 0.0;
+    for (int i = tid; i < S; i += SP_THREADS) {
+      double av = 0.0, tvv = 0.0;
+      for (int t = 0; t < T; ++t) {
+        av += A[i * T + t] * wt[t];
+        tvv += KA[i * T + t] * wt[t];
+      }
+      bv[i] = av;      // a, for the moment
+      tv[i] = tvv;
+      nt2 += tvv * tvv;
+    }
+    nt2 = block_sum(nt2, red);
+    const double int_ = nt2 > 0.0 ? rsqrt(nt2) : 0.0;
+    for (int i = tid; i < S; i += SP_THREADS) {
+      Wc[(size_t)i * L + comp] = bv[i] * int_;
+      tv[i] *= int_;
+      Tm[(size_t)i * L + comp] = tv[i];
+    }
+    __syncthreads();
+    // pctvar in Y:  q = Yp^T t  (t is centred, so Y0^T t = Yp^T t)
+    for (int t = warp; t < T; t += SP_WARPS) {
+      double v = 0.0;
+      for (int i = lane; i < S; i += 32) v += p.Yc[(size_t)piy[i] * T + t] * tv[i];
+      v = warp_sum(v);
+      if (lane == 0) qv[t] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double v = 0.0;
+      for (int t = 0; t < T; ++t) v += qv[t] * qv[t];
+      p.pct[(size_t)r * L + comp] = v / ssy;
+    }
+    // b = t;  g = Kx b
+    for (int i = tid; i < S; i += SP_THREADS) {
+      const double *krow = p.Kraw + (size_t)pix[i] * S;
+      double v = 0.0;
+      for (int j = 0; j < S; ++j) v += krow[pix[j]] * tv[j];
+      gv[i] = v;
+      bv[i] = tv[i];
+    }
+    __syncthreads();
+    {
+      double v = 0.0;
+      for (int i = tid; i < S; i += SP_THREADS) v += gv[i];
+      v = block_sum(v, red) / S;
+      for (int i = tid; i < S; i += SP_THREADS) gv[i] -= v;
+      __syncthreads();
+    }
+    // double modified Gram-Schmidt against the previous basis (Kx inner product)
+    for (int pass = 0; pass < 2; ++pass)
+      for (int j = 0; j < comp; ++j) {
+        double cf = 0.0;
+        for (int i = tid; i < S; i += SP_THREADS) cf += Gs[(size_t)i * L + j] * bv[i];
+        cf = block_sum(cf, red);
+        for (int i = tid; i < S; i += SP_THREADS) {
+          bv[i] -= cf * Bs[(size_t)i * L + j];
+          gv[i] -= cf * Gs[(size_t)i * L + j];
+        }
+        __syncthreads();
+      }
+    {
+      double v = 0.0;
+      for (int i = tid; i < S; i += SP_THREADS) v += bv[i] * gv[i];
+      v = block_sum(v, red);
+      const double s_ = v > 0.0 ? rsqrt(v) : 0.0;
+      for (int i = tid; i < S; i += SP_THREADS) {
+        bv[i] *= s_;
+        gv[i] *= s_;
+        Bs[(size_t)i * L + comp] = bv[i];
+        Gs[(size_t)i * L + comp] = gv[i];
+      }
+      __syncthreads();
+    }
+    if (comp + 1 == L) break;
+    // deflation:  A -= b (g^T A);  A -= B_prev (G_prev^T A)
+    colvec(gv, A, S, T, qv);
+    for (int e = tid; e < S * T; e += SP_THREADS) A[e] -= bv[e / T] * qv[e % T];
+    __syncthreads();
+    if (comp > 0) {
+      for (int o = warp; o < comp * T; o += SP_WARPS) {
+        const int j = o / T, t = o - j * T;
+        double v = 0.0;
+        for (int i = lane; i < S; i += 32) v += Gs[(size_t)i * L + j] * A[i * T + t];
+        v = warp_sum(v);
+        if (lane == 0) Z[o] = v;
+      }
+      __syncthreads();
+      for (int e = tid; e < S * T; e += SP_THREADS) {
+        const int i = e / T, t = e - i * T;
+        double v = 0.0;
+        for (int j = 0; j < comp; ++j) v += Bs[(size_t)i * L + j] * Z[j * T + t];
+        A[e] -= v;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (!p.emit_ops) return;
+
+  // ---- operands of x_weights = X0^T Wcoef (and, for bootstraps, signs + distrib) ----
+  double *flip = Z;      // [0, L): signs, [L, 2L): column means of Kpi Wcoef
+  for (int k = warp; k < L; k += SP_WARPS) {
+    double v = 0.0;
+    if (p.boot && p.So)
+      for (int i = lane; i < S; i += 32) v += Wc[(size_t)i * L + k] * p.So[(size_t)pix[i] * L + k];
+    v = warp_sum(v);
+    if (lane == 0) flip[k] = (p.boot && p.So) ? (v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0)) : 1.0;
+  }
+  __syncthreads();
+  // D[r*L + k][u] = flip_k * sum_{i: pix[i] = u} Wcoef[i][k]
+  for (int u = tid; u < p.lda; u += SP_THREADS) {
+    for (int k = 0; k < L; ++k) {
+      double v = 0.0;
+      if (u < S)
+        for (int i = 0; i < S; ++i)
+          if (pix[i] == u) v += Wc[(size_t)i * L + k];
+      p.D[((size_t)r * L + k) * p.lda + u] = v * flip[k];
+    }
+  }
+  if (!p.boot || !p.distrib) return;
+  // distrib[t][k] = flip_k (Yp^T Tm + ysum (kappa^T Wcoef) / S),  kappa = Kpi 1
+  for (int i = tid; i < S; i += SP_THREADS) {
+    const double *krow = p.Kraw + (size_t)pix[i] * S;
+    double v = 0.0;
+    for (int j = 0; j < S; ++j) v += krow[pix[j]];
+    gv[i] = v;
+  }
+  __syncthreads();
+  for (int k = warp; k < L; k += SP_WARPS) {
+    double v = 0.0;
+    for (int i = lane; i < S; i += 32) v += gv[i] * Wc[(size_t)i * L + k];
+    v = warp_sum(v);
+    if (lane == 0) flip[L + k] = v / S;
+  }
+  __syncthreads();
+  for (int o = warp; o < T * L; o += SP_WARPS) {
+    const int t = o / L, k = o - t * L;
+    double v = 0.0;
+    for (int i = lane; i < S; i += 32)
+      v += p.Yc[(size_t)piy[i] * T + t] * Tm[(size_t)i * L + k];
+    v = warp_sum(v);
+    if (lane == 0)
+      p.distrib[(size_t)r * T * L + o] = flip[k] * (v + ysum[t] * flip[L + k]);
+  }
+}
+
+size_t simpls_smem(int S, int T, int L) {
+  const int P = std::min(T, SP_PROBES), pe = P + (P & 1), ldz = pe | 1, halfz = pe / 2;
+  size_t d = 2 * (size_t)S * T + 3 * (size_t)S + (size_t)T * T + 4 * (size_t)T * P +
+             3 * (size_t)pe * ldz + (size_t)std::max(L * T, 2 * L) + 3 * pe + 4 * (size_t)T +
+             SP_WARPS + 2 + 3 * halfz;
+  size_t b = d * sizeof(double) + sizeof(int) * (2 * halfz + 2 * (size_t)S) +
+             sizeof(short2) * (halfz * (halfz + 1) / 2) + 16;
+  return b;
+}
+
+// x_weights (B, L) from the GEMM output rows (L, ldr) with sklearn's svd_flip
+// sign rule (largest-magnitude entry of every column positive): block per column
+__global__ void xweights_flip_kernel(const double *__restrict__ Rw, long long ldr, int B, int L,
+                                     double *__restrict__ xw) {
+  __shared__ double s_best[32];
+  __shared__ int s_idx[32];
+  const int k = blockIdx.x;
+  const double *row = Rw + (size_t)k * ldr;
+  double best = -1.0;
+  int bidx = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const double a = fabs(row[b]);
+    if (a > best) {
+      best = a;
+      bidx = b;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ob > best || (ob == best && oi < bidx)) {
+      best = ob;
+      bidx = oi;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) {
+    s_best[warp] = best;
+    s_idx[warp] = bidx;
+  }
+  __syncthreads();
+  best = s_best[0];
+  bidx = s_idx[0];
+  for (int w = 1; w < nw; ++w)
+    if (s_best[w] > best || (s_best[w] == best && s_idx[w] < bidx)) {
+      best = s_best[w];
+      bidx = s_idx[w];
+    }
+  const double sgn = row[bidx] < 0.0 ? -1.0 : 1.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) xw[(size_t)b * L + k] = sgn * row[b];
+}
+
+__global__ void transpose_kernel(const double *__restrict__ in, int rows, int cols, int ld_in,
+                                 double *__restrict__ out) {   // out (cols, rows) contiguous
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * ld_in + c] : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+// out = U with every column centred (block per column)
+__global__ void colcenter_kernel(const double *__restrict__ U, int B, int L,
+                                 double *__restrict__ out) {
+  __shared__ double red[32];
+  const int k = blockIdx.x;
+  double v = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) v += U[(size_t)b * L + k];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double m = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m += red[w];
+  m /= B;
+  for (int b = threadIdx.x; b < B; b += blockDim.x)
+    out[(size_t)b * L + k] = U[(size_t)b * L + k] - m;
+}
+
+__global__ void identity_blocks_kernel(double *M, int n, int L) {
+  const size_t total = (size_t)n * L * L;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)((e / L) % L), j = (int)(e % L);
+    M[e] = i == j ? 1.0 : 0.0;
+  }
+}
+
+}  // namespace
+
+int launch_transpose(plsb_ctx *h, const double *in, int rows, int cols, int ld_in, double *out,
+                     cudaStream_t st) {
+  KernelTimer kt(h, KC_PREP, st);
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, st>>>(in, rows, cols, ld_in, out);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
+int launch_colcenter(plsb_ctx *h, const double *U, int B, int L, double *out, cudaStream_t st) {
+  KernelTimer kt(h, KC_PREP, st);
+  colcenter_kernel<<<L, 256, 0, st>>>(U, B, L, out);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
+int launch_identity_blocks(plsb_ctx *h, double *M, int n, int L, cudaStream_t st) {
+  KernelTimer kt(h, KC_PREP, st);
+  const size_t total = (size_t)n * L * L;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 8);
+  identity_blocks_kernel<<<blocks, 256, 0, st>>>(M, n, L);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
+int launch_xweights_flip(plsb_ctx *h, const double *Rw, long long ldr, int B, int L, double *xw,
+                         cudaStream_t st) {
+  KernelTimer kt(h, KC_PREP, st);
+  xweights_flip_kernel<<<L, 256, 0, st>>>(Rw, ldr, B, L, xw);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
+// Runs the SIMPLS component loop for `count` resamples.  Scratch (Wcoef, Bs, Gs,
+// Tm: count*S*L doubles each) lives in h->G/H/M/lam; D (count*L rows x S_pad)
+// in h->A when emit_ops.
+int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit_ops,
+                  const double *omega, long long om_stride_r, long long om_stride_c, double *pct,
+                  double *distrib, cudaStream_t st) {
+  KernelTimer kt(h, KC_SMALL, st);
+  const Layout &l = h->lay;
+  if (count <= 0) return PLSB_OK;
+  PLSB_CHECK(l.T <= 32, PLSB_ERR_ARG, "SIMPLS engine supports at most 32 behaviours (T=%d)", l.T);
+  const size_t smem = simpls_smem(l.S, l.T, l.L);
+  PLSB_CHECK(smem <= 227 * 1024, PLSB_ERR_ARG,
+             "SIMPLS engine needs %zu bytes of shared memory per resample (S*T too large)", smem);
+  const size_t per = (size_t)l.S * l.L;
+  PLSB_TRY(h->G.ensure(sizeof(double) * per * count));
+  PLSB_TRY(h->H.ensure(sizeof(double) * per * count));
+  PLSB_TRY(h->M.ensure(sizeof(double) * per * count));
+  PLSB_TRY(h->lam.ensure(sizeof(double) * per * count));
+  SimplsParams p;
+  p.S = l.S; p.T = l.T; p.L = l.L;
+  p.p = std::min(l.T, SP_PROBES);
+  p.n_iter = (1 < 0.1 * std::min(l.B, l.T)) ? 7 : 4;   // sklearn: n_iter='auto', n_components=1
+  p.boot = boot; p.emit_ops = emit_ops; p.lda = l.S_pad;
+  p.Kraw = h->Cmat.as<double>();
+  p.Yc = h->Y.as<double>();
+  p.omega = omega; p.om_stride_r = om_stride_r; p.om_stride_c = om_stride_c;
+  p.So = h->has_original ? h->Sx.as<double>() : nullptr;
+  p.idx = idx;
+  p.Wcoef = h->G.as<double>(); p.Bs = h->H.as<double>(); p.Gs = h->M.as<double>();
+  p.Tm = h->lam.as<double>();
+  p.pct = pct; p.D = h->A.as<double>(); p.distrib = distrib;
+  PLSB_CHECK(l.T <= SP_PROBES || omega != nullptr, PLSB_ERR_ARG, "SIMPLS: missing Omega table");
+#define PLSB_SP(TT)                                                                            \
+  do {                                                                                         \
+    PLSB_CUDA(cudaFuncSetAttribute(simpls_kernel<TT>,                                          \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    simpls_kernel<TT><<<count, SP_THREADS, smem, st>>>(p);                                     \
+  } while (0)
+  if (l.T <= 8) PLSB_SP(8);
+  else if (l.T <= 16) PLSB_SP(16);
+  else if (l.T <= 24) PLSB_SP(24);
+  else PLSB_SP(32);
+#undef PLSB_SP
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
+}  // namespace plsb

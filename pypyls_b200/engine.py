@@ -21,6 +21,7 @@ MODES = {
     'behavioral': _cabi.PLSB_BEHAVIORAL_CORR,
     'behavioral_cov': _cabi.PLSB_BEHAVIORAL_COV,
     'meancentered': _cabi.PLSB_MEANCENTERED,
+    'regression': _cabi.PLSB_SIMPLS,
 }
 
 
@@ -62,7 +63,7 @@ class ResamplingEngine:
     """
 
     def __init__(self, mode, S, B, T, groups, n_cond=1, mean_centering=0,
-                 device=0, workspace_bytes=None):
+                 device=0, workspace_bytes=None, n_components=0):
         if not torch.cuda.is_available():
             raise RuntimeError('pypyls_b200 needs a CUDA device (B200, '
                                'sm_100a); there is no CPU fallback.')
@@ -74,6 +75,8 @@ class ResamplingEngine:
         self.groups, self.n_cond = groups, int(n_cond)
         self.J = len(groups) * self.n_cond
         self.K = self.J * self.T if mode != 'meancentered' else self.J
+        if mode == 'regression':
+            self.K = int(n_components)
         self.L = self.K
         pool = _FREE_HANDLES.setdefault(self.device.index, [])
         if pool:
@@ -90,7 +93,7 @@ class ResamplingEngine:
         garr = (C.c_int * len(groups))(*groups)
         _cabi.check(self._lib.plsb_configure(
             self._h, MODES[mode], self.S, self.B, self.T, len(groups), garr,
-            self.n_cond, int(mean_centering), 0))
+            self.n_cond, int(mean_centering), int(n_components)))
 
     # -- plumbing ----------------------------------------------------------
     def close(self):
@@ -246,6 +249,60 @@ class ResamplingEngine:
         _cabi.check(self._lib.plsb_crosscov(self._h, p, n, int(bool(bootstrap)),
                                             _ptr(out), self._stream()))
         return out
+
+    # -- SIMPLS (pls_regression) -------------------------------------------------
+    def _omega(self, omega, n):
+        if omega is None:
+            if self.T > 11:
+                raise ValueError('SIMPLS with more than 11 behaviours needs '
+                                 'the Gaussian test matrices')
+            return None
+        omega = self.to_device(omega)
+        if tuple(omega.shape) != (n, self.T, 11):
+            raise ValueError('omega must have shape ({}, {}, 11)'
+                             .format(n, self.T))
+        return omega
+
+    def simpls_decompose(self, omega=None):
+        """Original SIMPLS decomposition -> (x_weights (B,L), pctvar_y (L,)).
+        `omega` (L, T, 11): one Gaussian test matrix per component."""
+        omega = self._omega(omega, self.L)
+        xw, pct = self._f64(self.B, self.L), self._f64(self.L)
+        _cabi.check(self._lib.plsb_simpls_decompose(
+            self._h, _ptr(omega), _ptr(xw), _ptr(pct), self._stream()))
+        return xw, pct
+
+    def simpls_set_original(self, x_weights):
+        xw = self.to_device(x_weights)
+        _cabi.check(self._lib.plsb_simpls_set_original(self._h, _ptr(xw),
+                                                       self._stream()))
+        return self
+
+    def simpls_run_perms(self, idx, omega=None):
+        """pctvar in Y of every permutation, (count, L) on the device."""
+        idx = self.to_device_indices(idx)
+        n = int(idx.shape[0])
+        omega = self._omega(omega, n)
+        out = self._f64(n, self.L)
+        _cabi.check(self._lib.plsb_simpls_run_perms(
+            self._h, _ptr(idx), n, _ptr(omega), _ptr(out), self._stream()))
+        return out
+
+    def simpls_run_boots(self, idx, omega=None):
+        """(distrib (count,T,L), u_sum (B,L), u_square (B,L), pctvar
+        (count,L)) of the bootstraps, on the device."""
+        idx = self.to_device_indices(idx)
+        n = int(idx.shape[0])
+        omega = self._omega(omega, n)
+        pct = self._f64(n, self.L)
+        distrib = self._f64(n, self.T, self.L)
+        u_sum = torch.zeros((self.B, self.L), dtype=torch.float64,
+                            device=self.device)
+        u_square = torch.zeros_like(u_sum)
+        _cabi.check(self._lib.plsb_simpls_run_boots(
+            self._h, _ptr(idx), n, _ptr(omega), _ptr(pct), _ptr(distrib),
+            _ptr(u_sum), _ptr(u_square), self._stream()))
+        return distrib, u_sum, u_square, pct
 
     # -- statistics -----------------------------------------------------------
     def perm_pvals(self, d_perm, d_orig):

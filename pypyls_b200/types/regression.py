@@ -1,0 +1,185 @@
+# -*- coding: utf-8 -*-
+"""
+PLS regression (SIMPLS) front-end (interface of pyls/types/regression.py:
+189-440) on the CUDA resampling engine.
+"""
+
+import numpy as np
+import torch
+
+from .. import dist as pdist
+from .. import structures
+from ..base import BasePLS
+from ..engine import ResamplingEngine
+
+
+def resid_yscores(x_scores, y_scores):
+    """Orthogonalises every column of `y_scores` against the preceding
+    columns of `x_scores` (two Gram-Schmidt passes), as
+    pyls/types/regression.py:9-45.  (S, L) host arrays."""
+    x_scores = np.asarray(x_scores, dtype=float)
+    out = np.array(y_scores, dtype=float)
+    for comp in range(1, x_scores.shape[1]):
+        col = out[:, comp]
+        prev = x_scores[:, :comp]
+        for _ in range(2):
+            for j in range(comp):
+                col = col - (prev[:, j] @ col) * prev[:, j]
+        out[:, comp] = col
+    return out
+
+
+def gaussian_tables(seeds, T):
+    """(len(seeds), T, 11) test matrices: what sklearn's randomized_svd draws
+    for ``compute.svd(Cov, n_components=1, seed=i)`` with an integer seed
+    (pyls/types/regression.py:103 -> pyls/compute.py:48-49)."""
+    out = np.empty((len(seeds), T, 11))
+    for n, i in enumerate(seeds):
+        out[n] = np.random.RandomState(int(i)).normal(size=(T, 11))
+    return out
+
+
+class PLSRegression(BasePLS):
+    def __init__(self, X, Y, *, n_components=None, n_perm=5000, n_boot=5000,
+                 rotate=True, ci=95, aggfunc='mean', permsamples=None,
+                 bootsamples=None, seed=None, verbose=True, n_proc=None,
+                 **kwargs):
+        X, Y = np.array(X, dtype=float), np.array(Y, dtype=float)
+        if Y.ndim == 3:
+            raise NotImplementedError(
+                'Three-dimensional `Y` (aggfunc) is not part of the '
+                'accelerated path yet.')
+        if X.ndim != 2 or Y.ndim != 2:
+            raise ValueError('`X` and `Y` must be two-dimensional arrays.')
+        max_components = min(len(X) - 1, X.shape[1])
+        if n_components is None:
+            n_components = max_components
+        else:
+            n_components = int(n_components)
+            if n_components > max_components:
+                raise ValueError('Provided `n_components` cannot be greater '
+                                 'than {}'.format(max_components))
+        if np.isnan(X).any() or np.isnan(Y).any():
+            raise NotImplementedError(
+                'Rows with missing values (NaN) are not supported by the '
+                'accelerated path yet; drop them before the call.')
+        kwargs.update(n_split=0, test_split=0)
+        super().__init__(X=X, Y=Y, n_components=n_components, n_perm=n_perm,
+                         n_boot=n_boot, rotate=rotate, ci=ci, aggfunc=aggfunc,
+                         permsamples=permsamples, bootsamples=bootsamples,
+                         seed=seed, verbose=verbose, n_proc=n_proc, **kwargs)
+        self.n_components = n_components
+        self.results = self.run_pls(self.inputs.X, self.inputs.Y)
+
+    def engine_mode(self):
+        return 'regression'
+
+    def _make_engine(self, X, Y):
+        device = self.inputs.get('device')
+        if device is None:
+            device = torch.cuda.current_device() \
+                if torch.cuda.is_available() else 0
+        eng = ResamplingEngine('regression', X.shape[0], X.shape[1],
+                               Y.shape[1], [X.shape[0]], 1, device=device,
+                               workspace_bytes=self.inputs.get(
+                                   'workspace_bytes'),
+                               n_components=self.n_components)
+        eng.set_data(X, Y)
+        return eng
+
+    def run_pls(self, X, Y):
+        """Follows pyls/types/regression.py:375-428 and pyls/base.py:341-371."""
+        # the reference centres the caller's arrays in place; copies here
+        X -= np.mean(X, axis=0, keepdims=True)
+        Y -= np.mean(Y, axis=0, keepdims=True)
+        self.res = res = structures.PLSResults(inputs=self.inputs)
+        self.engine = eng = self._make_engine(X, Y)
+        T, L = Y.shape[1], self.n_components
+
+        # the reference draws one (T, 11) Gaussian matrix per component from
+        # the analysis' RandomState (compute.svd(..., seed=self.rs))
+        omega0 = np.stack([self.rs.normal(size=(T, 11)) for _ in range(L)])
+        xw, pct = eng.simpls_decompose(omega0 if T > 11 else None)
+        self._dev = dict(U=xw, d=torch.ones_like(pct), pct=pct)
+        res['x_weights'] = xw.cpu().numpy()
+        res['x_scores'] = eng.project_scores(xw).cpu().numpy()
+        varexp = pct.cpu().numpy()
+
+        n_omega = max(self.inputs.n_perm, self.inputs.n_boot)
+        self._omega = None
+        if T > 11 and n_omega > 0:
+            self._omega = eng.to_device(gaussian_tables(range(n_omega), T))
+
+        if self.inputs.n_perm > 0:
+            d_perm, _, _ = self.permutation(X, Y, seed=self.rs)
+            res['permres']['pvals'] = eng.perm_pvals(
+                self._dev['d_perm'], pct).cpu().numpy()
+            res['permres']['permsamples'] = self.permsamp
+            res['permres']['perm_singval'] = d_perm
+
+        res['y_loadings'] = Y.T @ res['x_scores']
+        res['y_scores'] = resid_yscores(res['x_scores'],
+                                        Y @ res['y_loadings'])
+
+        if self.inputs.n_boot > 0:
+            distrib, u_sum, u_square = self.bootstrap(X, Y, self.rs)
+            bsrs, uboot_se, corrci = self._boot_stats(add_orig=True)
+            res['bootres'].update(dict(x_weights_normed=bsrs,
+                                       x_weights_stderr=uboot_se,
+                                       y_loadings=res['y_loadings'],
+                                       y_loadings_boot=distrib,
+                                       y_loadings_ci=corrci,
+                                       bootsamples=self.bootsamp))
+        res['varexp'] = varexp
+        return res
+
+    def _omega_block(self, first, count):
+        return None if self._omega is None else \
+            self._omega[first:first + count]
+
+    def permutation(self, X, Y, seed=None):
+        """Replaces BasePLS.permutation + PLSRegression._single_perm
+        (pyls/types/regression.py:329-373): variance explained in Y per
+        component for every permutation of the rows of Y."""
+        n = self.inputs.n_perm
+        self.permsamp, block, first = self._table('perm', n, seed)
+        local = self.engine.simpls_run_perms(
+            block, self._omega_block(first, block.shape[0]))
+        d_perm = pdist.gather_resamples(local, n)
+        self._dev['d_perm'] = d_perm
+        return d_perm.cpu().numpy().T.copy(), None, None
+
+    def bootstrap(self, X, Y, seed=None):
+        """Replaces BasePLS.bootstrap + PLSRegression._single_boot
+        (pyls/types/regression.py:279-327)."""
+        n = self.inputs.n_boot
+        self.bootsamp, block, first = self._table('boot', n, seed)
+        distrib, u_sum, u_square, _ = self.engine.simpls_run_boots(
+            block, self._omega_block(first, block.shape[0]))
+        distrib = pdist.gather_resamples(distrib, n)
+        pdist.reduce_sum(u_sum, u_square)
+        self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
+        return (distrib.permute(1, 2, 0).contiguous().cpu().numpy(),
+                u_sum.cpu().numpy(), u_square.cpu().numpy())
+
+
+def pls_regression(X, Y, *, n_components=None, n_perm=5000, n_boot=5000,
+                   rotate=True, ci=95, aggfunc='mean', permsamples=None,
+                   bootsamples=None, seed=None, verbose=True, n_proc=None,
+                   **kwargs):
+    """
+    PLS regression (SIMPLS) of `Y` (S, T) on `X` (S, B); same call as
+    ``pyls.pls_regression`` (pyls/types/regression.py:432-440) with the
+    permutation test and bootstrap executed on the GPU.  Unlike the reference
+    the caller's arrays are not centred in place.  Two-dimensional `Y` without
+    missing values only; ``n_proc`` is accepted but unused.
+
+    Returns
+    -------
+    results : :obj:`pypyls_b200.structures.PLSResults`
+    """
+    pls = PLSRegression(X=X, Y=Y, n_components=n_components, n_perm=n_perm,
+                        n_boot=n_boot, rotate=rotate, ci=ci, aggfunc=aggfunc,
+                        permsamples=permsamples, bootsamples=bootsamples,
+                        seed=seed, verbose=verbose, n_proc=n_proc, **kwargs)
+    return pls.results

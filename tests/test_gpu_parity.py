@@ -306,3 +306,73 @@ def test_argument_errors_match_reference():
     with pytest.warns(UserWarning):
         pyls.meancentered_pls(X, groups=[10, 10], mean_centering=0, n_perm=0,
                               n_boot=0)
+
+
+# ---------------------------------------------------------------------------
+# pls_regression (SIMPLS).  The reference's own tests pin shapes only for this
+# type ("parity unpinned by the reference's tests"); parity rests on the
+# shimmed reference run stored in tests/golden/plsr_*.npz and on the oracle.
+@pytest.mark.parametrize('name', ['plsr_t12', 'plsr_t5'])
+def test_regression_matches_reference_golden(name):
+    import pypyls_b200 as pyls
+    ins, ref = load_golden(name)
+    X, Y = ins.pop('X'), ins.pop('Y')
+    out = pyls.pls_regression(X, Y, index_backend='reference', verbose=False,
+                              **ins)
+    assert np.array_equal(out.permres.permsamples, ref['permsamples'])
+    assert np.array_equal(out.bootres.bootsamples, ref['bootsamples'])
+    for k in ('x_weights', 'x_scores', 'y_scores', 'y_loadings', 'varexp'):
+        close(out[k], ref[k])
+    close(out.permres.perm_singval, ref['perm_singval'])
+    assert np.array_equal(out.permres.pvals, ref['pvals'])
+    close(out.bootres.y_loadings_boot, ref['y_loadings_boot'])
+    close(out.bootres.y_loadings_ci, ref['y_loadings_ci'])
+    close(out.bootres.x_weights_normed, ref['x_weights_normed'], rtol=1e-7)
+    close(out.bootres.x_weights_stderr, ref['x_weights_stderr'], rtol=1e-7)
+
+
+@pytest.mark.parametrize('S,B,T,L', [(60, 300, 12, 4), (50, 200, 20, 9),
+                                     (45, 120, 3, 2), (70, 90, 11, 5),
+                                     (33, 500, 1, 1)])
+def test_regression_matches_oracle(S, B, T, L):
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(S + T)
+    X, Y = rs.rand(S, B), rs.rand(S, T)
+    Y[:, :1] += X[:, :8] @ rs.rand(8, 1) * 0.3
+    ps = po.gen_permsamp([S], 1, 12, seed=1)
+    bs = po.gen_bootsamp([S], 1, 12, seed=2)
+    kw = dict(n_components=L, n_perm=12, n_boot=12, permsamples=ps,
+              bootsamples=bs, seed=4)
+    ref = po.pls_regression(X, Y, **kw)
+    out = pyls.pls_regression(X, Y, verbose=False, **kw)
+    for k in ('x_weights', 'x_scores', 'y_scores', 'y_loadings', 'varexp'):
+        close(out[k], ref[k])
+    close(out.permres.perm_singval, ref['perm_singval'])
+    assert np.array_equal(out.permres.pvals, ref['pvals'])
+    close(out.bootres.y_loadings_boot, ref['distrib'])
+    close(out.bootres.y_loadings_ci, ref['distrib_ci'])
+    close(out.bootres.x_weights_normed, ref['x_weights_normed'], rtol=1e-7)
+
+
+def test_regression_config4_shape_subset():
+    """BASELINE config 4 shapes (X 500x5000, Y 500x20, 10 components) on a
+    subset of resamples the oracle finishes in seconds, with a planted signal
+    (pure noise makes the reference's randomized SVD most
+    seed-sensitive) and on-device index tables."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(1234)
+    X, Y = rs.rand(500, 5000), rs.rand(500, 20)
+    Y[:, :3] += X[:, :50] @ rs.rand(50, 3) * 0.15
+    out = pyls.pls_regression(X, Y, n_components=10, n_perm=64, n_boot=64,
+                              seed=1234, verbose=False)
+    assert out.permres.perm_singval.shape == (10, 64)
+    assert out.bootres.y_loadings_boot.shape == (20, 10, 64)
+    Xc, Yc = X - X.mean(0), Y - Y.mean(0)
+    spec = po._Spec('regression', [500], 1, n_components=10)
+    for i in (0, 5):
+        want = po.single_perm(spec, Xc, Yc, out.permres.permsamples[:, i],
+                              None, seed=i)
+        close(out.permres.perm_singval[:, i], want)
+        d, u = po.single_boot(spec, Xc, Yc, out.bootres.bootsamples[:, i],
+                              out.x_weights, seed=i)
+        close(out.bootres.y_loadings_boot[..., i], d, rtol=1e-7)
