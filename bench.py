@@ -41,6 +41,17 @@ WORKLOADS = {
                  n_cond=2, n_perm=5000, n_boot=5000,
                  name='behavioral_pls X(80x10000) Y(80x10) groups=[20,20] '
                       'n_cond=2 n_perm=5000 n_boot=5000'),
+    # BASELINE.json configs[2]; X has 320 rows (the 160 of BASELINE.json do not
+    # fit groups=[40]*4 x n_cond=2)
+    'cfg3': dict(kind='meancentered', S=320, B=20000, T=1,
+                 groups=[40, 40, 40, 40], n_cond=2, n_perm=10000, n_boot=10000,
+                 name='meancentered_pls X(320x20000) groups=[40,40,40,40] '
+                      'n_cond=2 n_perm=10000 n_boot=10000'),
+    # BASELINE.json configs[3]
+    'cfg4': dict(kind='regression', S=500, B=5000, T=20, L=10, groups=[500],
+                 n_cond=1, n_perm=5000, n_boot=10000,
+                 name='pls_regression (SIMPLS) X(500x5000) Y(500x20) '
+                      'n_components=10 n_perm=5000 n_boot=10000'),
     # BASELINE.json configs[4] (per GPU share is set by --gpus in a real run)
     'cfg5': dict(kind='behavioral', S=200, B=100000, T=10, groups=[200],
                  n_cond=1, n_perm=10000, n_boot=10000,
@@ -75,7 +86,14 @@ def _cpu_init(wname):
     from oracle import pls_oracle as po
     w = WORKLOADS[wname]
     X, Y = make_data(w)
-    spec = po._Spec('behavioral', w['groups'], w['n_cond'])
+    if w['kind'] == 'regression':
+        X, Y = X - X.mean(0), Y - Y.mean(0)
+        spec = po._Spec('regression', [w['S']], 1, n_components=w['L'])
+    elif w['kind'] == 'meancentered':
+        spec = po._Spec('meancentered', w['groups'], w['n_cond'])
+        Y = spec.dummy
+    else:
+        spec = po._Spec('behavioral', w['groups'], w['n_cond'])
     U, d, V = po.decompose(spec, X, Y, seed=1234)
     _CPU.update(po=po, X=X, Y=Y, spec=spec, U=U, V=V)
 
@@ -217,7 +235,11 @@ def algorithmic_work(w, n_perm, n_boot):
     S, B, T = w['S'], w['B'], w['T']
     J = len(w['groups']) * w['n_cond']
     K = J * T
-    xcov = 2.0 * S * B * T * (n_perm + n_boot)       # 2*S*B*T_eff
+    # 2*S*B*T_eff per resample (T_eff = T behavioural, J mean-centred;
+    # SIMPLS: Cov plus t = X0 r, p = X0^T t per component)
+    t_eff = {'behavioral': T, 'meancentered': J,
+             'regression': T + 2 * w.get('L', 0)}[w['kind']]
+    xcov = 2.0 * S * B * t_eff * (n_perm + n_boot)
     return {
         'xcov_gemm': ('tensor', xcov),
         'gram_proj': ('tensor', 2.0 * K * (2 * K) * B * n_boot),
@@ -317,24 +339,46 @@ def main():
     n_perm, n_boot = w['n_perm'], w['n_boot']          # per GPU (weak scaling)
     P, R = n_perm * world, n_boot * world               # whole job
 
-    eng = ResamplingEngine('behavioral', w['S'], w['B'], w['T'], w['groups'],
-                           w['n_cond'], device=local_rank)
-    eng.set_data(Xh, Yh)
-    U, d, V = eng.decompose()
+    kind = w['kind']
+    if kind == 'regression':
+        from pypyls_b200.types.regression import gaussian_tables
+        eng = ResamplingEngine('regression', w['S'], w['B'], w['T'], [w['S']],
+                               1, device=local_rank, n_components=w['L'])
+        eng.set_data(Xh - Xh.mean(0, keepdim=True),
+                     Yh - Yh.mean(0, keepdim=True))
+        rs0 = np.random.RandomState(1234)
+        om0 = np.stack([rs0.normal(size=(w['T'], 11)) for _ in range(w['L'])])
+        U, d = eng.simpls_decompose(om0 if w['T'] > 11 else None)
+        om_p = om_b = None
+        if w['T'] > 11:
+            om = eng.to_device(gaussian_tables(
+                range(max(n_perm, n_boot) * world), w['T']))
+            om_p = om[rank * n_perm:(rank + 1) * n_perm]
+            om_b = om[rank * n_boot:(rank + 1) * n_boot]
+        bs, add_orig = U.contiguous(), True
+    else:
+        eng = ResamplingEngine(kind, w['S'], w['B'], w['T'], w['groups'],
+                               w['n_cond'], device=local_rank)
+        eng.set_data(Xh, Yh if kind == 'behavioral' else None)
+        U, d, V = eng.decompose()
+        bs, add_orig = (U * d[None, :]).contiguous(), kind == 'behavioral'
     idx_p, _ = eng.gen_perm_indices(1234, n_perm, first=rank * n_perm)
     idx_b, _ = eng.gen_boot_indices(1234, n_boot, first=rank * n_boot)
-    bs = (U * d[None, :]).contiguous()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
     def step():
-        d_perm = eng.run_perms(idx_p, rotate=True)
-        distrib, us, uq = eng.run_boots(idx_b)
+        if kind == 'regression':
+            d_perm = eng.simpls_run_perms(idx_p, om_p)
+            distrib, us, uq, _ = eng.simpls_run_boots(idx_b, om_b)
+        else:
+            d_perm = eng.run_perms(idx_p, rotate=True)
+            distrib, us, uq = eng.run_boots(idx_b)
         if world > 1:
             d_perm = pdist.gather_resamples(d_perm, P)
             distrib = pdist.gather_resamples(distrib, R)
             pdist.reduce_sum(us, uq)
         pv = eng.perm_pvals(d_perm, d)
-        bsr, se = eng.boot_ratio(bs, us, uq, R, True)
+        bsr, se = eng.boot_ratio(bs, us, uq, R, add_orig)
         lo, hi = eng.percentile(distrib, 2.5, 97.5)
         return pv, bsr, lo, hi
 
@@ -375,9 +419,15 @@ def main():
     e2e = None
     if not args.no_e2e:
         def call(seed):
-            return pyls.behavioral_pls(
-                Xh, Yh, groups=w['groups'], n_cond=w['n_cond'], n_perm=P,
-                n_boot=R, seed=seed, verbose=False, device=local_rank)
+            kw = dict(n_perm=P, n_boot=R, seed=seed, verbose=False,
+                      device=local_rank)
+            if kind == 'regression':
+                return pyls.pls_regression(Xh, Yh, n_components=w['L'], **kw)
+            if kind == 'meancentered':
+                return pyls.meancentered_pls(Xh, groups=w['groups'],
+                                             n_cond=w['n_cond'], **kw)
+            return pyls.behavioral_pls(Xh, Yh, groups=w['groups'],
+                                       n_cond=w['n_cond'], **kw)
         for i in range(2):
             call(100 + i)
         barrier()

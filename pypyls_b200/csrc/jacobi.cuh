@@ -21,14 +21,18 @@ struct JacobiScratch {
 // all rotations.  A and V are row-major with leading dimension ld; n is the
 // order, ne = n rounded up to even.  For odd n the extra index n is a dummy
 // player: row / column n of A and column n of V must be zero on entry (they
-// stay zero).  Called by every thread of the CTA.
-static __device__ void jacobi_sym(double *A, double *V, int n, int ld, const JacobiScratch &sc) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+// stay zero).  WARP = false: called by every thread of the CTA (CTA barriers);
+// WARP = true: called by the 32 lanes of ONE warp (warp barriers only), for
+// matrices small enough that CTA-wide barriers would dominate.
+template <bool WARP>
+static __device__ void jacobi_sym_t(double *A, double *V, int n, int ld, const JacobiScratch &sc) {
+  const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x;
+  const int warp = WARP ? 0 : (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int nthreads = WARP ? 32 : blockDim.x, nwarps = WARP ? 1 : (nthreads >> 5);
   const int ne = n + (n & 1);
   const int half = ne / 2;
   const int nb = half * (half + 1) / 2;
-  __syncthreads();
+  if (WARP) __syncwarp(); else __syncthreads();
   if (n < 2) return;
   for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
     int any = 0;
@@ -65,7 +69,8 @@ static __device__ void jacobi_sym(double *A, double *V, int n, int ld, const Jac
         sc.cst[3 * pi + 1] = s;
         sc.cst[3 * pi + 2] = t;
       }
-      any |= __syncthreads_or(active);
+      if (WARP) { __syncwarp(); any |= __any_sync(0xffffffffu, active); }
+      else any |= __syncthreads_or(active);
       // phase 1a: the 2 x 2 blocks of A
       for (int bi = tid; bi < nb; bi += nthreads) {
         const int a = sc.blk[bi].x, b = sc.blk[bi].y;
@@ -111,10 +116,15 @@ static __device__ void jacobi_sym(double *A, double *V, int n, int ld, const Jac
           V[i * ld + q] = s * vx + c * vy;
         }
       }
-      __syncthreads();
+      if (WARP) __syncwarp(); else __syncthreads();
     }
     if (!any) break;
   }
+}
+
+static __device__ __forceinline__ void jacobi_sym(double *A, double *V, int n, int ld,
+                                                  const JacobiScratch &sc) {
+  jacobi_sym_t<false>(A, V, n, ld, sc);
 }
 
 }  // namespace plsb

@@ -79,8 +79,9 @@ __device__ void gram_apply(const SimplsParams &p, const int *pix, const double *
 #pragma unroll
     for (int t = 0; t < TT; ++t) acc[t] = 0.0;
     const double *krow = p.Kraw + (size_t)pix[i] * S;
+#pragma unroll 4
     for (int j = 0; j < S; ++j) {
-      const double k = krow[pix[j]];
+      const double k = __ldg(krow + pix[j]);
       const double *aj = A + j * T;
 #pragma unroll
       for (int t = 0; t < TT; ++t)
@@ -204,26 +205,47 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
           CW[e] = v;
         }
         __syncthreads();
-        // modified Gram-Schmidt (two passes), warp 0: lanes over the T rows
-        if (warp == 0) {
-          for (int k = 0; k < P; ++k) {
-            for (int pass = 0; pass < 2; ++pass)
-              for (int j = 0; j < k; ++j) {
-                double d = 0.0;
-                for (int t = lane; t < T; t += 32) d += CW[t * P + j] * CW[t * P + k];
-                d = warp_sum(d);
-                for (int t = lane; t < T; t += 32) CW[t * P + k] -= d * CW[t * P + j];
-                __syncwarp();
-              }
-            double n2 = 0.0;
-            for (int t = lane; t < T; t += 32) n2 += CW[t * P + k] * CW[t * P + k];
-            n2 = warp_sum(n2);
-            const double sc_ = n2 > 0.0 ? rsqrt(n2) : 0.0;
-            for (int t = lane; t < T; t += 32) CW[t * P + k] *= sc_;
-            __syncwarp();
+        // orthonormalise the columns of CW (same span): Cholesky-QR, twice.
+        // Gram matrix -> upper Cholesky factor Rc (warp 0, lane = column) ->
+        // CW <- CW Rc^-1 (thread = row).  A vanishing pivot (rank-deficient
+        // CW, e.g. after many deflations) drops that column.
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int e = tid; e < P * P; e += SP_THREADS) {
+            const int a = e / P, b = e - a * P;
+            const int lo = min(a, b), hi = max(a, b);
+            double v = 0.0;
+            for (int t = 0; t < T; ++t) v += CW[t * P + lo] * CW[t * P + hi];
+            Gz[a * ldz + b] = v;
           }
+          __syncthreads();
+          if (warp == 0) {
+            double dmax = 0.0;
+            for (int k = 0; k < P; ++k) dmax = fmax(dmax, Gz[k * ldz + k]);
+            for (int k = 0; k < P; ++k) {
+              const double d = Gz[k * ldz + k];
+              const bool ok = d > 1e-26 * dmax && d > 0.0;
+              const double rkk = ok ? sqrt(d) : 0.0;
+              __syncwarp();
+              if (lane > k && lane < P) Gz[k * ldz + lane] = ok ? Gz[k * ldz + lane] / rkk : 0.0;
+              if (lane == k) Gz[k * ldz + k] = rkk;
+              __syncwarp();
+              if (lane > k && lane < P)
+                for (int i = k + 1; i <= lane; ++i)
+                  Gz[i * ldz + lane] -= Gz[k * ldz + i] * Gz[k * ldz + lane];
+              __syncwarp();
+            }
+          }
+          __syncthreads();
+          for (int t = tid; t < T; t += SP_THREADS) {
+            for (int j = 0; j < P; ++j) {
+              double v = CW[t * P + j];
+              for (int i = 0; i < j; ++i) v -= CW[t * P + i] * Gz[i * ldz + j];
+              const double rjj = Gz[j * ldz + j];
+              CW[t * P + j] = rjj > 0.0 ? v / rjj : 0.0;
+            }
+          }
+          __syncthreads();
         }
-        __syncthreads();
         for (int e = tid; e < T * P; e += SP_THREADS) W[e] = CW[e];
         __syncthreads();
       }
@@ -246,7 +268,9 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
       Gz[a * ldz + b] = v;
       Ez[a * ldz + b] = (a == b && a < P) ? 1.0 : 0.0;
     }
-    jacobi_sym(Gz, Ez, P, ldz, sc);
+    __syncthreads();
+    if (warp == 0) jacobi_sym_t<true>(Gz, Ez, P, ldz, sc);   // <= 12 x 12: one warp
+    __syncthreads();
     if (tid == 0) {
       double lmax = 0.0;
       for (int k = 0; k < P; ++k) lmax = fmax(lmax, Gz[k * ldz + k]);
@@ -274,7 +298,9 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
       Gz[a * ldz + b] = v;
       E2[a * ldz + b] = (a == b && a < P) ? 1.0 : 0.0;
     }
-    jacobi_sym(Gz, E2, P, ldz, sc);
+    __syncthreads();
+    if (warp == 0) jacobi_sym_t<true>(Gz, E2, P, ldz, sc);
+    __syncthreads();
     if (tid == 0) {
       int kmax = 0;
       for (int k = 1; k < P; ++k)
