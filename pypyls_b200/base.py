@@ -18,7 +18,7 @@ import torch
 
 from . import dist as pdist
 from . import structures
-from .engine import ResamplingEngine
+from .engine import ResamplingEngine, to_host
 from .resample import check_random_state, gen_bootsamp, gen_permsamp
 
 
@@ -133,10 +133,10 @@ class BasePLS():
         U, d, V = eng.decompose()
         self._replay_svd_draws()
         self._dev = dict(U=U, d=d, V=V)
-        res['x_weights'] = U.cpu().numpy()
-        res['singvals'] = np.diag(d.cpu().numpy())
-        res['y_weights'] = V.cpu().numpy()
-        res['x_scores'] = eng.project_scores(U).cpu().numpy()
+        res['x_weights'] = to_host(U)
+        res['singvals'] = np.diag(to_host(d))
+        res['y_weights'] = to_host(V)
+        res['x_scores'] = to_host(eng.project_scores(U))
 
         if self.inputs.n_perm > 0:
             d_perm, _, _ = self.permutation(X, Y, seed=self.rs)
@@ -173,7 +173,7 @@ class BasePLS():
             warnings.warn('WARNING: Duplicate {} used.'.format(
                 'permutations' if kind == 'perm' else 'bootstraps'))
         full = pdist.gather_resamples(block, n)
-        return full.cpu().numpy().T.astype(int), block, first
+        return to_host(full).T.astype(int), block, first
 
     def permutation(self, X, Y, seed=None):
         """
@@ -192,7 +192,7 @@ class BasePLS():
         local = self.engine.run_perms(block, rotate=rotate)
         d_perm = pdist.gather_resamples(local, n)
         self._dev['d_perm'] = d_perm
-        return d_perm.cpu().numpy().T.copy(), None, None
+        return to_host(d_perm).T.copy(), None, None
 
     def bootstrap(self, X, Y, seed=None):
         """
@@ -209,8 +209,8 @@ class BasePLS():
         distrib = pdist.gather_resamples(distrib, n)
         pdist.reduce_sum(u_sum, u_square)
         self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
-        return (distrib.permute(1, 2, 0).contiguous().cpu().numpy(),
-                u_sum.cpu().numpy(), u_square.cpu().numpy())
+        return (to_host(distrib.permute(1, 2, 0).contiguous()),
+                to_host(u_sum), to_host(u_square))
 
     def _boot_stats(self, add_orig):
         """Bootstrap ratios, standard errors and percentile intervals from the
@@ -224,5 +224,5 @@ class BasePLS():
         ci = 95 if ci is None else ci
         low = (100 - ci) / 2
         lo, hi = eng.percentile(dev['distrib'], low, 100 - low)
-        return (bsr.cpu().numpy(), se.cpu().numpy(),
-                torch.stack([lo, hi], dim=-1).cpu().numpy())
+        return (to_host(bsr), to_host(se),
+                to_host(torch.stack([lo, hi], dim=-1)))

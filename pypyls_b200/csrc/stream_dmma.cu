@@ -44,18 +44,18 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 }
 
 // ---- gram_proj ----------------------------------------------------------------
-constexpr int GD_BC = 64;            // columns of R per stage
 constexpr int GD_THREADS = 512;
 constexpr int GD_WARPS = GD_THREADS / 32;
-constexpr int GD_LDR = GD_BC + 4;    // 68
 
-template <int MF>
+// GD_BC = columns of R per stage (64 or 128)
+template <int MF, int GD_BC>
 __global__ void __launch_bounds__(GD_THREADS, 1)
 gram_proj_dmma_kernel(const double *__restrict__ R, long long ldr, int K, int B, int n_chunks,
                       const double *__restrict__ Uo, int L, int LP, int ldu,
                       double *__restrict__ G, double *__restrict__ H, int NG, int KG) {
   extern __shared__ __align__(16) double sm[];
   constexpr int KP = MF * 8;
+  constexpr int GD_LDR = GD_BC + 4;              // == 4 (mod 16)
   const int stage = KP * GD_LDR + GD_BC * ldu;   // doubles per ring slot
   const int NF = (KP + LP) / 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -256,6 +256,19 @@ accum_u_dmma_kernel(const double *__restrict__ R, long long ldr, int count, int 
   (void)LP;
 }
 
+template <int MF, int BC>
+int launch_gp_bc(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
+                 const double *Uo, int L, int LP, double *G, double *H, size_t smem, int NG, int KG,
+                 cudaStream_t st) {
+  PLSB_CUDA(cudaFuncSetAttribute(gram_proj_dmma_kernel<MF, BC>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_chunks = (int)(ldr / BC);
+  gram_proj_dmma_kernel<MF, BC><<<count, GD_THREADS, smem, st>>>(R, ldr, K, B, n_chunks, Uo, L, LP,
+                                                                 LP + 4, G, H, NG, KG);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
 template <int MF>
 int launch_gp(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
               const double *Uo, int L, int LP, double *G, double *H, cudaStream_t st) {
@@ -263,18 +276,21 @@ int launch_gp(plsb_ctx *h, const double *R, long long ldr, int count, int K, int
   const int ldu = LP + 4;
   const int NF = (KP + LP) / 8;
   const int NG = (NF + 1) / 2;
-  const int KG = std::max(1, std::min(GD_WARPS / NG, GD_BC / 4));
-  const size_t stage = (size_t)KP * GD_LDR + (size_t)GD_BC * ldu;
-  const size_t red = (size_t)KG * KP * NF * 8;
-  const size_t smem = sizeof(double) * std::max(2 * stage, red);
   PLSB_CHECK(NG <= GD_WARPS, PLSB_ERR_ARG, "gram_proj: too many output fragments");
-  PLSB_CUDA(cudaFuncSetAttribute(gram_proj_dmma_kernel<MF>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int n_chunks = (int)(ldr / GD_BC);
-  gram_proj_dmma_kernel<MF><<<count, GD_THREADS, smem, st>>>(R, ldr, K, B, n_chunks, Uo, L, LP,
-                                                             ldu, G, H, NG, KG);
-  PLSB_LAUNCHED(h);
-  return PLSB_OK;
+  auto smem_for = [&](int bc, int kg) {
+    const size_t stage = (size_t)KP * (bc + 4) + (size_t)bc * ldu;
+    const size_t red = (size_t)kg * KP * NF * 8;
+    return sizeof(double) * std::max(2 * stage, red);
+  };
+  // 128-column stages (fewer barriers, better balance of the contraction
+  // groups) when two of them fit, else 64
+  const int KG128 = std::max(1, std::min(GD_WARPS / NG, 128 / 4));
+  if (ldr % 128 == 0 && smem_for(128, KG128) <= 200 * 1024)
+    return launch_gp_bc<MF, 128>(h, R, ldr, count, K, B, Uo, L, LP, G, H, smem_for(128, KG128), NG,
+                                 KG128, st);
+  const int KG64 = std::max(1, std::min(GD_WARPS / NG, 64 / 4));
+  return launch_gp_bc<MF, 64>(h, R, ldr, count, K, B, Uo, L, LP, G, H, smem_for(64, KG64), NG, KG64,
+                              st);
 }
 
 template <int NFL>
@@ -302,8 +318,7 @@ int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int
   KernelTimer kt(h, KC_GRAM, st);
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(K >= 1 && K <= MAX_K, PLSB_ERR_ARG, "gram_proj: K=%d outside [1,%d]", K, MAX_K);
-  PLSB_CHECK(ldr % GD_BC == 0, PLSB_ERR_ARG, "gram_proj: row pitch %lld not a multiple of %d", ldr,
-             GD_BC);
+  PLSB_CHECK(ldr % 64 == 0, PLSB_ERR_ARG, "gram_proj: row pitch %lld not a multiple of 64", ldr);
   const bool proj = Uo && H;
   PLSB_CHECK(!proj || (L >= 1 && L <= MAX_K), PLSB_ERR_ARG, "gram_proj: L=%d", L);
   const int LP = proj ? round_up(L, 8) : 0;

@@ -25,6 +25,16 @@ MODES = {
 }
 
 
+def to_host(t):
+    """Device tensor -> NumPy array through pinned host memory (torch caches
+    pinned blocks, so repeated analyses reuse them)."""
+    if not t.is_cuda:
+        return t.numpy()
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t)
+    return out.numpy()
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 

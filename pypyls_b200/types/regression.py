@@ -10,7 +10,7 @@ import torch
 from .. import dist as pdist
 from .. import structures
 from ..base import BasePLS
-from ..engine import ResamplingEngine
+from ..engine import ResamplingEngine, to_host
 
 
 def resid_yscores(x_scores, y_scores):
@@ -101,8 +101,8 @@ class PLSRegression(BasePLS):
         omega0 = np.stack([self.rs.normal(size=(T, 11)) for _ in range(L)])
         xw, pct = eng.simpls_decompose(omega0 if T > 11 else None)
         self._dev = dict(U=xw, d=torch.ones_like(pct), pct=pct)
-        res['x_weights'] = xw.cpu().numpy()
-        res['x_scores'] = eng.project_scores(xw).cpu().numpy()
+        res['x_weights'] = to_host(xw)
+        res['x_scores'] = to_host(eng.project_scores(xw))
         varexp = pct.cpu().numpy()
 
         n_omega = max(self.inputs.n_perm, self.inputs.n_boot)
@@ -147,7 +147,7 @@ class PLSRegression(BasePLS):
             block, self._omega_block(first, block.shape[0]))
         d_perm = pdist.gather_resamples(local, n)
         self._dev['d_perm'] = d_perm
-        return d_perm.cpu().numpy().T.copy(), None, None
+        return to_host(d_perm).T.copy(), None, None
 
     def bootstrap(self, X, Y, seed=None):
         """Replaces BasePLS.bootstrap + PLSRegression._single_boot
@@ -159,8 +159,8 @@ class PLSRegression(BasePLS):
         distrib = pdist.gather_resamples(distrib, n)
         pdist.reduce_sum(u_sum, u_square)
         self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
-        return (distrib.permute(1, 2, 0).contiguous().cpu().numpy(),
-                u_sum.cpu().numpy(), u_square.cpu().numpy())
+        return (to_host(distrib.permute(1, 2, 0).contiguous()),
+                to_host(u_sum), to_host(u_square))
 
 
 def pls_regression(X, Y, *, n_components=None, n_perm=5000, n_boot=5000,
