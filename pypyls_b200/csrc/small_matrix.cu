@@ -3,12 +3,11 @@
 // The reference runs sklearn's randomized_svd on the (K, B) cross-covariance
 // of every resample (pyls/compute.py:36-49) and a second SVD inside
 // compute.procrustes (pyls/compute.py:260-262).  Both collapse onto K x K
-// symmetric eigenproblems once G = R R^T and H = R U_orig are known:
+// symmetric eigenproblems / polar factors once G = R R^T and H = R U_orig are known:
 //
 //   G = V diag(lam) V^T                      Jacobi on G
 //   d = sqrt(lam);  temp = H^T V d^-1        (= U_orig^T U_boot)
-//   temp^T temp = W diag(mu) W^T             Jacobi on temp^T temp
-//   N s = temp W;  Q = W N^T                 (= P^T N^T of compute.py:262)
+//   Q = polar(temp)^T                        (= P^T N^T of compute.py:262; Newton-Schulz)
 //   M = V Q                                  so that U_boot d Q = R^T M
 //
 // The eigen-solver is the cyclic two-sided Jacobi method with a round-robin
@@ -120,51 +119,66 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
     bufT[i * ld + j] = v * aux[j];
   }
   __syncthreads();
-  // S = temp^T temp -> bufA (zero padded to ne);  W <- I
-  for (int e = tid; e < ne * ne; e += SM_THREADS) {
-    const int i = e / ne, j = e - i * ne;
-    double v = 0.0;
-    if (i < L && j < L)
-      for (int k = 0; k < L; ++k) v += bufT[k * ld + i] * bufT[k * ld + j];
-    bufA[i * ld + j] = v;
-    bufW[i * ld + j] = (i == j && i < L) ? 1.0 : 0.0;
+  // Orthogonal polar factor of temp by the Newton-Schulz iteration
+  //   X <- X (3 I - X^T X) / 2,   X_0 = temp
+  // (singular values of temp are cosines of principal angles, <= 1 < sqrt(3), so
+  // it converges, quadratically at the end; exact-zero rows / columns -- the
+  // null directions -- stay zero, which is the rotation of the non-null
+  // subspace).  Only matrix products: no rotations, no barriers per pair.
+  double *X = bufT, *Y = bufW;
+  for (int it = 0; it < 100; ++it) {
+    for (int e = tid; e < L * L; e += SM_THREADS) {
+      const int i = e / L, j = e - i * L;
+      if (j < i) continue;
+      double v = 0.0;
+      for (int k = 0; k < L; ++k) v += X[k * ld + i] * X[k * ld + j];
+      bufA[i * ld + j] = v;
+      bufA[j * ld + i] = v;
+    }
+    __syncthreads();
+    if (it == 0) {
+      // |X^T X|_inf bounds sigma_max^2; the iteration needs sigma_max < sqrt(3).
+      // temp from orthonormal factors never triggers this (the polar factor
+      // does not depend on a positive scale of X).
+      for (int i = tid; i < L; i += SM_THREADS) {
+        double rs = 0.0;
+        for (int j = 0; j < L; ++j) rs += fabs(bufA[i * ld + j]);
+        aux[i] = rs;
+      }
+      __syncthreads();
+      double s = 0.0;
+      for (int i = 0; i < L; ++i) s = fmax(s, aux[i]);
+      if (s > 2.8) {
+        const double f2 = 2.8 / s, f = sqrt(f2);
+        for (int e = tid; e < L * L; e += SM_THREADS) {
+          const int i = e / L, j = e - i * L;
+          X[i * ld + j] *= f;
+          bufA[i * ld + j] *= f2;
+        }
+      }
+      __syncthreads();
+    }
+    int changed = 0;
+    for (int e = tid; e < L * L; e += SM_THREADS) {
+      const int i = e / L, j = e - i * L;
+      double v = 0.0;
+      for (int k = 0; k < L; ++k) v += X[i * ld + k] * bufA[k * ld + j];
+      const double x = X[i * ld + j];
+      const double y = 1.5 * x - 0.5 * v;
+      Y[i * ld + j] = y;
+      changed |= fabs(y - x) > 1e-14;
+    }
+    const int more = __syncthreads_or(changed);
+    double *t = X;
+    X = Y;
+    Y = t;
+    if (!more) break;
   }
-  // (S[i][j] and S[j][i] are the same sum in the same order: exactly symmetric)
-  jacobi_sym(bufA, bufW, L, ld, sc);   // bufW = W (right singular vectors)
-  // N s = temp W -> bufA
-  for (int e = tid; e < L * L; e += SM_THREADS) {
-    const int i = e / L, k = e - i * L;
-    double v = 0.0;
-    for (int j = 0; j < L; ++j) v += bufT[i * ld + j] * bufW[j * ld + k];
-    bufA[i * ld + k] = v;
-  }
-  __syncthreads();
-  // singular values = column norms of temp W
-  for (int k = tid; k < L; k += SM_THREADS) {
-    double v = 0.0;
-    for (int i = 0; i < L; ++i) v += bufA[i * ld + k] * bufA[i * ld + k];
-    lam[k] = sqrt(v);
-  }
-  __syncthreads();
-  double smax = 0.0;
-  for (int i = 0; i < L; ++i) smax = fmax(smax, lam[i]);
-  __syncthreads();
-  for (int k = tid; k < L; k += SM_THREADS)
-    aux[k] = (lam[k] > 1e-12 * smax && lam[k] > 0.0) ? 1.0 / lam[k] : 0.0;
-  __syncthreads();
-  // Q[i][j] = sum_k W[i][k] N[j][k]  -> bufT
-  for (int e = tid; e < L * L; e += SM_THREADS) {
-    const int i = e / L, j = e - i * L;
-    double v = 0.0;
-    for (int k = 0; k < L; ++k) v += bufW[i * ld + k] * bufA[j * ld + k] * aux[k];
-    bufT[i * ld + j] = v;
-  }
-  __syncthreads();
-  // M[a][j] = sum_i V[a][i] Q[i][j]
+  // Q = polar(temp)^T;  M[a][j] = sum_i V[a][i] Q[i][j] = sum_i V[a][i] X[j][i]
   for (int e = tid; e < K * L; e += SM_THREADS) {
     const int a = e / L, j = e - a * L;
     double v = 0.0;
-    for (int i = 0; i < K; ++i) v += bufV[a * ld + i] * bufT[i * ld + j];
+    for (int i = 0; i < K; ++i) v += bufV[a * ld + i] * X[j * ld + i];
     M_out[(size_t)r * K * L + e] = v;
   }
 }
