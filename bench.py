@@ -295,6 +295,8 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--workspace-gib', type=float, default=None,
+                    help='chunk workspace of the engine (default: library default)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -340,10 +342,13 @@ def main():
     P, R = n_perm * world, n_boot * world               # whole job
 
     kind = w['kind']
+    ws_bytes = None if args.workspace_gib is None else \
+        int(args.workspace_gib * (1 << 30))
     if kind == 'regression':
         from pypyls_b200.types.regression import gaussian_tables
         eng = ResamplingEngine('regression', w['S'], w['B'], w['T'], [w['S']],
-                               1, device=local_rank, n_components=w['L'])
+                               1, device=local_rank, n_components=w['L'],
+                               workspace_bytes=ws_bytes)
         eng.set_data(Xh - Xh.mean(0, keepdim=True),
                      Yh - Yh.mean(0, keepdim=True))
         rs0 = np.random.RandomState(1234)
@@ -358,7 +363,8 @@ def main():
         bs, add_orig = U.contiguous(), True
     else:
         eng = ResamplingEngine(kind, w['S'], w['B'], w['T'], w['groups'],
-                               w['n_cond'], device=local_rank)
+                               w['n_cond'], device=local_rank,
+                               workspace_bytes=ws_bytes)
         eng.set_data(Xh, Yh if kind == 'behavioral' else None)
         U, d, V = eng.decompose()
         bs, add_orig = (U * d[None, :]).contiguous(), kind == 'behavioral'
@@ -420,7 +426,7 @@ def main():
     if not args.no_e2e:
         def call(seed):
             kw = dict(n_perm=P, n_boot=R, seed=seed, verbose=False,
-                      device=local_rank)
+                      device=local_rank, workspace_bytes=ws_bytes)
             if kind == 'regression':
                 return pyls.pls_regression(Xh, Yh, n_components=w['L'], **kw)
             if kind == 'meancentered':

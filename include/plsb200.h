@@ -57,7 +57,7 @@ const char *plsb_last_error(void);
 /* Handle life cycle.  `device` is the CUDA ordinal. */
 int plsb_create(plsb_handle_t *out, int device);
 int plsb_destroy(plsb_handle_t h);
-/* Upper bound (bytes) for the per-chunk resample workspace (default 2 GiB). */
+/* Upper bound (bytes) for the per-chunk resample workspace (default 8 GiB). */
 int plsb_set_workspace_limit(plsb_handle_t h, uint64_t bytes);
 
 /*

@@ -119,7 +119,7 @@ struct plsb_ctx {
   int device = 0;
   plsb::Layout lay;
   bool configured = false, has_data = false, has_original = false;
-  uint64_t ws_limit = 2ull << 30;
+  uint64_t ws_limit = 8ull << 30;
   int64_t launches = 0;
   int sm_count = 148;
   // optional event timing: (class, start, stop) per launch since the last read

@@ -35,7 +35,11 @@ namespace {
 constexpr int SM_THREADS = 256;
 // mode 0: full decomposition -> M (K,L) [+ lam sorted descending if lam_out]
 // mode 1: eigen only -> V_out (K,K) columns sorted by descending eigenvalue, lam_out sorted
-//         (sqrt_lam != 0 writes sqrt(lam) instead: singular values of R)
+//         (sqrt_lam != 0 writes sqrt(lam) instead: singular values of R).  Needs two
+//         K x K tiles of shared memory only, so twice as many CTAs fit on an SM.
+// mode 2: rotation only: V_out / lam_out are INPUTS (what mode 1 wrote) -> M (K,L)
+// The drivers run mode 1 then mode 2: the Jacobi stage is latency bound and gains
+// from the higher occupancy.
 __global__ void __launch_bounds__(SM_THREADS)
 small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, int K, int L,
                     int mode, int sqrt_lam, const double *__restrict__ dorig,
@@ -46,9 +50,9 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
   const int nb = half * (half + 1) / 2;
   double *bufA = sm;                 // G, later temp^T temp, later N s
   double *bufV = bufA + ne * ld;     // V
-  double *bufT = bufV + ne * ld;     // temp, later Q
-  double *bufW = bufT + ne * ld;     // H, later W
-  double *lam = bufW + ne * ld;      // ne
+  double *bufT = bufV + ne * ld;     // temp, later Q          (modes 0, 2 only)
+  double *bufW = bufT + ne * ld;     // H, later W             (modes 0, 2 only)
+  double *lam = bufA + (mode == 1 ? 2 : 4) * ne * ld;   // ne
   double *aux = lam + ne;            // ne
   JacobiScratch sc;
   sc.cst = aux + ne;                                   // 3*half
@@ -63,6 +67,14 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
     int bi = a * half - a * (a - 1) / 2;   // blocks of the rows before a
     for (int b = a; b < half; ++b) sc.blk[bi++] = make_short2((short)a, (short)b);
   }
+  if (mode == 2) {
+    for (int e = tid; e < K * K; e += SM_THREADS) {
+      const int i = e / K, j = e - i * K;
+      bufV[i * ld + j] = V_out[(size_t)r * K * K + e];
+    }
+    for (int j = tid; j < K; j += SM_THREADS) lam[j] = lam_out[(size_t)r * K + j];
+    __syncthreads();
+  } else {
   for (int e = tid; e < ne * ne; e += SM_THREADS) {
     const int i = e / ne, j = e - i * ne;
     double g = 0.0;
@@ -84,6 +96,7 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
   if (lam_out)
     for (int j = tid; j < K; j += SM_THREADS)
       lam_out[(size_t)r * K + rank[j]] = sqrt_lam ? sqrt(lam[j]) : lam[j];
+  }
   if (mode == 1) {
     if (V_out)
       for (int e = tid; e < K * K; e += SM_THREADS) {
@@ -193,7 +206,7 @@ int launch_small(plsb_ctx *h, const double *G, const double *H, int count, int K
   PLSB_CHECK(mode == 1 || L == K, PLSB_ERR_ARG, "small decomposition: L=%d must equal K=%d", L, K);
   const int ne = K + (K & 1), ld = ne | 1, half = ne / 2;
   const int nb = half * (half + 1) / 2;
-  const size_t smem = sizeof(double) * (4 * (size_t)ne * ld + 2 * ne + 3 * half) +
+  const size_t smem = sizeof(double) * ((mode == 1 ? 2 : 4) * (size_t)ne * ld + 2 * ne + 3 * half) +
                       sizeof(int) * (2 * half + ne) + sizeof(short2) * nb + 16;
   PLSB_CUDA(cudaFuncSetAttribute(small_decomp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
@@ -207,7 +220,17 @@ int launch_small(plsb_ctx *h, const double *G, const double *H, int count, int K
 
 int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count, int K, int L,
                         const double *dorig, double *M, double *lam, cudaStream_t st) {
-  return launch_small(h, G, H, count, K, L, 0, 0, dorig, M, nullptr, lam, st);
+  if (count <= 0) return PLSB_OK;
+  // stage 1 (eigen-decomposition, 2 tiles of shared memory) then stage 2 (rotation)
+  const size_t kk = (size_t)K * K;
+  PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)count * (kk + K)));
+  double *V = h->misc.as<double>(), *lam_s = V + (size_t)count * kk;
+  PLSB_TRY(launch_small(h, G, nullptr, count, K, K, 1, 0, nullptr, nullptr, V, lam_s, st));
+  PLSB_TRY(launch_small(h, G, H, count, K, L, 2, 0, dorig, M, V, lam_s, st));
+  if (lam)
+    PLSB_CUDA(cudaMemcpyAsync(lam, lam_s, sizeof(double) * (size_t)count * K,
+                              cudaMemcpyDeviceToDevice, st));
+  return PLSB_OK;
 }
 
 int launch_sym_eig(plsb_ctx *h, const double *G, int count, int K, double *V, double *lam,

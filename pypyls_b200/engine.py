@@ -15,7 +15,7 @@ import torch
 
 from . import _cabi
 
-DEFAULT_WORKSPACE = 2 << 30      # bytes per chunk of stored cross-covariances
+DEFAULT_WORKSPACE = 8 << 30      # bytes per chunk of stored cross-covariances
 
 MODES = {
     'behavioral': _cabi.PLSB_BEHAVIORAL_CORR,
