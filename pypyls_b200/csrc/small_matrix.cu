@@ -3,29 +3,32 @@
 // The reference runs sklearn's randomized_svd on the (K, B) cross-covariance
 // of every resample (pyls/compute.py:36-49) and a second SVD inside
 // compute.procrustes (pyls/compute.py:260-262).  Both collapse onto K x K
-// symmetric eigenproblems / polar factors once G = R R^T and H = R U_orig are known:
+// problems once G = R R^T and H = R U_orig are known:
 //
-//   G = V diag(lam) V^T                      Jacobi on G
-//   d = sqrt(lam);  temp = H^T V d^-1        (= U_orig^T U_boot)
-//   Q = polar(temp)^T                        (= P^T N^T of compute.py:262; Newton-Schulz)
-//   M = V Q                                  so that U_boot d Q = R^T M
+//   eigen_kernel      G = V diag(lam) V^T                    (Jacobi)
+//   rotation_kernel   d = sqrt(lam);  temp = H^T V d^-1      (= U_orig^T U_boot)
+//                     Q = polar(temp)^T   (= P^T N^T of compute.py:262; Newton-Schulz)
+//                     M = V Q             so that U_boot d Q = R^T M
 //
-// The eigen-solver is the cyclic two-sided Jacobi method with a round-robin
-// (tournament) ordering.  The n/2 plane rotations of one round act on disjoint
-// index pairs, so the update A <- J^T A J decomposes into independent 2 x 2
-// blocks, one per (pair a, pair b): a thread reads the four entries of its
-// block, applies pair b's rotation from the right and pair a's from the left,
-// and writes the block and its mirror image.  Only blocks with a <= b are
-// computed (symmetry), the parameters of a rotation come from the diagonal
-// block of its pair, and a round needs two barriers.
+// eigen_kernel: cyclic two-sided Jacobi with a round-robin (tournament)
+// ordering.  The n/2 plane rotations of one round act on disjoint index pairs,
+// so the update A <- J^T A J decomposes into independent 2 x 2 blocks, one per
+// (pair a, pair b): a thread reads the four entries of its block, applies pair
+// b's rotation from the right and pair a's from the left, and writes the block
+// and its mirror image (jacobi.cuh).  Two K x K tiles of shared memory.
+//
+// rotation_kernel: the orthogonal polar factor comes from the Newton-Schulz
+// iteration X <- X (3 I - X^T X) / 2 -- matrix products only, done as
+// mma.sync.m8n8k4.f64 (DMMA) fragments out of shared memory.
 //
 // Numerically null directions (mean-centred PLS always has one: the cell
 // means minus their mean have rank J-1) are removed from the rotation: their
 // d^-1 is 0 and the rows of temp that belong to null ORIGINAL latent variables
-// are zeroed, so Q is the Procrustes rotation of the non-null subspace and the
-// null columns of R^T M are 0.  (The reference rotates with whatever unit
-// vectors its randomized SVD returns for the null directions, which perturbs
-// the other latent variables; see DESIGN.md.)
+// are zeroed; exact-zero rows / columns stay zero under Newton-Schulz, so Q is
+// the Procrustes rotation of the non-null subspace and the null columns of
+// R^T M are 0.  (The reference rotates with whatever unit vectors its
+// randomized SVD returns for the null directions, which perturbs the other
+// latent variables; see DESIGN.md.)
 #include "common.cuh"
 #include "jacobi.cuh"
 
@@ -33,32 +36,24 @@ namespace plsb {
 namespace {
 
 constexpr int SM_THREADS = 256;
-// mode 0: full decomposition -> M (K,L) [+ lam sorted descending if lam_out]
-// mode 1: eigen only -> V_out (K,K) columns sorted by descending eigenvalue, lam_out sorted
-//         (sqrt_lam != 0 writes sqrt(lam) instead: singular values of R).  Needs two
-//         K x K tiles of shared memory only, so twice as many CTAs fit on an SM.
-// mode 2: rotation only: V_out / lam_out are INPUTS (what mode 1 wrote) -> M (K,L)
-// The drivers run mode 1 then mode 2: the Jacobi stage is latency bound and gains
-// from the higher occupancy.
+constexpr int SM_WARPS = SM_THREADS / 32;
+
+// eigen-decomposition of the symmetric K x K matrices G[r]:
+//   V_out (K,K): eigenvectors in columns, sorted by descending eigenvalue
+//   lam_out (K): eigenvalues sorted descending (sqrt_lam: their square roots)
 __global__ void __launch_bounds__(SM_THREADS)
-small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, int K, int L,
-                    int mode, int sqrt_lam, const double *__restrict__ dorig,
-                    double *__restrict__ M_out, double *__restrict__ V_out,
-                    double *__restrict__ lam_out) {
+eigen_kernel(const double *__restrict__ G, int K, int sqrt_lam, double *__restrict__ V_out,
+             double *__restrict__ lam_out) {
   extern __shared__ __align__(16) double sm[];
   const int ne = K + (K & 1), ld = ne | 1, half = ne / 2;
-  const int nb = half * (half + 1) / 2;
-  double *bufA = sm;                 // G, later temp^T temp, later N s
+  double *bufA = sm;                 // G -> diag(lam)
   double *bufV = bufA + ne * ld;     // V
-  double *bufT = bufV + ne * ld;     // temp, later Q          (modes 0, 2 only)
-  double *bufW = bufT + ne * ld;     // H, later W             (modes 0, 2 only)
-  double *lam = bufA + (mode == 1 ? 2 : 4) * ne * ld;   // ne
-  double *aux = lam + ne;            // ne
+  double *lam = bufV + ne * ld;      // ne
   JacobiScratch sc;
-  sc.cst = aux + ne;                                   // 3*half
+  sc.cst = lam + ne;                                   // 3*half
   sc.pq = reinterpret_cast<int *>(sc.cst + 3 * half);  // 2*half
   int *rank = sc.pq + 2 * half;                        // ne
-  sc.blk = reinterpret_cast<short2 *>(rank + ne);      // nb
+  sc.blk = reinterpret_cast<short2 *>(rank + ne);      // half*(half+1)/2
   const int r = blockIdx.x, tid = threadIdx.x;
   const double *Gr = G + (size_t)r * K * K;
 
@@ -67,14 +62,6 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
     int bi = a * half - a * (a - 1) / 2;   // blocks of the rows before a
     for (int b = a; b < half; ++b) sc.blk[bi++] = make_short2((short)a, (short)b);
   }
-  if (mode == 2) {
-    for (int e = tid; e < K * K; e += SM_THREADS) {
-      const int i = e / K, j = e - i * K;
-      bufV[i * ld + j] = V_out[(size_t)r * K * K + e];
-    }
-    for (int j = tid; j < K; j += SM_THREADS) lam[j] = lam_out[(size_t)r * K + j];
-    __syncthreads();
-  } else {
   for (int e = tid; e < ne * ne; e += SM_THREADS) {
     const int i = e / ne, j = e - i * ne;
     double g = 0.0;
@@ -96,122 +83,161 @@ small_decomp_kernel(const double *__restrict__ G, const double *__restrict__ H, 
   if (lam_out)
     for (int j = tid; j < K; j += SM_THREADS)
       lam_out[(size_t)r * K + rank[j]] = sqrt_lam ? sqrt(lam[j]) : lam[j];
-  }
-  if (mode == 1) {
-    if (V_out)
-      for (int e = tid; e < K * K; e += SM_THREADS) {
-        const int i = e / K, j = e - i * K;
-        V_out[(size_t)r * K * K + (size_t)i * K + rank[j]] = bufV[i * ld + j];
-      }
-    return;
-  }
-
-  // d^-1 with a guard for numerically null directions
-  double lmax = 0.0;
-  for (int i = 0; i < K; ++i) lmax = fmax(lmax, lam[i]);
-  double dorig_max = 0.0;
-  if (dorig)
-    for (int i = 0; i < L; ++i) dorig_max = fmax(dorig_max, dorig[i]);
-  __syncthreads();
-  for (int j = tid; j < K; j += SM_THREADS)
-    aux[j] = (lam[j] > 1e-14 * lmax && lam[j] > 0.0) ? 1.0 / sqrt(lam[j]) : 0.0;
-  // bufW <- H (K x L)
-  const double *Hr = H + (size_t)r * K * L;
-  for (int e = tid; e < K * L; e += SM_THREADS) {
-    const int k = e / L, i = e - k * L;
-    bufW[k * ld + i] = Hr[e];
-  }
-  __syncthreads();
-  // temp[i][j] = sum_k H[k][i] V[k][j] / d_j   (L x L)
-  for (int e = tid; e < L * L; e += SM_THREADS) {
-    const int i = e / L, j = e - i * L;
-    double v = 0.0;
-    for (int k = 0; k < K; ++k) v += bufW[k * ld + i] * bufV[k * ld + j];
-    // a numerically null ORIGINAL latent variable has no direction to rotate onto
-    if (dorig && !(dorig[i] > 1e-10 * dorig_max)) v = 0.0;
-    bufT[i * ld + j] = v * aux[j];
-  }
-  __syncthreads();
-  // Orthogonal polar factor of temp by the Newton-Schulz iteration
-  //   X <- X (3 I - X^T X) / 2,   X_0 = temp
-  // (singular values of temp are cosines of principal angles, <= 1 < sqrt(3), so
-  // it converges, quadratically at the end; exact-zero rows / columns -- the
-  // null directions -- stay zero, which is the rotation of the non-null
-  // subspace).  Only matrix products: no rotations, no barriers per pair.
-  double *X = bufT, *Y = bufW;
-  for (int it = 0; it < 100; ++it) {
-    for (int e = tid; e < L * L; e += SM_THREADS) {
-      const int i = e / L, j = e - i * L;
-      if (j < i) continue;
-      double v = 0.0;
-      for (int k = 0; k < L; ++k) v += X[k * ld + i] * X[k * ld + j];
-      bufA[i * ld + j] = v;
-      bufA[j * ld + i] = v;
+  if (V_out)
+    for (int e = tid; e < K * K; e += SM_THREADS) {
+      const int i = e / K, j = e - i * K;
+      V_out[(size_t)r * K * K + (size_t)i * K + rank[j]] = bufV[i * ld + j];
     }
+}
+
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// C[m][n] = sum_k Aop(m,k) Bop(k,n) for an LP x LP x LP product out of shared
+// memory, Aop(m,k) = A[m*sam + k*sak], Bop(k,n) = B[k*sbk + n*sbn].  The
+// (LP/8)^2 output fragments are dealt round-robin to the warps; `epi(row, col,
+// value)` is called for every output element.  No barrier inside.
+template <typename Epi>
+__device__ __forceinline__ void small_mm(const double *A, int sam, int sak, const double *B,
+                                         int sbk, int sbn, int LP, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int nf = LP / 8;
+  for (int f = warp; f < nf * nf; f += SM_WARPS) {
+    const int i0 = (f / nf) * 8, j0 = (f % nf) * 8;
+    double c0 = 0.0, c1 = 0.0;
+    const double *pa = A + (i0 + g) * sam + q * sak;
+    const double *pb = B + q * sbk + (j0 + g) * sbn;
+    for (int k0 = 0; k0 < LP; k0 += 4) dmma_8x8x4(c0, c1, pa[k0 * sak], pb[k0 * sbk]);
+    epi(i0 + g, j0 + 2 * q, c0);
+    epi(i0 + g, j0 + 2 * q + 1, c1);
+  }
+}
+
+// M[r] (K,L) from V[r] (K,K), lam[r] (K) (eigen_kernel's output) and H[r] (K,L)
+__global__ void __launch_bounds__(SM_THREADS)
+rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
+                const double *__restrict__ lam_in, int K, int L,
+                const double *__restrict__ dorig, double *__restrict__ M_out) {
+  extern __shared__ __align__(16) double sm[];
+  const int LP = (K + 7) & ~7, ld = LP + 4;
+  double *Vs = sm;                // V          [LP][ld]
+  double *Hs = Vs + LP * ld;      // H, later the second iterate
+  double *Xs = Hs + LP * ld;      // temp = X_0
+  double *Bs = Xs + LP * ld;      // (3 I - X^T X) / 2
+  double *dinv = Bs + LP * ld;    // LP
+  double *omask = dinv + LP;      // LP: 1 for non-null original latent variables
+  const int r = blockIdx.x, tid = threadIdx.x;
+
+  for (int e = tid; e < LP * LP; e += SM_THREADS) {
+    const int i = e / LP, j = e - i * LP;
+    const bool in = i < K && j < K;
+    Vs[i * ld + j] = in ? V_in[(size_t)r * K * K + (size_t)i * K + j] : 0.0;
+    Hs[i * ld + j] = in ? H[(size_t)r * K * L + (size_t)i * L + j] : 0.0;
+  }
+  if (tid < LP) {
+    double lmax = 0.0, domax = 0.0;
+    for (int i = 0; i < K; ++i) lmax = fmax(lmax, lam_in[(size_t)r * K + i]);
+    if (dorig)
+      for (int i = 0; i < L; ++i) domax = fmax(domax, dorig[i]);
+    double di = 0.0, om = 0.0;
+    if (tid < K) {
+      const double l = lam_in[(size_t)r * K + tid];
+      // d^-1 with a guard for numerically null directions
+      di = (l > 1e-14 * lmax && l > 0.0) ? rsqrt(l) : 0.0;
+      // a numerically null ORIGINAL latent variable has no direction to rotate onto
+      om = (!dorig || dorig[tid] > 1e-10 * domax) ? 1.0 : 0.0;
+    }
+    dinv[tid] = di;
+    omask[tid] = om;
+  }
+  __syncthreads();
+  // temp[i][j] = omask_i * sum_k H[k][i] V[k][j] * dinv_j
+  small_mm(Hs, 1, ld, Vs, ld, 1, LP,
+           [&](int i, int j, double v) { Xs[i * ld + j] = v * omask[i] * dinv[j]; });
+  __syncthreads();
+
+  // Newton-Schulz:  X <- X (3 I - X^T X) / 2.  Singular values of temp are
+  // cosines of principal angles (<= 1 < sqrt(3)): it converges, quadratically
+  // at the end.
+  double *X = Xs, *Y = Hs;
+  for (int it = 0; it < 100; ++it) {
+    small_mm(X, 1, ld, X, ld, 1, LP, [&](int i, int j, double v) {
+      Bs[i * ld + j] = (i == j ? 1.5 : 0.0) - 0.5 * v;
+    });
     __syncthreads();
     if (it == 0) {
       // |X^T X|_inf bounds sigma_max^2; the iteration needs sigma_max < sqrt(3).
-      // temp from orthonormal factors never triggers this (the polar factor
-      // does not depend on a positive scale of X).
-      for (int i = tid; i < L; i += SM_THREADS) {
-        double rs = 0.0;
-        for (int j = 0; j < L; ++j) rs += fabs(bufA[i * ld + j]);
-        aux[i] = rs;
-      }
+      // (The polar factor does not depend on a positive scale of X.)
+      double rs = 0.0;
+      if (tid < LP)
+        for (int j = 0; j < LP; ++j) rs += fabs((tid == j ? 3.0 : 0.0) - 2.0 * Bs[tid * ld + j]);
+      // max over the CTA through an integer OR of the comparison is not enough:
+      // reduce the maximum with shuffles + shared memory
+      for (int o = 16; o > 0; o >>= 1) rs = fmax(rs, __shfl_xor_sync(0xffffffffu, rs, o));
+      __shared__ double s_red[SM_WARPS];
+      if ((tid & 31) == 0) s_red[tid >> 5] = rs;
       __syncthreads();
       double s = 0.0;
-      for (int i = 0; i < L; ++i) s = fmax(s, aux[i]);
+      for (int w = 0; w < SM_WARPS; ++w) s = fmax(s, s_red[w]);
       if (s > 2.8) {
         const double f2 = 2.8 / s, f = sqrt(f2);
-        for (int e = tid; e < L * L; e += SM_THREADS) {
-          const int i = e / L, j = e - i * L;
+        for (int e = tid; e < LP * LP; e += SM_THREADS) {
+          const int i = e / LP, j = e - i * LP;
           X[i * ld + j] *= f;
-          bufA[i * ld + j] *= f2;
+          const double xtx = (i == j ? 3.0 : 0.0) - 2.0 * Bs[i * ld + j];
+          Bs[i * ld + j] = (i == j ? 1.5 : 0.0) - 0.5 * f2 * xtx;
         }
       }
       __syncthreads();
     }
     int changed = 0;
-    for (int e = tid; e < L * L; e += SM_THREADS) {
-      const int i = e / L, j = e - i * L;
-      double v = 0.0;
-      for (int k = 0; k < L; ++k) v += X[i * ld + k] * bufA[k * ld + j];
-      const double x = X[i * ld + j];
-      const double y = 1.5 * x - 0.5 * v;
-      Y[i * ld + j] = y;
-      changed |= fabs(y - x) > 1e-14;
-    }
+    small_mm(X, ld, 1, Bs, ld, 1, LP, [&](int i, int j, double v) {
+      Y[i * ld + j] = v;
+      changed |= fabs(v - X[i * ld + j]) > 1e-14;
+    });
     const int more = __syncthreads_or(changed);
     double *t = X;
     X = Y;
     Y = t;
     if (!more) break;
   }
-  // Q = polar(temp)^T;  M[a][j] = sum_i V[a][i] Q[i][j] = sum_i V[a][i] X[j][i]
-  for (int e = tid; e < K * L; e += SM_THREADS) {
-    const int a = e / L, j = e - a * L;
-    double v = 0.0;
-    for (int i = 0; i < K; ++i) v += bufV[a * ld + i] * X[j * ld + i];
-    M_out[(size_t)r * K * L + e] = v;
-  }
+  // Q = polar(temp)^T;  M[a][j] = sum_i V[a][i] X[j][i]
+  small_mm(Vs, ld, 1, X, 1, ld, LP, [&](int a, int j, double v) {
+    if (a < K && j < L) M_out[(size_t)r * K * L + (size_t)a * L + j] = v;
+  });
 }
 
-int launch_small(plsb_ctx *h, const double *G, const double *H, int count, int K, int L, int mode,
-                 int sqrt_lam, const double *dorig, double *M, double *V, double *lam,
-                 cudaStream_t st) {
+int launch_eigen(plsb_ctx *h, const double *G, int count, int K, int sqrt_lam, double *V,
+                 double *lam, cudaStream_t st) {
   KernelTimer kt(h, KC_SMALL, st);
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(K >= 1 && K <= MAX_K, PLSB_ERR_ARG, "small decomposition: K=%d outside [1,%d]", K,
              MAX_K);
-  PLSB_CHECK(mode == 1 || L == K, PLSB_ERR_ARG, "small decomposition: L=%d must equal K=%d", L, K);
   const int ne = K + (K & 1), ld = ne | 1, half = ne / 2;
   const int nb = half * (half + 1) / 2;
-  const size_t smem = sizeof(double) * ((mode == 1 ? 2 : 4) * (size_t)ne * ld + 2 * ne + 3 * half) +
+  const size_t smem = sizeof(double) * (2 * (size_t)ne * ld + ne + 3 * half) +
                       sizeof(int) * (2 * half + ne) + sizeof(short2) * nb + 16;
-  PLSB_CUDA(cudaFuncSetAttribute(small_decomp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PLSB_CUDA(cudaFuncSetAttribute(eigen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-  small_decomp_kernel<<<count, SM_THREADS, smem, st>>>(G, H, K, L, mode, sqrt_lam, dorig, M, V,
-                                                       lam);
+  eigen_kernel<<<count, SM_THREADS, smem, st>>>(G, K, sqrt_lam, V, lam);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
+int launch_rotation(plsb_ctx *h, const double *H, const double *V, const double *lam, int count,
+                    int K, int L, const double *dorig, double *M, cudaStream_t st) {
+  KernelTimer kt(h, KC_SMALL, st);
+  if (count <= 0) return PLSB_OK;
+  PLSB_CHECK(L == K, PLSB_ERR_ARG, "small decomposition: L=%d must equal K=%d", L, K);
+  const int LP = round_up(K, 8), ld = LP + 4;
+  const size_t smem = sizeof(double) * (4 * (size_t)LP * ld + 2 * LP);
+  PLSB_CUDA(cudaFuncSetAttribute(rotation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  rotation_kernel<<<count, SM_THREADS, smem, st>>>(H, V, lam, K, L, dorig, M);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
@@ -221,12 +247,11 @@ int launch_small(plsb_ctx *h, const double *G, const double *H, int count, int K
 int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count, int K, int L,
                         const double *dorig, double *M, double *lam, cudaStream_t st) {
   if (count <= 0) return PLSB_OK;
-  // stage 1 (eigen-decomposition, 2 tiles of shared memory) then stage 2 (rotation)
   const size_t kk = (size_t)K * K;
   PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)count * (kk + K)));
   double *V = h->misc.as<double>(), *lam_s = V + (size_t)count * kk;
-  PLSB_TRY(launch_small(h, G, nullptr, count, K, K, 1, 0, nullptr, nullptr, V, lam_s, st));
-  PLSB_TRY(launch_small(h, G, H, count, K, L, 2, 0, dorig, M, V, lam_s, st));
+  PLSB_TRY(launch_eigen(h, G, count, K, 0, V, lam_s, st));
+  PLSB_TRY(launch_rotation(h, H, V, lam_s, count, K, L, dorig, M, st));
   if (lam)
     PLSB_CUDA(cudaMemcpyAsync(lam, lam_s, sizeof(double) * (size_t)count * K,
                               cudaMemcpyDeviceToDevice, st));
@@ -235,7 +260,7 @@ int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count
 
 int launch_sym_eig(plsb_ctx *h, const double *G, int count, int K, double *V, double *lam,
                    int sqrt_lam, cudaStream_t st) {
-  return launch_small(h, G, nullptr, count, K, K, 1, sqrt_lam, nullptr, nullptr, V, lam, st);
+  return launch_eigen(h, G, count, K, sqrt_lam, V, lam, st);
 }
 
 }  // namespace plsb
