@@ -34,8 +34,10 @@ def gaussian_tables(seeds, T):
     for ``compute.svd(Cov, n_components=1, seed=i)`` with an integer seed
     (pyls/types/regression.py:103 -> pyls/compute.py:48-49)."""
     out = np.empty((len(seeds), T, 11))
+    rs = np.random.RandomState(0)
     for n, i in enumerate(seeds):
-        out[n] = np.random.RandomState(int(i)).normal(size=(T, 11))
+        rs.seed(int(i))     # same stream as RandomState(i), 15x cheaper
+        out[n] = rs.standard_normal((T, 11))
     return out
 
 

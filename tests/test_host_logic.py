@@ -150,3 +150,38 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r'^\s*(from|import)\s+oracle', text,
                                      flags=re.M), f
                 assert 'pls_oracle' not in text, f
+
+
+def test_regression_host_helpers_match_reference_semantics():
+    """gaussian_tables reproduces sklearn's draw for an integer seed
+    (RandomState(i).normal(size=(T, 11))); resid_yscores equals the oracle's
+    restatement of pyls/types/regression.py:9-45."""
+    from pypyls_b200.types.regression import gaussian_tables, resid_yscores
+    tab = gaussian_tables([0, 7, 123456], 13)
+    for n, i in enumerate([0, 7, 123456]):
+        assert np.array_equal(tab[n],
+                              np.random.RandomState(i).normal(size=(13, 11)))
+    rs = np.random.RandomState(3)
+    xs, ys = rs.rand(30, 5), rs.rand(30, 5)
+    np.testing.assert_allclose(resid_yscores(xs, ys),
+                               po.resid_yscores(xs, ys), rtol=1e-13)
+
+
+def test_regression_front_end_argument_errors():
+    """pyls/tests/types/test_regression.py: n_components bound; the paths that
+    are not accelerated raise NotImplementedError before touching the GPU."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(1)
+    X, Y = rs.rand(20, 30), rs.rand(20, 4)
+    with pytest.raises(ValueError, match='n_components'):
+        pyls.pls_regression(X, Y, n_components=25, n_perm=0, n_boot=0)
+    with pytest.raises(NotImplementedError):
+        pyls.pls_regression(X, rs.rand(20, 4, 3), n_perm=0, n_boot=0)
+    Xn = X.copy()
+    Xn[3] = np.nan
+    with pytest.raises(NotImplementedError):
+        pyls.pls_regression(Xn, Y, n_perm=0, n_boot=0)
+    with pytest.raises(NotImplementedError):
+        pyls.behavioral_pls(X, Y, n_split=5, n_perm=2, n_boot=2)
+    with pytest.raises(NotImplementedError):
+        pyls.behavioral_pls(X, Y, test_split=10, n_perm=2, n_boot=2)
