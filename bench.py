@@ -477,6 +477,15 @@ def main():
                 'peak': None, 'unit': None, 'frac': None, 'traffic': None,
                 'kernel_ms_per_step': top_ms / args.steps,
                 'launches_per_step': top_n / args.steps}
+    # DRAM traffic of the class per step from the committed `ncu --set full`
+    # capture (dram__bytes_read.sum + dram__bytes_write.sum over its launches;
+    # profiles/r1_ncu_full_v4_summary.csv and ..._v2_... for the permutation
+    # launch); only known for the configuration that was captured
+    if (args.workload, world, top) == ('cfg2', 1, 'xcov_gemm') and \
+            args.workspace_gib is None:
+        roofline['traffic'] = 27.3e9
+        roofline['traffic_unit'] = 'bytes per step, all launches of the class'
+        roofline['algorithmic_flop_per_step'] = flops
     if bound == 'tensor' and flops:
         ach = flops * args.steps / (top_ms * 1e-3) / 1e12
         roofline.update(achieved=ach, peak=peak_tf, unit='TFLOP/s',

@@ -376,3 +376,103 @@ def test_regression_config4_shape_subset():
         d, u = po.single_boot(spec, Xc, Yc, out.bootres.bootsamples[:, i],
                               out.x_weights, seed=i)
         close(out.bootres.y_loadings_boot[..., i], d, rtol=1e-7)
+
+
+# ---------------------------------------------------------------------------
+# edge cases
+def test_no_resampling_requested():
+    """n_perm = n_boot = 0: only the original decomposition (the reference
+    leaves permres / bootres empty)."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(2)
+    X, Y = rs.rand(24, 70), rs.rand(24, 3)
+    out = pyls.behavioral_pls(X, Y, groups=[12, 12], n_perm=0, n_boot=0,
+                              seed=1)
+    ref = po.behavioral_pls(X, Y, groups=[12, 12], n_perm=0, n_boot=0, seed=1)
+    close(out.singvals, ref['singvals'])
+    close(out.x_weights, ref['x_weights'])
+    assert out.permres.get('pvals') is None
+    assert out.bootres.get('x_weights_normed') is None
+
+
+def test_single_resample_and_ragged_layout():
+    """One permutation, one bootstrap, unequal groups, odd sizes everywhere
+    (S = 23 rows, B = 131 features, T = 3)."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(5)
+    groups, n_cond = [4, 7], 1
+    X, Y = rs.rand(11, 131), rs.rand(11, 3)
+    ps = po.gen_permsamp(groups, n_cond, 1, seed=1)
+    bs = po.gen_bootsamp(groups, n_cond, 1, seed=2)
+    kw = dict(groups=groups, n_cond=n_cond, n_perm=1, n_boot=1, seed=3,
+              permsamples=ps, bootsamples=bs)
+    out = pyls.behavioral_pls(X, Y, verbose=False, **kw)
+    ref = po.behavioral_pls(X, Y, **kw)
+    close(out.permres.perm_singval, ref['perm_singval'])
+    close(out.bootres.y_loadings_boot, ref['distrib'])
+
+
+def test_largest_supported_decomposition():
+    """K = 80 latent variables (the documented maximum): 2 cells x T = 40."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(6)
+    groups, n_cond, T = [50, 50], 1, 40
+    X, Y = rs.rand(100, 400), rs.rand(100, T)
+    ps = po.gen_permsamp(groups, n_cond, 3, seed=1)
+    bs = po.gen_bootsamp(groups, n_cond, 3, seed=2)
+    kw = dict(groups=groups, n_cond=n_cond, n_perm=3, n_boot=3, seed=3,
+              permsamples=ps, bootsamples=bs)
+    out = pyls.behavioral_pls(X, Y, verbose=False, **kw)
+    ref = po.behavioral_pls(X, Y, **kw)
+    close(out.singvals, ref['singvals'])
+    close(out.permres.perm_singval, ref['perm_singval'])
+    close(out.bootres.y_loadings_boot, ref['distrib'])
+    # a bootstrap of 50 subjects has ~32 distinct ones < T = 40: every resampled
+    # cell block is rank deficient, so the ratios follow the null-safe rule
+    # (three bootstraps are too few to compare with the reference's noise)
+    check_rank_deficient_bsr(out, X, Y, ref['x_weights_normed'],
+                             np.ones(80, dtype=bool), min_corr=-1.0,
+                             max_dev=np.inf)
+
+
+def test_unsupported_shapes_fail_loudly():
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(7)
+    # K = 2 * 45 = 90 > 80
+    with pytest.raises(ValueError, match='maximum'):
+        pyls.behavioral_pls(rs.rand(60, 300), rs.rand(60, 45),
+                            groups=[30, 30], n_perm=2, n_boot=2)
+    # K = 12 latent variables but only 8 features
+    with pytest.raises(ValueError, match='features'):
+        pyls.behavioral_pls(rs.rand(40, 8), rs.rand(40, 12), n_perm=2,
+                            n_boot=2)
+
+
+def test_bad_resampling_tables_are_rejected():
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(8)
+    X, Y = rs.rand(20, 50), rs.rand(20, 2)
+    good = po.gen_permsamp([20], 1, 4, seed=1)
+    with pytest.raises(ValueError):
+        pyls.behavioral_pls(X, Y, n_perm=4, n_boot=0, permsamples=good[:, :3])
+    bad = good.copy()
+    bad[0, 0] = 20
+    with pytest.raises(ValueError, match='outside'):
+        pyls.behavioral_pls(X, Y, n_perm=4, n_boot=0, permsamples=bad)
+
+
+def test_constant_column_propagates_nan_like_the_reference():
+    """The reference does not guard zero variance (pyls/compute.py:84): a
+    constant column of X gives NaN in its row of the cross-correlation."""
+    from pypyls_b200.engine import ResamplingEngine
+    rs = np.random.RandomState(9)
+    X, Y = rs.rand(16, 40), rs.rand(16, 2)
+    X[:, 5] = 1.0
+    eng = ResamplingEngine('behavioral', 16, 40, 2, [16]).set_data(X, Y)
+    R = eng.crosscov().cpu().numpy()[0]
+    spec = po._Spec('behavioral', [16], 1)
+    with np.errstate(all='ignore'):
+        want = po.gen_covcorr(spec, X, Y)
+    assert np.all(np.isnan(R[:, 5])) and np.all(np.isnan(want[:, 5]))
+    keep = np.arange(40) != 5
+    close(R[:, keep], want[:, keep])
