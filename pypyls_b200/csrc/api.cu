@@ -93,6 +93,7 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, int n, bool boot, double *di
   g.N_pad = l.ldx;
   g.Kd = l.S_pad;
   g.ldc = l.ldx;
+  if (grouped) g.k_len = l.kr_max;
   if (scaled) {
     g.A = h->Ac.as<double>();
     g.X = h->Xglob.as<double>();
@@ -322,6 +323,7 @@ int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups,
     if (kb + nkc * GEMM_BK > l.S_pad) kb = l.S_pad - nkc * GEMM_BK;
     tab.push_back(kb);
     tab.push_back(kb + nkc * GEMM_BK);
+    l.kr_max = std::max(l.kr_max, nkc * GEMM_BK);
   }
   PLSB_TRY(h->tables.ensure(sizeof(int) * tab.size()));
   PLSB_CUDA(cudaMemcpy(h->tables.p, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -72,6 +73,12 @@ struct DevBuf {
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// integer tuning knob: environment variable `name` if set, else `dflt`
+inline int tune_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline long long round_up_ll(long long x, long long m) { return (x + m - 1) / m * m; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -107,6 +114,7 @@ struct Layout {
   std::vector<int> cell_start;  // first row of each cell (J+1 entries)
   int S_pad = 0;                // rows of the padded data matrices == lda of operands
   int ldx = 0;                  // leading dimension (elements) of padded (., B) matrices
+  int kr_max = 0;               // longest per-cell contraction range (multiple of GEMM_BK)
   bool behavioral() const { return mode == PLSB_BEHAVIORAL_CORR || mode == PLSB_BEHAVIORAL_COV; }
   bool corr() const { return mode == PLSB_BEHAVIORAL_CORR; }
   bool simpls() const { return mode == PLSB_SIMPLS; }
@@ -185,6 +193,7 @@ struct GemmArgs {
   int N_pad = 0;               // multiple of GEMM_BN (<= ldx)
   int Kd = 0;                  // contraction length, multiple of GEMM_BK (padding zero)
   const int2 *kranges = nullptr;  // optional per-M-tile [kbeg,kend), kbeg even
+  int k_len = 0;               // longest contraction range in kranges (0: Kd); picks the tile
   bool square_b = false;       // use X*X elementwise as the right operand
   // STORE epilogue
   double *C = nullptr;

@@ -13,6 +13,9 @@
 // k chunk) loops are flattened into one sequence so the ring never drains
 // between N tiles.  Shared-memory leading dimensions are == 4 (mod 16) doubles,
 // which makes every fragment load (8 rows x 4 k) bank-conflict free.
+// A second instantiation with a 64x128 CTA tile (warp tile 32x32, two CTAs per
+// SM) serves launches whose contraction per tile is so short that the store
+// epilogue dominates: of two resident CTAs one computes while the other writes.
 //
 // Epilogues:
 //   STORE     write C (optionally through a row map: operand row -> output row)
@@ -27,14 +30,19 @@ namespace plsb {
 namespace {
 
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int STAGES = 4;
 constexpr int LDA_S = BK + 4;           // 20
 constexpr int LDB_S = BN + 4;           // 132
-constexpr int A_STAGE = BM * LDA_S;     // doubles
 constexpr int B_STAGE = BK * LDB_S;     // doubles
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
 constexpr int NTHREADS = 256;
-constexpr int MF = 8, NF = 4;           // fragments per warp tile
+constexpr int NF = 4;                   // N fragments per warp tile (MF = 8 or 4 in M)
+// ring depth and staged column-scale rows per tile, by tile height
+__host__ __device__ constexpr int stages_of(int MF) { return MF == 8 ? 4 : 3; }
+__host__ __device__ constexpr int max_slots_of(int MF) { return MF == 8 ? 16 : 8; }
+__host__ __device__ constexpr int ring_doubles(int MF) { return stages_of(MF) * (2 * MF * 8 * LDA_S + B_STAGE); }
+__host__ __device__ constexpr int scale_doubles(int MF) { return stages_of(MF) * max_slots_of(MF) * LDB_S; }
+__host__ __device__ constexpr int smem_bytes(int MF, bool scaled) {
+  return (ring_doubles(MF) + (scaled ? scale_doubles(MF) : 0)) * (int)sizeof(double);
+}
 
 enum { EPI_STORE = 0, EPI_ROWSUMSQ = 1 };
 
@@ -54,16 +62,25 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
       : "d"(a), "d"(b));
 }
 
-template <int EPI, bool SQB>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// MF = M fragments per warp: CTA tile (2 * MF * 8) x 128
+template <int EPI, bool SQB, int MF>
+__global__ void __launch_bounds__(NTHREADS, MF == 8 ? 1 : 2)
 xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict__ X, int ldx,
                  int n_mtiles, int n_ntiles, int nt_per_split, const int2 *__restrict__ kranges,
                  int Kd, double *__restrict__ C, long long ldc, const int *__restrict__ row_map,
                  const double *__restrict__ scale, int scale_div, long long lds,
                  double *__restrict__ rowsq, int M_pad) {
+  constexpr int TM = 2 * MF * 8;          // rows of the CTA tile
+  constexpr int A_STAGE = TM * LDA_S;     // doubles
+  constexpr int STAGES = stages_of(MF);
+  constexpr int MAXS = max_slots_of(MF);
   extern __shared__ __align__(16) double smem[];
   double *As = smem;
   double *Bs = smem + STAGES * A_STAGE;
+  double *Sb = smem + ring_doubles(MF);   // [STAGES][MAXS][LDB_S] staged column scales
+  __shared__ int s_slot[TM];              // tile row -> staged scale row
+  __shared__ int s_srow[MAXS];            // staged scale row -> row of `scale`
+  __shared__ int s_nslot;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -78,14 +95,59 @@ xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict
 
   int kbeg = 0, kend = Kd;
   if (kranges) {
-    int2 kr = kranges[mtile];
+    // the ranges are tabulated per GEMM_BM (128) rows
+    int2 kr = kranges[(mtile * TM) / BM];
     kbeg = kr.x;
     kend = kr.y;
   }
   const int nkc = (kend - kbeg + BK - 1) / BK;     // k chunks per N tile
   const int total = (nt1 - nt0) * nkc;             // flattened pipeline steps
 
-  const double *Ablk = A + (size_t)mtile * BM * lda;
+  const double *Ablk = A + (size_t)mtile * TM * lda;
+
+  // Column scales (bootstrap z-scores of X) are shared by the scale_div operand
+  // rows of one (resample, cell): the few distinct rows a tile needs are staged
+  // in shared memory next to the tile's first k chunk, so that the epilogue
+  // does not wait on global loads.  Falls back to direct loads when a tile
+  // touches more than MAXS rows.
+  int nslot = 0;
+  int orow_i[MF], slot_i[MF];
+  if (EPI == EPI_STORE) {
+    if (scale) {
+      if (tid < TM) {
+        const int m = mtile * TM + tid;
+        const int orow = row_map ? row_map[m] : m;
+        s_slot[tid] = orow >= 0 ? orow / scale_div : -1;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int n = 0, prev = -1;
+        for (int t = 0; t < TM; ++t) {
+          const int sr = s_slot[t];
+          if (sr < 0) {
+            s_slot[t] = 0;
+            continue;
+          }
+          if (sr != prev) {
+            if (n < MAXS) s_srow[n] = sr;
+            ++n;
+            prev = sr;
+          }
+          s_slot[t] = n - 1;
+        }
+        s_nslot = n <= MAXS ? n : 0;
+      }
+      __syncthreads();
+      nslot = s_nslot;
+    }
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+      const int ml = wm * MF * 8 + i * 8 + g;
+      const int m = mtile * TM + ml;
+      orow_i[i] = row_map ? row_map[m] : m;
+      slot_i[i] = nslot > 0 ? s_slot[ml] : 0;
+    }
+  }
 
   // producer: issue the loads of flattened step `s` into ring slot s % STAGES
   auto issue = [&](int s) {
@@ -95,9 +157,9 @@ xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict
       const int k0 = kbeg + kc * BK;
       double *as = As + (s % STAGES) * A_STAGE;
       double *bs = Bs + (s % STAGES) * B_STAGE;
-      // A: 128 rows x 16 doubles = 1024 x 16 B, 4 per thread
+      // A: TM rows x 16 doubles = TM * 8 x 16 B, TM / 32 per thread
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < TM / 32; ++it) {
         int c = tid + it * NTHREADS;
         int row = c >> 3, seg = c & 7;
         cp_async16(as + row * LDA_S + seg * 2, Ablk + (size_t)row * lda + k0 + seg * 2);
@@ -109,6 +171,16 @@ xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict
         int c = tid + it * NTHREADS;
         int row = c >> 6, seg = c & 63;
         cp_async16(bs + row * LDB_S + seg * 2, xg + (size_t)row * ldx + seg * 2);
+      }
+      if (EPI == EPI_STORE && kc == 0 && nslot > 0) {
+        // scale rows of this N tile; buffer (tile ordinal) % STAGES is free again:
+        // the tile that used it finished its epilogue >= 1 iteration ago
+        double *sb = Sb + ((s / nkc) % STAGES) * MAXS * LDB_S;
+        for (int e = tid; e < nslot * (BN / 2); e += NTHREADS) {
+          const int sl = e / (BN / 2), seg = e - sl * (BN / 2);
+          cp_async16(sb + sl * LDB_S + seg * 2,
+                     scale + (size_t)s_srow[sl] * lds + (size_t)nt * BN + seg * 2);
+        }
       }
     }
     cp_async_commit();
@@ -133,7 +205,7 @@ xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict
     // refill the slot consumed in the previous iteration
     issue(s + STAGES - 1);
 
-    const double *as = As + (s % STAGES) * A_STAGE + (wm * 64 + g) * LDA_S + q;
+    const double *as = As + (s % STAGES) * A_STAGE + (wm * MF * 8 + g) * LDA_S + q;
     const double *bs = Bs + (s % STAGES) * B_STAGE + q * LDB_S + wn * 32 + g;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
@@ -154,15 +226,16 @@ xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict
     if (++kc == nkc) {
       // ---- epilogue of N tile `nt` ----
       if (EPI == EPI_STORE) {
+        const double *sb = Sb + (((s / nkc) % STAGES) * MAXS) * LDB_S + wn * 32 + 2 * q;
 #pragma unroll
         for (int i = 0; i < MF; ++i) {
-          const int m = mtile * BM + wm * 64 + i * 8 + g;
-          const int orow = row_map ? row_map[m] : m;
+          const int orow = orow_i[i];
           if (orow >= 0) {
             const size_t col = (size_t)nt * BN + wn * 32 + 2 * q;
             double *crow = C + (size_t)orow * ldc + col;
             if (scale) {
-              const double *srow = scale + (size_t)(orow / scale_div) * lds + col;
+              const double *srow = nslot > 0 ? sb + slot_i[i] * LDB_S
+                                             : scale + (size_t)(orow / scale_div) * lds + col;
 #pragma unroll
               for (int j = 0; j < NF; ++j) {
                 const double2 sc = *reinterpret_cast<const double2 *>(srow + j * 8);
@@ -197,33 +270,36 @@ xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict
     // reduce over the 4 lanes of a quad, then over the 4 N-warps through smem
     cp_async_wait<0>();
     __syncthreads();
-    double *red = smem;  // [4 wn][128 rows]
+    double *red = smem;  // [4 wn][TM rows]
 #pragma unroll
     for (int i = 0; i < MF; ++i) {
       double v = rsq[i];
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (q == 0) red[wn * BM + wm * 64 + i * 8 + g] = v;
+      if (q == 0) red[wn * TM + wm * MF * 8 + i * 8 + g] = v;
     }
     __syncthreads();
-    if (tid < BM) {
-      double v = red[tid] + red[BM + tid] + red[2 * BM + tid] + red[3 * BM + tid];
-      rowsq[(size_t)split * M_pad + (size_t)mtile * BM + tid] = v;
+    if (tid < TM) {
+      double v = red[tid] + red[TM + tid] + red[2 * TM + tid] + red[3 * TM + tid];
+      rowsq[(size_t)split * M_pad + (size_t)mtile * TM + tid] = v;
     }
   }
 }
 
-template <int EPI, bool SQB>
-int launch_variant(plsb_ctx *h, const GemmArgs &a, int n_mtiles, int n_ntiles, int n_splits,
-                   cudaStream_t st) {
+template <int EPI, bool SQB, int MF>
+int launch_variant(plsb_ctx *h, const GemmArgs &a, int n_ntiles, int n_splits, cudaStream_t st) {
   KernelTimer kt(h, KC_GEMM, st);
-  auto kern = xcov_gemm_kernel<EPI, SQB>;
-  PLSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  constexpr int TM = 2 * MF * 8;
+  auto kern = xcov_gemm_kernel<EPI, SQB, MF>;
+  const int smem = smem_bytes(MF, EPI == EPI_STORE && a.scale != nullptr);
+  PLSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int n_mtiles = a.M_pad / TM;
   const int nt_per_split = (n_ntiles + n_splits - 1) / n_splits;
   dim3 grid((unsigned)(n_mtiles * n_splits));
-  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(a.A, a.lda, a.X, a.ldx, n_mtiles, n_ntiles, nt_per_split,
-                                           a.kranges, a.Kd, a.C, a.ldc, a.row_map, a.scale,
-                                           a.scale_div, a.lds, a.rowsq, a.M_pad);
+  kern<<<grid, NTHREADS, smem, st>>>(a.A, a.lda, a.X, a.ldx, n_mtiles, n_ntiles,
+                                               nt_per_split, a.kranges, a.Kd, a.C, a.ldc,
+                                               a.row_map, a.scale, a.scale_div, a.lds, a.rowsq,
+                                               a.M_pad);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
@@ -247,17 +323,26 @@ int launch_gemm(plsb_ctx *h, const GemmArgs &a, cudaStream_t st) {
              BM, BN, BK);
   PLSB_CHECK(a.lda % 2 == 0 && a.ldx % 2 == 0, PLSB_ERR_ARG, "gemm: odd leading dimension");
   if (a.M_pad == 0 || a.N_pad == 0) return PLSB_OK;
-  const int n_mtiles = a.M_pad / BM, n_ntiles = a.N_pad / BN;
+  const int n_ntiles = a.N_pad / BN;
   const bool rowsq = a.rowsq != nullptr;
-  int n_splits = rowsq ? a.n_splits : gemm_pick_splits(h, n_mtiles, n_ntiles);
   if (rowsq) {
     PLSB_CHECK(a.n_splits >= 1, PLSB_ERR_ARG, "gemm: n_splits");
-    if (a.square_b) return launch_variant<EPI_ROWSUMSQ, true>(h, a, n_mtiles, n_ntiles, n_splits, st);
-    return launch_variant<EPI_ROWSUMSQ, false>(h, a, n_mtiles, n_ntiles, n_splits, st);
+    if (a.square_b) return launch_variant<EPI_ROWSUMSQ, true, 8>(h, a, n_ntiles, a.n_splits, st);
+    return launch_variant<EPI_ROWSUMSQ, false, 8>(h, a, n_ntiles, a.n_splits, st);
   }
   PLSB_CHECK(a.C != nullptr && a.ldc % 2 == 0, PLSB_ERR_ARG, "gemm: bad output");
-  if (a.square_b) return launch_variant<EPI_STORE, true>(h, a, n_mtiles, n_ntiles, n_splits, st);
-  return launch_variant<EPI_STORE, false>(h, a, n_mtiles, n_ntiles, n_splits, st);
+  // short contractions (block-diagonal operands: one cell's rows) are bound by the
+  // store epilogue: 64-row tiles, two CTAs per SM
+  const int klen = a.k_len > 0 ? a.k_len : a.Kd;
+  const bool small_tile = tune_int("PLSB_GEMM_SMALL_TILE", klen <= 64);
+  if (small_tile) {
+    const int n_splits = gemm_pick_splits(h, a.M_pad / 64, n_ntiles);
+    if (a.square_b) return launch_variant<EPI_STORE, true, 4>(h, a, n_ntiles, n_splits, st);
+    return launch_variant<EPI_STORE, false, 4>(h, a, n_ntiles, n_splits, st);
+  }
+  const int n_splits = gemm_pick_splits(h, a.M_pad / BM, n_ntiles);
+  if (a.square_b) return launch_variant<EPI_STORE, true, 8>(h, a, n_ntiles, n_splits, st);
+  return launch_variant<EPI_STORE, false, 8>(h, a, n_ntiles, n_splits, st);
 }
 
 }  // namespace plsb

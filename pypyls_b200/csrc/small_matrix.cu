@@ -54,15 +54,15 @@ eigen_kernel(const double *__restrict__ G, int K, int sqrt_lam, double *__restri
   sc.pq = reinterpret_cast<int *>(sc.cst + 3 * half);  // 2*half
   int *rank = sc.pq + 2 * half;                        // ne
   sc.blk = reinterpret_cast<short2 *>(rank + ne);      // half*(half+1)/2
-  const int r = blockIdx.x, tid = threadIdx.x;
+  const int r = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
   const double *Gr = G + (size_t)r * K * K;
 
   // block table: bi -> (a, b), a <= b
-  for (int a = tid; a < half; a += SM_THREADS) {
+  for (int a = tid; a < half; a += nthr) {
     int bi = a * half - a * (a - 1) / 2;   // blocks of the rows before a
     for (int b = a; b < half; ++b) sc.blk[bi++] = make_short2((short)a, (short)b);
   }
-  for (int e = tid; e < ne * ne; e += SM_THREADS) {
+  for (int e = tid; e < ne * ne; e += nthr) {
     const int i = e / ne, j = e - i * ne;
     double g = 0.0;
     // symmetrise: both triangles must agree exactly for the two-sided updates
@@ -71,20 +71,20 @@ eigen_kernel(const double *__restrict__ G, int K, int sqrt_lam, double *__restri
     bufV[i * ld + j] = (i == j && i < K) ? 1.0 : 0.0;
   }
   jacobi_sym(bufA, bufV, K, ld, sc);   // diag(bufA) = lam, bufV = V
-  for (int j = tid; j < K; j += SM_THREADS) lam[j] = fmax(bufA[j * ld + j], 0.0);
+  for (int j = tid; j < K; j += nthr) lam[j] = fmax(bufA[j * ld + j], 0.0);
   __syncthreads();
   // descending rank of every eigenvalue (ties broken by index)
-  for (int j = tid; j < K; j += SM_THREADS) {
+  for (int j = tid; j < K; j += nthr) {
     int rk = 0;
     for (int i = 0; i < K; ++i) rk += (lam[i] > lam[j]) || (lam[i] == lam[j] && i < j);
     rank[j] = rk;
   }
   __syncthreads();
   if (lam_out)
-    for (int j = tid; j < K; j += SM_THREADS)
+    for (int j = tid; j < K; j += nthr)
       lam_out[(size_t)r * K + rank[j]] = sqrt_lam ? sqrt(lam[j]) : lam[j];
   if (V_out)
-    for (int e = tid; e < K * K; e += SM_THREADS) {
+    for (int e = tid; e < K * K; e += nthr) {
       const int i = e / K, j = e - i * K;
       V_out[(size_t)r * K * K + (size_t)i * K + rank[j]] = bufV[i * ld + j];
     }
@@ -223,7 +223,10 @@ int launch_eigen(plsb_ctx *h, const double *G, int count, int K, int sqrt_lam, d
                       sizeof(int) * (2 * half + ne) + sizeof(short2) * nb + 16;
   PLSB_CUDA(cudaFuncSetAttribute(eigen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-  eigen_kernel<<<count, SM_THREADS, smem, st>>>(G, K, sqrt_lam, V, lam);
+  // one thread per 2 x 2 block of a Jacobi round (measured: fewer, busier threads lose)
+  const int threads = std::min(SM_THREADS, std::max(32, round_up(
+      tune_int("PLSB_EIGEN_THREADS", nb), 32)));
+  eigen_kernel<<<count, threads, smem, st>>>(G, K, sqrt_lam, V, lam);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }

@@ -1,15 +1,12 @@
-// FP64 tensor-core (DMMA m8n8k4) versions of the two streaming contractions
-// over the stored cross-covariance matrices R (count blocks of K rows x ldr).
+// accum_u: the FP64 tensor-core (DMMA m8n8k4) streaming contraction that turns
+// the stored cross-covariance matrices R (count blocks of K rows x ldr) and the
+// per-resample rotations M into the bootstrap sums (pyls/base.py:510-511 with
+// compute.procrustes, pyls/compute.py:260-262, folded into M):
 //
-//   gram_proj   [G | H] = R [R^T | U_orig]     (K x (K+L), contraction over B)
-//               one CTA per resample; R and U_orig tiles of 64 columns are
-//               staged with cp.async in a two-slot ring; the 16 warps split
-//               the output columns (2 fragments each) x the contraction steps
-//               and are reduced through shared memory at the end
-//   accum_u     U_r = R_r^T M_r (B x L) for every resample r of a split,
-//               u_sum += U_r, u_square += U_r^2 kept in registers; one CTA per
-//               (64 columns of R, split of the resamples), two-slot cp.async
-//               ring over the resamples, partial sums reduced afterwards
+//   U_r = R_r^T M_r (B x L) for every resample r of a split,
+//   u_sum += U_r, u_square += U_r^2 kept in registers; one CTA per
+//   (column tile of R, split of the resamples), cp.async ring over the
+//   resamples, partial sums reduced afterwards (stream_kernels.cu).
 //
 // Shared-memory leading dimensions are == 4 or 12 (mod 16) doubles so that
 // every fragment load (8 x 4 doubles) is bank-conflict free.
@@ -41,121 +38,6 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
-}
-
-// ---- gram_proj ----------------------------------------------------------------
-constexpr int GD_THREADS = 512;
-constexpr int GD_WARPS = GD_THREADS / 32;
-
-// GD_BC = columns of R per stage (64 or 128)
-template <int MF, int GD_BC>
-__global__ void __launch_bounds__(GD_THREADS, 1)
-gram_proj_dmma_kernel(const double *__restrict__ R, long long ldr, int K, int B, int n_chunks,
-                      const double *__restrict__ Uo, int L, int LP, int ldu,
-                      double *__restrict__ G, double *__restrict__ H, int NG, int KG) {
-  extern __shared__ __align__(16) double sm[];
-  constexpr int KP = MF * 8;
-  constexpr int GD_LDR = GD_BC + 4;              // == 4 (mod 16)
-  const int stage = KP * GD_LDR + GD_BC * ldu;   // doubles per ring slot
-  const int NF = (KP + LP) / 8;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, q = lane & 3;
-  const int r = blockIdx.x;
-  const double *Rr = R + (size_t)r * K * ldr;
-
-  // zero the padding that the copies never touch: rows >= K of Rs, columns >= L of Us
-  for (int s = 0; s < 2; ++s) {
-    double *Rs = sm + s * stage, *Us = Rs + KP * GD_LDR;
-    for (int e = tid; e < (KP - K) * GD_LDR; e += GD_THREADS) Rs[K * GD_LDR + e] = 0.0;
-    if (LP > L)
-      for (int e = tid; e < GD_BC * (LP - L); e += GD_THREADS) {
-        const int b = e / (LP - L), l = L + e - b * (LP - L);
-        Us[b * ldu + l] = 0.0;
-      }
-  }
-
-  auto load = [&](int ch, int slot) {
-    double *Rs = sm + slot * stage, *Us = Rs + KP * GD_LDR;
-    const int b0 = ch * GD_BC;
-    for (int e = tid; e < K * (GD_BC / 2); e += GD_THREADS) {
-      const int c = e / (GD_BC / 2), seg = e - c * (GD_BC / 2);
-      cp_async16(Rs + c * GD_LDR + seg * 2, Rr + (size_t)c * ldr + b0 + seg * 2);
-    }
-    if (LP > 0)
-      for (int e = tid; e < GD_BC * L; e += GD_THREADS) {
-        const int b = e / L, l = e - b * L;
-        const bool ok = b0 + b < B;
-        cp_async8(Us + b * ldu + l, ok ? Uo + (size_t)(b0 + b) * L + l : Uo, ok ? 8 : 0);
-      }
-    cp_async_commit();
-  };
-
-  const int ng = warp % NG, kg = warp / NG;
-  const bool active = kg < KG;
-  double acc[MF][2][2];
-#pragma unroll
-  for (int i = 0; i < MF; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  load(0, 0);
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    if (ch + 1 < n_chunks) {
-      load(ch + 1, (ch + 1) & 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    if (active) {
-      const double *Rs = sm + (ch & 1) * stage, *Us = Rs + KP * GD_LDR;
-      for (int kk = kg; kk < GD_BC / 4; kk += KG) {
-        double a[MF];
-#pragma unroll
-        for (int i = 0; i < MF; ++i) a[i] = Rs[(i * 8 + g) * GD_LDR + kk * 4 + q];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int nf = ng * 2 + j;
-          if (nf < NF) {
-            const int col0 = nf * 8;
-            const double bv = col0 < KP ? Rs[(col0 + g) * GD_LDR + kk * 4 + q]
-                                        : Us[(kk * 4 + q) * ldu + (col0 - KP) + g];
-#pragma unroll
-            for (int i = 0; i < MF; ++i) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], bv);
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  // reduce the contraction groups through shared memory: red[kg][row][col]
-  const int NCP = NF * 8;
-  double *red = sm;
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int nf = ng * 2 + j;
-      if (nf < NF) {
-#pragma unroll
-        for (int i = 0; i < MF; ++i) {
-          double *p = red + ((size_t)kg * KP + i * 8 + g) * NCP + nf * 8 + 2 * q;
-          p[0] = acc[i][j][0];
-          p[1] = acc[i][j][1];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  for (int e = tid; e < K * NCP; e += GD_THREADS) {
-    const int row = e / NCP, col = e - row * NCP;
-    double v = 0.0;
-    for (int s = 0; s < KG; ++s) v += red[((size_t)s * KP + row) * NCP + col];
-    if (col < K)
-      G[((size_t)r * K + row) * K + col] = v;
-    else if (col >= KP && col - KP < L)
-      H[((size_t)r * K + row) * L + (col - KP)] = v;
-  }
 }
 
 // ---- accum_u ------------------------------------------------------------------
@@ -256,43 +138,6 @@ accum_u_dmma_kernel(const double *__restrict__ R, long long ldr, int count, int 
   (void)LP;
 }
 
-template <int MF, int BC>
-int launch_gp_bc(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
-                 const double *Uo, int L, int LP, double *G, double *H, size_t smem, int NG, int KG,
-                 cudaStream_t st) {
-  PLSB_CUDA(cudaFuncSetAttribute(gram_proj_dmma_kernel<MF, BC>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int n_chunks = (int)(ldr / BC);
-  gram_proj_dmma_kernel<MF, BC><<<count, GD_THREADS, smem, st>>>(R, ldr, K, B, n_chunks, Uo, L, LP,
-                                                                 LP + 4, G, H, NG, KG);
-  PLSB_LAUNCHED(h);
-  return PLSB_OK;
-}
-
-template <int MF>
-int launch_gp(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
-              const double *Uo, int L, int LP, double *G, double *H, cudaStream_t st) {
-  constexpr int KP = MF * 8;
-  const int ldu = LP + 4;
-  const int NF = (KP + LP) / 8;
-  const int NG = (NF + 1) / 2;
-  PLSB_CHECK(NG <= GD_WARPS, PLSB_ERR_ARG, "gram_proj: too many output fragments");
-  auto smem_for = [&](int bc, int kg) {
-    const size_t stage = (size_t)KP * (bc + 4) + (size_t)bc * ldu;
-    const size_t red = (size_t)kg * KP * NF * 8;
-    return sizeof(double) * std::max(2 * stage, red);
-  };
-  // 128-column stages (fewer barriers, better balance of the contraction
-  // groups) when two of them fit, else 64
-  const int KG128 = std::max(1, std::min(GD_WARPS / NG, 128 / 4));
-  if (ldr % 128 == 0 && smem_for(128, KG128) <= 200 * 1024)
-    return launch_gp_bc<MF, 128>(h, R, ldr, count, K, B, Uo, L, LP, G, H, smem_for(128, KG128), NG,
-                                 KG128, st);
-  const int KG64 = std::max(1, std::min(GD_WARPS / NG, 64 / 4));
-  return launch_gp_bc<MF, 64>(h, R, ldr, count, K, B, Uo, L, LP, G, H, smem_for(64, KG64), NG, KG64,
-                              st);
-}
-
 template <int NFL>
 int launch_au(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
               const double *M, int L, int n_bt, int n_splits, int per_split, double *Psum,
@@ -310,32 +155,6 @@ int launch_au(plsb_ctx *h, const double *R, long long ldr, int count, int K, int
 }
 
 }  // namespace
-
-// R must be a (count*K rows, ldr) buffer whose row pitch ldr is a multiple of 64
-// and whose columns >= B are zero (the GEMM's padded output).
-int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
-                     const double *Uo, int L, double *G, double *H, cudaStream_t st) {
-  KernelTimer kt(h, KC_GRAM, st);
-  if (count <= 0) return PLSB_OK;
-  PLSB_CHECK(K >= 1 && K <= MAX_K, PLSB_ERR_ARG, "gram_proj: K=%d outside [1,%d]", K, MAX_K);
-  PLSB_CHECK(ldr % 64 == 0, PLSB_ERR_ARG, "gram_proj: row pitch %lld not a multiple of 64", ldr);
-  const bool proj = Uo && H;
-  PLSB_CHECK(!proj || (L >= 1 && L <= MAX_K), PLSB_ERR_ARG, "gram_proj: L=%d", L);
-  const int LP = proj ? round_up(L, 8) : 0;
-  const int Lk = proj ? L : 0;
-  switch (cdiv(K, 8)) {
-    case 1: return launch_gp<1>(h, R, ldr, count, K, B, Uo, Lk, LP, G, H, st);
-    case 2: return launch_gp<2>(h, R, ldr, count, K, B, Uo, Lk, LP, G, H, st);
-    case 3: return launch_gp<3>(h, R, ldr, count, K, B, Uo, Lk, LP, G, H, st);
-    case 4: return launch_gp<4>(h, R, ldr, count, K, B, Uo, Lk, LP, G, H, st);
-    case 5: return launch_gp<5>(h, R, ldr, count, K, B, Uo, Lk, LP, G, H, st);
-    case 6: return launch_gp<6>(h, R, ldr, count, K, B, Uo, Lk, LP, G, H, st);
-    case 7: return launch_gp<7>(h, R, ldr, count, K, B, Uo, Lk, LP, G, H, st);
-    case 8: return launch_gp<8>(h, R, ldr, count, K, B, Uo, Lk, LP, G, H, st);
-    case 9: return launch_gp<9>(h, R, ldr, count, K, B, Uo, Lk, LP, G, H, st);
-    default: return launch_gp<10>(h, R, ldr, count, K, B, Uo, Lk, LP, G, H, st);
-  }
-}
 
 int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
                    const double *M, int L, double *usum, double *usq, cudaStream_t st) {
