@@ -180,6 +180,19 @@ int plsb_crosscov(plsb_handle_t h, const int32_t *d_idx, int count,
 int plsb_small_decomp(plsb_handle_t h, const double *d_G, const double *d_H,
                       int count, int K, int L, const double *d_dorig,
                       double *d_M, double *d_lam, void *stream);
+/* The two streaming contractions around it, on caller-supplied dense matrices
+ * (the engine runs them on its padded workspace; these entries serve tests):
+ * G[r] (K,K) = R[r] R[r]^T and, if d_Uo is given, H[r] (K,L) = R[r] U_orig for
+ * `count` matrices R[r] (K,B) -- the inputs of plsb_small_decomp
+ * (pyls/compute.py:36-49, 260). */
+int plsb_gram_proj(plsb_handle_t h, const double *d_R, int count, int K, int B,
+                   const double *d_Uo, int L, double *d_G, double *d_H,
+                   void *stream);
+/* u_sum (B,L) += sum_r R[r]^T M[r], u_square (B,L) += sum_r (R[r]^T M[r])^2
+ * (pyls/base.py:510-511 with the Procrustes rotation folded into M). */
+int plsb_accum_u(plsb_handle_t h, const double *d_R, int count, int K, int B,
+                 const double *d_M, int L, double *d_usum, double *d_usquare,
+                 void *stream);
 
 /* ---- SIMPLS (pls_regression; mode PLSB_SIMPLS, n_groups = 1, n_cond = 1) -------
  * plsb_set_data takes X (S,B) and Y (S,T) already column-centred

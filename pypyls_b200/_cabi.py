@@ -43,6 +43,8 @@ PROTOTYPES = {
     'plsb_dgemm': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     'plsb_crosscov': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'plsb_small_decomp': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'plsb_gram_proj': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    'plsb_accum_u': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     'plsb_timing_enable': (_i, [_vp, _i]),
     'plsb_timing_classes': (_i, []),
     'plsb_timing_class_name': (C.c_char_p, [_i]),

@@ -191,7 +191,7 @@ int plsb_destroy(plsb_handle_t h) {
   DevBuf *bufs[] = {&h->tables, &h->Xraw, &h->Xcell, &h->Xglob, &h->Y,    &h->Cmat,  &h->Uo,
                     &h->Vo,     &h->dorig, &h->Sx,   &h->norms, &h->A,    &h->Ac,    &h->R,
                     &h->S1,     &h->S2,   &h->G,     &h->H,     &h->M,    &h->lam,   &h->rowsq,
-                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps};
+                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT};
   for (DevBuf *b : bufs) b->release();
   delete h;
   return PLSB_OK;
@@ -428,6 +428,9 @@ int plsb_set_original(plsb_handle_t h, const double *d_U, const double *d_d, con
                               cudaMemcpyDeviceToDevice, st));
   if (d_d != h->dorig.p)
     PLSB_CUDA(cudaMemcpyAsync(h->dorig.p, d_d, sizeof(double) * l.L, cudaMemcpyDeviceToDevice, st));
+  // transposed zero-padded copy (L, ldx) for gram_proj's TMA row copies
+  PLSB_TRY(h->UoT.ensure(sizeof(double) * (size_t)l.L * l.ldx));
+  PLSB_TRY(launch_transpose_pad(h, h->Uo.as<double>(), l.B, l.L, h->UoT.as<double>(), l.ldx, st));
   // Sx = X @ normalize(U_orig)   (pyls/types/behavioral.py:78, meancentered.py:98)
   PLSB_TRY(launch_colnorm(h, h->Uo.as<double>(), l.B, l.L, h->norms.as<double>(), st));
   PLSB_TRY(launch_xproj(h, h->Xraw.as<double>(), l.ldx, l.S, l.B, h->Uo.as<double>(), l.L,
@@ -451,7 +454,7 @@ int plsb_decompose(plsb_handle_t h, double *d_U, double *d_d, double *d_V, void 
   double *lam1 = h->lam.as<double>(), *lam2 = lam1 + l.K;
   double *uraw = h->misc.as<double>(), *usq = uraw + bl;
   // pass 1: eigenvectors of the Gram matrix R R^T (accurate to eps * cond(R)^2)
-  PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, 1, l.K, l.B, nullptr, 0, G1, nullptr, st));
+  PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, 1, l.K, nullptr, 0, G1, nullptr, st));
   PLSB_TRY(launch_sym_eig(h, G1, 1, l.K, V1, lam1, 0, st));
   // pass 2 (refinement): W = R^T V1 is computed from R itself, its Gram matrix
   // W^T W is diagonal up to pass 1's error and graded, so a second Jacobi
@@ -558,7 +561,7 @@ int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, int rotate,
     const int n = std::min(chunk, count - off);
     PLSB_TRY(crosscov_chunk(h, d_idx + (size_t)off * l.S, n, false, nullptr, st));
     PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * l.K * l.K));
-    PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, n, l.K, l.B, nullptr, 0,
+    PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, n, l.K, nullptr, 0,
                               h->G.as<double>(), nullptr, st));
     PLSB_TRY(launch_sym_eig(h, h->G.as<double>(), n, l.K, nullptr, d_dperm + (size_t)off * l.L, 1,
                             st));
@@ -583,7 +586,7 @@ int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, double *d_d
     PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * l.K * l.K));
     PLSB_TRY(h->H.ensure(sizeof(double) * (size_t)n * l.K * l.L));
     PLSB_TRY(h->M.ensure(sizeof(double) * (size_t)n * l.K * l.L));
-    PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, n, l.K, l.B, h->Uo.as<double>(), l.L,
+    PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, n, l.K, h->UoT.as<double>(), l.L,
                               h->G.as<double>(), h->H.as<double>(), st));
     PLSB_TRY(launch_small_decomp(h, h->G.as<double>(), h->H.as<double>(), n, l.K, l.L,
                                  h->dorig.as<double>(), h->M.as<double>(), nullptr, st));
@@ -745,6 +748,42 @@ int plsb_small_decomp(plsb_handle_t h, const double *d_G, const double *d_H, int
   PLSB_HANDLE(h);
   PLSB_CHECK(d_G && d_H && d_M && count >= 0, PLSB_ERR_ARG, "plsb_small_decomp: bad argument");
   return launch_small_decomp(h, d_G, d_H, count, K, L, d_dorig, d_M, d_lam, as_stream(stream));
+}
+
+// pads count matrices (K,B) into the R workspace with a row pitch that is a multiple of 128
+static int pad_R(plsb_ctx *h, const double *d_R, int count, int K, int B, long long *ldr,
+                 cudaStream_t st) {
+  *ldr = round_up(B, GEMM_BN);
+  PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)count * K * (size_t)*ldr));
+  return launch_pad_copy(h, d_R, count * K, B, h->R.as<double>(), count * K, (int)*ldr, st);
+}
+
+int plsb_gram_proj(plsb_handle_t h, const double *d_R, int count, int K, int B, const double *d_Uo,
+                   int L, double *d_G, double *d_H, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_R && d_G && count >= 0 && K >= 1 && B >= 1 && (!d_Uo || (d_H && L >= 1)),
+             PLSB_ERR_ARG, "plsb_gram_proj: bad argument");
+  cudaStream_t st = as_stream(stream);
+  long long ldr = 0;
+  PLSB_TRY(pad_R(h, d_R, count, K, B, &ldr, st));
+  const double *uot = nullptr;
+  if (d_Uo) {
+    PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)L * ldr));
+    PLSB_TRY(launch_transpose_pad(h, d_Uo, B, L, h->misc.as<double>(), ldr, st));
+    uot = h->misc.as<double>();
+  }
+  return launch_gram_proj(h, h->R.as<double>(), ldr, count, K, uot, L, d_G, d_H, st);
+}
+
+int plsb_accum_u(plsb_handle_t h, const double *d_R, int count, int K, int B, const double *d_M,
+                 int L, double *d_usum, double *d_usquare, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_R && d_M && d_usum && d_usquare && count >= 0 && K >= 1 && B >= 1 && L >= 1,
+             PLSB_ERR_ARG, "plsb_accum_u: bad argument");
+  cudaStream_t st = as_stream(stream);
+  long long ldr = 0;
+  PLSB_TRY(pad_R(h, d_R, count, K, B, &ldr, st));
+  return launch_accum_u(h, h->R.as<double>(), ldr, count, K, B, d_M, L, d_usum, d_usquare, st);
 }
 
 }  // extern "C"

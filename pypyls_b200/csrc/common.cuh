@@ -150,6 +150,7 @@ struct plsb_ctx {
   plsb::DevBuf Cmat;   // mean-centred: operator C (J, S)
   // original decomposition
   plsb::DevBuf Uo;     // (B, L)
+  plsb::DevBuf UoT;    // Uo transposed, (L, ldx) zero padded: gram_proj's TMA row copies
   plsb::DevBuf Vo;     // (K, L)
   plsb::DevBuf dorig;  // (L)
   plsb::DevBuf Sx;     // Xraw @ normalize(Uo)   (S, L)
@@ -237,8 +238,8 @@ int launch_finish_rowsq(plsb_ctx *h, const double *rowsq, int n_splits, int M_pa
                         double *out, cudaStream_t st);
 int launch_colscale(plsb_ctx *h, double *S1, const double *S2, int n_rows, long long ld,
                     cudaStream_t st);
-int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
-                     const double *Uo, int L, double *G, double *H, cudaStream_t st);
+int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K,
+                     const double *UoT, int L, double *G, double *H, cudaStream_t st);
 int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
                    const double *M, int L, double *usum, double *usq, cudaStream_t st);
 
@@ -254,6 +255,9 @@ int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit
                   double *distrib, cudaStream_t st);
 int launch_transpose(plsb_ctx *h, const double *in, int rows, int cols, int ld_in, double *out,
                      cudaStream_t st);
+// out (cols, ld_out) = in (rows, cols)^T, columns >= rows of out zeroed
+int launch_transpose_pad(plsb_ctx *h, const double *in, int rows, int cols, double *out,
+                         long long ld_out, cudaStream_t st);
 int launch_identity_blocks(plsb_ctx *h, double *M, int n, int L, cudaStream_t st);
 int launch_xweights_flip(plsb_ctx *h, const double *Rw, long long ldr, int B, int L, double *xw,
                          cudaStream_t st);

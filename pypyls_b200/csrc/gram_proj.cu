@@ -15,13 +15,20 @@
 //     4 (except for K > 56), so the four warps that share an SM sub-partition's
 //     DMMA pipe are the same slice of each group and the sub-partitions are
 //     balanced whatever the group sizes are;
-//   * R and U_orig tiles of BC columns are staged by cp.async through a ring
-//     of `nslot` slots (as many as fit shared memory), one barrier per stage;
+//   * U_orig is kept transposed (L rows of ldr doubles), so a stage is one tile
+//     of K + L rows x BC columns of [R; U_orig^T] and H = R (U_orig^T)^T has the
+//     same fragment addressing as G = R R^T.  The tiles are staged by TMA bulk
+//     copies (one cp.async.bulk per tile row, so that the rows keep a
+//     bank-conflict-free pitch) through a ring of `nslot` slots; a full / empty mbarrier pair per
+//     slot replaces CTA-wide barriers: a warp only waits for the stage it reads
+//     and may run one stage ahead of the slowest warp.  The copies of a stage
+//     are issued by the first K + BC threads (one row each) once every warp has
+//     released the slot;
 //   * the slices are reduced pairwise through shared memory at the end (fixed
 //     order: results are bit-reproducible).
 //
-// Shared-memory leading dimensions are == 4 or 12 (mod 16) doubles so that
-// every fragment load (8 x 4 doubles) is bank-conflict free.
+// The shared-memory row pitch is == 4 (mod 16) doubles so that every fragment
+// load (8 rows x 4 doubles) is bank-conflict free.
 #include "common.cuh"
 
 #include <type_traits>
@@ -29,19 +36,41 @@
 namespace plsb {
 namespace {
 
-__device__ __forceinline__ void cp_async16z(void *smem, const void *gmem, int src_bytes) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem),
-               "r"(src_bytes));
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void cp_async8z(void *smem, const void *gmem, int src_bytes) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem),
-               "r"(src_bytes));
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
   asm volatile(
@@ -100,8 +129,7 @@ constexpr int GP_WARPS = 16;
 template <int MF, int MFH, int BC, int NG> struct GpCfg {
   static constexpr int KP = MF * 8, LP = MFH * 8;
   static constexpr int LDR = BC + 4;                 // == 4 (mod 16)
-  static constexpr int LDU = LP + 4;                 // == 4 or 12 (mod 16)
-  static constexpr int STAGE = KP * LDR + BC * LDU;  // doubles per ring slot
+  static constexpr int STAGE = (KP + LP) * LDR;      // doubles per ring slot: [R; U_orig^T] tile
   static constexpr int FT = tri_count(MF) + MF * MFH;
   static constexpr int FPG = (FT + NG - 1) / NG;     // fragments per warp group
   static constexpr int KGW = GP_WARPS / NG;          // contraction slices per group
@@ -113,10 +141,9 @@ template <int MF, int MFH, int BC, int NG> struct GpCfg {
 };
 
 // one stage of DMMA work of warp group GID
-template <int MF, int MFH, int BC, int NG, int GID>
+template <int MF, int MFH, int BC, int NG, int GID, bool RAGGED>
 __device__ __forceinline__ void gp_compute(double (&acc)[GpCfg<MF, MFH, BC, NG>::FPG][2],
-                                           const double *Rs, const double *Us, int kg, int g,
-                                           int q) {
+                                           const double *Rs, int kg, int g, int q, int kvalid) {
   using C = GpCfg<MF, MFH, BC, NG>;
   constexpr int F0 = GID * C::FPG < C::FT ? GID * C::FPG : C::FT;
   constexpr int F1 = F0 + C::FPG < C::FT ? F0 + C::FPG : C::FT;
@@ -124,8 +151,9 @@ __device__ __forceinline__ void gp_compute(double (&acc)[GpCfg<MF, MFH, BC, NG>:
 #pragma unroll
     for (int kk = 0; kk < C::KKW; ++kk) {
       const int k0 = (kk * C::KGW + kg) * 4;
+      if (RAGGED && k0 >= kvalid) break;   // last stage of a row pitch that BC does not divide
       const double *ap = Rs + g * C::LDR + k0 + q;
-      const double *bp = Us + (k0 + q) * C::LDU + g;
+      const double *bp = ap + C::KP * C::LDR;      // rows of U_orig^T
       double a[MF], bh[MFH > 0 ? MFH : 1];
       static_for<0, MF>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
@@ -133,7 +161,7 @@ __device__ __forceinline__ void gp_compute(double (&acc)[GpCfg<MF, MFH, BC, NG>:
       });
       static_for<0, MFH>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
-        if constexpr (need_h(MF, F0, F1, j)) bh[j] = bp[j * 8];
+        if constexpr (need_h(MF, F0, F1, j)) bh[j] = bp[j * 8 * C::LDR];
       });
       static_for<F0, F1>([&](auto fc) {
         constexpr int f = decltype(fc)::value;
@@ -179,85 +207,79 @@ __device__ __forceinline__ void gp_store(const double (&acc)[GpCfg<MF, MFH, BC, 
   });
 }
 
+constexpr int GP_MAX_SLOTS = 8;
+
 template <int MF, int MFH, int BC, int NG>
 __global__ void __launch_bounds__(GP_THREADS, 1)
-gram_proj_kernel(const double *__restrict__ R, long long ldr, int K, int B, int n_chunks,
-                 int nslot, const double *__restrict__ Uo, int L, double *__restrict__ G,
+gram_proj_kernel(const double *__restrict__ R, long long ldr, int K, int n_chunks, int nslot,
+                 const double *__restrict__ UoT, int L, double *__restrict__ G,
                  double *__restrict__ H) {
   using C = GpCfg<MF, MFH, BC, NG>;
   extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) uint64_t full_bar[GP_MAX_SLOTS], empty_bar[GP_MAX_SLOTS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, q = lane & 3;
   const int ng = warp / C::KGW, kg = warp % C::KGW;
   const int r = blockIdx.x;
-  const double *Rr = R + (size_t)r * K * ldr;
 
-  // zero the padding that the copies never touch: rows >= K of Rs, columns >= L of Us
-  for (int s = 0; s < nslot; ++s) {
-    double *Rs = sm + (size_t)s * C::STAGE, *Us = Rs + C::KP * C::LDR;
-    for (int e = tid; e < (C::KP - K) * C::LDR; e += GP_THREADS) Rs[K * C::LDR + e] = 0.0;
-    if (C::LP > L)
-      for (int e = tid; e < BC * (C::LP - L); e += GP_THREADS) {
-        const int b = e / (C::LP - L), l = L + e - b * (C::LP - L);
-        Us[b * C::LDU + l] = 0.0;
-      }
-  }
-
-  const bool l_even = (L & 1) == 0;
-  auto load = [&](int ch) {
-    if (ch < n_chunks) {
-      double *Rs = sm + (size_t)(ch % nslot) * C::STAGE, *Us = Rs + C::KP * C::LDR;
-      const int b0 = ch * BC;
-      for (int e = tid; e < K * (BC / 2); e += GP_THREADS) {
-        const int c = e / (BC / 2), seg = e - c * (BC / 2);
-        const bool ok = b0 + seg * 2 < ldr;
-        cp_async16z(Rs + c * C::LDR + seg * 2, ok ? Rr + (size_t)c * ldr + b0 + seg * 2 : Rr,
-                    ok ? 16 : 0);
-      }
-      if (MFH > 0) {
-        if (l_even) {
-          const int hl = L >> 1;
-          for (int e = tid; e < BC * hl; e += GP_THREADS) {
-            const int b = e / hl, l = (e - b * hl) * 2;
-            const bool ok = b0 + b < B;
-            cp_async16z(Us + b * C::LDU + l, ok ? Uo + (size_t)(b0 + b) * L + l : Uo, ok ? 16 : 0);
-          }
-        } else {
-          for (int e = tid; e < BC * L; e += GP_THREADS) {
-            const int b = e / L, l = e - b * L;
-            const bool ok = b0 + b < B;
-            cp_async8z(Us + b * C::LDU + l, ok ? Uo + (size_t)(b0 + b) * L + l : Uo, ok ? 8 : 0);
-          }
-        }
-      }
+  // zero the ring once: the padding rows (>= K, >= L) are never written by the copies
+  for (int e = tid; e < nslot * C::STAGE; e += GP_THREADS) sm[e] = 0.0;
+  // copy duty: one row of the [R; U_orig^T] tile per stage and thread
+  const int n_copy = K + (MFH > 0 ? L : 0);
+  if (tid == 0) {
+    for (int s = 0; s < nslot; ++s) {
+      mbar_init(&full_bar[s], n_copy);   // every copying thread arrives with its byte count
+      mbar_init(&empty_bar[s], GP_WARPS);
     }
-    cp_async_commit();
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  // the zeros (generic proxy) must be ordered before the TMA writes (async proxy)
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncthreads();
+
+  const bool issuer = tid < n_copy;
+  const bool issuer_warp = warp * 32 < n_copy;
+  const double *c_src = tid < K ? R + ((size_t)r * K + tid) * ldr : UoT + (size_t)(tid - K) * ldr;
+  const int c_dst = (tid < K ? tid : C::KP + (tid - K)) * C::LDR;   // doubles from the slot start
+  auto issue = [&](int ch) {          // stage ch -> slot ch % nslot
+    if (issuer) {
+      const int slot = ch % nslot;
+      const long long b0 = (long long)ch * BC;
+      const unsigned bytes = (unsigned)sizeof(double) * (unsigned)min((long long)BC, ldr - b0);
+      mbar_arrive_expect_tx(&full_bar[slot], bytes);
+      tma_load_1d(sm + (size_t)slot * C::STAGE + c_dst, c_src + b0, bytes, &full_bar[slot]);
+    }
   };
 
   double acc[C::FPG][2];
 #pragma unroll
   for (int f = 0; f < C::FPG; ++f) acc[f][0] = acc[f][1] = 0.0;
 
-  for (int s = 0; s < nslot - 1; ++s) load(s);
+  if (issuer_warp)
+    for (int s = 0; s < nslot - 1 && s < n_chunks; ++s) issue(s);
   for (int ch = 0; ch < n_chunks; ++ch) {
-    // groups committed so far: ch + nslot - 1; stage ch has landed when at most
-    // nslot - 2 of the most recent ones are pending
-    switch (nslot) {
-      case 2: cp_async_wait<0>(); break;
-      case 3: cp_async_wait<1>(); break;
-      case 4: cp_async_wait<2>(); break;
-      case 5: cp_async_wait<3>(); break;
-      default: cp_async_wait<4>(); break;
+    // refill the slot of stage ch - 1 with stage ch + nslot - 1 once every warp released it
+    const int rf = ch + nslot - 1;
+    if (issuer_warp && rf < n_chunks) {
+      if (ch >= 1) mbar_wait(&empty_bar[(ch - 1) % nslot], ((ch - 1) / nslot) & 1);
+      issue(rf);
     }
-    __syncthreads();
-    load(ch + nslot - 1);   // refills the slot consumed in the previous iteration
-    const double *Rs = sm + (size_t)(ch % nslot) * C::STAGE, *Us = Rs + C::KP * C::LDR;
+    const int slot = ch % nslot;
+    mbar_wait(&full_bar[slot], (ch / nslot) & 1);
+    const double *Rs = sm + (size_t)slot * C::STAGE;
+    const int kvalid = (int)min((long long)BC, ldr - (long long)ch * BC);
     static_for<0, NG>([&](auto gc) {
       constexpr int GID = decltype(gc)::value;
-      if (ng == GID) gp_compute<MF, MFH, BC, NG, GID>(acc, Rs, Us, kg, g, q);
+      if (ng == GID) {
+        if (kvalid == BC)
+          gp_compute<MF, MFH, BC, NG, GID, false>(acc, Rs, kg, g, q, kvalid);
+        else
+          gp_compute<MF, MFH, BC, NG, GID, true>(acc, Rs, kg, g, q, kvalid);
+      }
     });
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[slot]);
   }
-  cp_async_wait<0>();
   __syncthreads();
 
   // pairwise reduction of the contraction slices: slices [s, 2s) hand their
@@ -292,22 +314,24 @@ gram_proj_kernel(const double *__restrict__ R, long long ldr, int K, int B, int 
   }
 }
 
-constexpr size_t GP_SMEM_MAX = 227 * 1024;
+constexpr size_t GP_SMEM_MAX = 226 * 1024;   // + the static mbarrier arrays
 
 template <int MF, int MFH, int BC, int NG>
-int launch_cfg(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
-               const double *Uo, int L, double *G, double *H, cudaStream_t st) {
+int launch_cfg(plsb_ctx *h, const double *R, long long ldr, int count, int K, const double *UoT,
+               int L, double *G, double *H, cudaStream_t st) {
   using C = GpCfg<MF, MFH, BC, NG>;
   const size_t stage = sizeof(double) * C::STAGE;
   const size_t red = sizeof(double2) * 32 * C::FPG * (GP_WARPS / 2);
+  PLSB_CHECK(ldr % 4 == 0, PLSB_ERR_ARG, "gram_proj: row pitch %lld not a multiple of 4", ldr);
   const int n_chunks = (int)((ldr + BC - 1) / BC);
-  int nslot = (int)std::min<size_t>(6, GP_SMEM_MAX / stage);
+  int nslot = (int)std::min<size_t>(GP_MAX_SLOTS, GP_SMEM_MAX / stage);
   nslot = std::max(2, std::min(nslot, n_chunks + 1));
+  nslot = tune_int("PLSB_GP_SLOTS", nslot);
   const size_t smem = std::max(stage * nslot, red);
   PLSB_CHECK(smem <= GP_SMEM_MAX, PLSB_ERR_ARG, "gram_proj: %zu bytes of shared memory", smem);
   auto kern = gram_proj_kernel<MF, MFH, BC, NG>;
   PLSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<count, GP_THREADS, smem, st>>>(R, ldr, K, B, n_chunks, nslot, Uo, L, G, H);
+  kern<<<count, GP_THREADS, smem, st>>>(R, ldr, K, n_chunks, nslot, UoT, L, G, H);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
@@ -315,53 +339,55 @@ int launch_cfg(plsb_ctx *h, const double *R, long long ldr, int count, int K, in
 // stage width / group count per problem size: enough DMMA work between two
 // barriers, as many bytes in flight as shared memory allows
 template <int MF, int MFH>
-int launch_mf(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
-              const double *Uo, int L, double *G, double *H, cudaStream_t st) {
+int launch_mf(plsb_ctx *h, const double *R, long long ldr, int count, int K, const double *UoT,
+              int L, double *G, double *H, cudaStream_t st) {
+  // ~40-70 KB per stage: enough DMMA work per mbarrier round trip, >= 3 slots in flight
   constexpr int FT = tri_count(MF) + MF * MFH;
+  constexpr int ROWS = (MF + MFH) * 8;
   if constexpr (FT <= 4)
-    return launch_cfg<MF, MFH, 256, 1>(h, R, ldr, count, K, B, Uo, L, G, H, st);
+    return launch_cfg<MF, MFH, (ROWS <= 16 ? 512 : 256), 1>(h, R, ldr, count, K, UoT, L, G, H, st);
   else if constexpr (FT <= 12)
-    return launch_cfg<MF, MFH, 256, 2>(h, R, ldr, count, K, B, Uo, L, G, H, st);
-  else if constexpr (MF <= 3)
-    return launch_cfg<MF, MFH, 128, 4>(h, R, ldr, count, K, B, Uo, L, G, H, st);
-  else if constexpr (MF <= 7)
-    return launch_cfg<MF, MFH, 64, 4>(h, R, ldr, count, K, B, Uo, L, G, H, st);
+    return launch_cfg<MF, MFH, 256, 2>(h, R, ldr, count, K, UoT, L, G, H, st);
+  else if constexpr (ROWS <= 48)
+    return launch_cfg<MF, MFH, 128, 4>(h, R, ldr, count, K, UoT, L, G, H, st);
+  else if constexpr (ROWS <= 112)
+    return launch_cfg<MF, MFH, 64, 4>(h, R, ldr, count, K, UoT, L, G, H, st);
   else
-    return launch_cfg<MF, MFH, 32, 8>(h, R, ldr, count, K, B, Uo, L, G, H, st);
+    return launch_cfg<MF, MFH, 32, 8>(h, R, ldr, count, K, UoT, L, G, H, st);
 }
 
 template <int MF>
-int launch_proj(plsb_ctx *h, bool proj, const double *R, long long ldr, int count, int K, int B,
-                const double *Uo, int L, double *G, double *H, cudaStream_t st) {
-  if (proj) return launch_mf<MF, MF>(h, R, ldr, count, K, B, Uo, L, G, H, st);
-  return launch_mf<MF, 0>(h, R, ldr, count, K, B, nullptr, 0, G, nullptr, st);
+int launch_proj(plsb_ctx *h, bool proj, const double *R, long long ldr, int count, int K,
+                const double *UoT, int L, double *G, double *H, cudaStream_t st) {
+  if (proj) return launch_mf<MF, MF>(h, R, ldr, count, K, UoT, L, G, H, st);
+  return launch_mf<MF, 0>(h, R, ldr, count, K, nullptr, 0, G, nullptr, st);
 }
 
 }  // namespace
 
-// R must be a (count*K rows, ldr) buffer whose row pitch ldr is even and whose
-// columns >= B are zero (the GEMM's padded output).  Uo (B, L) needs L == K
-// rounded to the same number of 8-column fragments (the engine has L == K).
-int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
-                     const double *Uo, int L, double *G, double *H, cudaStream_t st) {
+// R must be a (count*K rows, ldr) buffer whose row pitch ldr is a multiple of 4
+// and whose columns >= B are zero (the GEMM's padded output).  UoT is U_orig
+// transposed, (L rows, ldr) with zero columns >= B; L and K must span the same
+// number of 8-column fragments (the engine has L == K); null: G only.
+int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K,
+                     const double *UoT, int L, double *G, double *H, cudaStream_t st) {
   KernelTimer kt(h, KC_GRAM, st);
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(K >= 1 && K <= MAX_K, PLSB_ERR_ARG, "gram_proj: K=%d outside [1,%d]", K, MAX_K);
-  PLSB_CHECK(ldr % 2 == 0 && ldr >= B, PLSB_ERR_ARG, "gram_proj: bad row pitch %lld", ldr);
-  const bool proj = Uo && H;
+  const bool proj = UoT && H;
   PLSB_CHECK(!proj || cdiv(L, 8) == cdiv(K, 8), PLSB_ERR_ARG,
              "gram_proj: L=%d and K=%d must span the same number of fragments", L, K);
   switch (cdiv(K, 8)) {
-    case 1: return launch_proj<1>(h, proj, R, ldr, count, K, B, Uo, L, G, H, st);
-    case 2: return launch_proj<2>(h, proj, R, ldr, count, K, B, Uo, L, G, H, st);
-    case 3: return launch_proj<3>(h, proj, R, ldr, count, K, B, Uo, L, G, H, st);
-    case 4: return launch_proj<4>(h, proj, R, ldr, count, K, B, Uo, L, G, H, st);
-    case 5: return launch_proj<5>(h, proj, R, ldr, count, K, B, Uo, L, G, H, st);
-    case 6: return launch_proj<6>(h, proj, R, ldr, count, K, B, Uo, L, G, H, st);
-    case 7: return launch_proj<7>(h, proj, R, ldr, count, K, B, Uo, L, G, H, st);
-    case 8: return launch_proj<8>(h, proj, R, ldr, count, K, B, Uo, L, G, H, st);
-    case 9: return launch_proj<9>(h, proj, R, ldr, count, K, B, Uo, L, G, H, st);
-    default: return launch_proj<10>(h, proj, R, ldr, count, K, B, Uo, L, G, H, st);
+    case 1: return launch_proj<1>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
+    case 2: return launch_proj<2>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
+    case 3: return launch_proj<3>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
+    case 4: return launch_proj<4>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
+    case 5: return launch_proj<5>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
+    case 6: return launch_proj<6>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
+    case 7: return launch_proj<7>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
+    case 8: return launch_proj<8>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
+    case 9: return launch_proj<9>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
+    default: return launch_proj<10>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
   }
 }
 

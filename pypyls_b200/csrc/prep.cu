@@ -25,6 +25,25 @@ __global__ void pad_copy_kernel(const double *__restrict__ X, int S, int B,
   }
 }
 
+// out (cols, ld_out) = in (rows, cols)^T through a 32 x 32 tile; columns >= rows of out zeroed
+__global__ void transpose_pad_kernel(const double *__restrict__ in, int rows, int cols,
+                                     double *__restrict__ out, long long ld_out) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.y * 32;
+  const long long r0 = (long long)blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long r = r0 + threadIdx.x;
+    if (c < cols && r < ld_out) out[(size_t)c * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+
 __global__ void unpad_copy_kernel(const double *__restrict__ in, long long ld_in, int rows,
                                   int cols, double *__restrict__ out) {
   const size_t total = (size_t)rows * cols;
@@ -227,6 +246,16 @@ int launch_pad_copy(plsb_ctx *h, const double *X, int S, int B, double *out, int
   const size_t total = (size_t)S_pad * ldx;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 16);
   pad_copy_kernel<<<blocks, 256, 0, st>>>(X, S, B, out, S_pad, ldx);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
+int launch_transpose_pad(plsb_ctx *h, const double *in, int rows, int cols, double *out,
+                         long long ld_out, cudaStream_t st) {
+  KernelTimer kt(h, KC_PREP, st);
+  if (cols <= 0 || ld_out <= 0) return PLSB_OK;
+  dim3 grid((unsigned)((ld_out + 31) / 32), (unsigned)cdiv(cols, 32)), block(32, 8);
+  transpose_pad_kernel<<<grid, block, 0, st>>>(in, rows, cols, out, ld_out);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }

@@ -365,6 +365,32 @@ class ResamplingEngine:
             _ptr(lam), self._stream()))
         return M, lam
 
+    def gram_proj(self, R, Uo=None):
+        """G[r] = R[r] R[r]^T and H[r] = R[r] Uo for a stack R (n, K, B)."""
+        R = self.to_device(R)
+        n, K, B = (int(x) for x in R.shape)
+        Uo = None if Uo is None else self.to_device(Uo)
+        L = 0 if Uo is None else int(Uo.shape[1])
+        G = self._f64(n, K, K)
+        H = None if Uo is None else self._f64(n, K, L)
+        _cabi.check(self._lib.plsb_gram_proj(
+            self._h, _ptr(R), n, K, B, _ptr(Uo), L, _ptr(G), _ptr(H),
+            self._stream()))
+        return G, H
+
+    def accum_u(self, R, M):
+        """sum_r R[r]^T M[r] and sum_r (R[r]^T M[r])^2 for stacks R (n, K, B),
+        M (n, K, L)."""
+        R, M = self.to_device(R), self.to_device(M)
+        n, K, B = (int(x) for x in R.shape)
+        L = int(M.shape[2])
+        us = torch.zeros((B, L), dtype=torch.float64, device=self.device)
+        uq = torch.zeros_like(us)
+        _cabi.check(self._lib.plsb_accum_u(
+            self._h, _ptr(R), n, K, B, _ptr(M), L, _ptr(us), _ptr(uq),
+            self._stream()))
+        return us, uq
+
     # -- per-kernel-class timing (bench) ---------------------------------------
     def timing_enable(self, on=True):
         _cabi.check(self._lib.plsb_timing_enable(self._h, int(bool(on))))

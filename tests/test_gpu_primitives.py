@@ -77,6 +77,33 @@ def test_small_decomp_matches_lapack(torch_cuda, K):
         assert rel_err(got, want) < 1e-9, (K, r, rel_err(got, want))
 
 
+@pytest.mark.parametrize('K', [1, 2, 3, 7, 8, 9, 10, 16, 17, 24, 25, 33, 40, 41,
+                               48, 49, 57, 64, 65, 73, 80])
+@pytest.mark.parametrize('B', [50, 128, 777])
+def test_gram_proj_and_accum_u_match_numpy(torch_cuda, K, B):
+    """The two streaming DMMA contractions around the small decomposition, for
+    every fragment count (K / 8) and for column counts that are not multiples
+    of the stage width."""
+    rs = np.random.RandomState(1000 * K + B)
+    n = 5
+    eng = make_engine('behavioral', 4, 8, 1, [4])
+    Rs = rs.randn(n, K, B)
+    Uo = rs.randn(B, K)
+    G, H = eng.gram_proj(Rs, Uo)
+    G, H = G.cpu().numpy(), H.cpu().numpy()
+    wantG = np.einsum('rkb,rjb->rkj', Rs, Rs)
+    assert rel_err(G, wantG) < 1e-13
+    assert np.array_equal(G, G.transpose(0, 2, 1))       # exactly symmetric
+    assert rel_err(H, np.einsum('rkb,bl->rkl', Rs, Uo)) < 1e-13
+    G2, H2 = eng.gram_proj(Rs)                            # Gram matrix only
+    assert H2 is None and rel_err(G2.cpu().numpy(), wantG) < 1e-13
+    M = rs.randn(n, K, K)
+    us, uq = eng.accum_u(Rs, M)
+    U = np.einsum('rkb,rkl->rbl', Rs, M)
+    assert rel_err(us.cpu().numpy(), U.sum(0)) < 1e-12
+    assert rel_err(uq.cpu().numpy(), (U ** 2).sum(0)) < 1e-12
+
+
 def test_small_decomp_rank_deficient(torch_cuda):
     """A numerically null direction (mean-centred PLS always has one) must
     not poison the other latent variables."""
