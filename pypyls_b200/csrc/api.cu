@@ -460,13 +460,18 @@ int plsb_decompose(plsb_handle_t h, double *d_U, double *d_d, double *d_V, void 
   // W^T W is diagonal up to pass 1's error and graded, so a second Jacobi
   // recovers the small singular directions to working precision
   PLSB_CUDA(cudaMemsetAsync(uraw, 0, sizeof(double) * 2 * bl, st));
-  PLSB_TRY(launch_accum_u(h, h->R.as<double>(), l.ldx, 1, l.K, l.B, V1, l.L, uraw, usq, st));
+  const int ldm = accum_ldm(l.L);
+  PLSB_TRY(h->M.ensure(sizeof(double) * (size_t)l.K * ldm));
+  double *Mp = h->M.as<double>();   // rotation in accum_u's padded layout
+  PLSB_TRY(launch_pad_copy(h, V1, l.K, l.L, Mp, l.K, ldm, st));
+  PLSB_TRY(launch_accum_u(h, h->R.as<double>(), l.ldx, 1, l.K, l.B, Mp, l.L, uraw, usq, st));
   PLSB_TRY(launch_colgram(h, uraw, l.B, l.K, G2, st));
   PLSB_TRY(launch_sym_eig(h, G2, 1, l.K, V2, lam2, 0, st));
   PLSB_TRY(launch_matmul_small(h, V1, V2, l.K, d_V, st));
   // U d = R^T V, then column norms / signs (sklearn svd_flip on the B-side factor)
   PLSB_CUDA(cudaMemsetAsync(uraw, 0, sizeof(double) * 2 * bl, st));
-  PLSB_TRY(launch_accum_u(h, h->R.as<double>(), l.ldx, 1, l.K, l.B, d_V, l.L, uraw, usq, st));
+  PLSB_TRY(launch_pad_copy(h, d_V, l.K, l.L, Mp, l.K, ldm, st));
+  PLSB_TRY(launch_accum_u(h, h->R.as<double>(), l.ldx, 1, l.K, l.B, Mp, l.L, uraw, usq, st));
   PLSB_TRY(launch_normalize_flip(h, uraw, l.B, l.L, lam2, d_U, d_V, l.K, d_d, st));
   return plsb_set_original(h, d_U, d_d, d_V, stream);
 }
@@ -585,11 +590,12 @@ int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, double *d_d
                             d_distrib + (size_t)off * l.K * l.L, st));
     PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * l.K * l.K));
     PLSB_TRY(h->H.ensure(sizeof(double) * (size_t)n * l.K * l.L));
-    PLSB_TRY(h->M.ensure(sizeof(double) * (size_t)n * l.K * l.L));
+    const int ldm = accum_ldm(l.L);
+    PLSB_TRY(h->M.ensure(sizeof(double) * (size_t)n * l.K * ldm));
     PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, n, l.K, h->UoT.as<double>(), l.L,
                               h->G.as<double>(), h->H.as<double>(), st));
     PLSB_TRY(launch_small_decomp(h, h->G.as<double>(), h->H.as<double>(), n, l.K, l.L,
-                                 h->dorig.as<double>(), h->M.as<double>(), nullptr, st));
+                                 h->dorig.as<double>(), h->M.as<double>(), ldm, nullptr, st));
     PLSB_TRY(launch_accum_u(h, h->R.as<double>(), l.ldx, n, l.K, l.B, h->M.as<double>(), l.L,
                             d_usum, d_usquare, st));
   }
@@ -735,8 +741,8 @@ int plsb_simpls_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, cons
     PLSB_TRY(simpls_weights_gemm(h, n, st));
     // u_sum += x_weights_r, u_square += x_weights_r^2 (pyls/base.py:510-511): the shared
     // accumulation kernel with identity rotations
-    PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)n * l.L * l.L));
-    PLSB_TRY(launch_identity_blocks(h, h->misc.as<double>(), n, l.L, st));
+    PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)n * l.L * accum_ldm(l.L)));
+    PLSB_TRY(launch_identity_blocks(h, h->misc.as<double>(), n, l.L, accum_ldm(l.L), st));
     PLSB_TRY(launch_accum_u(h, h->R.as<double>(), l.ldx, n, l.L, l.B, h->misc.as<double>(), l.L,
                             d_usum, d_usquare, st));
   }
@@ -747,7 +753,7 @@ int plsb_small_decomp(plsb_handle_t h, const double *d_G, const double *d_H, int
                       int L, const double *d_dorig, double *d_M, double *d_lam, void *stream) {
   PLSB_HANDLE(h);
   PLSB_CHECK(d_G && d_H && d_M && count >= 0, PLSB_ERR_ARG, "plsb_small_decomp: bad argument");
-  return launch_small_decomp(h, d_G, d_H, count, K, L, d_dorig, d_M, d_lam, as_stream(stream));
+  return launch_small_decomp(h, d_G, d_H, count, K, L, d_dorig, d_M, L, d_lam, as_stream(stream));
 }
 
 // pads count matrices (K,B) into the R workspace with a row pitch that is a multiple of 128
@@ -783,7 +789,11 @@ int plsb_accum_u(plsb_handle_t h, const double *d_R, int count, int K, int B, co
   cudaStream_t st = as_stream(stream);
   long long ldr = 0;
   PLSB_TRY(pad_R(h, d_R, count, K, B, &ldr, st));
-  return launch_accum_u(h, h->R.as<double>(), ldr, count, K, B, d_M, L, d_usum, d_usquare, st);
+  const int ldm = accum_ldm(L);
+  PLSB_TRY(h->M.ensure(sizeof(double) * (size_t)count * K * ldm));
+  PLSB_TRY(launch_pad_copy(h, d_M, count * K, L, h->M.as<double>(), count * K, ldm, st));
+  return launch_accum_u(h, h->R.as<double>(), ldr, count, K, B, h->M.as<double>(), L, d_usum,
+                        d_usquare, st);
 }
 
 }  // extern "C"

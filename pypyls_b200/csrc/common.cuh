@@ -82,6 +82,9 @@ inline int tune_int(const char *name, int dflt) {
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline long long round_up_ll(long long x, long long m) { return (x + m - 1) / m * m; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// row pitch (doubles) of the rotation matrices M (count, K, pitch) that accum_u streams:
+// the bank-conflict-free shared-memory pitch, so one bulk copy moves a whole matrix
+inline int accum_ldm(int L) { return round_up(L, 8) + 4; }
 
 // ---- GEMM tile geometry (gemm_dmma.cu) --------------------------------------
 constexpr int GEMM_BM = 128;
@@ -244,8 +247,9 @@ int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K
                    const double *M, int L, double *usum, double *usq, cudaStream_t st);
 
 // small matrices (small_matrix.cu)
+// M is written as (count, K, ldm): ldm == L dense, ldm == accum_ldm(L) for launch_accum_u
 int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count, int K, int L,
-                        const double *dorig, double *M, double *lam, cudaStream_t st);
+                        const double *dorig, double *M, int ldm, double *lam, cudaStream_t st);
 int launch_sym_eig(plsb_ctx *h, const double *G, int count, int K, double *V, double *lam,
                    int sqrt_lam, cudaStream_t st);
 
@@ -258,7 +262,7 @@ int launch_transpose(plsb_ctx *h, const double *in, int rows, int cols, int ld_i
 // out (cols, ld_out) = in (rows, cols)^T, columns >= rows of out zeroed
 int launch_transpose_pad(plsb_ctx *h, const double *in, int rows, int cols, double *out,
                          long long ld_out, cudaStream_t st);
-int launch_identity_blocks(plsb_ctx *h, double *M, int n, int L, cudaStream_t st);
+int launch_identity_blocks(plsb_ctx *h, double *M, int n, int L, int ldm, cudaStream_t st);
 int launch_xweights_flip(plsb_ctx *h, const double *Rw, long long ldr, int B, int L, double *xw,
                          cudaStream_t st);
 int launch_colcenter(plsb_ctx *h, const double *U, int B, int L, double *out, cudaStream_t st);

@@ -550,11 +550,11 @@ __global__ void colcenter_kernel(const double *__restrict__ U, int B, int L,
     out[(size_t)b * L + k] = U[(size_t)b * L + k] - m;
 }
 
-__global__ void identity_blocks_kernel(double *M, int n, int L) {
-  const size_t total = (size_t)n * L * L;
+__global__ void identity_blocks_kernel(double *M, int n, int L, int ldm) {   // (n, L, ldm)
+  const size_t total = (size_t)n * L * ldm;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
        e += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)((e / L) % L), j = (int)(e % L);
+    const int i = (int)((e / ldm) % L), j = (int)(e % ldm);
     M[e] = i == j ? 1.0 : 0.0;
   }
 }
@@ -577,11 +577,11 @@ int launch_colcenter(plsb_ctx *h, const double *U, int B, int L, double *out, cu
   return PLSB_OK;
 }
 
-int launch_identity_blocks(plsb_ctx *h, double *M, int n, int L, cudaStream_t st) {
+int launch_identity_blocks(plsb_ctx *h, double *M, int n, int L, int ldm, cudaStream_t st) {
   KernelTimer kt(h, KC_PREP, st);
-  const size_t total = (size_t)n * L * L;
+  const size_t total = (size_t)n * L * ldm;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 8);
-  identity_blocks_kernel<<<blocks, 256, 0, st>>>(M, n, L);
+  identity_blocks_kernel<<<blocks, 256, 0, st>>>(M, n, L, ldm);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }

@@ -121,7 +121,7 @@ __device__ __forceinline__ void small_mm(const double *A, int sam, int sak, cons
 __global__ void __launch_bounds__(SM_THREADS)
 rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
                 const double *__restrict__ lam_in, int K, int L,
-                const double *__restrict__ dorig, double *__restrict__ M_out) {
+                const double *__restrict__ dorig, double *__restrict__ M_out, int ldm) {
   extern __shared__ __align__(16) double sm[];
   const int LP = (K + 7) & ~7, ld = LP + 4;
   double *Vs = sm;                // V          [LP][ld]
@@ -207,8 +207,13 @@ rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
   }
   // Q = polar(temp)^T;  M[a][j] = sum_i V[a][i] X[j][i]
   small_mm(Vs, ld, 1, X, 1, ld, LP, [&](int a, int j, double v) {
-    if (a < K && j < L) M_out[(size_t)r * K * L + (size_t)a * L + j] = v;
+    if (a < K && j < L) M_out[((size_t)r * K + a) * ldm + j] = v;
   });
+  // padding columns of a padded output pitch
+  for (int e = tid; e < K * (ldm - L); e += SM_THREADS) {
+    const int a = e / (ldm - L), j = L + e - a * (ldm - L);
+    M_out[((size_t)r * K + a) * ldm + j] = 0.0;
+  }
 }
 
 int launch_eigen(plsb_ctx *h, const double *G, int count, int K, int sqrt_lam, double *V,
@@ -232,7 +237,7 @@ int launch_eigen(plsb_ctx *h, const double *G, int count, int K, int sqrt_lam, d
 }
 
 int launch_rotation(plsb_ctx *h, const double *H, const double *V, const double *lam, int count,
-                    int K, int L, const double *dorig, double *M, cudaStream_t st) {
+                    int K, int L, const double *dorig, double *M, int ldm, cudaStream_t st) {
   KernelTimer kt(h, KC_SMALL, st);
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(L == K, PLSB_ERR_ARG, "small decomposition: L=%d must equal K=%d", L, K);
@@ -240,7 +245,7 @@ int launch_rotation(plsb_ctx *h, const double *H, const double *V, const double 
   const size_t smem = sizeof(double) * (4 * (size_t)LP * ld + 2 * LP);
   PLSB_CUDA(cudaFuncSetAttribute(rotation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-  rotation_kernel<<<count, SM_THREADS, smem, st>>>(H, V, lam, K, L, dorig, M);
+  rotation_kernel<<<count, SM_THREADS, smem, st>>>(H, V, lam, K, L, dorig, M, ldm);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
@@ -248,13 +253,14 @@ int launch_rotation(plsb_ctx *h, const double *H, const double *V, const double 
 }  // namespace
 
 int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count, int K, int L,
-                        const double *dorig, double *M, double *lam, cudaStream_t st) {
+                        const double *dorig, double *M, int ldm, double *lam, cudaStream_t st) {
   if (count <= 0) return PLSB_OK;
+  PLSB_CHECK(ldm >= L, PLSB_ERR_ARG, "small decomposition: output pitch %d < L=%d", ldm, L);
   const size_t kk = (size_t)K * K;
   PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)count * (kk + K)));
   double *V = h->misc.as<double>(), *lam_s = V + (size_t)count * kk;
   PLSB_TRY(launch_eigen(h, G, count, K, 0, V, lam_s, st));
-  PLSB_TRY(launch_rotation(h, H, V, lam_s, count, K, L, dorig, M, st));
+  PLSB_TRY(launch_rotation(h, H, V, lam_s, count, K, L, dorig, M, ldm, st));
   if (lam)
     PLSB_CUDA(cudaMemcpyAsync(lam, lam_s, sizeof(double) * (size_t)count * K,
                               cudaMemcpyDeviceToDevice, st));
