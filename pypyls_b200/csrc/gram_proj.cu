@@ -5,7 +5,7 @@
 // Procrustes step of a bootstrap needs (pyls/compute.py:36-49, 260: the
 // randomized SVD of R and the U_orig^T U_boot product collapse onto G and H).
 //
-// Work decomposition (16 warps):
+// Work decomposition (16 consumer warps + 2 producer warps):
 //   * G is symmetric: only the MF (MF + 1) / 2 upper fragments (8 x 8) are
 //     computed; with the MF * MFH fragments of H that is FT fragments, dealt
 //     in contiguous runs to NG warp groups (compile-time tables, so every
@@ -17,13 +17,13 @@
 //     balanced whatever the group sizes are;
 //   * U_orig is kept transposed (L rows of ldr doubles), so a stage is one tile
 //     of K + L rows x BC columns of [R; U_orig^T] and H = R (U_orig^T)^T has the
-//     same fragment addressing as G = R R^T.  The tiles are staged by TMA bulk
-//     copies (one cp.async.bulk per tile row, so that the rows keep a
-//     bank-conflict-free pitch) through a ring of `nslot` slots; a full / empty mbarrier pair per
-//     slot replaces CTA-wide barriers: a warp only waits for the stage it reads
-//     and may run one stage ahead of the slowest warp.  The copies of a stage
-//     are issued by the first K + BC threads (one row each) once every warp has
-//     released the slot;
+//     same fragment addressing as G = R R^T.  The producer warps stage the
+//     tiles with cp.async (16 B per thread and copy, rows at a bank-conflict-free
+//     pitch) through a ring of `nslot` slots and signals a "full" mbarrier per
+//     slot through cp.async.mbarrier.arrive; the 16 consumer warps release slots
+//     through an "empty" mbarrier.  No CTA-wide barrier in the loop: a warp only
+//     waits for the stage it reads.  (Measured: per-row TMA bulk copies of
+//     0.5 KB are issue-bound here, 72 % of the DMMA peak instead of ~80 %.);
 //   * the slices are reduced pairwise through shared memory at the end (fixed
 //     order: results are bit-reproducible).
 //
@@ -45,11 +45,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
   asm volatile(
       "{\n"
@@ -63,14 +58,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes,
-                                            uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
-          "r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
+}
+// the mbarrier receives one arrival when all earlier cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// barrier among the consumer warps only (the producers have left by then)
+__device__ __forceinline__ void consumer_sync() {
+  asm volatile("bar.sync 1, 512;\n" ::: "memory");
 }
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
   asm volatile(
@@ -123,8 +121,10 @@ __host__ __device__ constexpr bool need_h(int MF, int F0, int F1, int j) {
   return false;
 }
 
-constexpr int GP_THREADS = 512;
-constexpr int GP_WARPS = 16;
+constexpr int GP_WARPS = 16;                         // consumer warps
+constexpr int GP_CONSUMERS = GP_WARPS * 32;
+constexpr int GP_PRODUCERS = 64;                     // producer threads (2 warps)
+constexpr int GP_THREADS = GP_CONSUMERS + GP_PRODUCERS;
 
 template <int MF, int MFH, int BC, int NG> struct GpCfg {
   static constexpr int KP = MF * 8, LP = MFH * 8;
@@ -224,46 +224,56 @@ gram_proj_kernel(const double *__restrict__ R, long long ldr, int K, int n_chunk
 
   // zero the ring once: the padding rows (>= K, >= L) are never written by the copies
   for (int e = tid; e < nslot * C::STAGE; e += GP_THREADS) sm[e] = 0.0;
-  // copy duty: one row of the [R; U_orig^T] tile per stage and thread
-  const int n_copy = K + (MFH > 0 ? L : 0);
   if (tid == 0) {
     for (int s = 0; s < nslot; ++s) {
-      mbar_init(&full_bar[s], n_copy);   // every copying thread arrives with its byte count
+      mbar_init(&full_bar[s], GP_PRODUCERS);
       mbar_init(&empty_bar[s], GP_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  // the zeros (generic proxy) must be ordered before the TMA writes (async proxy)
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
 
-  const bool issuer = tid < n_copy;
-  const bool issuer_warp = warp * 32 < n_copy;
-  const double *c_src = tid < K ? R + ((size_t)r * K + tid) * ldr : UoT + (size_t)(tid - K) * ldr;
-  const int c_dst = (tid < K ? tid : C::KP + (tid - K)) * C::LDR;   // doubles from the slot start
-  auto issue = [&](int ch) {          // stage ch -> slot ch % nslot
-    if (issuer) {
+  if (warp >= GP_WARPS) {
+    // ---- producers: 16-byte segments of the rows of [R; U_orig^T], stage after stage ----
+    constexpr int SEGS = BC / 2;                       // segments per tile row
+    constexpr int RPP = SEGS <= GP_PRODUCERS ? GP_PRODUCERS / SEGS : 1;   // rows per pass
+    const int p = tid - GP_CONSUMERS;
+    const int row0 = SEGS <= GP_PRODUCERS ? p / SEGS : 0;
+    const int seg0 = SEGS <= GP_PRODUCERS ? p - row0 * SEGS : p;
+    const int nu = MFH > 0 ? L : 0;
+    const double *Rr = R + (size_t)r * K * ldr;
+    for (int ch = 0; ch < n_chunks; ++ch) {
       const int slot = ch % nslot;
+      if (ch >= nslot) mbar_wait(&empty_bar[slot], ((ch / nslot) - 1) & 1);
       const long long b0 = (long long)ch * BC;
-      const unsigned bytes = (unsigned)sizeof(double) * (unsigned)min((long long)BC, ldr - b0);
-      mbar_arrive_expect_tx(&full_bar[slot], bytes);
-      tma_load_1d(sm + (size_t)slot * C::STAGE + c_dst, c_src + b0, bytes, &full_bar[slot]);
+      const int kvalid = (int)min((long long)BC, ldr - b0);
+      double *dst = sm + (size_t)slot * C::STAGE;
+      for (int seg = seg0; seg < SEGS && seg * 2 < kvalid; seg += GP_PRODUCERS) {
+        const double *src = Rr + (size_t)row0 * ldr + b0 + seg * 2;
+        double *d = dst + row0 * C::LDR + seg * 2;
+        for (int row = row0; row < K; row += RPP) {
+          cp_async16(d, src);
+          src += (size_t)RPP * ldr;
+          d += RPP * C::LDR;
+        }
+        src = UoT + (size_t)row0 * ldr + b0 + seg * 2;
+        d = dst + (C::KP + row0) * C::LDR + seg * 2;
+        for (int row = row0; row < nu; row += RPP) {
+          cp_async16(d, src);
+          src += (size_t)RPP * ldr;
+          d += RPP * C::LDR;
+        }
+      }
+      cp_async_arrive(&full_bar[slot]);
     }
-  };
+    return;
+  }
 
   double acc[C::FPG][2];
 #pragma unroll
   for (int f = 0; f < C::FPG; ++f) acc[f][0] = acc[f][1] = 0.0;
 
-  if (issuer_warp)
-    for (int s = 0; s < nslot - 1 && s < n_chunks; ++s) issue(s);
   for (int ch = 0; ch < n_chunks; ++ch) {
-    // refill the slot of stage ch - 1 with stage ch + nslot - 1 once every warp released it
-    const int rf = ch + nslot - 1;
-    if (issuer_warp && rf < n_chunks) {
-      if (ch >= 1) mbar_wait(&empty_bar[(ch - 1) % nslot], ((ch - 1) / nslot) & 1);
-      issue(rf);
-    }
     const int slot = ch % nslot;
     mbar_wait(&full_bar[slot], (ch / nslot) & 1);
     const double *Rs = sm + (size_t)slot * C::STAGE;
@@ -280,7 +290,7 @@ gram_proj_kernel(const double *__restrict__ R, long long ldr, int K, int n_chunk
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[slot]);
   }
-  __syncthreads();
+  consumer_sync();
 
   // pairwise reduction of the contraction slices: slices [s, 2s) hand their
   // sums to slices [0, s)
@@ -292,7 +302,7 @@ gram_proj_kernel(const double *__restrict__ R, long long ldr, int K, int n_chunk
 #pragma unroll
       for (int f = 0; f < C::FPG; ++f) p[f * 32] = make_double2(acc[f][0], acc[f][1]);
     }
-    __syncthreads();
+    consumer_sync();
     if (kg < s) {
       const double2 *p = red + ((size_t)(ng * s + kg) * C::FPG) * 32 + lane;
 #pragma unroll
@@ -302,7 +312,7 @@ gram_proj_kernel(const double *__restrict__ R, long long ldr, int K, int n_chunk
         acc[f][1] += v.y;
       }
     }
-    __syncthreads();
+    consumer_sync();
   }
   if (kg == 0) {
     double *Gr = G + (size_t)r * K * K;
