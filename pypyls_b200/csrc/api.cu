@@ -60,12 +60,12 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, int n, bool boot, double *di
   PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)Mw_op * l.S_pad));
   PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)Mw_pad * l.ldx));
   int *map_w = nullptr, *map_c = nullptr;
-  int2 *kr_w = nullptr, *kr_c = nullptr;
+  int4 *kr_w = nullptr, *kr_c = nullptr;
   if (grouped) {
     const size_t n_int = (size_t)Mw_op + (size_t)Mc_op;
     const size_t n_kr = (size_t)(Mw_op + Mc_op) / GEMM_BM;
-    PLSB_TRY(h->maps.ensure(sizeof(int2) * n_kr + sizeof(int) * n_int));
-    kr_w = h->maps.as<int2>();
+    PLSB_TRY(h->maps.ensure(sizeof(int4) * n_kr + sizeof(int) * n_int));
+    kr_w = h->maps.as<int4>();
     kr_c = kr_w + Mw_op / GEMM_BM;
     map_w = reinterpret_cast<int *>(kr_c + Mc_op / GEMM_BM);
     map_c = map_w + Mw_op;
@@ -314,7 +314,7 @@ int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups,
     acc += groups[g];
   }
   tab.push_back(acc);   // n_groups + 1
-  if (tab.size() % 2) tab.push_back(0);   // keep the int2 table 8-byte aligned
+  while (tab.size() % 4) tab.push_back(0);   // keep the int4 table 16-byte aligned
   const size_t kr_off = tab.size();
   for (int j = 0; j < l.J; ++j) {
     // contraction range of cell j: even start, whole GEMM_BK chunks, inside [0, S_pad)
@@ -323,6 +323,9 @@ int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups,
     if (kb + nkc * GEMM_BK > l.S_pad) kb = l.S_pad - nkc * GEMM_BK;
     tab.push_back(kb);
     tab.push_back(kb + nkc * GEMM_BK);
+    // k steps of 4 that touch the cell's rows: operand columns outside are structural zeros
+    tab.push_back(kb + ((l.cell_start[j] - kb) & ~3));
+    tab.push_back(kb + round_up(l.cell_start[j + 1] - kb, 4));
     l.kr_max = std::max(l.kr_max, nkc * GEMM_BK);
   }
   PLSB_TRY(h->tables.ensure(sizeof(int) * tab.size()));
@@ -331,7 +334,7 @@ int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups,
   h->d_cell_of_row = h->d_cell_start + (l.J + 1);
   h->d_cell_n = h->d_cell_of_row + S;
   h->d_group_start = h->d_cell_n + l.J;
-  h->d_cell_kr = reinterpret_cast<const int2 *>(h->tables.as<int>() + kr_off);
+  h->d_cell_kr = reinterpret_cast<const int4 *>(h->tables.as<int>() + kr_off);
 
   if (l.mode == PLSB_MEANCENTERED) {
     // C (J,S): "cell mean minus centring mean" as a row operator

@@ -143,7 +143,9 @@ struct plsb_ctx {
   plsb::DevBuf tables;
   const int *d_cell_start = nullptr, *d_cell_of_row = nullptr, *d_cell_n = nullptr,
             *d_group_start = nullptr;
-  const int2 *d_cell_kr = nullptr;   // per cell: contraction range [kbeg, kend) of its rows
+  // per cell: staged contraction range [x, y) (whole GEMM_BK chunks) and the k steps of 4
+  // inside it that touch the cell's rows [z, w)
+  const int4 *d_cell_kr = nullptr;
 
   // data-dependent state (set_data); all (S_pad, ldx) zero padded
   plsb::DevBuf Xraw;   // raw X
@@ -196,7 +198,7 @@ struct GemmArgs {
   int M_pad = 0;               // multiple of GEMM_BM
   int N_pad = 0;               // multiple of GEMM_BN (<= ldx)
   int Kd = 0;                  // contraction length, multiple of GEMM_BK (padding zero)
-  const int2 *kranges = nullptr;  // optional per-M-tile [kbeg,kend), kbeg even
+  const int4 *kranges = nullptr;  // optional per-M-tile [kbeg,kend) (kbeg even) + non-zero k steps [z,w)
   int k_len = 0;               // longest contraction range in kranges (0: Kd); picks the tile
   bool square_b = false;       // use X*X elementwise as the right operand
   // STORE epilogue
@@ -234,7 +236,7 @@ enum BuildKind { BUILD_ROT = 0, BUILD_PLAIN = 1, BUILD_BOOT = 2 };
 int launch_build(plsb_ctx *h, int kind, const int32_t *idx, int count, double *A, double *Ac,
                  double *distrib, long long cellpad_w, long long cellpad_c, cudaStream_t st);
 int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long cellpad,
-                      int *row_map, int2 *kranges, cudaStream_t st);
+                      int *row_map, int4 *kranges, cudaStream_t st);
 
 // streaming kernels over stored R (stream_kernels.cu)
 int launch_finish_rowsq(plsb_ctx *h, const double *rowsq, int n_splits, int M_pad, int n_rows,

@@ -66,7 +66,7 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 template <int EPI, bool SQB, int MF>
 __global__ void __launch_bounds__(NTHREADS, MF == 8 ? 1 : 2)
 xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict__ X, int ldx,
-                 int n_mtiles, int n_ntiles, int nt_per_split, const int2 *__restrict__ kranges,
+                 int n_mtiles, int n_ntiles, int nt_per_split, const int4 *__restrict__ kranges,
                  int Kd, double *__restrict__ C, long long ldc, const int *__restrict__ row_map,
                  const double *__restrict__ scale, int scale_div, long long lds,
                  double *__restrict__ rowsq, int M_pad) {
@@ -93,12 +93,14 @@ xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict
   const int nt1 = min(nt0 + nt_per_split, n_ntiles);
   if (nt0 >= nt1) return;
 
-  int kbeg = 0, kend = Kd;
+  int kbeg = 0, kend = Kd, vbeg = 0, vend = Kd;
   if (kranges) {
     // the ranges are tabulated per GEMM_BM (128) rows
-    int2 kr = kranges[(mtile * TM) / BM];
+    int4 kr = kranges[(mtile * TM) / BM];
     kbeg = kr.x;
     kend = kr.y;
+    vbeg = kr.z;   // k steps outside [vbeg, vend) multiply structural zeros of A: skipped
+    vend = kr.w;
   }
   const int nkc = (kend - kbeg + BK - 1) / BK;     // k chunks per N tile
   const int total = (nt1 - nt0) * nkc;             // flattened pipeline steps
@@ -207,8 +209,10 @@ xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict
 
     const double *as = As + (s % STAGES) * A_STAGE + (wm * MF * 8 + g) * LDA_S + q;
     const double *bs = Bs + (s % STAGES) * B_STAGE + q * LDB_S + wn * 32 + g;
+    const int kabs = kbeg + kc * BK;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
+      if (kabs + kk * 4 < vbeg || kabs + kk * 4 >= vend) continue;
       double af[MF], bf[NF];
 #pragma unroll
       for (int i = 0; i < MF; ++i) af[i] = as[i * 8 * LDA_S + kk * 4];

@@ -209,8 +209,8 @@ __global__ void build_meancentered_kernel(BuildParams p) {
 // are padding (-1).  Every 128-row tile lies inside one cell and contracts
 // only over that cell's rows of the data matrix.
 __global__ void build_maps_kernel(int n, int rows_pc, int stride_r, int J, long long cellpad,
-                                  const int2 *__restrict__ cell_kr, int *__restrict__ row_map,
-                                  int2 *__restrict__ kranges) {
+                                  const int4 *__restrict__ cell_kr, int *__restrict__ row_map,
+                                  int4 *__restrict__ kranges) {
   const long long total = (long long)J * cellpad;
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < total;
        m += (long long)gridDim.x * blockDim.x) {
@@ -229,7 +229,7 @@ __global__ void build_maps_kernel(int n, int rows_pc, int stride_r, int J, long 
 }  // namespace
 
 int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long cellpad,
-                      int *row_map, int2 *kranges, cudaStream_t st) {
+                      int *row_map, int4 *kranges, cudaStream_t st) {
   KernelTimer kt(h, KC_BUILD, st);
   const long long total = (long long)h->lay.J * cellpad;
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
