@@ -121,6 +121,12 @@ int plsb_gen_boot_indices(plsb_handle_t h, uint64_t seed, int64_t first,
  */
 int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count,
                    int rotate, double *d_dperm, void *stream);
+/* The same for pre-permuted behaviour matrices (`permsamples` of shape (P,S,T)
+ * with permindices=False, pyls/base.py:636-639, 689-692: spatial-null models
+ * hand in Y already permuted): d_Yperm (count,S,T), X stays in place.
+ * Behavioural modes only. */
+int plsb_run_perms_prepermuted(plsb_handle_t h, const double *d_Yperm, int count,
+                               int rotate, double *d_dperm, void *stream);
 
 /*
  * Bootstrap loop.  Replaces BasePLS.bootstrap + _single_boot

@@ -347,14 +347,17 @@ def decompose(spec, X, Y, seed=None):
 # per-resample bodies (pyls/base.py)
 # --------------------------------------------------------------------------
 
-def single_perm(spec, X, Y, perminds, original_v, seed=None):
+def single_perm(spec, X, Y, perminds, original_v, seed=None, use_permind=True):
     """One permutation -> (L,) permuted singular values.  Follows
-    pyls/base.py:654-712 with use_permind=True and n_split=None; the permuted
-    operand is Y for behavioral (base.py:599) and X for mean-centered
-    (pyls/types/meancentered.py:125)."""
+    pyls/base.py:654-712 with n_split=None; the permuted operand is Y for
+    behavioral (base.py:599) and X for mean-centered
+    (pyls/types/meancentered.py:125).  use_permind=False: ``perminds`` is a
+    pre-permuted Y matrix used as it is (base.py:689-692)."""
     if spec.kind == 'regression':
         return _regression_single_perm(spec, X, Y, perminds, seed)
-    if spec.kind == 'meancentered':
+    if not use_permind:
+        Xp, Yp = X, perminds
+    elif spec.kind == 'meancentered':
         Xp, Yp = X[perminds], Y
     else:
         Xp, Yp = X, Y[perminds]
@@ -413,11 +416,15 @@ def run_boots_nullsafe(spec, X, Y, bootsamp, original_u, d_orig):
     return np.stack(distrib, axis=-1), u_sum, u_square
 
 
-def run_perms(spec, X, Y, permsamp, original_v, first=0, count=None):
-    """d_perm (L, count) over columns [first, first+count) of ``permsamp``;
-    resample i uses seed=i exactly like pyls/base.py:644-650."""
+def run_perms(spec, X, Y, permsamp, original_v, first=0, count=None,
+              use_permind=True):
+    """d_perm (L, count) over [first, first+count) of the last axis of
+    ``permsamp`` -- (S, P) index vectors or, with use_permind=False, (S, T, P)
+    pre-permuted Y matrices; resample i uses seed=i exactly like
+    pyls/base.py:644-650."""
     count = permsamp.shape[-1] - first if count is None else count
-    cols = [single_perm(spec, X, Y, permsamp[:, i], original_v, seed=i)
+    cols = [single_perm(spec, X, Y, permsamp[..., i], original_v, seed=i,
+                        use_permind=use_permind)
             for i in range(first, first + count)]
     return np.stack(cols, axis=-1)
 
@@ -540,11 +547,12 @@ def _finish_boot(res, orig_bs, distrib, u_sum, u_square, n, ci, add_orig):
 
 def behavioral_pls(X, Y, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
                    covariance=False, rotate=True, ci=95, permsamples=None,
-                   bootsamples=None, seed=None):
-    """pyls.behavioral_pls with test_split=0, n_split=0, permindices=True.
-    Follows pyls/base.py:341-399 and pyls/types/behavioral.py:172-227,
-    including the order in which the seeded RandomState is consumed
-    (original SVD -> gen_permsamp -> gen_bootsamp)."""
+                   bootsamples=None, seed=None, permindices=True):
+    """pyls.behavioral_pls with test_split=0, n_split=0.  Follows
+    pyls/base.py:341-399 and pyls/types/behavioral.py:172-227, including the
+    order in which the seeded RandomState is consumed (original SVD ->
+    gen_permsamp -> gen_bootsamp).  permindices=False: ``permsamples`` is a
+    (P, S, T) stack of pre-permuted Y matrices (base.py:636-639)."""
     X, Y = np.asarray(X), np.asarray(Y)
     groups = [len(X) // n_cond] if groups is None else list(np.atleast_1d(groups))
     spec = _Spec('behavioral', groups, n_cond, covariance=covariance,
@@ -557,7 +565,12 @@ def behavioral_pls(X, Y, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
     if n_perm > 0:
         if permsamples is None:
             permsamples = gen_permsamp(groups, n_cond, n_perm, seed=rs)
-        d_perm = run_perms(spec, X, Y, permsamples, V)
+        if permindices:
+            d_perm = run_perms(spec, X, Y, permsamples, V)
+        else:
+            d_perm = run_perms(spec, X, Y,
+                               np.transpose(permsamples, (1, 2, 0)), V,
+                               use_permind=False)
         res['pvals'] = perm_sig(d, d_perm)
         res['permsamples'] = permsamples
         res['perm_singval'] = d_perm

@@ -80,11 +80,6 @@ class BasePLS():
             raise NotImplementedError(
                 'Split-half resampling (n_split) is not part of the '
                 'accelerated path yet; pass n_split=0.')
-        if self.inputs.get('permsamples') is not None and \
-                self.inputs.get('permindices') is False:
-            raise NotImplementedError(
-                'Pre-permuted Y arrays (permindices=False) are not part of '
-                'the accelerated path yet; pass index tables.')
         self.engine = None
 
     # -- engine ------------------------------------------------------------
@@ -186,13 +181,34 @@ class BasePLS():
             Split-half correlations are not computed by this engine.
         """
         n = self.inputs.n_perm
-        self.permsamp, block, _ = self._table('perm', n, seed)
         rotate = self.inputs.get('rotate')
         rotate = True if rotate is None else bool(rotate)
-        local = self.engine.run_perms(block, rotate=rotate)
+        given = self.inputs.get('permsamples')
+        if given is not None and self.inputs.get('permindices') is False:
+            # pre-permuted Y matrices, (P, S, T) (pyls/base.py:636-639, 689-692)
+            local = self._prepermuted(given, n, rotate)
+        else:
+            self.permsamp, block, _ = self._table('perm', n, seed)
+            local = self.engine.run_perms(block, rotate=rotate)
         d_perm = pdist.gather_resamples(local, n)
         self._dev['d_perm'] = d_perm
         return to_host(d_perm).T.copy(), None, None
+
+    def _prepermuted(self, given, n, rotate):
+        eng = self.engine
+        if self.inputs.get('Y') is None or eng.T < 1 or \
+                not self.engine_mode().startswith('behavioral'):
+            raise ValueError('Pre-permuted `permsamples` (permindices=False) '
+                             'need an analysis with a Y matrix.')
+        shape = tuple(given.shape)
+        if len(shape) != 3 or shape != (n, eng.S, eng.T):
+            raise ValueError('Provided pre-permuted `permsamples` must have '
+                             'shape ({}, {}, {}); got {}'.format(
+                                 n, eng.S, eng.T, shape))
+        self.permsamp = given
+        first, count = pdist.my_block(n)
+        return eng.run_perms_prepermuted(given[first:first + count],
+                                         rotate=rotate)
 
     def bootstrap(self, X, Y, seed=None):
         """

@@ -45,8 +45,8 @@ int zero_tail(double *A, long long rows, long long rows_pad, int lda, cudaStream
 // that cell's rows of the data matrix -- so they are laid out grouped by cell
 // (every 128-row GEMM tile inside one cell), the GEMM contracts each tile over
 // its cell's rows only and a row map puts the result back in resample order.
-int crosscov_chunk(plsb_ctx *h, const int32_t *idx, int n, bool boot, double *distrib,
-                   cudaStream_t st) {
+int crosscov_chunk(plsb_ctx *h, const int32_t *idx, const double *yperm, int n, bool boot,
+                   double *distrib, cudaStream_t st) {
   const Layout &l = h->lay;
   const bool grouped = l.behavioral() && l.J > 1;
   const bool scaled = boot && l.corr();
@@ -85,7 +85,7 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, int n, bool boot, double *di
       PLSB_TRY(zero_tail(h->Ac.as<double>(), Mc, Mc_op, l.S_pad, st));
     }
   }
-  PLSB_TRY(launch_build(h, boot ? BUILD_BOOT : BUILD_PLAIN, idx, n, h->A.as<double>(),
+  PLSB_TRY(launch_build(h, boot ? BUILD_BOOT : BUILD_PLAIN, idx, yperm, n, h->A.as<double>(),
                         scaled ? h->Ac.as<double>() : nullptr, distrib, cellpad_w, cellpad_c, st));
   GemmArgs g;
   g.lda = l.S_pad;
@@ -448,7 +448,7 @@ int plsb_decompose(plsb_handle_t h, double *d_U, double *d_d, double *d_V, void 
   const Layout &l = h->lay;
   cudaStream_t st = as_stream(stream);
   PLSB_CHECK(d_U && d_d && d_V, PLSB_ERR_ARG, "plsb_decompose: null output");
-  PLSB_TRY(crosscov_chunk(h, nullptr, 1, false, nullptr, st));
+  PLSB_TRY(crosscov_chunk(h, nullptr, nullptr, 1, false, nullptr, st));
   const size_t kk = (size_t)l.K * l.K, bl = (size_t)l.B * l.L;
   PLSB_TRY(h->G.ensure(sizeof(double) * 4 * kk));
   PLSB_TRY(h->lam.ensure(sizeof(double) * 2 * l.K));
@@ -513,7 +513,8 @@ int plsb_crosscov(plsb_handle_t h, const int32_t *d_idx, int count, int bootstra
   const int chunk = chunk_size(h, bootstrap != 0, count);
   for (int off = 0; off < count; off += chunk) {
     const int n = std::min(chunk, count - off);
-    PLSB_TRY(crosscov_chunk(h, d_idx ? d_idx + (size_t)off * l.S : nullptr, n, bootstrap != 0,
+    PLSB_TRY(crosscov_chunk(h, d_idx ? d_idx + (size_t)off * l.S : nullptr, nullptr, n,
+                            bootstrap != 0,
                             nullptr, st));
     PLSB_TRY(launch_unpad_copy(h, h->R.as<double>(), l.ldx, n * l.K, l.B,
                                d_R + (size_t)off * l.K * l.B, st));
@@ -521,15 +522,14 @@ int plsb_crosscov(plsb_handle_t h, const int32_t *d_idx, int count, int bootstra
   return PLSB_OK;
 }
 
-int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, int rotate, double *d_dperm,
-                   void *stream) {
-  PLSB_HANDLE(h);
+// permutations from index vectors (d_idx) or from pre-permuted Y matrices (d_yperm)
+static int run_perms_impl(plsb_ctx *h, const int32_t *d_idx, const double *d_yperm, int count,
+                          int rotate, double *d_dperm, cudaStream_t st) {
   PLSB_CHECK(h->has_data, PLSB_ERR_STATE, "plsb_run_perms before plsb_set_data");
   PLSB_CHECK(!rotate || h->has_original, PLSB_ERR_STATE,
              "plsb_run_perms(rotate) before the original decomposition is set");
-  PLSB_CHECK(d_idx && d_dperm && count >= 0, PLSB_ERR_ARG, "plsb_run_perms: bad argument");
   const Layout &l = h->lay;
-  cudaStream_t st = as_stream(stream);
+  const size_t ystride = (size_t)l.S * l.T;
   if (rotate) {
     // |R^T v_j| for every original y-weight v_j: A = V^T-weighted operand, row sums of squares
     const size_t per = sizeof(double) * (size_t)l.L * l.S_pad;
@@ -542,8 +542,9 @@ int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, int rotate,
       const long long M = (long long)n * l.L, M_pad = round_up_ll(M, GEMM_BM);
       PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)M_pad * l.S_pad));
       PLSB_TRY(zero_tail(h->A.as<double>(), M, M_pad, l.S_pad, st));
-      PLSB_TRY(launch_build(h, BUILD_ROT, d_idx + (size_t)off * l.S, n, h->A.as<double>(), nullptr,
-                            nullptr, 0, 0, st));
+      PLSB_TRY(launch_build(h, BUILD_ROT, d_idx ? d_idx + (size_t)off * l.S : nullptr,
+                            d_yperm ? d_yperm + off * ystride : nullptr, n, h->A.as<double>(),
+                            nullptr, nullptr, 0, 0, st));
       const int n_mtiles = (int)(M_pad / GEMM_BM);
       const int n_splits = gemm_pick_splits(h, n_mtiles, n_ntiles);
       PLSB_TRY(h->rowsq.ensure(sizeof(double) * (size_t)n_splits * M_pad));
@@ -567,7 +568,8 @@ int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, int rotate,
   const int chunk = chunk_size(h, false, count);
   for (int off = 0; off < count; off += chunk) {
     const int n = std::min(chunk, count - off);
-    PLSB_TRY(crosscov_chunk(h, d_idx + (size_t)off * l.S, n, false, nullptr, st));
+    PLSB_TRY(crosscov_chunk(h, d_idx ? d_idx + (size_t)off * l.S : nullptr,
+                            d_yperm ? d_yperm + off * ystride : nullptr, n, false, nullptr, st));
     PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * l.K * l.K));
     PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, n, l.K, nullptr, 0,
                               h->G.as<double>(), nullptr, st));
@@ -575,6 +577,23 @@ int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, int rotate,
                             st));
   }
   return PLSB_OK;
+}
+
+int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, int rotate, double *d_dperm,
+                   void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_idx && d_dperm && count >= 0, PLSB_ERR_ARG, "plsb_run_perms: bad argument");
+  return run_perms_impl(h, d_idx, nullptr, count, rotate, d_dperm, as_stream(stream));
+}
+
+int plsb_run_perms_prepermuted(plsb_handle_t h, const double *d_Yperm, int count, int rotate,
+                               double *d_dperm, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_Yperm && d_dperm && count >= 0, PLSB_ERR_ARG,
+             "plsb_run_perms_prepermuted: bad argument");
+  PLSB_CHECK(h->lay.behavioral(), PLSB_ERR_ARG,
+             "plsb_run_perms_prepermuted: only behavioural analyses have a Y matrix to permute");
+  return run_perms_impl(h, nullptr, d_Yperm, count, rotate, d_dperm, as_stream(stream));
 }
 
 int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, double *d_distrib,
@@ -589,7 +608,7 @@ int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, double *d_d
   const int chunk = chunk_size(h, true, count);
   for (int off = 0; off < count; off += chunk) {
     const int n = std::min(chunk, count - off);
-    PLSB_TRY(crosscov_chunk(h, d_idx + (size_t)off * l.S, n, true,
+    PLSB_TRY(crosscov_chunk(h, d_idx + (size_t)off * l.S, nullptr, n, true,
                             d_distrib + (size_t)off * l.K * l.L, st));
     PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * l.K * l.K));
     PLSB_TRY(h->H.ensure(sizeof(double) * (size_t)n * l.K * l.L));

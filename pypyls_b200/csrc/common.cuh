@@ -233,8 +233,9 @@ int launch_matmul_small(plsb_ctx *h, const double *A, const double *Bm, int n, d
 
 // operand builders / distrib (operands.cu)
 enum BuildKind { BUILD_ROT = 0, BUILD_PLAIN = 1, BUILD_BOOT = 2 };
-int launch_build(plsb_ctx *h, int kind, const int32_t *idx, int count, double *A, double *Ac,
-                 double *distrib, long long cellpad_w, long long cellpad_c, cudaStream_t st);
+int launch_build(plsb_ctx *h, int kind, const int32_t *idx, const double *yperm, int count,
+                 double *A, double *Ac, double *distrib, long long cellpad_w, long long cellpad_c,
+                 cudaStream_t st);
 int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long cellpad,
                       int *row_map, int4 *kranges, cudaStream_t st);
 

@@ -14,7 +14,8 @@
 //     BOOT   A[r*K+(g,t), u] = sum_{s in g, src[s]=u} zy[s,t]        (x 1/(n-1) for covariance)
 //            Ac[r*J+g, u]    = #{s in g : src[s]=u}                  (column statistics)
 //            distrib[r]      = per-cell xcorr(Sx[src], Y[src])       (behavioral.py:54-80)
-//     zy = Y[src] z-scored (ddof=1) or centred within each cell.
+//     zy = Y[src] z-scored (ddof=1) or centred within each cell; permutations may
+//     instead bring their own Y (pre-permuted matrices, pyls/base.py:636-639, 689-692).
 //   mean-centred (pyls/types/meancentered.py:50-125, pyls/compute.py:267-357)
 //     AR[j,u] = sum_{s: src[s]=u} C[j,s];  ROT: A = V^T AR;  PLAIN/BOOT: A = AR;
 //     distrib[r] = AR @ Sx.
@@ -28,6 +29,7 @@ struct BuildParams {
   int S, T, J, K, L, lda, corr, kind;
   long long cellpad_w, cellpad_c;   // > 0: rows grouped by cell, cell g starts at g * cellpad
   const double *Y;
+  const double *Yperm;              // optional (count, S, T): resample r uses Yperm[r] as its Y
   const int *cell_start, *cell_of_row;
   const double *Vo, *Sx, *Cmat;
   double *A, *Ac, *distrib;
@@ -48,7 +50,7 @@ __global__ void build_behavioral_kernel(BuildParams p) {
   __syncthreads();
   for (int e = tid; e < S * T; e += nt) {
     const int s = e / T, t = e - s * T;
-    Yp[e] = p.Y[(size_t)src[s] * T + t];
+    Yp[e] = p.Yperm ? p.Yperm[((size_t)r * S + s) * T + t] : p.Y[(size_t)src[s] * T + t];
   }
   __syncthreads();
   for (int c = tid; c < J * T; c += nt) {
@@ -239,8 +241,9 @@ int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long c
   return PLSB_OK;
 }
 
-int launch_build(plsb_ctx *h, int kind, const int32_t *idx, int count, double *A, double *Ac,
-                 double *distrib, long long cellpad_w, long long cellpad_c, cudaStream_t st) {
+int launch_build(plsb_ctx *h, int kind, const int32_t *idx, const double *yperm, int count,
+                 double *A, double *Ac, double *distrib, long long cellpad_w, long long cellpad_c,
+                 cudaStream_t st) {
   KernelTimer kt(h, KC_BUILD, st);
   const Layout &l = h->lay;
   if (count <= 0) return PLSB_OK;
@@ -250,6 +253,9 @@ int launch_build(plsb_ctx *h, int kind, const int32_t *idx, int count, double *A
   p.corr = l.corr() ? 1 : 0;
   p.kind = kind;
   p.Y = h->Y.as<double>();
+  p.Yperm = yperm;
+  PLSB_CHECK(!yperm || (l.behavioral() && kind != BUILD_BOOT), PLSB_ERR_ARG,
+             "pre-permuted Y matrices only apply to behavioural permutations");
   p.cell_start = h->d_cell_start;
   p.cell_of_row = h->d_cell_of_row;
   p.Vo = h->Vo.as<double>();

@@ -232,6 +232,20 @@ class ResamplingEngine:
             _ptr(out), self._stream()))
         return out
 
+    def run_perms_prepermuted(self, Yperm, rotate=True):
+        """Permuted singular values (count, L) for pre-permuted behaviour
+        matrices Yperm (count, S, T) -- `permsamples` with permindices=False
+        (pyls/base.py:636-639, 689-692); X stays in place."""
+        Yperm = self.to_device(Yperm)
+        if Yperm.dim() != 3 or tuple(Yperm.shape[1:]) != (self.S, self.T):
+            raise ValueError('pre-permuted Y must have shape (n, {}, {}); got '
+                             '{}'.format(self.S, self.T, tuple(Yperm.shape)))
+        out = self._f64(Yperm.shape[0], self.L)
+        _cabi.check(self._lib.plsb_run_perms_prepermuted(
+            self._h, _ptr(Yperm), int(Yperm.shape[0]), int(bool(rotate)),
+            _ptr(out), self._stream()))
+        return out
+
     def run_boots(self, idx, u_sum=None, u_square=None):
         """(distrib (count,K,L), u_sum (B,L), u_square (B,L)) on the device
         (BasePLS.bootstrap, pyls/base.py:439-576)."""

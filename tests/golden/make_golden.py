@@ -112,6 +112,26 @@ def behavioral_cases():
          flat(r, 'b'))
 
 
+def prepermuted_case():
+    """`permsamples` as a (P, S, T) stack of pre-permuted Y matrices with
+    permindices=False (pyls/base.py:636-639, 689-692): the spatial-null use."""
+    rs = np.random.RandomState(4242)
+    X, Y = rs.rand(36, 90), rs.rand(36, 5)
+    Y[:, 0] += X[:, :8].mean(axis=1)
+    groups, n_cond, P = [10, 8], 2, 30
+    Yp = np.stack([Y[rs.permutation(36)] + 0.05 * rs.rand(36, 5)
+                   for _ in range(P)])
+    for tag, rot in (('rot', True), ('norot', False)):
+        kw = dict(groups=groups, n_cond=n_cond, n_perm=P, n_boot=0, seed=11,
+                  rotate=rot)
+        r = pyls.behavioral_pls(X, Y, test_split=0, n_split=0,
+                                permsamples=Yp, permindices=False,
+                                verbose=False, **kw)
+        out = flat(r, 'b')
+        out.pop('permsamples', None)
+        save('bpls_prepermuted_' + tag, dict(X=X, Y=Y, Yperm=Yp, **kw), out)
+
+
 def meancentered_cases():
     rs = np.random.RandomState(1234)
     X = rs.rand(48, 50)
@@ -187,6 +207,7 @@ def matlab_cases():
 
 if __name__ == '__main__':
     behavioral_cases()
+    prepermuted_case()
     meancentered_cases()
     regression_cases()
     index_cases()

@@ -96,6 +96,49 @@ def test_behavioral_matches_reference_golden(name):
     close(out.bootres.x_weights_stderr, ref['x_weights_stderr'], rtol=1e-7)
 
 
+@pytest.mark.parametrize('name', ['bpls_prepermuted_rot',
+                                  'bpls_prepermuted_norot'])
+def test_prepermuted_y_matches_reference_golden(name):
+    """Pre-permuted Y matrices (`permsamples` (P, S, T), permindices=False;
+    pyls/base.py:636-639, 689-692) against the reference's own output."""
+    import pypyls_b200 as pyls
+    ins, ref = load_golden(name)
+    X, Y, Yp = ins.pop('X'), ins.pop('Y'), ins.pop('Yperm')
+    out = pyls.behavioral_pls(X, Y, permsamples=Yp, permindices=False,
+                              verbose=False, **ins)
+    for k in ('x_weights', 'y_weights', 'singvals'):
+        close(out[k], ref[k])
+    close(out.permres.perm_singval, ref['perm_singval'])
+    assert np.array_equal(out.permres.pvals, ref['pvals'])
+    assert out.permres.permsamples.shape == Yp.shape
+
+
+def test_prepermuted_y_equals_index_permutations():
+    """Y[perm] handed in as a matrix gives what the index vector gives, also
+    across chunk boundaries (tiny workspace) and for a covariance analysis."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(5)
+    groups, n_cond = [12, 9], 2
+    X, Y = rs.rand(42, 300), rs.rand(42, 6)
+    ps = po.gen_permsamp(groups, n_cond, 50, seed=3)
+    Yp = np.stack([Y[ps[:, i]] for i in range(50)])
+    for cov in (False, True):
+        kw = dict(groups=groups, n_cond=n_cond, n_perm=50, n_boot=0, seed=1,
+                  covariance=cov, verbose=False)
+        a = pyls.behavioral_pls(X, Y, permsamples=ps, **kw)
+        b = pyls.behavioral_pls(X, Y, permsamples=Yp, permindices=False,
+                                workspace_bytes=1 << 20, **kw)
+        close(b.permres.perm_singval, a.permres.perm_singval, rtol=1e-12)
+        assert np.array_equal(a.permres.pvals, b.permres.pvals)
+    with pytest.raises(ValueError):
+        pyls.behavioral_pls(X, Y, permsamples=Yp[:, :-1], permindices=False,
+                            **kw)
+    with pytest.raises(ValueError):
+        pyls.meancentered_pls(X, groups=groups, n_cond=n_cond, n_perm=50,
+                              n_boot=0, permsamples=Yp, permindices=False,
+                              verbose=False)
+
+
 @pytest.mark.parametrize('name', MPLS)
 def test_meancentered_matches_reference_golden(name):
     import pypyls_b200 as pyls
