@@ -478,16 +478,28 @@ def main():
                 'kernel_ms_per_step': top_ms / args.steps,
                 'launches_per_step': top_n / args.steps}
     # DRAM traffic of the class per step from the committed `ncu --set full`
-    # capture (dram__bytes_read.sum + dram__bytes_write.sum over its launches;
-    # profiles/r1_ncu_full_v4_summary.csv and ..._v2_... for the permutation
-    # launch); only known for the configuration that was captured
+    # capture (dram__bytes_read.sum + dram__bytes_write.sum over its launches,
+    # profiles/r1_ncu_full_v6_summary.csv: permutation launch 0.14 GB, per full
+    # bootstrap chunk 0.66 + 0.66 + 7.74 GB, last chunk 2.7 GB); only known for
+    # the configuration that was captured
     if (args.workload, world, top) == ('cfg2', 1, 'xcov_gemm') and \
             args.workspace_gib is None:
-        roofline['traffic'] = 27.3e9
+        roofline['traffic'] = 20.9e9
         roofline['traffic_unit'] = 'bytes per step, all launches of the class'
-        roofline['algorithmic_flop_per_step'] = flops
+    roofline['algorithmic_flop_per_step'] = flops
+    # flop the launches really execute: rotated permutations contract L rows per
+    # resample (|R^T v_j| for every original y-weight) instead of T per cell
+    if top == 'xcov_gemm' and kind == 'behavioral':
+        J = len(w['groups']) * w['n_cond']
+        ng = w['S'] / J
+        executed = 2.0 * w['S'] * w['B'] * (J * w['T']) * n_perm + \
+            2.0 * ng * w['B'] * (J * (w['T'] + 2)) * n_boot
+        roofline['executed_flop_per_step'] = executed
     if bound == 'tensor' and flops:
         ach = flops * args.steps / (top_ms * 1e-3) / 1e12
+        if roofline.get('executed_flop_per_step'):
+            roofline['frac_executed'] = roofline['executed_flop_per_step'] * \
+                args.steps / (top_ms * 1e-3) / 1e12 / peak_tf
         roofline.update(achieved=ach, peak=peak_tf, unit='TFLOP/s',
                         frac=ach / peak_tf,
                         peak_source='cuBLAS DGEMM 8192^3 measured in this run '
