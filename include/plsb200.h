@@ -121,6 +121,13 @@ int plsb_gen_boot_indices(plsb_handle_t h, uint64_t seed, int64_t first,
  */
 int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count,
                    int rotate, double *d_dperm, void *stream);
+/* Rotated permutation singular values in SAMPLE SPACE (an algorithmic fast path,
+ * not the cross-covariance GEMM): |R^T v_j|^2 = a_j^T (Xp Xp^T) a_j with the
+ * S x S Gram matrix of the fixed data matrix computed once per plsb_set_data
+ * and a_j the operand rows plsb_run_perms would contract with the data.  Same
+ * arguments and results as plsb_run_perms(rotate = 1). */
+int plsb_run_perms_gram(plsb_handle_t h, const int32_t *d_idx, int count,
+                        double *d_dperm, void *stream);
 /* The same for pre-permuted behaviour matrices (`permsamples` of shape (P,S,T)
  * with permindices=False, pyls/base.py:636-639, 689-692: spatial-null models
  * hand in Y already permuted): d_Yperm (count,S,T), X stays in place.

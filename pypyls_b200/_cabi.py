@@ -36,6 +36,7 @@ PROTOTYPES = {
     'plsb_gen_perm_indices': (_i, [_vp, _u64, _i64, _i, _vp, _ip, _vp]),
     'plsb_gen_boot_indices': (_i, [_vp, _u64, _i64, _i, _vp, _ip, _vp]),
     'plsb_run_perms': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    'plsb_run_perms_gram': (_i, [_vp, _vp, _i, _vp, _vp]),
     'plsb_run_perms_prepermuted': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'plsb_run_boots': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     'plsb_perm_pvals': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -43,7 +43,10 @@ class BasePLS():
         reference's keys: ``index_backend`` ('device' -- counter-based
         generator on the GPU, default; 'reference' -- host tables replaying
         the reference's NumPy stream for the given seed), ``device`` (CUDA
-        ordinal) and ``workspace_bytes``.
+        ordinal), ``workspace_bytes`` and ``perm_path`` ('gemm': every
+        permutation runs the cross-covariance contraction, default; 'gram':
+        rotated permutations are evaluated in sample space through the S x S
+        Gram matrix of the data -- same values, no B-sized work).
     """
 
     engine_mode = None
@@ -189,7 +192,13 @@ class BasePLS():
             local = self._prepermuted(given, n, rotate)
         else:
             self.permsamp, block, _ = self._table('perm', n, seed)
-            local = self.engine.run_perms(block, rotate=rotate)
+            path = self.inputs.get('perm_path') or 'gemm'
+            if path not in ('gemm', 'gram'):
+                raise ValueError("perm_path must be 'gemm' or 'gram'")
+            if path == 'gram' and rotate:
+                local = self.engine.run_perms_gram(block)
+            else:
+                local = self.engine.run_perms(block, rotate=rotate)
         d_perm = pdist.gather_resamples(local, n)
         self._dev['d_perm'] = d_perm
         return to_host(d_perm).T.copy(), None, None

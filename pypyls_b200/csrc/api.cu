@@ -191,7 +191,7 @@ int plsb_destroy(plsb_handle_t h) {
   DevBuf *bufs[] = {&h->tables, &h->Xraw, &h->Xcell, &h->Xglob, &h->Y,    &h->Cmat,  &h->Uo,
                     &h->Vo,     &h->dorig, &h->Sx,   &h->norms, &h->A,    &h->Ac,    &h->R,
                     &h->S1,     &h->S2,   &h->G,     &h->H,     &h->M,    &h->lam,   &h->rowsq,
-                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT};
+                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx};
   for (DevBuf *b : bufs) b->release();
   delete h;
   return PLSB_OK;
@@ -408,6 +408,7 @@ int plsb_set_data(plsb_handle_t h, const double *d_X, const double *d_Y, void *s
   PLSB_TRY(launch_prep_cells(h, h->Xraw.as<double>(), xcell, h->Xglob.as<double>(), st));
   h->has_data = true;
   h->has_original = false;
+  h->has_kx = false;
   return PLSB_OK;
 }
 
@@ -584,6 +585,64 @@ int plsb_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, int rotate,
   PLSB_HANDLE(h);
   PLSB_CHECK(d_idx && d_dperm && count >= 0, PLSB_ERR_ARG, "plsb_run_perms: bad argument");
   return run_perms_impl(h, d_idx, nullptr, count, rotate, d_dperm, as_stream(stream));
+}
+
+// Kx = Xp Xp^T (S_pad x S_pad, pitch round_up(S_pad, 128)) of the permutation data matrix
+static int ensure_gram(plsb_ctx *h, cudaStream_t st) {
+  if (h->has_kx) return PLSB_OK;
+  const Layout &l = h->lay;
+  const int N_pad = round_up(l.S_pad, GEMM_BN);
+  PLSB_TRY(h->Kx.ensure(sizeof(double) * (size_t)l.S_pad * N_pad));
+  PLSB_TRY(h->Ac.ensure(sizeof(double) * (size_t)l.ldx * l.S_pad));
+  PLSB_TRY(h->S1.ensure(sizeof(double) * (size_t)l.S_pad * l.S_pad));
+  // Xp^T (ldx, S_pad), then the dense product (padding columns of Xp are zero)
+  PLSB_TRY(launch_transpose(h, perm_data(h), l.S_pad, l.ldx, l.ldx, h->Ac.as<double>(), st));
+  PLSB_TRY(dense_gemm(h, perm_data(h), h->Ac.as<double>(), l.S_pad, l.S_pad, l.ldx,
+                      h->S1.as<double>(), st));
+  PLSB_TRY(launch_pad_copy(h, h->S1.as<double>(), l.S_pad, l.S_pad, h->Kx.as<double>(), l.S_pad,
+                           N_pad, st));
+  h->has_kx = true;
+  return PLSB_OK;
+}
+
+int plsb_run_perms_gram(plsb_handle_t h, const int32_t *d_idx, int count, double *d_dperm,
+                        void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->has_original && !h->lay.simpls(), PLSB_ERR_STATE,
+             "plsb_run_perms_gram needs data and the original decomposition");
+  PLSB_CHECK(d_idx && d_dperm && count >= 0, PLSB_ERR_ARG, "plsb_run_perms_gram: bad argument");
+  const Layout &l = h->lay;
+  cudaStream_t st = as_stream(stream);
+  PLSB_TRY(ensure_gram(h, st));
+  const int N_pad = round_up(l.S_pad, GEMM_BN);
+  const size_t per = sizeof(double) * (size_t)l.L * (l.S_pad + N_pad);
+  int chunk = (int)std::min<long long>(count,
+                                       std::max<long long>(1, (long long)(h->ws_limit / per)));
+  chunk = (int)std::min<long long>(chunk, ((1ll << 31) - 1024) / l.L);
+  for (int off = 0; off < count; off += chunk) {
+    const int n = std::min(chunk, count - off);
+    const long long M = (long long)n * l.L, M_pad = round_up_ll(M, GEMM_BM);
+    PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)M_pad * l.S_pad));
+    PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)M_pad * N_pad));
+    PLSB_TRY(zero_tail(h->A.as<double>(), M, M_pad, l.S_pad, st));
+    PLSB_TRY(launch_build(h, BUILD_ROT, d_idx + (size_t)off * l.S, nullptr, n, h->A.as<double>(),
+                          nullptr, nullptr, 0, 0, st));
+    GemmArgs g;
+    g.A = h->A.as<double>();
+    g.lda = l.S_pad;
+    g.X = h->Kx.as<double>();
+    g.ldx = N_pad;
+    g.M_pad = (int)M_pad;
+    g.N_pad = N_pad;
+    g.Kd = l.S_pad;
+    g.k_len = l.S_pad;
+    g.C = h->R.as<double>();
+    g.ldc = N_pad;
+    PLSB_TRY(launch_gemm(h, g, st));
+    PLSB_TRY(launch_rowdot_sqrt(h, h->R.as<double>(), N_pad, h->A.as<double>(), l.S_pad, l.S_pad,
+                                M, d_dperm + (size_t)off * l.L, st));
+  }
+  return PLSB_OK;
 }
 
 int plsb_run_perms_prepermuted(plsb_handle_t h, const double *d_Yperm, int count, int rotate,

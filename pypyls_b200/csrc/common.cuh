@@ -155,6 +155,8 @@ struct plsb_ctx {
   plsb::DevBuf Cmat;   // mean-centred: operator C (J, S)
   // original decomposition
   plsb::DevBuf Uo;     // (B, L)
+  plsb::DevBuf Kx;     // Gram matrix of the permutation data matrix, (S_pad, round_up(S_pad,128))
+  bool has_kx = false;
   plsb::DevBuf UoT;    // Uo transposed, (L, ldx) zero padded: gram_proj's TMA row copies
   plsb::DevBuf Vo;     // (K, L)
   plsb::DevBuf dorig;  // (L)
@@ -242,6 +244,8 @@ int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long c
 // streaming kernels over stored R (stream_kernels.cu)
 int launch_finish_rowsq(plsb_ctx *h, const double *rowsq, int n_splits, int M_pad, int n_rows,
                         double *out, cudaStream_t st);
+int launch_rowdot_sqrt(plsb_ctx *h, const double *T, long long ldt, const double *A, int lda,
+                       int n_cols, long long n_rows, double *out, cudaStream_t st);
 int launch_colscale(plsb_ctx *h, double *S1, const double *S2, int n_rows, long long ld,
                     cudaStream_t st);
 int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K,

@@ -21,6 +21,20 @@ __global__ void finish_rowsq_kernel(const double *__restrict__ rowsq, int n_spli
   out[m] = sqrt(v);
 }
 
+// out[m] = sqrt(sum_u T[m,u] * A[m,u]): quadratic forms a^T Kx a from T = A Kx
+// (sample-space permutation singular values); one warp per row
+__global__ void rowdot_sqrt_kernel(const double *__restrict__ T, long long ldt,
+                                   const double *__restrict__ A, int lda, int n_cols,
+                                   long long n_rows, double *__restrict__ out) {
+  const long long m = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m >= n_rows) return;
+  double v = 0.0;
+  for (int u = lane; u < n_cols; u += 32) v += T[m * ldt + u] * A[m * lda + u];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) out[m] = sqrt(fmax(v, 0.0));
+}
+
 __global__ void colscale_kernel(double *__restrict__ S1, const double *__restrict__ S2, int n_rows,
                                 long long ld, int B, int J, const int *__restrict__ cell_n) {
   const size_t total = (size_t)n_rows * ld;
@@ -63,6 +77,16 @@ int launch_finish_rowsq(plsb_ctx *h, const double *rowsq, int n_splits, int M_pa
   KernelTimer kt(h, KC_STATS, st);
   if (n_rows <= 0) return PLSB_OK;
   finish_rowsq_kernel<<<cdiv(n_rows, 256), 256, 0, st>>>(rowsq, n_splits, M_pad, n_rows, out);
+  PLSB_LAUNCHED(h);
+  return PLSB_OK;
+}
+
+int launch_rowdot_sqrt(plsb_ctx *h, const double *T, long long ldt, const double *A, int lda,
+                       int n_cols, long long n_rows, double *out, cudaStream_t st) {
+  KernelTimer kt(h, KC_STATS, st);
+  if (n_rows <= 0) return PLSB_OK;
+  const long long blocks = (n_rows * 32 + 255) / 256;
+  rowdot_sqrt_kernel<<<(unsigned)blocks, 256, 0, st>>>(T, ldt, A, lda, n_cols, n_rows, out);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }

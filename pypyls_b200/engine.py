@@ -232,6 +232,16 @@ class ResamplingEngine:
             _ptr(out), self._stream()))
         return out
 
+    def run_perms_gram(self, idx):
+        """Rotated permuted singular values through the S x S Gram matrix of
+        the data (sample-space fast path; same result as run_perms(rotate=True)
+        without the cross-covariance GEMM)."""
+        idx = self.to_device_indices(idx)
+        out = self._f64(idx.shape[0], self.L)
+        _cabi.check(self._lib.plsb_run_perms_gram(
+            self._h, _ptr(idx), int(idx.shape[0]), _ptr(out), self._stream()))
+        return out
+
     def run_perms_prepermuted(self, Yperm, rotate=True):
         """Permuted singular values (count, L) for pre-permuted behaviour
         matrices Yperm (count, S, T) -- `permsamples` with permindices=False

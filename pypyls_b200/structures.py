@@ -90,14 +90,15 @@ class ResDict(dict):
 
 class PLSInputs(ResDict):
     """Inputs of an analysis (pyls/structures.py:146-172).  ``index_backend``,
-    ``device`` and ``workspace_bytes`` are additions of this engine."""
+    ``device``, ``workspace_bytes`` and ``perm_path`` are additions of this
+    engine."""
 
     allowed = [
         'X', 'Y', 'groups', 'n_cond', 'n_perm', 'n_boot', 'n_split',
         'test_split', 'test_size', 'mean_centering', 'covariance', 'rotate',
         'ci', 'seed', 'verbose', 'n_proc', 'bootsamples', 'permsamples',
         'method', 'n_components', 'aggfunc', 'permindices',
-        'index_backend', 'device', 'workspace_bytes',
+        'index_backend', 'device', 'workspace_bytes', 'perm_path',
     ]
 
     def __init__(self, **kwargs):

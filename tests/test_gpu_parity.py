@@ -113,6 +113,34 @@ def test_prepermuted_y_matches_reference_golden(name):
     assert out.permres.permsamples.shape == Yp.shape
 
 
+@pytest.mark.parametrize('kind', ['behavioral', 'behavioral_cov',
+                                  'meancentered'])
+def test_gram_permutation_path_equals_gemm_path(kind):
+    """perm_path='gram' (sample-space quadratic forms with the S x S Gram matrix
+    of the data) reproduces the rotated permutation singular values of the
+    cross-covariance GEMM path, also across chunk boundaries."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(8)
+    groups, n_cond = [13, 10], 2
+    X, Y = rs.rand(46, 1500), rs.rand(46, 5)
+    ps = po.gen_permsamp(groups, n_cond, 60, seed=3)
+    kw = dict(groups=groups, n_cond=n_cond, n_perm=60, n_boot=0, seed=1,
+              permsamples=ps, verbose=False)
+    if kind == 'meancentered':
+        run = lambda **k: pyls.meancentered_pls(X, mean_centering=1, **kw, **k)
+    else:
+        run = lambda **k: pyls.behavioral_pls(
+            X, Y, covariance=kind.endswith('cov'), **kw, **k)
+    a = run()
+    b = run(perm_path='gram', workspace_bytes=1 << 20)
+    keep = ~np.isclose(a.singvals, 0)
+    close(b.permres.perm_singval[keep], a.permres.perm_singval[keep],
+          rtol=1e-10)
+    assert np.array_equal(a.permres.pvals[keep], b.permres.pvals[keep])
+    with pytest.raises(ValueError):
+        run(perm_path='fft')
+
+
 def test_prepermuted_y_equals_index_permutations():
     """Y[perm] handed in as a matrix gives what the index vector gives, also
     across chunk boundaries (tiny workspace) and for a covariance analysis."""
