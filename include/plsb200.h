@@ -207,6 +207,20 @@ int plsb_accum_u(plsb_handle_t h, const double *d_R, int count, int K, int B,
                  const double *d_M, int L, double *d_usum, double *d_usquare,
                  void *stream);
 
+/*
+ * Cross-validation of a behavioural analysis.  Replaces BehavioralPLS.crossval +
+ * _single_crossval (pyls/types/behavioral.py:82-170) and compute.rescale_test
+ * (pyls/compute.py:129-151) for `count` train / test splits at once:
+ *   d_train (count,S) int32, non-zero = training row (a column of gen_splits,
+ *   pyls/base.py:162-229, with test_size = the held-out fraction);
+ *   max_test = largest number of test rows of any split (K + max_test rounded
+ *   up to a multiple of T must not exceed 80);
+ *   d_r, d_r2 (count,T): Pearson r and R^2 of every behaviour, predicted from
+ *   the training decomposition, against the held-out rows.
+ */
+int plsb_crossval(plsb_handle_t h, const int32_t *d_train, int count, int max_test,
+                  double *d_r, double *d_r2, void *stream);
+
 /* ---- SIMPLS (pls_regression; mode PLSB_SIMPLS, n_groups = 1, n_cond = 1) -------
  * plsb_set_data takes X (S,B) and Y (S,T) already column-centred
  * (pyls/types/regression.py:395-396).  `d_omega` tables hold the Gaussian test

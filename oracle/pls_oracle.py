@@ -161,6 +161,38 @@ def gen_bootsamp(groups, n_cond, n_boot, seed=None):
     return out
 
 
+def gen_splits(groups, n_cond, n_split, seed=None, test_size=0.5):
+    """Train / split-half masks (S, n_split) bool.  Follows pyls/base.py:162-229:
+    per group a coin flip between ceil and floor of n_g * (1 - test_size)
+    subjects drawn without replacement, conditions follow their subject,
+    duplicate columns rejected, give up (warn once) after 500 tries."""
+    groups = [int(g) for g in groups]
+    n_subj = sum(groups)
+    rs = check_random_state(seed)
+    bounds = np.concatenate([[0], np.cumsum(groups)])
+    out = np.zeros((n_subj * n_cond, n_split), dtype=bool)
+    warned = False
+    for i in range(n_split):
+        tries, bad = 0, True
+        while bad and tries < 500:
+            tries, bad = tries + 1, False
+            split = np.zeros(n_subj, dtype=bool)
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                take = rs.choice([np.ceil, np.floor])
+                num = int(take((b - a) * (1 - test_size)))
+                split[rs.choice(np.arange(a, b), size=num, replace=False)] = True
+            # rows: groups stacked, conditions within group, subjects within
+            half = np.hstack([np.tile(split[a:b], n_cond)
+                              for a, b in zip(bounds[:-1], bounds[1:])])
+            if i and (half[:, None] == out[:, :i]).all(axis=0).any():
+                bad = True
+        if tries == 500 and not warned:
+            warnings.warn('WARNING: Duplicate split halves used.')
+            warned = True
+        out[:, i] = half
+    return out
+
+
 # --------------------------------------------------------------------------
 # numeric primitives (pyls/compute.py)
 # --------------------------------------------------------------------------
@@ -204,6 +236,23 @@ def normalize(X, axis=0):
     out = out / nrm
     out[np.broadcast_to(zero, out.shape)] = 0
     return out
+
+
+def rescale_test(X_train, X_test, Y_train, U, V):
+    """Out-of-sample prediction of Y.  pyls/compute.py:129-151 (scipy's zmap
+    written out: test columns standardised with the training mean / ddof=1
+    standard deviation)."""
+    mu = X_train.mean(axis=0, keepdims=True)
+    sd = X_train.std(axis=0, ddof=1, keepdims=True)
+    return ((X_test - mu) / sd) @ U @ V.T + Y_train.mean(axis=0, keepdims=True)
+
+
+def r2_score_raw(y_true, y_pred):
+    """sklearn.metrics.r2_score(..., multioutput='raw_values') for columns
+    with non-constant truth (pyls/types/behavioral.py:168)."""
+    num = ((y_true - y_pred) ** 2).sum(axis=0)
+    den = ((y_true - y_true.mean(axis=0)) ** 2).sum(axis=0)
+    return 1 - num / den
 
 
 def perm_sig(orig, perm):
@@ -429,6 +478,33 @@ def run_perms(spec, X, Y, permsamp, original_v, first=0, count=None,
     return np.stack(cols, axis=-1)
 
 
+def single_crossval(spec, X, Y, inds, seed=None):
+    """One train / test split -> (r (T,), r2 (T,)).  Follows
+    BehavioralPLS._single_crossval, pyls/types/behavioral.py:125-170."""
+    dummy = spec.dummy
+    Xtr, Ytr, dtr = X[inds], Y[inds], dummy[inds]
+    Xte, Yte, dte = X[~inds], Y[~inds], dummy[~inds]
+    U, d, V = svd(gen_covcorr(spec, Xtr, Ytr, dummy=dtr), seed=seed)
+    pred = []
+    for n, V_spl in enumerate(np.split(V, dummy.shape[-1])):
+        tr, te = dtr[:, n].astype(bool), dte[:, n].astype(bool)
+        pred.append(rescale_test(Xtr[tr], Xte[te], Ytr[tr], U, V_spl))
+    pred = np.vstack(pred)
+    return efficient_corr(Yte, pred), r2_score_raw(Yte, pred)
+
+
+def crossval(spec, X, Y, n_split, test_size=0.25, seed=None, splits=None):
+    """(r_scores (T, C), r2_scores (T, C)) over C train / test splits.
+    BehavioralPLS.crossval, pyls/types/behavioral.py:82-123."""
+    if splits is None:
+        splits = gen_splits(spec.groups, spec.n_cond, n_split, seed=seed,
+                            test_size=test_size)
+    out = [single_crossval(spec, X, Y, splits[:, i], seed=i)
+           for i in range(splits.shape[1])]
+    r, r2 = [np.stack(o, axis=-1) for o in zip(*out)]
+    return r, r2
+
+
 def run_boots(spec, X, Y, bootsamp, original_u, first=0, count=None):
     """(distrib (K, L, count), u_sum, u_square) as pyls/base.py:439-528."""
     count = bootsamp.shape[-1] - first if count is None else count
@@ -547,8 +623,9 @@ def _finish_boot(res, orig_bs, distrib, u_sum, u_square, n, ci, add_orig):
 
 def behavioral_pls(X, Y, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
                    covariance=False, rotate=True, ci=95, permsamples=None,
-                   bootsamples=None, seed=None, permindices=True):
-    """pyls.behavioral_pls with test_split=0, n_split=0.  Follows
+                   bootsamples=None, seed=None, permindices=True,
+                   test_split=0, test_size=0.25):
+    """pyls.behavioral_pls with n_split=0.  Follows
     pyls/base.py:341-399 and pyls/types/behavioral.py:172-227, including the
     order in which the seeded RandomState is consumed (original SVD ->
     gen_permsamp -> gen_bootsamp).  permindices=False: ``permsamples`` is a
@@ -586,6 +663,11 @@ def behavioral_pls(X, Y, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
         res['bootsamples'] = bootsamples
         _finish_boot(res, U @ d, distrib, u_sum, u_square, n_boot + 1, ci,
                      add_orig=True)
+    if test_split and test_size > 0:
+        # pyls/types/behavioral.py:217-219: seeded by the analysis' RandomState
+        # after the bootstrap table has been drawn
+        res['pearson_r'], res['r_squared'] = crossval(
+            spec, X, Y, test_split, test_size=test_size, seed=rs)
     res['varexp'] = np.diag(varexp(d))
     res['singvals'] = np.diag(d)
     return res

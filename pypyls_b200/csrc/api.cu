@@ -837,6 +837,107 @@ int plsb_small_decomp(plsb_handle_t h, const double *d_G, const double *d_H, int
   return launch_small_decomp(h, d_G, d_H, count, K, L, d_dorig, d_M, L, d_lam, as_stream(stream));
 }
 
+// one chunk of train / test splits: see crossval.cu
+static int crossval_chunk(plsb_ctx *h, const int32_t *mask, int n, int max_test, double *d_r,
+                          double *d_r2, cudaStream_t st) {
+  const Layout &l = h->lay;
+  const int stride = l.K + round_up(max_test, l.T);   // rows of a split's stacked matrix
+  const int rpr = stride / l.T;                        // rows of a split in S1 / S2
+  const long long cellpad_w = round_up_ll((long long)n * l.T, GEMM_BM);
+  const long long cellpad_c = round_up_ll(n, GEMM_BM);
+  const long long Mw_op = cellpad_w * l.J, Mc_op = cellpad_c * l.J;
+  const long long Z_rows = round_up_ll((long long)n * stride, GEMM_BM);
+  const long long S_rows = round_up_ll((long long)n * rpr, GEMM_BM);
+  PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)Mw_op * l.S_pad));
+  PLSB_TRY(h->Ac.ensure(sizeof(double) * (size_t)Mc_op * l.S_pad));
+  PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)Z_rows * l.ldx));
+  PLSB_TRY(h->S1.ensure(sizeof(double) * (size_t)S_rows * l.ldx));
+  PLSB_TRY(h->S2.ensure(sizeof(double) * (size_t)S_rows * l.ldx));
+  const size_t n_kr = (size_t)(Mw_op + Mc_op) / GEMM_BM;
+  PLSB_TRY(h->maps.ensure(sizeof(int4) * n_kr + sizeof(int) * (size_t)(Mw_op + Mc_op)));
+  int4 *kr_w = h->maps.as<int4>(), *kr_c = kr_w + Mw_op / GEMM_BM;
+  int *map_w = reinterpret_cast<int *>(kr_c + Mc_op / GEMM_BM), *map_c = map_w + Mw_op;
+  PLSB_TRY(h->part.ensure(sizeof(double) * (size_t)n * l.J * l.T + sizeof(int) * (size_t)n * l.J));
+  double *ytrain = h->part.as<double>();
+  int *ntrain = reinterpret_cast<int *>(ytrain + (size_t)n * l.J * l.T);
+  double *Z = h->R.as<double>();
+
+  PLSB_CUDA(cudaMemsetAsync(h->A.p, 0, sizeof(double) * (size_t)Mw_op * l.S_pad, st));
+  PLSB_CUDA(cudaMemsetAsync(h->Ac.p, 0, sizeof(double) * (size_t)Mc_op * l.S_pad, st));
+  PLSB_CUDA(cudaMemsetAsync(Z, 0, sizeof(double) * (size_t)Z_rows * l.ldx, st));
+  PLSB_TRY(launch_build_maps(h, n, l.T, stride, cellpad_w, map_w, kr_w, st));
+  PLSB_TRY(launch_build_maps(h, n, 1, rpr, cellpad_c, map_c, kr_c, st));
+  PLSB_TRY(launch_build(h, BUILD_TRAIN, mask, nullptr, n, h->A.as<double>(), h->Ac.as<double>(),
+                        nullptr, cellpad_w, cellpad_c, st, ntrain, ytrain));
+  // sums and sums of squares of the (globally standardised) training rows of every cell
+  GemmArgs g;
+  g.lda = l.S_pad;
+  g.ldx = l.ldx;
+  g.N_pad = l.ldx;
+  g.Kd = l.S_pad;
+  g.ldc = l.ldx;
+  g.k_len = l.kr_max;
+  g.X = h->Xglob.as<double>();
+  g.A = h->Ac.as<double>();
+  g.M_pad = (int)Mc_op;
+  g.row_map = map_c;
+  g.kranges = kr_c;
+  g.C = h->S1.as<double>();
+  PLSB_TRY(launch_gemm(h, g, st));
+  g.C = h->S2.as<double>();
+  g.square_b = true;
+  PLSB_TRY(launch_gemm(h, g, st));
+  g.square_b = false;
+  PLSB_TRY(launch_rescale_test(h, mask, n, max_test, h->S1.as<double>(), h->S2.as<double>(), rpr,
+                               ntrain, Z, stride, st));
+  if (l.corr()) {
+    PLSB_TRY(launch_colscale(h, h->S1.as<double>(), h->S2.as<double>(), n * rpr, l.ldx, st, rpr,
+                             ntrain));
+    g.scale = h->S1.as<double>();
+    g.scale_div = l.T;
+    g.lds = l.ldx;
+  }
+  g.A = h->A.as<double>();
+  g.M_pad = (int)Mw_op;
+  g.row_map = map_w;
+  g.kranges = kr_w;
+  g.C = Z;
+  PLSB_TRY(launch_gemm(h, g, st));
+  // one Gram pass over [R; X_resc]: G = R R^T and P = X_resc R^T
+  const size_t gz = (size_t)stride * stride, kk = (size_t)l.K * l.K;
+  PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * gz));
+  PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)n * (kk + l.K)));
+  double *V = h->misc.as<double>(), *lam = V + (size_t)n * kk;
+  PLSB_TRY(launch_gram_proj(h, Z, l.ldx, n, stride, nullptr, 0, h->G.as<double>(), nullptr, st));
+  PLSB_TRY(launch_sym_eig(h, h->G.as<double>(), n, l.K, V, lam, 0, st, stride, (long long)gz));
+  return launch_cv_score(h, mask, n, max_test, h->G.as<double>(), stride, V, lam, ytrain, d_r,
+                         d_r2, st);
+}
+
+int plsb_crossval(plsb_handle_t h, const int32_t *d_train, int count, int max_test, double *d_r,
+                  double *d_r2, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->lay.behavioral(), PLSB_ERR_STATE,
+             "plsb_crossval needs a behavioural handle with data");
+  PLSB_CHECK(d_train && d_r && d_r2 && count >= 0 && max_test >= 1, PLSB_ERR_ARG,
+             "plsb_crossval: bad argument");
+  const Layout &l = h->lay;
+  const int stride = l.K + round_up(max_test, l.T);
+  PLSB_CHECK(stride <= MAX_K, PLSB_ERR_ARG,
+             "plsb_crossval: K + test rows = %d exceeds the supported %d rows per split "
+             "(use a smaller test_size)", stride, MAX_K);
+  cudaStream_t st = as_stream(stream);
+  const size_t per = sizeof(double) * ((size_t)stride * l.ldx + (size_t)(l.K + l.J) * l.S_pad +
+                                       2 * (size_t)(stride / l.T) * l.ldx);
+  const int chunk = (int)std::max<long long>(1, std::min<long long>(count, h->ws_limit / per));
+  for (int off = 0; off < count; off += chunk) {
+    const int n = std::min(chunk, count - off);
+    PLSB_TRY(crossval_chunk(h, d_train + (size_t)off * l.S, n, max_test,
+                            d_r + (size_t)off * l.T, d_r2 + (size_t)off * l.T, st));
+  }
+  return PLSB_OK;
+}
+
 // pads count matrices (K,B) into the R workspace with a row pitch that is a multiple of 128
 static int pad_R(plsb_ctx *h, const double *d_R, int count, int K, int B, long long *ldr,
                  cudaStream_t st) {

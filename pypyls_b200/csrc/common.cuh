@@ -234,10 +234,10 @@ int launch_matmul_small(plsb_ctx *h, const double *A, const double *Bm, int n, d
                         cudaStream_t st);
 
 // operand builders / distrib (operands.cu)
-enum BuildKind { BUILD_ROT = 0, BUILD_PLAIN = 1, BUILD_BOOT = 2 };
+enum BuildKind { BUILD_ROT = 0, BUILD_PLAIN = 1, BUILD_BOOT = 2, BUILD_TRAIN = 3 };
 int launch_build(plsb_ctx *h, int kind, const int32_t *idx, const double *yperm, int count,
                  double *A, double *Ac, double *distrib, long long cellpad_w, long long cellpad_c,
-                 cudaStream_t st);
+                 cudaStream_t st, int *ntrain = nullptr, double *ytrain = nullptr);
 int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long cellpad,
                       int *row_map, int4 *kranges, cudaStream_t st);
 
@@ -247,7 +247,7 @@ int launch_finish_rowsq(plsb_ctx *h, const double *rowsq, int n_splits, int M_pa
 int launch_rowdot_sqrt(plsb_ctx *h, const double *T, long long ldt, const double *A, int lda,
                        int n_cols, long long n_rows, double *out, cudaStream_t st);
 int launch_colscale(plsb_ctx *h, double *S1, const double *S2, int n_rows, long long ld,
-                    cudaStream_t st);
+                    cudaStream_t st, int rows_per_resample = 0, const int *nrow = nullptr);
 int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K,
                      const double *UoT, int L, double *G, double *H, cudaStream_t st);
 int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
@@ -257,8 +257,9 @@ int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K
 // M is written as (count, K, ldm): ldm == L dense, ldm == accum_ldm(L) for launch_accum_u
 int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count, int K, int L,
                         const double *dorig, double *M, int ldm, double *lam, cudaStream_t st);
+// G[r] is read at G + r * g_stride with row pitch ldg (0, 0: dense K x K blocks)
 int launch_sym_eig(plsb_ctx *h, const double *G, int count, int K, double *V, double *lam,
-                   int sqrt_lam, cudaStream_t st);
+                   int sqrt_lam, cudaStream_t st, int ldg = 0, long long g_stride = 0);
 
 // SIMPLS (simpls.cu)
 int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit_ops,
@@ -273,6 +274,14 @@ int launch_identity_blocks(plsb_ctx *h, double *M, int n, int L, int ldm, cudaSt
 int launch_xweights_flip(plsb_ctx *h, const double *Rw, long long ldr, int B, int L, double *xw,
                          cudaStream_t st);
 int launch_colcenter(plsb_ctx *h, const double *U, int B, int L, double *out, cudaStream_t st);
+
+// cross-validation (crossval.cu)
+int launch_rescale_test(plsb_ctx *h, const int32_t *mask, int count, int max_test,
+                        const double *S1, const double *S2, int rows_per_resample,
+                        const int *ntrain, double *Z, int stride, cudaStream_t st);
+int launch_cv_score(plsb_ctx *h, const int32_t *mask, int count, int max_test, const double *Gz,
+                    int stride, const double *V, const double *lam, const double *ytrain,
+                    double *r_out, double *r2_out, cudaStream_t st);
 
 // index generation (indexgen.cu), statistics (stats.cu)
 int gen_indices(plsb_ctx *h, bool boot, uint64_t seed, int64_t first, int count, int32_t *d_idx,

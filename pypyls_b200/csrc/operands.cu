@@ -14,6 +14,10 @@
 //     BOOT   A[r*K+(g,t), u] = sum_{s in g, src[s]=u} zy[s,t]        (x 1/(n-1) for covariance)
 //            Ac[r*J+g, u]    = #{s in g : src[s]=u}                  (column statistics)
 //            distrib[r]      = per-cell xcorr(Sx[src], Y[src])       (behavioral.py:54-80)
+//     TRAIN  like BOOT for a train / test split (cross-validation,
+//            pyls/types/behavioral.py:125-170): idx[s] != 0 marks a training row;
+//            all cell statistics run over the training rows only, and the
+//            per-cell training counts and Y means are written out
 //     zy = Y[src] z-scored (ddof=1) or centred within each cell; permutations may
 //     instead bring their own Y (pre-permuted matrices, pyls/base.py:636-639, 689-692).
 //   mean-centred (pyls/types/meancentered.py:50-125, pyls/compute.py:267-357)
@@ -33,6 +37,8 @@ struct BuildParams {
   const int *cell_start, *cell_of_row;
   const double *Vo, *Sx, *Cmat;
   double *A, *Ac, *distrib;
+  int *ntrain;        // TRAIN: (count, J) training rows per cell
+  double *ytrain;     // TRAIN: (count, J, T) mean of Y over the training rows of every cell
 };
 
 __global__ void build_behavioral_kernel(BuildParams p) {
@@ -46,32 +52,49 @@ __global__ void build_behavioral_kernel(BuildParams p) {
   int *src = reinterpret_cast<int *>(sxi + J * L);  // S
   const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 
-  for (int s = tid; s < S; s += nt) src[s] = p.idx ? p.idx[(size_t)r * S + s] : s;
+  const bool train = p.kind == BUILD_TRAIN;
+  for (int s = tid; s < S; s += nt) {
+    int v = p.idx ? p.idx[(size_t)r * S + s] : s;
+    if (train) v = v != 0 ? s : -1;      // a training row is its own source, a test row has none
+    src[s] = v;
+  }
   __syncthreads();
   for (int e = tid; e < S * T; e += nt) {
     const int s = e / T, t = e - s * T;
-    Yp[e] = p.Yperm ? p.Yperm[((size_t)r * S + s) * T + t] : p.Y[(size_t)src[s] * T + t];
+    Yp[e] = p.Yperm ? p.Yperm[((size_t)r * S + s) * T + t]
+                    : (src[s] >= 0 ? p.Y[(size_t)src[s] * T + t] : 0.0);
   }
   __syncthreads();
+  // cell statistics over the rows that have a source (all of them except in TRAIN)
   for (int c = tid; c < J * T; c += nt) {
     const int g = c / T, t = c - g * T;
-    const int r0 = p.cell_start[g], r1 = p.cell_start[g + 1], n = r1 - r0;
+    const int r0 = p.cell_start[g], r1 = p.cell_start[g + 1];
+    int n = 0;
     double m = 0.0;
-    for (int s = r0; s < r1; ++s) m += Yp[s * T + t];
+    for (int s = r0; s < r1; ++s)
+      if (src[s] >= 0) {
+        m += Yp[s * T + t];
+        ++n;
+      }
     m /= n;
     double v = 0.0;
-    for (int s = r0; s < r1; ++s) {
-      const double d = Yp[s * T + t] - m;
-      v += d * d;
-    }
+    for (int s = r0; s < r1; ++s)
+      if (src[s] >= 0) {
+        const double d = Yp[s * T + t] - m;
+        v += d * d;
+      }
     ymean[c] = m;
     yistd[c] = p.corr ? 1.0 / sqrt(v / (n - 1)) : 1.0;
+    if (train) {
+      p.ytrain[(size_t)r * J * T + c] = m;
+      if (t == 0) p.ntrain[(size_t)r * J + g] = n;
+    }
   }
   __syncthreads();
   for (int e = tid; e < S * T; e += nt) {
     const int s = e / T, t = e - s * T;
     const int c = p.cell_of_row[s] * T + t;
-    Yp[e] = (Yp[e] - ymean[c]) * yistd[c];
+    Yp[e] = src[s] >= 0 ? (Yp[e] - ymean[c]) * yistd[c] : 0.0;
   }
   __syncthreads();
 
@@ -113,10 +136,13 @@ __global__ void build_behavioral_kernel(BuildParams p) {
       const int g = row / T, t = row - g * T;
       const int r0 = p.cell_start[g], r1 = p.cell_start[g + 1];
       double val = 0.0;
+      int n = 0;
       if (u < S)
-        for (int s = r0; s < r1; ++s)
+        for (int s = r0; s < r1; ++s) {
           if (src[s] == u) val += Yp[s * T + t];
-      if (!p.corr) val /= (r1 - r0 - 1);
+          n += src[s] >= 0;
+        }
+      if (!p.corr) val /= (n - 1);
       const size_t orow = p.cellpad_w ? (size_t)g * p.cellpad_w + (size_t)r * T + t
                                       : (size_t)r * K + row;
       p.A[orow * lda + u] = val;
@@ -243,7 +269,7 @@ int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long c
 
 int launch_build(plsb_ctx *h, int kind, const int32_t *idx, const double *yperm, int count,
                  double *A, double *Ac, double *distrib, long long cellpad_w, long long cellpad_c,
-                 cudaStream_t st) {
+                 cudaStream_t st, int *ntrain, double *ytrain) {
   KernelTimer kt(h, KC_BUILD, st);
   const Layout &l = h->lay;
   if (count <= 0) return PLSB_OK;
@@ -254,14 +280,17 @@ int launch_build(plsb_ctx *h, int kind, const int32_t *idx, const double *yperm,
   p.kind = kind;
   p.Y = h->Y.as<double>();
   p.Yperm = yperm;
-  PLSB_CHECK(!yperm || (l.behavioral() && kind != BUILD_BOOT), PLSB_ERR_ARG,
+  PLSB_CHECK(!yperm || (l.behavioral() && kind != BUILD_BOOT && kind != BUILD_TRAIN), PLSB_ERR_ARG,
              "pre-permuted Y matrices only apply to behavioural permutations");
+  PLSB_CHECK(kind != BUILD_TRAIN || (l.behavioral() && idx && ntrain && ytrain), PLSB_ERR_ARG,
+             "train / test operands need a behavioural analysis, masks and output buffers");
   p.cell_start = h->d_cell_start;
   p.cell_of_row = h->d_cell_of_row;
   p.Vo = h->Vo.as<double>();
   p.Sx = h->Sx.as<double>();
   p.Cmat = h->Cmat.as<double>();
   p.A = A; p.Ac = Ac; p.distrib = distrib;
+  p.ntrain = ntrain; p.ytrain = ytrain;
   p.cellpad_w = cellpad_w; p.cellpad_c = cellpad_c;
   if (kind == BUILD_ROT || (kind == BUILD_BOOT && distrib))
     PLSB_CHECK(h->has_original, PLSB_ERR_STATE, "operand builder needs the original decomposition");

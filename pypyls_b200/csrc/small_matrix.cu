@@ -42,8 +42,8 @@ constexpr int SM_WARPS = SM_THREADS / 32;
 //   V_out (K,K): eigenvectors in columns, sorted by descending eigenvalue
 //   lam_out (K): eigenvalues sorted descending (sqrt_lam: their square roots)
 __global__ void __launch_bounds__(SM_THREADS)
-eigen_kernel(const double *__restrict__ G, int K, int sqrt_lam, double *__restrict__ V_out,
-             double *__restrict__ lam_out) {
+eigen_kernel(const double *__restrict__ G, int ldg, long long g_stride, int K, int sqrt_lam,
+             double *__restrict__ V_out, double *__restrict__ lam_out) {
   extern __shared__ __align__(16) double sm[];
   const int ne = K + (K & 1), ld = ne | 1, half = ne / 2;
   double *bufA = sm;                 // G -> diag(lam)
@@ -55,7 +55,7 @@ eigen_kernel(const double *__restrict__ G, int K, int sqrt_lam, double *__restri
   int *rank = sc.pq + 2 * half;                        // ne
   sc.blk = reinterpret_cast<short2 *>(rank + ne);      // half*(half+1)/2
   const int r = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
-  const double *Gr = G + (size_t)r * K * K;
+  const double *Gr = G + (size_t)r * g_stride;
 
   // block table: bi -> (a, b), a <= b
   for (int a = tid; a < half; a += nthr) {
@@ -66,7 +66,7 @@ eigen_kernel(const double *__restrict__ G, int K, int sqrt_lam, double *__restri
     const int i = e / ne, j = e - i * ne;
     double g = 0.0;
     // symmetrise: both triangles must agree exactly for the two-sided updates
-    if (i < K && j < K) g = 0.5 * (Gr[(size_t)i * K + j] + Gr[(size_t)j * K + i]);
+    if (i < K && j < K) g = 0.5 * (Gr[(size_t)i * ldg + j] + Gr[(size_t)j * ldg + i]);
     bufA[i * ld + j] = g;
     bufV[i * ld + j] = (i == j && i < K) ? 1.0 : 0.0;
   }
@@ -217,7 +217,7 @@ rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
 }
 
 int launch_eigen(plsb_ctx *h, const double *G, int count, int K, int sqrt_lam, double *V,
-                 double *lam, cudaStream_t st) {
+                 double *lam, cudaStream_t st, int ldg = 0, long long g_stride = 0) {
   KernelTimer kt(h, KC_SMALL, st);
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(K >= 1 && K <= MAX_K, PLSB_ERR_ARG, "small decomposition: K=%d outside [1,%d]", K,
@@ -231,7 +231,9 @@ int launch_eigen(plsb_ctx *h, const double *G, int count, int K, int sqrt_lam, d
   // one thread per 2 x 2 block of a Jacobi round (measured: fewer, busier threads lose)
   const int threads = std::min(SM_THREADS, std::max(32, round_up(
       tune_int("PLSB_EIGEN_THREADS", nb), 32)));
-  eigen_kernel<<<count, threads, smem, st>>>(G, K, sqrt_lam, V, lam);
+  if (ldg <= 0) ldg = K;
+  if (g_stride <= 0) g_stride = (long long)K * K;
+  eigen_kernel<<<count, threads, smem, st>>>(G, ldg, g_stride, K, sqrt_lam, V, lam);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
@@ -268,8 +270,8 @@ int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count
 }
 
 int launch_sym_eig(plsb_ctx *h, const double *G, int count, int K, double *V, double *lam,
-                   int sqrt_lam, cudaStream_t st) {
-  return launch_eigen(h, G, count, K, sqrt_lam, V, lam, st);
+                   int sqrt_lam, cudaStream_t st, int ldg, long long g_stride) {
+  return launch_eigen(h, G, count, K, sqrt_lam, V, lam, st, ldg, g_stride);
 }
 
 }  // namespace plsb

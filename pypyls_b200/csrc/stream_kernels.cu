@@ -35,15 +35,19 @@ __global__ void rowdot_sqrt_kernel(const double *__restrict__ T, long long ldt,
   if (lane == 0) out[m] = sqrt(fmax(v, 0.0));
 }
 
+// rows come in groups of `rpr` per resample, the first J of a group are its cells; the
+// row count of a (resample, cell) is cell_n[cell] or, with nrow, nrow[resample * J + cell]
 __global__ void colscale_kernel(double *__restrict__ S1, const double *__restrict__ S2, int n_rows,
-                                long long ld, int B, int J, const int *__restrict__ cell_n) {
+                                long long ld, int B, int J, int rpr,
+                                const int *__restrict__ cell_n, const int *__restrict__ nrow) {
   const size_t total = (size_t)n_rows * ld;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
        e += (size_t)gridDim.x * blockDim.x) {
     const int row = (int)(e / ld), b = (int)(e % ld);
+    const int cell = row % rpr;
     double out = 0.0;
-    if (b < B) {
-      const double n = (double)cell_n[row % J];
+    if (b < B && cell < J) {
+      const double n = nrow ? (double)nrow[(size_t)(row / rpr) * J + cell] : (double)cell_n[cell];
       const double s1 = S1[e], s2 = S2[e];
       const double var = (s2 - s1 * s1 / n) / (n - 1.0);
       out = 1.0 / ((n - 1.0) * sqrt(var));
@@ -92,12 +96,14 @@ int launch_rowdot_sqrt(plsb_ctx *h, const double *T, long long ldt, const double
 }
 
 int launch_colscale(plsb_ctx *h, double *S1, const double *S2, int n_rows, long long ld,
-                    cudaStream_t st) {
+                    cudaStream_t st, int rows_per_resample, const int *nrow) {
   KernelTimer kt(h, KC_STATS, st);
   if (n_rows <= 0) return PLSB_OK;
   const size_t total = (size_t)n_rows * ld;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 32);
-  colscale_kernel<<<blocks, 256, 0, st>>>(S1, S2, n_rows, ld, h->lay.B, h->lay.J, h->d_cell_n);
+  const int rpr = rows_per_resample > 0 ? rows_per_resample : h->lay.J;
+  colscale_kernel<<<blocks, 256, 0, st>>>(S1, S2, n_rows, ld, h->lay.B, h->lay.J, rpr,
+                                          h->d_cell_n, nrow);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }

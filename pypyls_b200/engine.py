@@ -256,6 +256,25 @@ class ResamplingEngine:
             _ptr(out), self._stream()))
         return out
 
+    def crossval(self, train):
+        """Cross-validated Pearson r and R^2, (count, T) each, for train / test
+        masks `train` (S, count) bool as gen_splits returns them
+        (BehavioralPLS.crossval, pyls/types/behavioral.py:82-170)."""
+        train = np.asarray(train)
+        if train.ndim != 2 or train.shape[0] != self.S:
+            raise ValueError('train / test masks must have shape ({}, n); got '
+                             '{}'.format(self.S, train.shape))
+        n_test = (train == 0).sum(axis=0)
+        if n_test.min() < 2:
+            raise ValueError('every split needs at least two held-out rows')
+        mask = self.to_device(np.ascontiguousarray(train.T), dtype=torch.int32)
+        n = int(mask.shape[0])
+        r, r2 = self._f64(n, self.T), self._f64(n, self.T)
+        _cabi.check(self._lib.plsb_crossval(
+            self._h, _ptr(mask), n, int(n_test.max()), _ptr(r), _ptr(r2),
+            self._stream()))
+        return r, r2
+
     def run_boots(self, idx, u_sum=None, u_square=None):
         """(distrib (count,K,L), u_sum (B,L), u_square (B,L)) on the device
         (BasePLS.bootstrap, pyls/base.py:439-576)."""

@@ -2,8 +2,8 @@
 """
 Host-side resampling tables that replay the reference's NumPy random stream.
 
-``gen_permsamp`` / ``gen_bootsamp`` return, for a given seed, exactly the
-tables of pyls/base.py:10-79 and :82-159 (same draws from the same
+``gen_permsamp`` / ``gen_bootsamp`` / ``gen_splits`` return, for a given seed,
+exactly the tables of pyls/base.py:10-79, :82-159 and :162-229 (same draws from the same
 ``RandomState`` in the same order), which is what "identical seeds" parity
 against the CPU reference needs.  The only change is how duplicates are found:
 the reference compares each candidate column with all earlier ones
@@ -133,6 +133,43 @@ def gen_bootsamp(groups, n_cond, n_boot, seed=None, verbose=True):
         out[:, i] = col
         for k, s in zip(keys, seen):
             s.add(k)
+    return out
+
+
+def gen_splits(groups, n_cond, n_split, seed=None, test_size=0.5):
+    """
+    Train / split masks (S, n_split) bool; bit-identical to
+    pyls/base.py:162-229 for the same ``seed`` state: per group one
+    ``randint(0, 2)`` (ceil or floor of n_g * (1 - test_size) subjects) and one
+    ``permutation(n_g)`` whose head is the chosen subjects -- the draws
+    ``RandomState.choice`` makes there.
+    """
+    groups, bounds, _ = _layout(groups, n_cond)
+    n_subj = int(bounds[-1])
+    rs = check_random_state(seed)
+    out = np.zeros((n_subj * n_cond, n_split), dtype=bool)
+    seen = set()
+    warned = False
+    for i in range(n_split):
+        tries = 0
+        while True:
+            tries += 1
+            rows = []
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                frac = (b - a) * (1 - test_size)
+                num = int(np.floor(frac) if rs.randint(0, 2) else np.ceil(frac))
+                mask = np.zeros(b - a, dtype=bool)
+                mask[rs.permutation(b - a)[:num]] = True
+                rows.append(np.tile(mask, n_cond))
+            col = np.concatenate(rows)
+            key = col.tobytes()
+            if key not in seen or tries >= 500:
+                break
+        if tries == 500 and not warned:
+            warnings.warn('WARNING: Duplicate split halves used.')
+            warned = True
+        out[:, i] = col
+        seen.add(key)
     return out
 
 

@@ -16,10 +16,6 @@ class BehavioralPLS(BasePLS):
                  covariance=False, rotate=True, ci=95, permsamples=None,
                  bootsamples=None, seed=None, verbose=True, n_proc=None,
                  **kwargs):
-        if test_split:
-            raise NotImplementedError(
-                'Cross-validation (test_split) is not part of the accelerated '
-                'path yet; pass test_split=0.')
         X, Y = np.asarray(X), np.asarray(Y)
         if X.ndim != 2 or Y.ndim != 2:
             raise ValueError('`X` and `Y` must be two-dimensional arrays.')
@@ -35,9 +31,27 @@ class BehavioralPLS(BasePLS):
         return 'behavioral_cov' if self.inputs.get('covariance') \
             else 'behavioral'
 
+    def crossval(self, X, Y, groups=None, seed=None):
+        """
+        Cross-validation on the device (replaces pyls/types/behavioral.py:82-170):
+        ``test_split`` train / test splits generated like the reference does
+        (gen_splits, pyls/base.py:162-229, replaying its NumPy stream), every
+        split decomposed and scored in one batched launch sequence.
+
+        Returns
+        -------
+        r_scores, r2_scores : (T, C) numpy.ndarray
+        """
+        from ..engine import to_host
+        from ..resample import gen_splits
+        splits = gen_splits(self.inputs.groups, self.inputs.n_cond,
+                            self.inputs.test_split, seed=seed,
+                            test_size=self.inputs.test_size)
+        r, r2 = self.engine.crossval(splits)
+        return to_host(r).T.copy(), to_host(r2).T.copy()
+
     def run_pls(self, X, Y):
-        """Follows pyls/types/behavioral.py:172-227 (cross-validation
-        excluded)."""
+        """Follows pyls/types/behavioral.py:172-227."""
         res = super().run_pls(X, Y)
         eng = self.engine
 
@@ -64,6 +78,12 @@ class BehavioralPLS(BasePLS):
                                        y_loadings_ci=corrci,
                                        bootsamples=self.bootsamp))
 
+        # cross-validated prediction of Y (pyls/types/behavioral.py:217-219)
+        if self.inputs.get('test_split') is not None and \
+                (self.inputs.get('test_size') or 0) > 0:
+            r, r2 = self.crossval(X, Y, seed=self.rs)
+            res['cvres'].update(dict(pearson_r=r, r_squared=r2))
+
         sq = np.diag(res['singvals']) ** 2
         res['varexp'] = sq / np.sum(sq)
         res['singvals'] = np.diag(res['singvals'])
@@ -81,8 +101,9 @@ def behavioral_pls(X, Y, *, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
     permutation test and bootstrap executed on the GPU.
 
     Differences from the reference front-end: ``test_split`` defaults to 0
-    (cross-validation is not accelerated), ``n_split`` must be 0, and
-    ``n_proc`` is accepted but unused (resamples run as one batched launch).
+    (the reference's default is 100; pass it to get ``cvres``), ``n_split``
+    must be 0, and ``n_proc`` is accepted but unused (resamples run as one
+    batched launch).
     Extra keywords: ``index_backend``, ``device``, ``workspace_bytes``.
 
     Returns

@@ -132,6 +132,23 @@ def prepermuted_case():
         save('bpls_prepermuted_' + tag, dict(X=X, Y=Y, Yperm=Yp, **kw), out)
 
 
+def crossval_case():
+    """Cross-validation (test_split train / test splits, BehavioralPLS.crossval,
+    pyls/types/behavioral.py:82-170)."""
+    rs = np.random.RandomState(777)
+    X, Y = rs.rand(48, 60), rs.rand(48, 4)
+    Y[:, :2] += X[:, :12] @ rs.rand(12, 2) * 0.4
+    for tag, extra in (('corr', {}), ('cov', dict(covariance=True))):
+        kw = dict(groups=[14, 10], n_cond=2, n_perm=10, n_boot=10, seed=31,
+                  test_split=15, test_size=0.25, **extra)
+        r = pyls.behavioral_pls(X, Y, n_split=0, permindices=True,
+                                verbose=False, **kw)
+        out = flat(r, 'b')
+        out['pearson_r'] = r['cvres']['pearson_r']
+        out['r_squared'] = r['cvres']['r_squared']
+        save('bpls_crossval_' + tag, dict(X=X, Y=Y, **kw), out)
+
+
 def meancentered_cases():
     rs = np.random.RandomState(1234)
     X = rs.rand(48, 50)
@@ -208,6 +225,7 @@ def matlab_cases():
 if __name__ == '__main__':
     behavioral_cases()
     prepermuted_case()
+    crossval_case()
     meancentered_cases()
     regression_cases()
     index_cases()

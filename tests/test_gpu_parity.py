@@ -113,6 +113,54 @@ def test_prepermuted_y_matches_reference_golden(name):
     assert out.permres.permsamples.shape == Yp.shape
 
 
+@pytest.mark.parametrize('name', ['bpls_crossval_corr', 'bpls_crossval_cov'])
+def test_crossval_matches_reference_golden(name):
+    """Cross-validation (test_split; pyls/types/behavioral.py:82-170) against
+    the reference's own output: with index_backend='reference' the seeded
+    RandomState is consumed exactly as the reference consumes it, so the
+    train / test splits are the same."""
+    import pypyls_b200 as pyls
+    ins, ref = load_golden(name)
+    X, Y = ins.pop('X'), ins.pop('Y')
+    out = pyls.behavioral_pls(X, Y, index_backend='reference', verbose=False,
+                              **ins)
+    assert np.array_equal(out.bootres.bootsamples, ref['bootsamples'])
+    close(out.cvres.pearson_r, ref['pearson_r'])
+    close(out.cvres.r_squared, ref['r_squared'], atol=1e-9)
+
+
+@pytest.mark.parametrize('groups,n_cond,T,cov,test_size', [
+    ([30], 1, 3, False, 0.25),
+    ([9, 11, 8], 2, 2, False, 0.3),
+    ([20, 20], 2, 10, True, 0.25),
+])
+def test_crossval_matches_oracle(groups, n_cond, T, cov, test_size):
+    """Other layouts against the oracle, also across chunk boundaries."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(21)
+    S, B = sum(groups) * n_cond, 400
+    X, Y = rs.rand(S, B), rs.rand(S, T)
+    Y[:, 0] += X[:, :20].mean(axis=1) * 3
+    kw = dict(groups=groups, n_cond=n_cond, n_perm=0, n_boot=0, seed=9,
+              covariance=cov, test_split=12, test_size=test_size)
+    ref = po.behavioral_pls(X, Y, **kw)
+    for ws in (None, 1 << 20):
+        out = pyls.behavioral_pls(X, Y, verbose=False, workspace_bytes=ws,
+                                  **kw)
+        close(out.cvres.pearson_r, ref['pearson_r'])
+        close(out.cvres.r_squared, ref['r_squared'], atol=1e-9)
+    assert out.cvres.pearson_r.shape == (T, 12)
+
+
+def test_crossval_rejects_too_many_test_rows():
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(2)
+    X, Y = rs.rand(120, 300), rs.rand(120, 10)
+    with pytest.raises(ValueError, match='test'):
+        pyls.behavioral_pls(X, Y, n_perm=0, n_boot=0, test_split=5,
+                            test_size=0.75, verbose=False)
+
+
 @pytest.mark.parametrize('kind', ['behavioral', 'behavioral_cov',
                                   'meancentered'])
 def test_gram_permutation_path_equals_gemm_path(kind):

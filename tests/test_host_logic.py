@@ -183,5 +183,21 @@ def test_regression_front_end_argument_errors():
         pyls.pls_regression(Xn, Y, n_perm=0, n_boot=0)
     with pytest.raises(NotImplementedError):
         pyls.behavioral_pls(X, Y, n_split=5, n_perm=2, n_boot=2)
-    with pytest.raises(NotImplementedError):
-        pyls.behavioral_pls(X, Y, test_split=10, n_perm=2, n_boot=2)
+
+
+@pytest.mark.parametrize('groups,n_cond,test_size', [([20, 20], 2, 0.25),
+                                                     ([7, 9, 5], 3, 0.5),
+                                                     ([30], 1, 0.25)])
+def test_gen_splits_replays_the_reference_stream(groups, n_cond, test_size):
+    """The product's gen_splits draws what the oracle's restatement of
+    pyls/base.py:162-229 draws (the oracle is pinned against the reference by
+    the cross-validation golden vectors)."""
+    from oracle import pls_oracle as po
+    from pypyls_b200.resample import gen_splits
+    a = gen_splits(groups, n_cond, 40, seed=5, test_size=test_size)
+    b = po.gen_splits(groups, n_cond, 40, seed=5, test_size=test_size)
+    assert a.dtype == bool and np.array_equal(a, b)
+    assert len(set(map(bytes, a.T))) == 40          # no duplicate splits
+    # conditions follow their subject
+    n_subj = sum(groups)
+    assert a.sum() % n_cond == 0 and a.shape[0] == n_subj * n_cond
