@@ -478,12 +478,18 @@ def main():
                                              n_cond=w['n_cond'], **kw)
             return pyls.behavioral_pls(Xh, Yh, groups=w['groups'],
                                        n_cond=w['n_cond'], **kw)
-        for i in range(2):
-            call(100 + i)
+        # warm-up holds on to the previous result like the timed loop does, so that
+        # the pinned host blocks of two live results exist before timing starts
+        for i in range(3):
+            out = call(100 + i)
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
+            tc = time.perf_counter()
             out = call(i)
+            if os.environ.get('PLSB_BENCH_DEBUG'):
+                print('rank %d e2e call %d: %.1f ms' % (
+                    rank, i, 1e3 * (time.perf_counter() - tc)), file=sys.stderr)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=device)

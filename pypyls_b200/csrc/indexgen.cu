@@ -164,20 +164,54 @@ __global__ void hash_kernel(const int32_t *__restrict__ idx, int total, int S, i
   hashes[e] = hsh;
 }
 
+// Duplicate detection through an open-addressing hash table keyed by (segment,
+// hash of the segment's rows); the value of a key is the SMALLEST column index that
+// carries it.  Column i repeats an earlier column iff that index is < i and the rows
+// agree (the compare guards against hash collisions with the table's owner).
+constexpr unsigned long long HT_EMPTY = ~0ull;
+
+__device__ __forceinline__ unsigned long long ht_key(uint64_t hsh, int sg) {
+  unsigned long long k = hsh ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(sg + 1));
+  return k == HT_EMPTY ? k - 1 : k;
+}
+
+__global__ void ht_insert_kernel(const uint64_t *__restrict__ hashes, int total, int n_seg,
+                                 unsigned long long *__restrict__ keys, int *__restrict__ vals,
+                                 unsigned mask) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total * n_seg) return;
+  const int id = e / n_seg, sg = e - id * n_seg;
+  const unsigned long long key = ht_key(hashes[e], sg);
+  unsigned slot = (unsigned)(key * 0xD6E8FEB86659FD93ull >> 32) & mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(&keys[slot], HT_EMPTY, key);
+    if (prev == HT_EMPTY || prev == key) {
+      atomicMin(&vals[slot], id);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
 // flags[i] = 1 when column i repeats an earlier column (in any segment) and may
 // still be re-drawn; counters[0] = columns to re-draw, counters[1] = exhausted
 __global__ void dup_kernel(const int32_t *__restrict__ idx, int total, int S, int n_seg,
                            const int *__restrict__ seg_bounds,
-                           const uint64_t *__restrict__ hashes, const int *__restrict__ attempts,
-                           int *__restrict__ flags, int *__restrict__ counters) {
+                           const uint64_t *__restrict__ hashes,
+                           const unsigned long long *__restrict__ keys,
+                           const int *__restrict__ vals, unsigned mask,
+                           const int *__restrict__ attempts, int *__restrict__ flags,
+                           int *__restrict__ counters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   bool dup = false;
   for (int sg = 0; sg < n_seg && !dup; ++sg) {
-    const uint64_t mine = hashes[(size_t)i * n_seg + sg];
-    const int a = seg_bounds[sg], b = seg_bounds[sg + 1];
-    for (int j = 0; j < i && !dup; ++j) {
-      if (hashes[(size_t)j * n_seg + sg] != mine) continue;
+    const unsigned long long key = ht_key(hashes[(size_t)i * n_seg + sg], sg);
+    unsigned slot = (unsigned)(key * 0xD6E8FEB86659FD93ull >> 32) & mask;
+    while (keys[slot] != key) slot = (slot + 1) & mask;   // the key was inserted: it is there
+    const int j = vals[slot];
+    if (j < i) {
+      const int a = seg_bounds[sg], b = seg_bounds[sg + 1];
       bool same = true;
       for (int s = a; s < b && same; ++s)
         same = idx[(size_t)i * S + s] == idx[(size_t)j * S + s];
@@ -230,14 +264,22 @@ int gen_indices(plsb_ctx *h, bool boot, uint64_t seed, int64_t first, int count,
     seg[1] = l.S;
   }
   PLSB_TRY(h->idxall.ensure(sizeof(int32_t) * (size_t)total * l.S));
-  const size_t n_int = (size_t)total * 2 + (size_t)total * l.n_subj + 2 + (n_seg + 1);
-  PLSB_TRY(h->flags.ensure(sizeof(int) * n_int + sizeof(uint64_t) * ((size_t)total * n_seg + 1)));
+  // hash table: power of two >= 2 x (columns x segments)
+  size_t ht_size = 1024;
+  while (ht_size < 2 * (size_t)total * n_seg) ht_size <<= 1;
+  const unsigned ht_mask = (unsigned)(ht_size - 1);
+  const size_t n_int = (size_t)total * 2 + (size_t)total * l.n_subj + 2 + (n_seg + 1) + ht_size;
+  PLSB_TRY(h->flags.ensure(sizeof(int) * n_int +
+                           sizeof(uint64_t) * ((size_t)total * n_seg + 1 + ht_size)));
   uint64_t *hashes = h->flags.as<uint64_t>();
-  int *flags = reinterpret_cast<int *>(hashes + (size_t)total * n_seg + 1);
+  unsigned long long *ht_keys =
+      reinterpret_cast<unsigned long long *>(hashes + (size_t)total * n_seg + 1);
+  int *flags = reinterpret_cast<int *>(ht_keys + ht_size);
   int *attempts = flags + total;
   int *scratch = attempts + total;
   int *counters = scratch + (size_t)total * l.n_subj;
   int *d_seg = counters + 2;
+  int *ht_vals = d_seg + (n_seg + 1);
   PLSB_CUDA(cudaMemcpyAsync(d_seg, seg.data(), sizeof(int) * (n_seg + 1), cudaMemcpyHostToDevice,
                             st));
   const int tb = 128, nb = cdiv(total, tb);
@@ -271,8 +313,13 @@ int gen_indices(plsb_ctx *h, bool boot, uint64_t seed, int64_t first, int count,
     hash_kernel<<<cdiv(total * n_seg, tb), tb, 0, st>>>(p.idx, total, l.S, n_seg, d_seg, hashes);
     PLSB_LAUNCHED(h);
     PLSB_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(int), st));
-    dup_kernel<<<nb, tb, 0, st>>>(p.idx, total, l.S, n_seg, d_seg, hashes, attempts, flags,
-                                  counters);
+    PLSB_CUDA(cudaMemsetAsync(ht_keys, 0xFF, sizeof(unsigned long long) * ht_size, st));
+    PLSB_CUDA(cudaMemsetAsync(ht_vals, 0x7F, sizeof(int) * ht_size, st));
+    ht_insert_kernel<<<cdiv(total * n_seg, tb), tb, 0, st>>>(hashes, total, n_seg, ht_keys,
+                                                             ht_vals, ht_mask);
+    PLSB_LAUNCHED(h);
+    dup_kernel<<<nb, tb, 0, st>>>(p.idx, total, l.S, n_seg, d_seg, hashes, ht_keys, ht_vals,
+                                  ht_mask, attempts, flags, counters);
     PLSB_LAUNCHED(h);
     PLSB_CUDA(cudaMemcpyAsync(host_counters, counters, 2 * sizeof(int), cudaMemcpyDeviceToHost,
                               st));
