@@ -146,9 +146,12 @@ class BasePLS():
 
     def _table(self, kind, n, seed):
         """Resampling table for this analysis: user-provided, replayed on the
-        host, or generated on the device.  Returns (host (S, n) int array,
-        device (n_local, S) int32 block of this rank, first id of the block).
-        """
+        host, or generated on the device.  Returns (host, block, first):
+        `block` is the device (n_local, S) int32 block of this rank starting at
+        resample id `first`; `host` is a callable that gives the (S, n) int
+        array of the whole table -- for device-generated tables the copy to
+        the host is deferred so that it overlaps the resampling kernels the
+        caller queues first."""
         eng = self.engine
         key = 'permsamples' if kind == 'perm' else 'bootsamples'
         first, count = pdist.my_block(n)
@@ -163,7 +166,7 @@ class BasePLS():
                 raise ValueError('Provided `{}` must have shape ({}, {}); got '
                                  '{}'.format(key, eng.S, n, given.shape))
             block = eng.to_device_indices(given[:, first:first + count])
-            return given, block, first
+            return (lambda: given), block, first
         gen = eng.gen_perm_indices if kind == 'perm' else eng.gen_boot_indices
         block, exhausted = gen(_device_seed(check_random_state(seed)), count,
                                first=first)
@@ -171,7 +174,7 @@ class BasePLS():
             warnings.warn('WARNING: Duplicate {} used.'.format(
                 'permutations' if kind == 'perm' else 'bootstraps'))
         full = pdist.gather_resamples(block, n)
-        return to_host(full).T.astype(int), block, first
+        return (lambda: to_host(full).T.astype(int)), block, first
 
     def permutation(self, X, Y, seed=None):
         """
@@ -191,14 +194,15 @@ class BasePLS():
             # pre-permuted Y matrices, (P, S, T) (pyls/base.py:636-639, 689-692)
             local = self._prepermuted(given, n, rotate)
         else:
-            self.permsamp, block, _ = self._table('perm', n, seed)
             path = self.inputs.get('perm_path') or 'gemm'
             if path not in ('gemm', 'gram'):
                 raise ValueError("perm_path must be 'gemm' or 'gram'")
+            host_table, block, _ = self._table('perm', n, seed)
             if path == 'gram' and rotate:
                 local = self.engine.run_perms_gram(block)
             else:
                 local = self.engine.run_perms(block, rotate=rotate)
+            self.permsamp = host_table()     # overlaps the kernels queued above
         d_perm = pdist.gather_resamples(local, n)
         self._dev['d_perm'] = d_perm
         return to_host(d_perm).T.copy(), None, None
@@ -229,8 +233,9 @@ class BasePLS():
         u_sum, u_square : (B, L) numpy.ndarray
         """
         n = self.inputs.n_boot
-        self.bootsamp, block, _ = self._table('boot', n, seed)
+        host_table, block, _ = self._table('boot', n, seed)
         distrib, u_sum, u_square = self.engine.run_boots(block)
+        self.bootsamp = host_table()         # overlaps the kernels queued above
         distrib = pdist.gather_resamples(distrib, n)
         pdist.reduce_sum(u_sum, u_square)
         self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)

@@ -144,9 +144,10 @@ class PLSRegression(BasePLS):
         (pyls/types/regression.py:329-373): variance explained in Y per
         component for every permutation of the rows of Y."""
         n = self.inputs.n_perm
-        self.permsamp, block, first = self._table('perm', n, seed)
+        host_table, block, first = self._table('perm', n, seed)
         local = self.engine.simpls_run_perms(
             block, self._omega_block(first, block.shape[0]))
+        self.permsamp = host_table()
         d_perm = pdist.gather_resamples(local, n)
         self._dev['d_perm'] = d_perm
         return to_host(d_perm).T.copy(), None, None
@@ -155,9 +156,10 @@ class PLSRegression(BasePLS):
         """Replaces BasePLS.bootstrap + PLSRegression._single_boot
         (pyls/types/regression.py:279-327)."""
         n = self.inputs.n_boot
-        self.bootsamp, block, first = self._table('boot', n, seed)
+        host_table, block, first = self._table('boot', n, seed)
         distrib, u_sum, u_square, _ = self.engine.simpls_run_boots(
             block, self._omega_block(first, block.shape[0]))
+        self.bootsamp = host_table()
         distrib = pdist.gather_resamples(distrib, n)
         pdist.reduce_sum(u_sum, u_square)
         self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
