@@ -146,6 +146,11 @@ int plsb_run_perms_prepermuted(plsb_handle_t h, const double *d_Yperm, int count
 int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count,
                    double *d_distrib, double *d_usum, double *d_usquare,
                    void *stream);
+/* Resamples plsb_run_boots handles per internal pass for the current workspace
+ * limit (<= count).  A caller that wants each pass's slice of `distrib` as soon as
+ * it is final (to overlap its device->host copy with the next pass) can call
+ * plsb_run_boots on blocks of this size; u_sum / u_square accumulate across calls. */
+int plsb_boot_chunk(plsb_handle_t h, int count);
 
 /* compute.perm_sig (pyls/compute.py:154-181): strict '>' count.
  * d_dperm (count,L), d_dorig (L) -> d_pvals (L). */

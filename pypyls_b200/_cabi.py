@@ -40,6 +40,7 @@ PROTOTYPES = {
     'plsb_run_perms_prepermuted': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'plsb_run_boots': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     'plsb_crossval': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    'plsb_boot_chunk': (_i, [_vp, _i]),
     'plsb_perm_pvals': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     'plsb_percentile': (_i, [_vp, _vp, _i, _i, _dbl, _dbl, _vp, _vp, _vp]),
     'plsb_boot_ratio': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),

@@ -234,6 +234,15 @@ class BasePLS():
         """
         n = self.inputs.n_boot
         host_table, block, _ = self._table('boot', n, seed)
+        if pdist.world()[1] == 1:
+            # single GPU: every internal pass's slice of `distrib` goes to the host
+            # on a side stream while the next pass computes
+            distrib, host, u_sum, u_square = \
+                self.engine.run_boots_streamed(block)
+            self.bootsamp = host_table()
+            self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
+            us, uq = to_host(u_sum), to_host(u_square)   # synchronises the stream
+            return host.numpy().transpose(1, 2, 0), us, uq
         distrib, u_sum, u_square = self.engine.run_boots(block)
         self.bootsamp = host_table()         # overlaps the kernels queued above
         distrib = pdist.gather_resamples(distrib, n)

@@ -683,6 +683,11 @@ int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, double *d_d
   return PLSB_OK;
 }
 
+int plsb_boot_chunk(plsb_handle_t h, int count) {
+  if (!h || !h->configured || count <= 0) return 0;
+  return chunk_size(h, true, count);
+}
+
 int plsb_perm_pvals(plsb_handle_t h, const double *d_dperm, int count, int L, const double *d_dorig,
                     double *d_pvals, void *stream) {
   PLSB_HANDLE(h);

@@ -43,6 +43,7 @@ def _ptr(t):
 # an engine borrows a free handle and gives it back when closed, so repeated
 # analyses do not pay cudaMalloc / cudaFree of the workspaces again.
 _FREE_HANDLES = {}
+_COPY_STREAMS = {}     # device index -> side stream for overlapped device->host copies
 
 
 def release_workspaces():
@@ -289,6 +290,37 @@ class ResamplingEngine:
             self._h, _ptr(idx), n, _ptr(distrib), _ptr(u_sum), _ptr(u_square),
             self._stream()))
         return distrib, u_sum, u_square
+
+    def run_boots_streamed(self, idx):
+        """run_boots in blocks of the library's internal pass size; the block's
+        slice of `distrib` is copied to pinned host memory on a side stream
+        while the next block computes.  Returns (distrib on the device,
+        the same (count, K, L) on the host, u_sum, u_square)."""
+        idx = self.to_device_indices(idx)
+        n = int(idx.shape[0])
+        distrib = self._f64(n, self.K, self.L)
+        host = torch.empty((n, self.K, self.L), dtype=torch.float64,
+                           pin_memory=True)
+        u_sum = torch.zeros((self.B, self.L), dtype=torch.float64,
+                            device=self.device)
+        u_square = torch.zeros_like(u_sum)
+        chunk = max(1, int(self._lib.plsb_boot_chunk(self._h, n))) if n else 1
+        main = torch.cuda.current_stream(self.device)
+        side = _COPY_STREAMS.get(self.device.index)
+        if side is None:
+            side = _COPY_STREAMS[self.device.index] = torch.cuda.Stream(self.device)
+        for a in range(0, n, chunk):
+            b = min(n, a + chunk)
+            _cabi.check(self._lib.plsb_run_boots(
+                self._h, _ptr(idx[a:b]), b - a, _ptr(distrib[a:b]),
+                _ptr(u_sum), _ptr(u_square), self._stream()))
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                host[a:b].copy_(distrib[a:b], non_blocking=True)
+        main.wait_stream(side)
+        return distrib, host, u_sum, u_square
 
     def crosscov(self, idx=None, bootstrap=False):
         """Cross-covariance matrices (count, K, B) of the given resamples;
