@@ -226,6 +226,36 @@ int plsb_accum_u(plsb_handle_t h, const double *d_R, int count, int K, int B,
 int plsb_crossval(plsb_handle_t h, const int32_t *d_train, int count, int max_test,
                   double *d_r, double *d_r2, void *stream);
 
+/*
+ * Split-half reliability of the singular vectors.  Replaces BasePLS.split_half
+ * (pyls/base.py:714-770) for `count` data sets at once -- the call inside every
+ * permutation (base.py:704-708: d_idx (count,S) permutation table, or d_yperm
+ * (count,S,T) pre-permuted behaviour matrices; use_original = 0: every data set
+ * is scored against its own decomposition) and the one on the original data
+ * (base.py:373-380: d_idx = d_yperm = NULL, count = 1, use_original = 1: the
+ * decomposition installed by plsb_decompose / plsb_set_original).
+ *   d_masks (count, n_split, S) int32: half / half masks, non-zero = first half
+ *   (columns of gen_splits(..., test_size=0.5), pyls/base.py:162-229; the
+ *   reference draws a fresh set per permutation, seeded by its number);
+ *   d_ucorr, d_vcorr (count, L): correlations between the two halves of the
+ *   projected left / right singular vectors, averaged over the masks.
+ * Needs 2 K <= 80.  Numerically null latent variables report 0.
+ */
+/* Device counterpart of gen_splits (pyls/base.py:162-229): `count` sets (ids
+ * first .. first+count-1; one per permutation, base.py:704-708) of `n_split`
+ * masks, d_masks (count, n_split, S) int32 0/1.  Per group a coin flip between
+ * ceil and floor of n_g * train_fraction subjects, drawn without replacement;
+ * conditions follow their subject; a mask equal to an earlier one of its set is
+ * re-drawn (<= 500 draws, *h_n_exhausted counts the masks that hit the cap).
+ * Counter-based: a set depends on (seed, id) only. */
+int plsb_gen_split_masks(plsb_handle_t h, uint64_t seed, int64_t first, int count,
+                         int n_split, double train_fraction, int32_t *d_masks,
+                         int *h_n_exhausted, void *stream);
+int plsb_split_half(plsb_handle_t h, const int32_t *d_idx, const double *d_yperm,
+                    int count, const int32_t *d_masks, int n_split,
+                    int use_original, double *d_ucorr, double *d_vcorr,
+                    void *stream);
+
 /* ---- SIMPLS (pls_regression; mode PLSB_SIMPLS, n_groups = 1, n_cond = 1) -------
  * plsb_set_data takes X (S,B) and Y (S,T) already column-centred
  * (pyls/types/regression.py:395-396).  `d_omega` tables hold the Gaussian test

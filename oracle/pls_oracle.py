@@ -396,9 +396,33 @@ def decompose(spec, X, Y, seed=None):
 # per-resample bodies (pyls/base.py)
 # --------------------------------------------------------------------------
 
-def single_perm(spec, X, Y, perminds, original_v, seed=None, use_permind=True):
-    """One permutation -> (L,) permuted singular values.  Follows
-    pyls/base.py:654-712 with n_split=None; the permuted operand is Y for
+def split_half(spec, X, Y, ud, vd, n_split, seed=None, splits=None):
+    """Split-half reliability of the singular vectors -> (ucorr (L,), vcorr
+    (L,)).  Follows pyls/base.py:714-770: ``n_split`` half/half masks from
+    gen_splits(seed, test_size=0.5); for every mask the cross-covariance of
+    either half is projected on the scaled singular vectors ``vd = V d^-1``
+    (-> B x L) and ``ud = U d^-1`` (-> K x L) and matching columns of the two
+    halves are correlated; the correlations are averaged over the masks."""
+    if splits is None:
+        splits = gen_splits(spec.groups, spec.n_cond, n_split, seed=seed,
+                            test_size=0.5)
+    dummy = spec.dummy
+    ucorr = np.zeros((ud.shape[-1], n_split))
+    vcorr = np.zeros((vd.shape[-1], n_split))
+    for i in range(n_split):
+        spl = splits[:, i].astype(bool)
+        D1 = gen_covcorr(spec, X[spl], Y[spl], dummy[spl])
+        D2 = gen_covcorr(spec, X[~spl], Y[~spl], dummy[~spl])
+        ucorr[:, i] = efficient_corr(D1.T @ vd, D2.T @ vd)
+        vcorr[:, i] = efficient_corr(D1 @ ud, D2 @ ud)
+    return ucorr.mean(axis=-1), vcorr.mean(axis=-1)
+
+
+def single_perm(spec, X, Y, perminds, original_v, seed=None, use_permind=True,
+                n_split=None):
+    """One permutation -> (L,) permuted singular values (and, with
+    ``n_split``, the split-half correlations of the permuted data).  Follows
+    pyls/base.py:654-712; the permuted operand is Y for
     behavioral (base.py:599) and X for mean-centered
     (pyls/types/meancentered.py:125).  use_permind=False: ``perminds`` is a
     pre-permuted Y matrix used as it is (base.py:689-692)."""
@@ -413,8 +437,16 @@ def single_perm(spec, X, Y, perminds, original_v, seed=None, use_permind=True):
     U, d, V = decompose(spec, Xp, Yp, seed=seed)
     if spec.rotate:
         rot = procrustes(original_v, V, d)
-        return np.sqrt(np.sum(rot ** 2, axis=0))
-    return np.diag(d)
+        ssd = np.sqrt(np.sum(rot ** 2, axis=0))
+    else:
+        ssd = np.diag(d)
+    if n_split is None:
+        return ssd
+    # pyls/base.py:704-708: the permutation's own (un-rotated) decomposition,
+    # masks seeded by the permutation number
+    di = np.linalg.inv(d)
+    ucorr, vcorr = split_half(spec, Xp, Yp, U @ di, V @ di, n_split, seed=seed)
+    return ssd, ucorr, vcorr
 
 
 def single_boot(spec, X, Y, inds, original_u, seed=None):
@@ -476,6 +508,33 @@ def run_perms(spec, X, Y, permsamp, original_v, first=0, count=None,
                         use_permind=use_permind)
             for i in range(first, first + count)]
     return np.stack(cols, axis=-1)
+
+
+def run_perms_split(spec, X, Y, permsamp, original_v, n_split, first=0,
+                    count=None, use_permind=True):
+    """run_perms with split-half resampling inside every permutation ->
+    (d_perm (L, count), ucorrs (L, count), vcorrs (L, count));
+    pyls/base.py:644-652 with n_split set."""
+    count = permsamp.shape[-1] - first if count is None else count
+    out = [single_perm(spec, X, Y, permsamp[..., i], original_v, seed=i,
+                       use_permind=use_permind, n_split=n_split)
+           for i in range(first, first + count)]
+    return tuple(np.stack([o[k] for o in out], axis=-1) for k in range(3))
+
+
+def _split_results(spec, X, Y, res, U, d, V, n_split, ucorrs, vcorrs, rs, ci):
+    """Split-half block of BasePLS.run_pls (pyls/base.py:373-397): the
+    original data's correlations (masks drawn from the analysis' RandomState
+    after the permutation table), their p-values against the permuted
+    correlations and percentile limits of the latter."""
+    di = np.linalg.inv(d)
+    ou, ov = split_half(spec, X, Y, U @ di, V @ di, n_split, seed=rs)
+    res['ucorr'], res['vcorr'] = ou, ov
+    res['ucorr_pvals'] = perm_sig(np.diag(ou), ucorrs)
+    res['vcorr_pvals'] = perm_sig(np.diag(ov), vcorrs)
+    res['ucorr_lolim'], res['ucorr_uplim'] = boot_ci(ucorrs, ci=ci)
+    res['vcorr_lolim'], res['vcorr_uplim'] = boot_ci(vcorrs, ci=ci)
+    res['perm_ucorr'], res['perm_vcorr'] = ucorrs, vcorrs
 
 
 def single_crossval(spec, X, Y, inds, seed=None):
@@ -624,8 +683,8 @@ def _finish_boot(res, orig_bs, distrib, u_sum, u_square, n, ci, add_orig):
 def behavioral_pls(X, Y, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
                    covariance=False, rotate=True, ci=95, permsamples=None,
                    bootsamples=None, seed=None, permindices=True,
-                   test_split=0, test_size=0.25):
-    """pyls.behavioral_pls with n_split=0.  Follows
+                   test_split=0, test_size=0.25, n_split=None):
+    """pyls.behavioral_pls.  Follows
     pyls/base.py:341-399 and pyls/types/behavioral.py:172-227, including the
     order in which the seeded RandomState is consumed (original SVD ->
     gen_permsamp -> gen_bootsamp).  permindices=False: ``permsamples`` is a
@@ -642,15 +701,19 @@ def behavioral_pls(X, Y, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
     if n_perm > 0:
         if permsamples is None:
             permsamples = gen_permsamp(groups, n_cond, n_perm, seed=rs)
-        if permindices:
-            d_perm = run_perms(spec, X, Y, permsamples, V)
+        table = permsamples if permindices else \
+            np.transpose(permsamples, (1, 2, 0))
+        if n_split:
+            d_perm, ucorrs, vcorrs = run_perms_split(
+                spec, X, Y, table, V, n_split, use_permind=permindices)
         else:
-            d_perm = run_perms(spec, X, Y,
-                               np.transpose(permsamples, (1, 2, 0)), V,
-                               use_permind=False)
+            d_perm = run_perms(spec, X, Y, table, V, use_permind=permindices)
         res['pvals'] = perm_sig(d, d_perm)
         res['permsamples'] = permsamples
         res['perm_singval'] = d_perm
+        if n_split:
+            _split_results(spec, X, Y, res, U, d, V, n_split, ucorrs, vcorrs,
+                           rs, ci)
     cells = np.repeat(groups, n_cond)
     res['y_scores'] = np.vstack([
         y @ v for y, v in zip(np.split(Y, np.cumsum(cells)[:-1]),
@@ -675,8 +738,8 @@ def behavioral_pls(X, Y, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
 
 def meancentered_pls(X, groups=None, n_cond=1, mean_centering=0, n_perm=5000,
                      n_boot=5000, rotate=True, ci=95, permsamples=None,
-                     bootsamples=None, seed=None):
-    """pyls.meancentered_pls with n_split=0, permindices=True.  Follows
+                     bootsamples=None, seed=None, n_split=None):
+    """pyls.meancentered_pls with permindices=True.  Follows
     pyls/types/meancentered.py:11-48 (argument fix-ups) and :127-179."""
     X = np.asarray(X)
     groups = [len(X) // n_cond] if groups is None else list(np.atleast_1d(groups))
@@ -698,10 +761,17 @@ def meancentered_pls(X, groups=None, n_cond=1, mean_centering=0, n_perm=5000,
     if n_perm > 0:
         if permsamples is None:
             permsamples = gen_permsamp(groups, n_cond, n_perm, seed=rs)
-        d_perm = run_perms(spec, X, Y, permsamples, V)
+        if n_split:
+            d_perm, ucorrs, vcorrs = run_perms_split(spec, X, Y, permsamples,
+                                                     V, n_split)
+        else:
+            d_perm = run_perms(spec, X, Y, permsamples, V)
         res['pvals'] = perm_sig(d, d_perm)
         res['permsamples'] = permsamples
         res['perm_singval'] = d_perm
+        if n_split:
+            _split_results(spec, X, Y, res, U, d, V, n_split, ucorrs, vcorrs,
+                           rs, ci)
     res['y_scores'] = Y @ V
     dm = get_mean_center(X, Y, n_cond, mean_centering, False) @ U
     res['contrast'] = np.vstack([dm[c].mean(axis=0)

@@ -19,7 +19,8 @@ import torch
 from . import dist as pdist
 from . import structures
 from .engine import ResamplingEngine, to_host
-from .resample import check_random_state, gen_bootsamp, gen_permsamp
+from .resample import (check_random_state, gen_bootsamp, gen_permsamp,
+                       gen_splits)
 
 
 def _device_seed(rs):
@@ -79,10 +80,6 @@ class BasePLS():
             self.inputs['index_backend'] = backend = 'device'
         if backend not in ('device', 'reference'):
             raise ValueError("index_backend must be 'device' or 'reference'")
-        if self.inputs.get('n_split') is not None:
-            raise NotImplementedError(
-                'Split-half resampling (n_split) is not part of the '
-                'accelerated path yet; pass n_split=0.')
         self.engine = None
 
     # -- engine ------------------------------------------------------------
@@ -137,12 +134,71 @@ class BasePLS():
         res['x_scores'] = to_host(eng.project_scores(U))
 
         if self.inputs.n_perm > 0:
-            d_perm, _, _ = self.permutation(X, Y, seed=self.rs)
+            d_perm, ucorrs, vcorrs = self.permutation(X, Y, seed=self.rs)
             res['permres']['pvals'] = eng.perm_pvals(
                 self._dev['d_perm'], d).cpu().numpy()
             res['permres']['permsamples'] = self.permsamp
             res['permres']['perm_singval'] = d_perm
+
+            if self.inputs.n_split is not None:
+                # split-half reliability of the original singular vectors and
+                # its permutation statistics (pyls/base.py:373-397)
+                ou, ov = self.split_half(X, Y, seed=self.rs)
+                dev = self._dev
+                ci = self.inputs.get('ci')
+                ci = 95 if ci is None else ci
+                low = (100 - ci) / 2
+                out = {}
+                for name, orig, perm in (('ucorr', ou, dev['ucorrs']),
+                                         ('vcorr', ov, dev['vcorrs'])):
+                    lo, hi = eng.percentile(perm, low, 100 - low)
+                    out[name] = to_host(orig)
+                    out[name + '_pvals'] = to_host(eng.perm_pvals(perm, orig))
+                    out[name + '_lolim'] = to_host(lo)
+                    out[name + '_uplim'] = to_host(hi)
+                res['splitres'].update(out)
         return res
+
+    def _split_masks(self, first, count):
+        """Half / half masks of the permutations [first, first + count):
+        (count, n_split, S).  The reference draws a fresh set inside every
+        permutation from ``RandomState(i)``, i the permutation's number
+        (pyls/base.py:646-648, 704-708); index_backend='reference' replays
+        that on the host, 'device' generates them with the counter-based
+        generator on the GPU."""
+        n_split = self.inputs.n_split
+        if self.inputs.index_backend == 'reference':
+            return np.stack([
+                gen_splits(self.inputs.groups, self.inputs.n_cond, n_split,
+                           seed=i, test_size=0.5).T
+                for i in range(first, first + count)]).astype(np.int32)
+        masks, exhausted = self.engine.gen_split_masks(
+            self._split_seed, count, n_split, first=first)
+        if exhausted:
+            warnings.warn('WARNING: Duplicate split halves used.')
+        return masks
+
+    def split_half(self, X, Y, seed=None):
+        """
+        Split-half correlations of the original decomposition on the device
+        (replaces pyls/base.py:714-770 as called from run_pls, :373-380).
+
+        Returns
+        -------
+        ucorr, vcorr : (L,) device tensors
+        """
+        n_split = self.inputs.n_split
+        if self.inputs.index_backend == 'reference':
+            masks = gen_splits(self.inputs.groups, self.inputs.n_cond, n_split,
+                               seed=seed, test_size=0.5).T[None]
+            masks = masks.astype(np.int32)
+        else:
+            masks, exhausted = self.engine.gen_split_masks(
+                _device_seed(check_random_state(seed)), 1, n_split)
+            if exhausted:
+                warnings.warn('WARNING: Duplicate split halves used.')
+        uc, vc = self.engine.split_half(masks, use_original=True)
+        return uc[0], vc[0]
 
     def _table(self, kind, n, seed):
         """Resampling table for this analysis: user-provided, replayed on the
@@ -183,29 +239,45 @@ class BasePLS():
         Returns
         -------
         d_perm : (L, P) numpy.ndarray
-        ucorrs, vcorrs : None
-            Split-half correlations are not computed by this engine.
+        ucorrs, vcorrs : (L, P) numpy.ndarray or None
+            Split-half correlations of every permutation (``n_split``)
         """
         n = self.inputs.n_perm
         rotate = self.inputs.get('rotate')
         rotate = True if rotate is None else bool(rotate)
         given = self.inputs.get('permsamples')
+        n_split = self.inputs.n_split
+        if n_split is not None and self.inputs.index_backend != 'reference':
+            self._split_seed = _device_seed(check_random_state(seed))
+        split_of = None
         if given is not None and self.inputs.get('permindices') is False:
             # pre-permuted Y matrices, (P, S, T) (pyls/base.py:636-639, 689-692)
             local = self._prepermuted(given, n, rotate)
+            first, count = pdist.my_block(n)
+            split_of = dict(Yperm=given[first:first + count])
         else:
             path = self.inputs.get('perm_path') or 'gemm'
             if path not in ('gemm', 'gram'):
                 raise ValueError("perm_path must be 'gemm' or 'gram'")
-            host_table, block, _ = self._table('perm', n, seed)
+            host_table, block, first = self._table('perm', n, seed)
+            count = int(block.shape[0])
             if path == 'gram' and rotate:
                 local = self.engine.run_perms_gram(block)
             else:
                 local = self.engine.run_perms(block, rotate=rotate)
             self.permsamp = host_table()     # overlaps the kernels queued above
+            split_of = dict(idx=block)
         d_perm = pdist.gather_resamples(local, n)
         self._dev['d_perm'] = d_perm
-        return to_host(d_perm).T.copy(), None, None
+        if n_split is None:
+            return to_host(d_perm).T.copy(), None, None
+        # split-half resampling of every permuted data set (pyls/base.py:704-708)
+        uc, vc = self.engine.split_half(self._split_masks(first, count),
+                                        **split_of)
+        uc, vc = pdist.gather_resamples(uc, n), pdist.gather_resamples(vc, n)
+        self._dev.update(ucorrs=uc, vcorrs=vc)
+        return (to_host(d_perm).T.copy(), to_host(uc).T.copy(),
+                to_host(vc).T.copy())
 
     def _prepermuted(self, given, n, rotate):
         eng = self.engine

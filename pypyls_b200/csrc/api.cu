@@ -503,6 +503,16 @@ int plsb_gen_boot_indices(plsb_handle_t h, uint64_t seed, int64_t first, int cou
   return gen_indices(h, true, seed, first, count, d_idx, h_n_exhausted, as_stream(stream));
 }
 
+int plsb_gen_split_masks(plsb_handle_t h, uint64_t seed, int64_t first, int count, int n_split,
+                         double train_fraction, int32_t *d_masks, int *h_n_exhausted,
+                         void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->configured, PLSB_ERR_STATE, "index generation before plsb_configure");
+  PLSB_CHECK(d_masks != nullptr, PLSB_ERR_ARG, "plsb_gen_split_masks: null output");
+  return gen_split_masks(h, seed, first, count, n_split, train_fraction, d_masks, h_n_exhausted,
+                         as_stream(stream));
+}
+
 int plsb_crosscov(plsb_handle_t h, const int32_t *d_idx, int count, int bootstrap, double *d_R,
                   void *stream) {
   PLSB_HANDLE(h);
@@ -939,6 +949,167 @@ int plsb_crossval(plsb_handle_t h, const int32_t *d_train, int count, int max_te
     const int n = std::min(chunk, count - off);
     PLSB_TRY(crossval_chunk(h, d_train + (size_t)off * l.S, n, max_test,
                             d_r + (size_t)off * l.T, d_r2 + (size_t)off * l.T, st));
+  }
+  return PLSB_OK;
+}
+
+// ---- split-half resampling (splithalf.cu) ----------------------------------------
+
+// Z (nh*K rows, ldx) in h->R: cross-covariances of nh halves.  Half r is side (r & 1) of
+// mask (r >> 1), see HalfSpec; the column statistics of a behavioural correlation run
+// over the rows of the half only (like a training split of the cross-validation).
+static int halves_chunk(plsb_ctx *h, const int32_t *masks, const double *yperm,
+                        const HalfSpec &hs, int nh, cudaStream_t st) {
+  const Layout &l = h->lay;
+  const bool grouped = l.behavioral() && l.J > 1;
+  const bool scaled = l.corr();
+  const long long Mw = (long long)nh * l.K, Mc = (long long)nh * l.J;
+  const long long cellpad_w = grouped ? round_up_ll((long long)nh * l.T, GEMM_BM) : 0;
+  const long long cellpad_c = grouped ? round_up_ll(nh, GEMM_BM) : 0;
+  const long long Mw_op = grouped ? cellpad_w * l.J : round_up_ll(Mw, GEMM_BM);
+  const long long Mc_op = grouped ? cellpad_c * l.J : round_up_ll(Mc, GEMM_BM);
+  const long long Mw_pad = round_up_ll(Mw, GEMM_BM), Mc_pad = round_up_ll(Mc, GEMM_BM);
+  PLSB_CHECK(Mw_op < (1ll << 31) - 1, PLSB_ERR_ARG, "chunk of %d halves is too large", nh);
+  PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)Mw_op * l.S_pad));
+  PLSB_TRY(h->R.ensure(sizeof(double) * (size_t)Mw_pad * l.ldx));
+  int *map_w = nullptr, *map_c = nullptr;
+  int4 *kr_w = nullptr, *kr_c = nullptr;
+  if (grouped) {
+    const size_t n_kr = (size_t)(Mw_op + Mc_op) / GEMM_BM;
+    PLSB_TRY(h->maps.ensure(sizeof(int4) * n_kr + sizeof(int) * (size_t)(Mw_op + Mc_op)));
+    kr_w = h->maps.as<int4>();
+    kr_c = kr_w + Mw_op / GEMM_BM;
+    map_w = reinterpret_cast<int *>(kr_c + Mc_op / GEMM_BM);
+    map_c = map_w + Mw_op;
+    PLSB_CUDA(cudaMemsetAsync(h->A.p, 0, sizeof(double) * (size_t)Mw_op * l.S_pad, st));
+    PLSB_TRY(launch_build_maps(h, nh, l.T, l.K, cellpad_w, map_w, kr_w, st));
+  } else {
+    PLSB_TRY(zero_tail(h->A.as<double>(), Mw, Mw_op, l.S_pad, st));
+  }
+  int *ncell = nullptr;
+  if (l.behavioral()) {
+    PLSB_TRY(h->part.ensure(sizeof(int) * (size_t)nh * l.J));
+    ncell = h->part.as<int>();
+  }
+  if (scaled) {
+    PLSB_TRY(h->Ac.ensure(sizeof(double) * (size_t)Mc_op * l.S_pad));
+    PLSB_TRY(h->S1.ensure(sizeof(double) * (size_t)Mc_pad * l.ldx));
+    PLSB_TRY(h->S2.ensure(sizeof(double) * (size_t)Mc_pad * l.ldx));
+    if (grouped) {
+      PLSB_CUDA(cudaMemsetAsync(h->Ac.p, 0, sizeof(double) * (size_t)Mc_op * l.S_pad, st));
+      PLSB_TRY(launch_build_maps(h, nh, 1, l.J, cellpad_c, map_c, kr_c, st));
+    } else {
+      PLSB_TRY(zero_tail(h->Ac.as<double>(), Mc, Mc_op, l.S_pad, st));
+    }
+  }
+  PLSB_TRY(launch_build(h, BUILD_HALF, masks, yperm, nh, h->A.as<double>(),
+                        scaled ? h->Ac.as<double>() : nullptr, nullptr, cellpad_w, cellpad_c, st,
+                        ncell, nullptr, &hs));
+  GemmArgs g;
+  g.lda = l.S_pad;
+  g.ldx = l.ldx;
+  g.N_pad = l.ldx;
+  g.Kd = l.S_pad;
+  g.ldc = l.ldx;
+  if (grouped) g.k_len = l.kr_max;
+  if (scaled) {
+    g.A = h->Ac.as<double>();
+    g.X = h->Xglob.as<double>();
+    g.M_pad = (int)Mc_op;
+    g.row_map = map_c;
+    g.kranges = kr_c;
+    g.C = h->S1.as<double>();
+    PLSB_TRY(launch_gemm(h, g, st));
+    g.C = h->S2.as<double>();
+    g.square_b = true;
+    PLSB_TRY(launch_gemm(h, g, st));
+    g.square_b = false;
+    PLSB_TRY(launch_colscale(h, h->S1.as<double>(), h->S2.as<double>(), (int)Mc, l.ldx, st, l.J,
+                             ncell));
+    g.scale = h->S1.as<double>();
+    g.scale_div = l.T;
+    g.lds = l.ldx;
+  }
+  g.A = h->A.as<double>();
+  g.X = h->Xglob.as<double>();
+  g.M_pad = (int)Mw_op;
+  g.row_map = map_w;
+  g.kranges = kr_w;
+  g.C = h->R.as<double>();
+  PLSB_TRY(launch_gemm(h, g, st));
+  return PLSB_OK;
+}
+
+int plsb_split_half(plsb_handle_t h, const int32_t *d_idx, const double *d_yperm, int count,
+                    const int32_t *d_masks, int n_split, int use_original, double *d_ucorr,
+                    double *d_vcorr, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && !h->lay.simpls(), PLSB_ERR_STATE,
+             "plsb_split_half needs a behavioural or mean-centred handle with data");
+  PLSB_CHECK(!use_original || h->has_original, PLSB_ERR_STATE,
+             "plsb_split_half(use_original) before the original decomposition is set");
+  PLSB_CHECK(d_masks && d_ucorr && d_vcorr && count >= 0 && n_split >= 1, PLSB_ERR_ARG,
+             "plsb_split_half: bad argument");
+  PLSB_CHECK(!(d_idx && d_yperm), PLSB_ERR_ARG,
+             "plsb_split_half: give a permutation table or pre-permuted Y matrices, not both");
+  PLSB_CHECK(!d_yperm || h->lay.behavioral(), PLSB_ERR_ARG,
+             "plsb_split_half: only behavioural analyses have a Y matrix to permute");
+  const Layout &l = h->lay;
+  const int K = l.K, K2 = 2 * K;
+  PLSB_CHECK(K2 <= MAX_K, PLSB_ERR_ARG,
+             "plsb_split_half: 2 K = %d exceeds the supported %d rows per pair of halves", K2,
+             MAX_K);
+  cudaStream_t st = as_stream(stream);
+  PLSB_CUDA(cudaMemsetAsync(d_ucorr, 0, sizeof(double) * (size_t)count * K, st));
+  PLSB_CUDA(cudaMemsetAsync(d_vcorr, 0, sizeof(double) * (size_t)count * K, st));
+  // halves per pass from the workspace limit; whole permutations when they fit
+  const int halves_max = std::max(2, chunk_size(h, true, INT32_MAX / 2));
+  int np = 1, ns = n_split;
+  if (halves_max >= 2 * n_split)
+    np = (int)std::min<long long>(count, halves_max / (2 * n_split));
+  else
+    ns = std::max(1, halves_max / 2);
+  const size_t ystride = (size_t)l.S * l.T, kk = (size_t)K * K;
+  for (int off = 0; off < count; off += np) {
+    const int n = std::min(np, count - off);
+    const int32_t *idx = d_idx ? d_idx + (size_t)off * l.S : nullptr;
+    const double *yp = d_yperm ? d_yperm + (size_t)off * ystride : nullptr;
+    // the data sets being split: R_p, their decomposition and the projection blocks
+    PLSB_CHECK(idx || yp || n == 1, PLSB_ERR_ARG,
+               "plsb_split_half: several data sets need a permutation table");
+    PLSB_TRY(crosscov_chunk(h, idx, yp, n, false, nullptr, st));
+    PLSB_TRY(h->misc.ensure(sizeof(double) * ((size_t)n * K2 * l.ldx + (size_t)n * (kk + K))));
+    double *PB = h->misc.as<double>();
+    double *V = PB + (size_t)n * K2 * l.ldx, *dv = V + (size_t)n * kk;
+    PLSB_TRY(launch_projblock(h, h->R.as<double>(), n, PB, st));
+    long long v_stride = (long long)kk, d_stride = K;
+    if (use_original) {
+      V = h->Vo.as<double>();
+      dv = h->dorig.as<double>();
+      v_stride = d_stride = 0;
+    } else {
+      PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * kk));
+      PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, n, K, nullptr, 0, h->G.as<double>(),
+                                nullptr, st));
+      PLSB_TRY(launch_sym_eig(h, h->G.as<double>(), n, K, V, dv, 1, st));
+    }
+    for (int s0 = 0; s0 < n_split; s0 += ns) {
+      const int nsc = std::min(ns, n_split - s0);
+      const int pairs = n * nsc;
+      HalfSpec hs;
+      hs.yidx = idx;
+      hs.ns = nsc;
+      hs.s0 = s0;
+      hs.n_split = n_split;
+      PLSB_TRY(halves_chunk(h, d_masks + (size_t)off * n_split * l.S, yp, hs, 2 * pairs, st));
+      PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)pairs * K2 * K2));
+      PLSB_TRY(h->H.ensure(sizeof(double) * (size_t)pairs * K2 * K2));
+      PLSB_TRY(launch_gram_proj(h, h->R.as<double>(), l.ldx, pairs, K2, PB, K2, h->G.as<double>(),
+                                h->H.as<double>(), st, (long long)K2 * l.ldx, nsc));
+      PLSB_TRY(launch_splithalf_score(h, h->G.as<double>(), h->H.as<double>(), n, nsc, V, v_stride,
+                                      dv, d_stride, n_split, d_ucorr + (size_t)off * K,
+                                      d_vcorr + (size_t)off * K, st));
+    }
   }
   return PLSB_OK;
 }

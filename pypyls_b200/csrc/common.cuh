@@ -234,10 +234,17 @@ int launch_matmul_small(plsb_ctx *h, const double *A, const double *Bm, int n, d
                         cudaStream_t st);
 
 // operand builders / distrib (operands.cu)
-enum BuildKind { BUILD_ROT = 0, BUILD_PLAIN = 1, BUILD_BOOT = 2, BUILD_TRAIN = 3 };
+enum BuildKind { BUILD_ROT = 0, BUILD_PLAIN = 1, BUILD_BOOT = 2, BUILD_TRAIN = 3, BUILD_HALF = 4 };
+// BUILD_HALF: `idx` holds split-half masks (n_perm, n_split, S); operand block r is half
+// (r & 1) of mask (r >> 1) = (permutation (r >> 1) / ns, split s0 + (r >> 1) % ns)
+struct HalfSpec {
+  const int32_t *yidx = nullptr;   // optional (n_perm, S) permutation table of the data being split
+  int ns = 1, s0 = 0, n_split = 1;
+};
 int launch_build(plsb_ctx *h, int kind, const int32_t *idx, const double *yperm, int count,
                  double *A, double *Ac, double *distrib, long long cellpad_w, long long cellpad_c,
-                 cudaStream_t st, int *ntrain = nullptr, double *ytrain = nullptr);
+                 cudaStream_t st, int *ntrain = nullptr, double *ytrain = nullptr,
+                 const HalfSpec *half = nullptr);
 int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long cellpad,
                       int *row_map, int4 *kranges, cudaStream_t st);
 
@@ -249,7 +256,8 @@ int launch_rowdot_sqrt(plsb_ctx *h, const double *T, long long ldt, const double
 int launch_colscale(plsb_ctx *h, double *S1, const double *S2, int n_rows, long long ld,
                     cudaStream_t st, int rows_per_resample = 0, const int *nrow = nullptr);
 int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K,
-                     const double *UoT, int L, double *G, double *H, cudaStream_t st);
+                     const double *UoT, int L, double *G, double *H, cudaStream_t st,
+                     long long uot_stride = 0, int uot_div = 1);
 int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
                    const double *M, int L, double *usum, double *usq, cudaStream_t st);
 
@@ -283,9 +291,18 @@ int launch_cv_score(plsb_ctx *h, const int32_t *mask, int count, int max_test, c
                     int stride, const double *V, const double *lam, const double *ytrain,
                     double *r_out, double *r2_out, cudaStream_t st);
 
+// split-half resampling (splithalf.cu)
+int launch_projblock(plsb_ctx *h, const double *R, int n, double *PB, cudaStream_t st);
+int launch_splithalf_score(plsb_ctx *h, const double *G, const double *H, int n_perm, int ns,
+                           const double *V, long long v_stride, const double *d,
+                           long long d_stride, int n_split, double *ucorr, double *vcorr,
+                           cudaStream_t st);
+
 // index generation (indexgen.cu), statistics (stats.cu)
 int gen_indices(plsb_ctx *h, bool boot, uint64_t seed, int64_t first, int count, int32_t *d_idx,
                 int *h_n_exhausted, cudaStream_t st);
+int gen_split_masks(plsb_ctx *h, uint64_t seed, int64_t first, int count, int n_split, double frac,
+                    int32_t *d_masks, int *h_n_exhausted, cudaStream_t st);
 int launch_pvals(plsb_ctx *h, const double *dperm, int count, int L, const double *dorig,
                  double *pvals, cudaStream_t st);
 int launch_percentile(plsb_ctx *h, const double *distrib, int count, int n_series, double qlo,

@@ -212,8 +212,8 @@ constexpr int GP_MAX_SLOTS = 8;
 template <int MF, int MFH, int BC, int NG>
 __global__ void __launch_bounds__(GP_THREADS, 1)
 gram_proj_kernel(const double *__restrict__ R, long long ldr, int K, int n_chunks, int nslot,
-                 const double *__restrict__ UoT, int L, double *__restrict__ G,
-                 double *__restrict__ H) {
+                 const double *__restrict__ UoT, long long uot_stride, int uot_div, int L,
+                 double *__restrict__ G, double *__restrict__ H) {
   using C = GpCfg<MF, MFH, BC, NG>;
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) uint64_t full_bar[GP_MAX_SLOTS], empty_bar[GP_MAX_SLOTS];
@@ -256,7 +256,7 @@ gram_proj_kernel(const double *__restrict__ R, long long ldr, int K, int n_chunk
           src += (size_t)RPP * ldr;
           d += RPP * C::LDR;
         }
-        src = UoT + (size_t)row0 * ldr + b0 + seg * 2;
+        src = UoT + (size_t)(r / uot_div) * uot_stride + (size_t)row0 * ldr + b0 + seg * 2;
         d = dst + (C::KP + row0) * C::LDR + seg * 2;
         for (int row = row0; row < nu; row += RPP) {
           cp_async16(d, src);
@@ -328,7 +328,7 @@ constexpr size_t GP_SMEM_MAX = 226 * 1024;   // + the static mbarrier arrays
 
 template <int MF, int MFH, int BC, int NG>
 int launch_cfg(plsb_ctx *h, const double *R, long long ldr, int count, int K, const double *UoT,
-               int L, double *G, double *H, cudaStream_t st) {
+               int L, double *G, double *H, cudaStream_t st, long long us, int ud) {
   using C = GpCfg<MF, MFH, BC, NG>;
   const size_t stage = sizeof(double) * C::STAGE;
   const size_t red = sizeof(double2) * 32 * C::FPG * (GP_WARPS / 2);
@@ -341,7 +341,7 @@ int launch_cfg(plsb_ctx *h, const double *R, long long ldr, int count, int K, co
   PLSB_CHECK(smem <= GP_SMEM_MAX, PLSB_ERR_ARG, "gram_proj: %zu bytes of shared memory", smem);
   auto kern = gram_proj_kernel<MF, MFH, BC, NG>;
   PLSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<count, GP_THREADS, smem, st>>>(R, ldr, K, n_chunks, nslot, UoT, L, G, H);
+  kern<<<count, GP_THREADS, smem, st>>>(R, ldr, K, n_chunks, nslot, UoT, us, ud, L, G, H);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
@@ -350,27 +350,28 @@ int launch_cfg(plsb_ctx *h, const double *R, long long ldr, int count, int K, co
 // barriers, as many bytes in flight as shared memory allows
 template <int MF, int MFH>
 int launch_mf(plsb_ctx *h, const double *R, long long ldr, int count, int K, const double *UoT,
-              int L, double *G, double *H, cudaStream_t st) {
+              int L, double *G, double *H, cudaStream_t st, long long us, int ud) {
   // ~40-70 KB per stage: enough DMMA work per mbarrier round trip, >= 3 slots in flight
   constexpr int FT = tri_count(MF) + MF * MFH;
   constexpr int ROWS = (MF + MFH) * 8;
   if constexpr (FT <= 4)
-    return launch_cfg<MF, MFH, (ROWS <= 16 ? 512 : 256), 1>(h, R, ldr, count, K, UoT, L, G, H, st);
+    return launch_cfg<MF, MFH, (ROWS <= 16 ? 512 : 256), 1>(h, R, ldr, count, K, UoT, L, G, H, st, us, ud);
   else if constexpr (FT <= 12)
-    return launch_cfg<MF, MFH, 256, 2>(h, R, ldr, count, K, UoT, L, G, H, st);
+    return launch_cfg<MF, MFH, 256, 2>(h, R, ldr, count, K, UoT, L, G, H, st, us, ud);
   else if constexpr (ROWS <= 48)
-    return launch_cfg<MF, MFH, 128, 4>(h, R, ldr, count, K, UoT, L, G, H, st);
+    return launch_cfg<MF, MFH, 128, 4>(h, R, ldr, count, K, UoT, L, G, H, st, us, ud);
   else if constexpr (ROWS <= 112)
-    return launch_cfg<MF, MFH, 64, 4>(h, R, ldr, count, K, UoT, L, G, H, st);
+    return launch_cfg<MF, MFH, 64, 4>(h, R, ldr, count, K, UoT, L, G, H, st, us, ud);
   else
-    return launch_cfg<MF, MFH, 32, 8>(h, R, ldr, count, K, UoT, L, G, H, st);
+    return launch_cfg<MF, MFH, 32, 8>(h, R, ldr, count, K, UoT, L, G, H, st, us, ud);
 }
 
 template <int MF>
 int launch_proj(plsb_ctx *h, bool proj, const double *R, long long ldr, int count, int K,
-                const double *UoT, int L, double *G, double *H, cudaStream_t st) {
-  if (proj) return launch_mf<MF, MF>(h, R, ldr, count, K, UoT, L, G, H, st);
-  return launch_mf<MF, 0>(h, R, ldr, count, K, nullptr, 0, G, nullptr, st);
+                const double *UoT, int L, double *G, double *H, cudaStream_t st, long long us,
+                int ud) {
+  if (proj) return launch_mf<MF, MF>(h, R, ldr, count, K, UoT, L, G, H, st, us, ud);
+  return launch_mf<MF, 0>(h, R, ldr, count, K, nullptr, 0, G, nullptr, st, 0, 1);
 }
 
 }  // namespace
@@ -378,9 +379,12 @@ int launch_proj(plsb_ctx *h, bool proj, const double *R, long long ldr, int coun
 // R must be a (count*K rows, ldr) buffer whose row pitch ldr is a multiple of 4
 // and whose columns >= B are zero (the GEMM's padded output).  UoT is U_orig
 // transposed, (L rows, ldr) with zero columns >= B; L and K must span the same
-// number of 8-column fragments (the engine has L == K); null: G only.
+// number of 8-column fragments (the engine has L == K); null: G only.  Matrix r
+// is projected on the block UoT + (r / uot_div) * uot_stride (split-half: one
+// block per permutation, shared by its split halves).
 int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K,
-                     const double *UoT, int L, double *G, double *H, cudaStream_t st) {
+                     const double *UoT, int L, double *G, double *H, cudaStream_t st,
+                     long long uot_stride, int uot_div) {
   KernelTimer kt(h, KC_GRAM, st);
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(K >= 1 && K <= MAX_K, PLSB_ERR_ARG, "gram_proj: K=%d outside [1,%d]", K, MAX_K);
@@ -388,16 +392,16 @@ int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int
   PLSB_CHECK(!proj || cdiv(L, 8) == cdiv(K, 8), PLSB_ERR_ARG,
              "gram_proj: L=%d and K=%d must span the same number of fragments", L, K);
   switch (cdiv(K, 8)) {
-    case 1: return launch_proj<1>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
-    case 2: return launch_proj<2>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
-    case 3: return launch_proj<3>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
-    case 4: return launch_proj<4>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
-    case 5: return launch_proj<5>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
-    case 6: return launch_proj<6>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
-    case 7: return launch_proj<7>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
-    case 8: return launch_proj<8>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
-    case 9: return launch_proj<9>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
-    default: return launch_proj<10>(h, proj, R, ldr, count, K, UoT, L, G, H, st);
+    case 1: return launch_proj<1>(h, proj, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
+    case 2: return launch_proj<2>(h, proj, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
+    case 3: return launch_proj<3>(h, proj, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
+    case 4: return launch_proj<4>(h, proj, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
+    case 5: return launch_proj<5>(h, proj, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
+    case 6: return launch_proj<6>(h, proj, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
+    case 7: return launch_proj<7>(h, proj, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
+    case 8: return launch_proj<8>(h, proj, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
+    case 9: return launch_proj<9>(h, proj, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
+    default: return launch_proj<10>(h, proj, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
   }
 }
 

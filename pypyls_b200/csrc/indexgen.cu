@@ -230,6 +230,65 @@ __global__ void dup_kernel(const int32_t *__restrict__ idx, int total, int S, in
   flags[i] = f;
 }
 
+// Half / half (or train / test) masks, the device counterpart of gen_splits
+// (pyls/base.py:162-229).  One CTA makes the `n_split` masks of one set (the
+// reference draws a fresh set per permutation, base.py:704-708, and one for
+// the original data): per group a coin flip between ceil and floor of
+// n_g * frac subjects (base.py:205-206), drawn without replacement by
+// selection sampling; conditions follow their subject (base.py:211-215); a mask
+// equal to an earlier one of the same set is re-drawn, at most 500 draws per
+// mask (base.py:200-201, 217-222).  Stream: Philox keyed by (seed, set id,
+// attempt, split), so a set does not depend on how the sets are sharded.
+__global__ void __launch_bounds__(128)
+gen_splits_kernel(uint64_t seed, long long first, int n_split, double frac, int S, int n_groups,
+                  int n_cond, const int *__restrict__ group_start, int32_t *__restrict__ masks,
+                  int *__restrict__ n_exhausted) {
+  extern __shared__ unsigned long long sh_hash[];   // n_split hashes, then n_split redo flags
+  int *redo = reinterpret_cast<int *>(sh_hash + n_split);
+  __shared__ int s_again;
+  const int set = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t id = (uint32_t)(first + set);
+  int32_t *out = masks + (size_t)set * n_split * S;
+  for (int i = tid; i < n_split; i += nt) redo[i] = 1;
+  for (int round = 0; round < MAX_TRIES; ++round) {
+    if (tid == 0) s_again = 0;
+    __syncthreads();
+    for (int i = tid; i < n_split; i += nt) {
+      if (!redo[i]) continue;
+      Philox rng(seed, id, (uint32_t)round, 0x10000u + (uint32_t)i);
+      int32_t *col = out + (size_t)i * S;
+      unsigned long long hsh = 1469598103934665603ull;
+      for (int g = 0; g < n_groups; ++g) {
+        const int a = group_start[g], ng = group_start[g + 1] - a;
+        const double want = ng * frac;
+        int need = (rng.next() & 1u) ? (int)floor(want) : (int)ceil(want);
+        for (int k = 0; k < ng; ++k) {
+          const int sel = (int)rng.below((uint32_t)(ng - k)) < need ? 1 : 0;
+          need -= sel;
+          for (int c = 0; c < n_cond; ++c) col[n_cond * a + c * ng + k] = sel;
+          hsh = (hsh ^ (unsigned long long)(sel + 1)) * 1099511628211ull;
+        }
+      }
+      sh_hash[i] = hsh;
+    }
+    __syncthreads();
+    // a mask that repeats an earlier mask of the set is drawn again
+    for (int i = tid; i < n_split; i += nt) {
+      bool dup = false;
+      const unsigned long long hi = sh_hash[i];
+      for (int j = 0; j < i && !dup; ++j) dup = sh_hash[j] == hi;
+      if (dup && round + 1 >= MAX_TRIES) {
+        atomicAdd(n_exhausted, 1);
+        dup = false;
+      }
+      redo[i] = dup ? 1 : 0;
+      if (dup) s_again = 1;
+    }
+    __syncthreads();
+    if (!s_again) break;
+  }
+}
+
 __global__ void fill_int_kernel(int *p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -330,6 +389,28 @@ int gen_indices(plsb_ctx *h, bool boot, uint64_t seed, int64_t first, int count,
   PLSB_CUDA(cudaMemcpyAsync(d_idx, h->idxall.as<int32_t>() + (size_t)first * l.S,
                             sizeof(int32_t) * (size_t)count * l.S, cudaMemcpyDeviceToDevice, st));
   PLSB_CUDA(cudaStreamSynchronize(st));
+  return PLSB_OK;
+}
+
+int gen_split_masks(plsb_ctx *h, uint64_t seed, int64_t first, int count, int n_split, double frac,
+                    int32_t *d_masks, int *h_n_exhausted, cudaStream_t st) {
+  KernelTimer kt(h, KC_INDEX, st);
+  const Layout &l = h->lay;
+  PLSB_CHECK(first >= 0 && count >= 0 && first + count < (1ll << 30) && n_split >= 1 &&
+                 n_split < 0x10000 && frac > 0.0 && frac < 1.0,
+             PLSB_ERR_ARG, "split generation: bad argument");
+  if (h_n_exhausted) *h_n_exhausted = 0;
+  if (count == 0) return PLSB_OK;
+  PLSB_TRY(h->flags.ensure(sizeof(int)));
+  int *counter = h->flags.as<int>();
+  PLSB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+  gen_splits_kernel<<<count, 128, (sizeof(unsigned long long) + sizeof(int)) * n_split, st>>>(
+      seed, first, n_split, frac, l.S, l.n_groups, l.n_cond, h->d_group_start, d_masks, counter);
+  PLSB_LAUNCHED(h);
+  if (h_n_exhausted) {
+    PLSB_CUDA(cudaMemcpyAsync(h_n_exhausted, counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PLSB_CUDA(cudaStreamSynchronize(st));
+  }
   return PLSB_OK;
 }
 

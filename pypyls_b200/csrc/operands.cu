@@ -18,11 +18,15 @@
 //            pyls/types/behavioral.py:125-170): idx[s] != 0 marks a training row;
 //            all cell statistics run over the training rows only, and the
 //            per-cell training counts and Y means are written out
+//     HALF   one half of a split-half mask (pyls/base.py:714-770) of permuted data:
+//            operand row block r is half (r & 1) of mask r >> 1; the rows of the half
+//            are a TRAIN set whose behaviours come through the permutation `yidx`
 //     zy = Y[src] z-scored (ddof=1) or centred within each cell; permutations may
 //     instead bring their own Y (pre-permuted matrices, pyls/base.py:636-639, 689-692).
 //   mean-centred (pyls/types/meancentered.py:50-125, pyls/compute.py:267-357)
 //     AR[j,u] = sum_{s: src[s]=u} C[j,s];  ROT: A = V^T AR;  PLAIN/BOOT: A = AR;
-//     distrib[r] = AR @ Sx.
+//     distrib[r] = AR @ Sx.  HALF: C is rebuilt from the rows of the half (cell mean of
+//     the half minus the half's centring mean) and scattered through the permutation.
 #include "common.cuh"
 
 namespace plsb {
@@ -37,9 +41,22 @@ struct BuildParams {
   const int *cell_start, *cell_of_row;
   const double *Vo, *Sx, *Cmat;
   double *A, *Ac, *distrib;
-  int *ntrain;        // TRAIN: (count, J) training rows per cell
+  int *ntrain;        // TRAIN / HALF: (count, J) training rows per cell
   double *ytrain;     // TRAIN: (count, J, T) mean of Y over the training rows of every cell
+  // HALF: idx = masks (., n_split, S); operand block r -> mask (r >> 1): permutation
+  // (r >> 1) / half_ns, split half_s0 + (r >> 1) % half_ns; side r & 1 (0: mask != 0)
+  const int32_t *yidx;   // optional (n_perm, S) permutation table of the data being split
+  int half_ns, half_s0, half_nsplit;
+  int n_cond, mean_centering;
 };
+
+// is position s inside half r, and which permutation does half r belong to
+__device__ __forceinline__ bool half_member(const BuildParams &p, int r, int s, int *perm) {
+  const int m = r >> 1, pl = m / p.half_ns, sp = p.half_s0 + (m - pl * p.half_ns);
+  *perm = pl;
+  const bool v = p.idx[((size_t)pl * p.half_nsplit + sp) * p.S + s] != 0;
+  return (r & 1) ? !v : v;
+}
 
 __global__ void build_behavioral_kernel(BuildParams p) {
   extern __shared__ __align__(16) double sm[];
@@ -52,17 +69,33 @@ __global__ void build_behavioral_kernel(BuildParams p) {
   int *src = reinterpret_cast<int *>(sxi + J * L);  // S
   const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 
-  const bool train = p.kind == BUILD_TRAIN;
+  const bool half = p.kind == BUILD_HALF;
+  const bool train = p.kind == BUILD_TRAIN || half;
+  int yr = r;                            // which pre-permuted Y / permutation this block uses
   for (int s = tid; s < S; s += nt) {
-    int v = p.idx ? p.idx[(size_t)r * S + s] : s;
-    if (train) v = v != 0 ? s : -1;      // a training row is its own source, a test row has none
+    int v;
+    if (half) {
+      v = half_member(p, r, s, &yr) ? s : -1;
+    } else {
+      v = p.idx ? p.idx[(size_t)r * S + s] : s;
+      if (train) v = v != 0 ? s : -1;    // a training row is its own source, a test row has none
+    }
     src[s] = v;
   }
+  if (half) yr = (r >> 1) / p.half_ns;
   __syncthreads();
   for (int e = tid; e < S * T; e += nt) {
     const int s = e / T, t = e - s * T;
-    Yp[e] = p.Yperm ? p.Yperm[((size_t)r * S + s) * T + t]
-                    : (src[s] >= 0 ? p.Y[(size_t)src[s] * T + t] : 0.0);
+    double y = 0.0;
+    if (src[s] >= 0) {
+      if (p.Yperm)
+        y = p.Yperm[((size_t)yr * S + s) * T + t];
+      else if (half)
+        y = p.Y[(size_t)(p.yidx ? p.yidx[(size_t)yr * S + s] : s) * T + t];
+      else
+        y = p.Y[(size_t)src[s] * T + t];
+    }
+    Yp[e] = y;
   }
   __syncthreads();
   // cell statistics over the rows that have a source (all of them except in TRAIN)
@@ -86,7 +119,7 @@ __global__ void build_behavioral_kernel(BuildParams p) {
     ymean[c] = m;
     yistd[c] = p.corr ? 1.0 / sqrt(v / (n - 1)) : 1.0;
     if (train) {
-      p.ytrain[(size_t)r * J * T + c] = m;
+      if (p.ytrain) p.ytrain[(size_t)r * J * T + c] = m;
       if (t == 0) p.ntrain[(size_t)r * J + g] = n;
     }
   }
@@ -195,6 +228,55 @@ __global__ void build_meancentered_kernel(BuildParams p) {
   double *AR = sm;                                   // J*S
   int *src = reinterpret_cast<int *>(AR + J * S);    // S
   const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  if (p.kind == BUILD_HALF) {
+    // rows of the half: cell means of the half minus the half's centring mean
+    // (compute.get_mean_center on X[perm][half], pyls/compute.py:267-357), as an
+    // operator on the rows of X
+    __shared__ int nh[MAX_K + 1];          // rows of the half per cell, [J] their total
+    int *inh = src + S;                    // S flags
+    int pl = 0;
+    for (int s = tid; s < S; s += nt) {
+      inh[s] = half_member(p, r, s, &pl) ? 1 : 0;
+      src[s] = p.yidx ? p.yidx[(size_t)((r >> 1) / p.half_ns) * S + s] : s;
+    }
+    __syncthreads();
+    for (int j = tid; j <= J; j += nt) {
+      int n = 0;
+      const int r0 = j < J ? p.cell_start[j] : 0, r1 = j < J ? p.cell_start[j + 1] : S;
+      for (int s = r0; s < r1; ++s) n += inh[s];
+      nh[j] = n;
+    }
+    __syncthreads();
+    const int n_cond = p.n_cond, n_groups = J / n_cond;
+    for (int e = tid; e < J * S; e += nt) AR[e] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < J * S; e += nt) {
+      const int j = e / S, s = e - j * S;
+      if (!inh[s]) continue;
+      const int cs = p.cell_of_row[s];
+      double val = cs == j ? 1.0 / nh[j] : 0.0;
+      if (p.mean_centering == 0) {
+        const int g = j / n_cond;
+        if (cs / n_cond == g) {
+          int ng = 0;
+          for (int c = 0; c < n_cond; ++c) ng += nh[g * n_cond + c];
+          val -= 1.0 / ng;
+        }
+      } else if (p.mean_centering == 1) {
+        if (cs % n_cond == j % n_cond) val -= 1.0 / ((double)n_groups * nh[cs]);
+      } else {
+        val -= 1.0 / nh[J];
+      }
+      AR[j * S + src[s]] = val;            // src is a permutation: one writer per element
+    }
+    __syncthreads();
+    double *Ar = p.A + (size_t)r * J * lda;
+    for (int e = tid; e < J * lda; e += nt) {
+      const int j = e / lda, u = e - j * lda;
+      Ar[e] = u < S ? AR[j * S + u] : 0.0;
+    }
+    return;
+  }
   for (int s = tid; s < S; s += nt) src[s] = p.idx ? p.idx[(size_t)r * S + s] : s;
   __syncthreads();
   for (int e = tid; e < J * S; e += nt) {
@@ -269,7 +351,7 @@ int launch_build_maps(plsb_ctx *h, int n, int rows_pc, int stride_r, long long c
 
 int launch_build(plsb_ctx *h, int kind, const int32_t *idx, const double *yperm, int count,
                  double *A, double *Ac, double *distrib, long long cellpad_w, long long cellpad_c,
-                 cudaStream_t st, int *ntrain, double *ytrain) {
+                 cudaStream_t st, int *ntrain, double *ytrain, const HalfSpec *half) {
   KernelTimer kt(h, KC_BUILD, st);
   const Layout &l = h->lay;
   if (count <= 0) return PLSB_OK;
@@ -284,6 +366,14 @@ int launch_build(plsb_ctx *h, int kind, const int32_t *idx, const double *yperm,
              "pre-permuted Y matrices only apply to behavioural permutations");
   PLSB_CHECK(kind != BUILD_TRAIN || (l.behavioral() && idx && ntrain && ytrain), PLSB_ERR_ARG,
              "train / test operands need a behavioural analysis, masks and output buffers");
+  PLSB_CHECK(kind != BUILD_HALF || (half && idx && half->ns >= 1 && (!l.behavioral() || ntrain)),
+             PLSB_ERR_ARG, "split-half operands need masks and a split layout");
+  p.yidx = half ? half->yidx : nullptr;
+  p.half_ns = half ? half->ns : 1;
+  p.half_s0 = half ? half->s0 : 0;
+  p.half_nsplit = half ? half->n_split : 1;
+  p.n_cond = l.n_cond;
+  p.mean_centering = l.mean_centering;
   p.cell_start = h->d_cell_start;
   p.cell_of_row = h->d_cell_of_row;
   p.Vo = h->Vo.as<double>();
@@ -304,7 +394,7 @@ int launch_build(plsb_ctx *h, int kind, const int32_t *idx, const double *yperm,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     build_behavioral_kernel<<<count, 256, smem, st>>>(p);
   } else {
-    smem = sizeof(double) * (size_t)l.J * l.S + sizeof(int) * (size_t)l.S;
+    smem = sizeof(double) * (size_t)l.J * l.S + sizeof(int) * 2 * (size_t)l.S;
     PLSB_CHECK(smem <= 200 * 1024, PLSB_ERR_ARG,
                "mean-centred operand builder needs %zu bytes of shared memory (J*S too large)", smem);
     PLSB_CUDA(cudaFuncSetAttribute(build_meancentered_kernel,

@@ -222,6 +222,19 @@ class ResamplingEngine:
         """Bootstrap table (pyls/base.py:82-159); see gen_perm_indices."""
         return self._gen(self._lib.plsb_gen_boot_indices, seed, first, count)
 
+    def gen_split_masks(self, seed, count, n_split, first=0, train_fraction=0.5):
+        """(count, n_split, S) int32 half / half masks for the sets (one per
+        permutation) [first, first+count) and the number of masks that hit
+        the 500-draw cap (gen_splits, pyls/base.py:162-229)."""
+        masks = torch.empty((count, n_split, self.S), dtype=torch.int32,
+                            device=self.device)
+        n_ex = C.c_int(0)
+        _cabi.check(self._lib.plsb_gen_split_masks(
+            self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)), int(first),
+            int(count), int(n_split), float(train_fraction), _ptr(masks),
+            C.byref(n_ex), self._stream()))
+        return masks, int(n_ex.value)
+
     # -- resampling drivers ---------------------------------------------------
     def run_perms(self, idx, rotate=True):
         """Permuted singular values, (count, L) on the device
@@ -275,6 +288,42 @@ class ResamplingEngine:
             self._h, _ptr(mask), n, int(n_test.max()), _ptr(r), _ptr(r2),
             self._stream()))
         return r, r2
+
+    def split_half(self, masks, idx=None, Yperm=None, use_original=False):
+        """Split-half correlations (ucorr, vcorr), (count, L) each on the
+        device (BasePLS.split_half, pyls/base.py:714-770) of `count` data sets:
+        the permutations `idx` ((S, count) host table or (count, S) device
+        block), the pre-permuted behaviour matrices `Yperm` (count, S, T), or
+        -- with neither -- the un-permuted data (count = 1).  `masks`:
+        (count, n_split, S) half / half masks, non-zero = first half.
+        ``use_original``: score against the installed original decomposition
+        instead of every data set's own."""
+        if isinstance(masks, torch.Tensor):
+            masks = masks.to(device=self.device, dtype=torch.int32).contiguous()
+        else:
+            masks = self.to_device(np.ascontiguousarray(masks),
+                                   dtype=torch.int32)
+        if masks.dim() != 3 or masks.shape[2] != self.S:
+            raise ValueError('split-half masks must have shape (count, '
+                             'n_split, {}); got {}'.format(
+                                 self.S, tuple(masks.shape)))
+        n, n_split = int(masks.shape[0]), int(masks.shape[1])
+        if idx is not None:
+            idx = self.to_device_indices(idx)
+            if int(idx.shape[0]) != n:
+                raise ValueError('one set of masks per permutation is needed')
+        if Yperm is not None:
+            Yperm = self.to_device(Yperm)
+            if tuple(Yperm.shape) != (n, self.S, self.T):
+                raise ValueError('pre-permuted Y must have shape ({}, {}, {})'
+                                 .format(n, self.S, self.T))
+        if idx is None and Yperm is None and n != 1:
+            raise ValueError('the un-permuted data is one data set')
+        uc, vc = self._f64(n, self.L), self._f64(n, self.L)
+        _cabi.check(self._lib.plsb_split_half(
+            self._h, _ptr(idx), _ptr(Yperm), n, _ptr(masks), n_split,
+            int(bool(use_original)), _ptr(uc), _ptr(vc), self._stream()))
+        return uc, vc
 
     def run_boots(self, idx, u_sum=None, u_square=None):
         """(distrib (count,K,L), u_sum (B,L), u_square (B,L)) on the device

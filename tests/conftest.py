@@ -22,7 +22,7 @@ def load_golden(name):
     ins = {k[3:]: z[k] for k in z.files if k.startswith('in_')}
     outs = {k[4:]: z[k] for k in z.files if k.startswith('out_')}
     for k in ('n_cond', 'n_perm', 'n_boot', 'seed', 'mean_centering',
-              'n_components', 'ci'):
+              'n_components', 'ci', 'n_split', 'test_split'):
         if k in ins:
             ins[k] = int(ins[k])
     for k in ('rotate', 'covariance'):

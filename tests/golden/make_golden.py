@@ -12,7 +12,8 @@ Shims (none touches arithmetic):
   3. ``PLSRegression._single_perm`` is wrapped so it accepts the
      ``samples=/use_permind=`` call of pyls/base.py:646-648 (its signature at
      pyls/types/regression.py:329 is stale).
-Always test_split=0 and n_split=0.
+test_split=0 and n_split=0 except in the cross-validation and split-half
+cases.
 
 Run:  python tests/golden/make_golden.py
 """
@@ -149,6 +150,34 @@ def crossval_case():
         save('bpls_crossval_' + tag, dict(X=X, Y=Y, **kw), out)
 
 
+def splithalf_cases():
+    """Split-half resampling inside the permutation loop (n_split,
+    pyls/base.py:373-397, 704-708, 714-770)."""
+    keys = ('ucorr', 'vcorr', 'ucorr_pvals', 'vcorr_pvals', 'ucorr_lolim',
+            'ucorr_uplim', 'vcorr_lolim', 'vcorr_uplim')
+    rs = np.random.RandomState(99)
+    X, Y = rs.rand(48, 60), rs.rand(48, 4)
+    Y[:, :2] += X[:, :12] @ rs.rand(12, 2) * 0.4
+    for tag, extra in (('rot', dict(rotate=True)),
+                       ('cov_norot', dict(rotate=False, covariance=True))):
+        kw = dict(groups=[14, 10], n_cond=2, n_perm=20, n_boot=0, seed=5,
+                  n_split=6, **extra)
+        r = pyls.behavioral_pls(X, Y, test_split=0, permindices=True,
+                                verbose=False, **kw)
+        out = flat(r, 'b')
+        out.update({k: np.asarray(r['splitres'][k]) for k in keys})
+        save('bpls_split_' + tag, dict(X=X, Y=Y, **kw), out)
+    X = rs.rand(48, 50)
+    X[:16] += 0.3 * rs.rand(1, 50)
+    for mc in (0, 1, 2):
+        kw = dict(groups=[8, 10, 6], n_cond=2, mean_centering=mc, n_perm=20,
+                  n_boot=0, seed=5, n_split=6)
+        r = pyls.meancentered_pls(X, permindices=True, verbose=False, **kw)
+        out = flat(r, 'm')
+        out.update({k: np.asarray(r['splitres'][k]) for k in keys})
+        save('mpls_split_mc%d' % mc, dict(X=X, **kw), out)
+
+
 def meancentered_cases():
     rs = np.random.RandomState(1234)
     X = rs.rand(48, 50)
@@ -223,7 +252,11 @@ def matlab_cases():
 
 
 if __name__ == '__main__':
+    if sys.argv[1:] == ['splithalf']:
+        splithalf_cases()
+        sys.exit(0)
     behavioral_cases()
+    splithalf_cases()
     prepermuted_case()
     crossval_case()
     meancentered_cases()
