@@ -101,9 +101,9 @@ def behavioral_pls(X, Y, *, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
     permutation test and bootstrap executed on the GPU.
 
     Differences from the reference front-end: ``test_split`` defaults to 0
-    (the reference's default is 100; pass it to get ``cvres``), ``n_split``
-    must be 0, and ``n_proc`` is accepted but unused (resamples run as one
-    batched launch).
+    (the reference's default is 100; pass it to get ``cvres``) and ``n_proc``
+    is accepted but unused (resamples run as one batched launch).  ``n_split``
+    runs the split-half resampling on the device (needs 2 K <= 80).
     Extra keywords: ``index_backend``, ``device``, ``workspace_bytes``.
 
     Returns

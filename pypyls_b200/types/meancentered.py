@@ -98,7 +98,8 @@ def meancentered_pls(X, *, groups=None, n_cond=1, mean_centering=0,
     Mean-centered PLS of `X` (S, B) sorted into `groups` and conditions; same
     call as ``pyls.meancentered_pls`` (pyls/types/meancentered.py:182-195)
     with the permutation test and bootstrap executed on the GPU.
-    ``n_split`` must be 0; ``n_proc`` is accepted but unused.
+    ``n_split`` runs the split-half resampling on the device; ``n_proc`` is
+    accepted but unused.
 
     Returns
     -------

@@ -181,8 +181,6 @@ def test_regression_front_end_argument_errors():
     Xn[3] = np.nan
     with pytest.raises(NotImplementedError):
         pyls.pls_regression(Xn, Y, n_perm=0, n_boot=0)
-    with pytest.raises(NotImplementedError):
-        pyls.behavioral_pls(X, Y, n_split=5, n_perm=2, n_boot=2)
 
 
 @pytest.mark.parametrize('groups,n_cond,test_size', [([20, 20], 2, 0.25),
