@@ -69,38 +69,101 @@ __device__ void colvec(const double *x, const double *M, int S, int T, double *o
   __syncthreads();
 }
 
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// KA = H (Kpi A), Kpi[i][j] = Kraw[pix[i]][pix[j]], H = column centring.  Once per
+// resample (the component loop keeps KA current with the rank-one terms of the
+// deflation).  DMMA m8n8k4: a warp owns 4 row fragments x all TT/8 column
+// fragments; the Kraw fragments come straight from global memory (L2 resident;
+// 8 rows x 4 consecutive columns = whole 32-byte sectors for permutations, nearly so
+// for the sorted bootstrap tables), the A fragments from shared memory.
 template <int TT>
 __device__ void gram_apply(const SimplsParams &p, const int *pix, const double *A, double *KA,
                            double *csum) {
-  // KA = H (Kpi A):  row i of Kpi is a gather of row pix[i] of Kraw
+  constexpr int NT = TT / 8, MT = 4;
   const int S = p.S, T = p.T;
-  for (int i = threadIdx.x; i < S; i += SP_THREADS) {
-    double acc[TT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int n_mt = (S + 7) / 8;
+  for (int m0 = warp * MT; m0 < n_mt; m0 += SP_WARPS * MT) {
+    double acc[MT][NT][2];
+    const double *krow[MT];
 #pragma unroll
-    for (int t = 0; t < TT; ++t) acc[t] = 0.0;
-    const double *krow = p.Kraw + (size_t)pix[i] * S;
-#pragma unroll 4
-    for (int j = 0; j < S; ++j) {
-      const double k = __ldg(krow + pix[j]);
-      const double *aj = A + j * T;
+    for (int mi = 0; mi < MT; ++mi) {
+      krow[mi] = p.Kraw + (size_t)pix[min((m0 + mi) * 8 + g, S - 1)] * S;
 #pragma unroll
-      for (int t = 0; t < TT; ++t)
-        if (t < T) acc[t] += k * aj[t];
+      for (int ni = 0; ni < NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    }
+    int bcol[NT];   // padded columns re-read column T-1: finite, results discarded
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) bcol[ni] = min(ni * 8 + g, T - 1);
+#pragma unroll 2
+    for (int j0 = 0; j0 < S; j0 += 4) {
+      const int j = j0 + q;
+      const bool ok = j < S;
+      const int jc = ok ? j : S - 1;
+      const int col = pix[jc];
+      double a[MT], bf[NT];
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) a[mi] = ok ? __ldg(krow[mi] + col) : 0.0;
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) bf[ni] = ok ? A[jc * T + bcol[ni]] : 0.0;
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
     }
 #pragma unroll
-    for (int t = 0; t < TT; ++t)
-      if (t < T) KA[i * T + t] = acc[t];
+    for (int mi = 0; mi < MT; ++mi) {
+      const int row = (m0 + mi) * 8 + g;
+      if (row >= S) continue;
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) {
+        const int c = ni * 8 + 2 * q;
+        if (c < T) KA[row * T + c] = acc[mi][ni][0];
+        if (c + 1 < T) KA[row * T + c + 1] = acc[mi][ni][1];
+      }
+    }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int t = warp; t < T; t += SP_WARPS) {
+  const int wl = threadIdx.x >> 5, ll = threadIdx.x & 31;
+  for (int t = wl; t < T; t += SP_WARPS) {
     double v = 0.0;
-    for (int i = lane; i < S; i += 32) v += KA[i * T + t];
+    for (int i = ll; i < S; i += 32) v += KA[i * T + t];
     v = warp_sum(v);
-    if (lane == 0) csum[t] = v / S;
+    if (ll == 0) csum[t] = v / S;
   }
   __syncthreads();
   for (int e = threadIdx.x; e < S * T; e += SP_THREADS) KA[e] -= csum[e % T];
+  __syncthreads();
+}
+
+// out[i] = sum_j Kraw[pix[i]][pix[j]] x[j]: a warp per pair of rows, lanes along the
+// row (coalesced for permutations, nearly so for sorted bootstrap tables); barrier
+__device__ void kx_matvec(const SimplsParams &p, const int *pix, const double *x, double *out) {
+  const int S = p.S, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp * 2; i < S; i += SP_WARPS * 2) {
+    const int i1 = min(i + 1, S - 1);
+    const double *r0 = p.Kraw + (size_t)pix[i] * S, *r1 = p.Kraw + (size_t)pix[i1] * S;
+    double v0 = 0.0, v1 = 0.0;
+#pragma unroll 4
+    for (int j = lane; j < S; j += 32) {
+      const int c = pix[j];
+      const double xj = x ? x[j] : 1.0;
+      v0 += __ldg(r0 + c) * xj;
+      v1 += __ldg(r1 + c) * xj;
+    }
+    v0 = warp_sum(v0);
+    v1 = warp_sum(v1);
+    if (lane == 0) {
+      out[i] = v0;
+      if (i + 1 < S) out[i + 1] = v1;
+    }
+  }
   __syncthreads();
 }
 
@@ -177,8 +240,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
   }
   ssy = block_sum(ssy, red);
 
+  gram_apply<TT>(p, pix, A, KA, csum);
   for (int comp = 0; comp < L; ++comp) {
-    gram_apply<TT>(p, pix, A, KA, csum);
     // C = A^T KA (upper triangle, mirrored)
     for (int e = tid; e < T * T; e += SP_THREADS) {
       const int t1 = e / T, t2 = e - t1 * T;
@@ -353,14 +416,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
       p.pct[(size_t)r * L + comp] = v / ssy;
     }
     // b = t;  g = Kx b
-    for (int i = tid; i < S; i += SP_THREADS) {
-      const double *krow = p.Kraw + (size_t)pix[i] * S;
-      double v = 0.0;
-      for (int j = 0; j < S; ++j) v += krow[pix[j]] * tv[j];
-      gv[i] = v;
-      bv[i] = tv[i];
-    }
-    __syncthreads();
+    for (int i = tid; i < S; i += SP_THREADS) bv[i] = tv[i];
+    kx_matvec(p, pix, tv, gv);
     {
       double v = 0.0;
       for (int i = tid; i < S; i += SP_THREADS) v += gv[i];
@@ -394,9 +451,14 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
       __syncthreads();
     }
     if (comp + 1 == L) break;
-    // deflation:  A -= b (g^T A);  A -= B_prev (G_prev^T A)
+    // deflation:  A -= b (g^T A);  A -= B_prev (G_prev^T A); the same rank-one terms
+    // keep KA = Kx A current (Kx b = g, Kx B_prev = G_prev): no second Kx A product
     colvec(gv, A, S, T, qv);
-    for (int e = tid; e < S * T; e += SP_THREADS) A[e] -= bv[e / T] * qv[e % T];
+    for (int e = tid; e < S * T; e += SP_THREADS) {
+      const double q_ = qv[e % T];
+      A[e] -= bv[e / T] * q_;
+      KA[e] -= gv[e / T] * q_;
+    }
     __syncthreads();
     if (comp > 0) {
       for (int o = warp; o < comp * T; o += SP_WARPS) {
@@ -409,9 +471,13 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
       __syncthreads();
       for (int e = tid; e < S * T; e += SP_THREADS) {
         const int i = e / T, t = e - i * T;
-        double v = 0.0;
-        for (int j = 0; j < comp; ++j) v += Bs[(size_t)i * L + j] * Z[j * T + t];
+        double v = 0.0, w = 0.0;
+        for (int j = 0; j < comp; ++j) {
+          v += Bs[(size_t)i * L + j] * Z[j * T + t];
+          w += Gs[(size_t)i * L + j] * Z[j * T + t];
+        }
         A[e] -= v;
+        KA[e] -= w;
       }
       __syncthreads();
     }
@@ -441,13 +507,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
   }
   if (!p.boot || !p.distrib) return;
   // distrib[t][k] = flip_k (Yp^T Tm + ysum (kappa^T Wcoef) / S),  kappa = Kpi 1
-  for (int i = tid; i < S; i += SP_THREADS) {
-    const double *krow = p.Kraw + (size_t)pix[i] * S;
-    double v = 0.0;
-    for (int j = 0; j < S; ++j) v += krow[pix[j]];
-    gv[i] = v;
-  }
-  __syncthreads();
+  kx_matvec(p, pix, nullptr, gv);
   for (int k = warp; k < L; k += SP_WARPS) {
     double v = 0.0;
     for (int i = lane; i < S; i += 32) v += gv[i] * Wc[(size_t)i * L + k];
