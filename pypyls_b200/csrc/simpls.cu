@@ -11,12 +11,13 @@
 //
 //   A = Y0 (deflated in place);   KA = Kx A;   C = A^T KA            (= Cov^T Cov)
 //   W = orth(C^n_iter Omega)  (T x p, p = min(T, 11); the randomized range finder)
-//   Gz = W^T C W = E diag(lz) E^T;   Bm = lz^-1/2 E^T W^T C;   uh = top left singular vector
-//   wt = W E lz^-1/2 uh;   a = A wt;   t = KA wt;   x_weights column = X0^T a / |t|
+//   Gz = W^T C W = Rc^T Rc (Cholesky);   Bm = Rc^-T W^T C;   uh = top left singular vector
+//   wt = W Rc^-1 uh;   a = A wt;   t = KA wt;   x_weights column = X0^T a / |t|
 //   pctvar_y = |Yp^T t|^2 / |Y0|^2;   b = MGS(t) in the Kx inner product;   A -= b (Kx b)^T A ...
 //
-// (the eigen form of the 11-dimensional step replaces the reference's QR of a
-// possibly rank-deficient B x 11 matrix; it selects the same vector).  Only the
+// (the Cholesky form of the 11-dimensional step is the reference's final QR of the
+// B x 11 range matrix, restated on its Gram matrix; dependent columns are dropped,
+// which selects the same vector).  Only the
 // final x_weights = X0^T Wcoef of a bootstrap needs a B-sized product; it goes
 // through the shared DMMA GEMM as L operand rows per resample.
 // The tests check this against the direct B-space restatement of the reference.
@@ -26,7 +27,7 @@
 namespace plsb {
 namespace {
 
-constexpr int SP_THREADS = 512;
+constexpr int SP_THREADS = 256;
 constexpr int SP_WARPS = SP_THREADS / 32;
 constexpr int SP_PROBES = 11;   // n_components (1) + n_oversamples (10) of randomized_svd
 
@@ -36,6 +37,7 @@ struct SimplsParams {
   const int32_t *idx;
   long long om_stride_r, om_stride_c;
   double *Wcoef, *Bs, *Gs, *Tm;   // (n, S, L) each
+  double *KAbuf;                  // (n, S, T): Kx A of every resample (L2-resident scratch)
   double *pct, *D, *distrib;
 };
 
@@ -67,6 +69,31 @@ __device__ void colvec(const double *x, const double *M, int S, int T, double *o
     if (lane == 0) out[t] = v;
   }
   __syncthreads();
+}
+
+// Upper Cholesky factor of the symmetric P x P matrix G (upper triangle used), in
+// place, by ONE warp: G = Rc^T Rc.  A pivot at or below rel * max(diag) is dropped
+// (its row of Rc is zero): a rank-deficient Gram matrix keeps the span of its
+// independent columns.  The trailing update is spread over all lanes.
+__device__ void warp_chol(double *G, int P, int ld, double rel) {
+  const int lane = threadIdx.x & 31;
+  double dmax = 0.0;
+  for (int k = 0; k < P; ++k) dmax = fmax(dmax, G[k * ld + k]);
+  for (int k = 0; k < P; ++k) {
+    const double d = G[k * ld + k];
+    const bool ok = d > rel * dmax && d > 0.0;
+    const double rkk = ok ? sqrt(d) : 0.0;
+    __syncwarp();
+    if (lane > k && lane < P) G[k * ld + lane] = ok ? G[k * ld + lane] / rkk : 0.0;
+    if (lane == k) G[k * ld + k] = rkk;
+    __syncwarp();
+    const int m = P - k - 1;
+    for (int e = lane; e < m * m; e += 32) {
+      const int i = k + 1 + e / m, j = k + 1 + e % m;
+      if (j >= i) G[i * ld + j] -= G[k * ld + i] * G[k * ld + j];
+    }
+    __syncwarp();
+  }
 }
 
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
@@ -168,7 +195,7 @@ __device__ void kx_matvec(const SimplsParams &p, const int *pix, const double *x
 }
 
 template <int TT>
-__global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
+__global__ void __launch_bounds__(SP_THREADS, 2) simpls_kernel(SimplsParams p) {
   extern __shared__ __align__(16) double sm[];
   const int S = p.S, T = p.T, L = p.L, P = p.p;
   const int pe = P + (P & 1), ldz = pe | 1, halfz = pe / 2;
@@ -176,8 +203,11 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
   const int r = blockIdx.x;
   // ---- shared memory carve-up ----
   double *A = sm;                  // S*T
-  double *KA = A + S * T;          // S*T
-  double *tv = KA + S * T;         // S
+  // KA = Kx A lives in global memory (streamed, L2 resident): A alone in shared
+  // memory lets two resamples share an SM, so one's single-warp sections (Cholesky,
+  // Jacobi) overlap the other's work
+  double *KA = p.KAbuf + (size_t)blockIdx.x * S * T;
+  double *tv = A + S * T;          // S
   double *bv = tv + S;             // S
   double *gv = bv + S;             // S
   double *C = gv + S;              // T*T
@@ -281,23 +311,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
             Gz[a * ldz + b] = v;
           }
           __syncthreads();
-          if (warp == 0) {
-            double dmax = 0.0;
-            for (int k = 0; k < P; ++k) dmax = fmax(dmax, Gz[k * ldz + k]);
-            for (int k = 0; k < P; ++k) {
-              const double d = Gz[k * ldz + k];
-              const bool ok = d > 1e-26 * dmax && d > 0.0;
-              const double rkk = ok ? sqrt(d) : 0.0;
-              __syncwarp();
-              if (lane > k && lane < P) Gz[k * ldz + lane] = ok ? Gz[k * ldz + lane] / rkk : 0.0;
-              if (lane == k) Gz[k * ldz + k] = rkk;
-              __syncwarp();
-              if (lane > k && lane < P)
-                for (int i = k + 1; i <= lane; ++i)
-                  Gz[i * ldz + lane] -= Gz[k * ldz + i] * Gz[k * ldz + lane];
-              __syncwarp();
-            }
-          }
+          if (warp == 0) warp_chol(Gz, P, ldz, 1e-26);
           __syncthreads();
           for (int t = tid; t < T; t += SP_THREADS) {
             for (int j = 0; j < P; ++j) {
@@ -321,36 +335,28 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
       F[e] = v;
     }
     __syncthreads();
-    for (int e = tid; e < pe * pe; e += SP_THREADS) {
-      const int a = e / pe, b = e - a * pe;
+    // Gz = W^T C W = (M W)^T (M W) = Rc^T Rc: Q = M W Rc^-1 is the orthonormal basis of
+    // the range (the reference's final QR); Bm = Q^T M = Rc^-T F
+    for (int e = tid; e < P * P; e += SP_THREADS) {
+      const int a = e / P, b = e - a * P;
+      const int lo = min(a, b), hi = max(a, b);   // one summation order for both triangles
       double v = 0.0;
-      if (a < P && b < P) {
-        const int lo = min(a, b), hi = max(a, b);   // one summation order for both triangles
-        for (int t = 0; t < T; ++t) v += F[lo * T + t] * W[t * P + hi];
-      }
-      Gz[a * ldz + b] = v;
-      Ez[a * ldz + b] = (a == b && a < P) ? 1.0 : 0.0;
+      for (int t = 0; t < T; ++t) v += F[lo * T + t] * W[t * P + hi];
+      Ez[a * ldz + b] = v;
     }
     __syncthreads();
-    if (warp == 0) jacobi_sym_t<true>(Gz, Ez, P, ldz, sc);   // <= 12 x 12: one warp
+    if (warp == 0) warp_chol(Ez, P, ldz, 1e-12);
     __syncthreads();
-    if (tid == 0) {
-      double lmax = 0.0;
-      for (int k = 0; k < P; ++k) lmax = fmax(lmax, Gz[k * ldz + k]);
-      for (int k = 0; k < P; ++k) {
-        const double l = Gz[k * ldz + k];
-        inv[k] = (l > 1e-12 * lmax && l > 0.0) ? rsqrt(l) : 0.0;
+    for (int t = tid; t < T; t += SP_THREADS) {
+      for (int j = 0; j < P; ++j) {
+        double v = F[j * T + t];
+        for (int i = 0; i < j; ++i) v -= Ez[i * ldz + j] * Bm[i * T + t];
+        const double rjj = Ez[j * ldz + j];
+        Bm[j * T + t] = rjj > 0.0 ? v / rjj : 0.0;
       }
     }
     __syncthreads();
-    // Bm = diag(inv) Ez^T F (P x T);  BB = Bm Bm^T -> Gz;  E2 = I
-    for (int e = tid; e < P * T; e += SP_THREADS) {
-      const int k = e / T, t = e - k * T;
-      double v = 0.0;
-      for (int a = 0; a < P; ++a) v += Ez[a * ldz + k] * F[a * T + t];
-      Bm[e] = v * inv[k];
-    }
-    __syncthreads();
+    // top left singular vector uh of Bm: eigenvector of Bm Bm^T (P x P)
     for (int e = tid; e < pe * pe; e += SP_THREADS) {
       const int a = e / pe, b = e - a * pe;
       double v = 0.0;
@@ -368,11 +374,12 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
       int kmax = 0;
       for (int k = 1; k < P; ++k)
         if (Gz[k * ldz + k] > Gz[kmax * ldz + kmax]) kmax = k;
-      // yv = Ez (inv o uh)
-      for (int a = 0; a < P; ++a) {
-        double v = 0.0;
-        for (int k = 0; k < P; ++k) v += Ez[a * ldz + k] * inv[k] * E2[k * ldz + kmax];
-        yv[a] = v;
+      // yv = Rc^-1 uh  (back substitution; dropped pivots stay out)
+      for (int k = P - 1; k >= 0; --k) {
+        double v = E2[k * ldz + kmax];
+        for (int j = k + 1; j < P; ++j) v -= Ez[k * ldz + j] * yv[j];
+        const double rkk = Ez[k * ldz + k];
+        yv[k] = rkk > 0.0 ? v / rkk : 0.0;
       }
     }
     __syncthreads();
@@ -497,12 +504,20 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
   __syncthreads();
   // D[r*L + k][u] = flip_k * sum_{i: pix[i] = u} Wcoef[i][k]
   for (int u = tid; u < p.lda; u += SP_THREADS) {
-    for (int k = 0; k < L; ++k) {
-      double v = 0.0;
+    for (int k0 = 0; k0 < L; k0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) v[kk] = 0.0;
       if (u < S)
         for (int i = 0; i < S; ++i)
-          if (pix[i] == u) v += Wc[(size_t)i * L + k];
-      p.D[((size_t)r * L + k) * p.lda + u] = v * flip[k];
+          if (pix[i] == u) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              if (k0 + kk < L) v[kk] += Wc[(size_t)i * L + k0 + kk];
+          }
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        if (k0 + kk < L) p.D[((size_t)r * L + k0 + kk) * p.lda + u] = v[kk] * flip[k0 + kk];
     }
   }
   if (!p.boot || !p.distrib) return;
@@ -528,7 +543,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) simpls_kernel(SimplsParams p) {
 
 size_t simpls_smem(int S, int T, int L) {
   const int P = std::min(T, SP_PROBES), pe = P + (P & 1), ldz = pe | 1, halfz = pe / 2;
-  size_t d = 2 * (size_t)S * T + 3 * (size_t)S + (size_t)T * T + 4 * (size_t)T * P +
+  size_t d = (size_t)S * T + 3 * (size_t)S + (size_t)T * T + 4 * (size_t)T * P +
              3 * (size_t)pe * ldz + (size_t)std::max(L * T, 2 * L) + 3 * pe + 4 * (size_t)T +
              SP_WARPS + 2 + 3 * halfz;
   size_t b = d * sizeof(double) + sizeof(int) * (2 * halfz + 2 * (size_t)S) +
@@ -672,6 +687,7 @@ int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit
   PLSB_TRY(h->H.ensure(sizeof(double) * per * count));
   PLSB_TRY(h->M.ensure(sizeof(double) * per * count));
   PLSB_TRY(h->lam.ensure(sizeof(double) * per * count));
+  PLSB_TRY(h->S2.ensure(sizeof(double) * (size_t)l.S * l.T * count));
   SimplsParams p;
   p.S = l.S; p.T = l.T; p.L = l.L;
   p.p = std::min(l.T, SP_PROBES);
@@ -684,6 +700,7 @@ int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit
   p.idx = idx;
   p.Wcoef = h->G.as<double>(); p.Bs = h->H.as<double>(); p.Gs = h->M.as<double>();
   p.Tm = h->lam.as<double>();
+  p.KAbuf = h->S2.as<double>();
   p.pct = pct; p.D = h->A.as<double>(); p.distrib = distrib;
   PLSB_CHECK(l.T <= SP_PROBES || omega != nullptr, PLSB_ERR_ARG, "SIMPLS: missing Omega table");
 #define PLSB_SP(TT)                                                                            \
