@@ -27,8 +27,7 @@ struct JacobiScratch {
 template <bool WARP>
 static __device__ void jacobi_sym_t(double *A, double *V, int n, int ld, const JacobiScratch &sc) {
   const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x;
-  const int warp = WARP ? 0 : (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const int nthreads = WARP ? 32 : blockDim.x, nwarps = WARP ? 1 : (nthreads >> 5);
+  const int nthreads = WARP ? 32 : blockDim.x;
   const int ne = n + (n & 1);
   const int half = ne / 2;
   const int nb = half * (half + 1) / 2;
@@ -104,17 +103,16 @@ static __device__ void jacobi_sym_t(double *A, double *V, int n, int ld, const J
         A[pb * ld + qa] = z10;
         A[qb * ld + qa] = z11;
       }
-      // phase 1b: V <- V J (a warp per pair, lanes over the rows)
-      for (int pi = warp; pi < half; pi += nwarps) {
+      // phase 1b: V <- V J, one (pair, row) item per thread
+      for (int e = tid; e < half * n; e += nthreads) {
+        const int pi = e / n, i = e - pi * n;
         const double s = sc.cst[3 * pi + 1];
         if (s == 0.0) continue;
         const double c = sc.cst[3 * pi];
         const int p = sc.pq[2 * pi], q = sc.pq[2 * pi + 1];
-        for (int i = lane; i < n; i += 32) {
-          const double vx = V[i * ld + p], vy = V[i * ld + q];
-          V[i * ld + p] = c * vx - s * vy;
-          V[i * ld + q] = s * vx + c * vy;
-        }
+        const double vx = V[i * ld + p], vy = V[i * ld + q];
+        V[i * ld + p] = c * vx - s * vy;
+        V[i * ld + q] = s * vx + c * vy;
       }
       if (WARP) __syncwarp(); else __syncthreads();
     }

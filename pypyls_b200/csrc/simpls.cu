@@ -298,11 +298,15 @@ __global__ void __launch_bounds__(SP_THREADS, 2) simpls_kernel(SimplsParams p) {
           CW[e] = v;
         }
         __syncthreads();
-        // orthonormalise the columns of CW (same span): Cholesky-QR, twice.
-        // Gram matrix -> upper Cholesky factor Rc (warp 0, lane = column) ->
-        // CW <- CW Rc^-1 (thread = row).  A vanishing pivot (rank-deficient
-        // CW, e.g. after many deflations) drops that column.
-        for (int pass = 0; pass < 2; ++pass) {
+        // normalise the columns of CW (same span): Cholesky-QR -- Gram matrix ->
+        // upper Cholesky factor Rc (warp 0) -> CW <- CW Rc^-1 (thread = row).
+        // One pass keeps the basis well conditioned between power iterations
+        // (orthogonal to eps * cond^2, the span to eps * cond); the last iteration
+        // runs it twice so that W is orthonormal to working precision.  A
+        // vanishing pivot (rank-deficient CW, e.g. after many deflations) drops
+        // that column.
+        const int n_pass = (it + 1 == p.n_iter) ? 2 : 1;
+        for (int pass = 0; pass < n_pass; ++pass) {
           for (int e = tid; e < P * P; e += SP_THREADS) {
             const int a = e / P, b = e - a * P;
             const int lo = min(a, b), hi = max(a, b);
