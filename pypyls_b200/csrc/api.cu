@@ -755,7 +755,7 @@ static int simpls_weights_gemm(plsb_ctx *h, int n, cudaStream_t st) {
 
 static int simpls_chunk(const plsb_ctx *h, int count, bool boot) {
   const Layout &l = h->lay;
-  size_t per = sizeof(double) * (4 * (size_t)l.S * l.L + (size_t)l.S * l.T);
+  size_t per = sizeof(double) * (4 * (size_t)l.S * l.L + 2 * (size_t)l.S * l.T);
   if (boot) per += sizeof(double) * ((size_t)l.L * l.S_pad + (size_t)l.L * l.ldx + (size_t)l.L * l.L);
   long long n = std::max<long long>(1, (long long)(h->ws_limit / per));
   n = std::min<long long>(n, ((1ll << 31) - 1024) / std::max(l.L, 1));

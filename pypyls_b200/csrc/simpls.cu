@@ -27,7 +27,8 @@
 namespace plsb {
 namespace {
 
-constexpr int SP_THREADS = 256;
+constexpr int SP_THREADS = 128;
+constexpr int SP_MIN_CTAS = 4;   // resamples per SM: their single-warp sections overlap
 constexpr int SP_WARPS = SP_THREADS / 32;
 constexpr int SP_PROBES = 11;   // n_components (1) + n_oversamples (10) of randomized_svd
 
@@ -37,7 +38,7 @@ struct SimplsParams {
   const int32_t *idx;
   long long om_stride_r, om_stride_c;
   double *Wcoef, *Bs, *Gs, *Tm;   // (n, S, L) each
-  double *KAbuf;                  // (n, S, T): Kx A of every resample (L2-resident scratch)
+  double *Abuf, *KAbuf;           // (n, S, T) each: A and Kx A of every resample (L2-resident scratch)
   double *pct, *D, *distrib;
 };
 
@@ -195,19 +196,19 @@ __device__ void kx_matvec(const SimplsParams &p, const int *pix, const double *x
 }
 
 template <int TT>
-__global__ void __launch_bounds__(SP_THREADS, 2) simpls_kernel(SimplsParams p) {
+__global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsParams p) {
   extern __shared__ __align__(16) double sm[];
   const int S = p.S, T = p.T, L = p.L, P = p.p;
   const int pe = P + (P & 1), ldz = pe | 1, halfz = pe / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = blockIdx.x;
   // ---- shared memory carve-up ----
-  double *A = sm;                  // S*T
-  // KA = Kx A lives in global memory (streamed, L2 resident): A alone in shared
-  // memory lets two resamples share an SM, so one's single-warp sections (Cholesky,
-  // Jacobi) overlap the other's work
+  // A and KA = Kx A live in global memory (streamed, L2 resident): with only the
+  // small matrices in shared memory several resamples share an SM, so one's
+  // single-warp sections (Cholesky, Jacobi) overlap the others' work
+  double *A = p.Abuf + (size_t)blockIdx.x * S * T;
   double *KA = p.KAbuf + (size_t)blockIdx.x * S * T;
-  double *tv = A + S * T;          // S
+  double *tv = sm;                 // S
   double *bv = tv + S;             // S
   double *gv = bv + S;             // S
   double *C = gv + S;              // T*T
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(SP_THREADS, 2) simpls_kernel(SimplsParams p) {
 
 size_t simpls_smem(int S, int T, int L) {
   const int P = std::min(T, SP_PROBES), pe = P + (P & 1), ldz = pe | 1, halfz = pe / 2;
-  size_t d = (size_t)S * T + 3 * (size_t)S + (size_t)T * T + 4 * (size_t)T * P +
+  size_t d = 3 * (size_t)S + (size_t)T * T + 4 * (size_t)T * P +
              3 * (size_t)pe * ldz + (size_t)std::max(L * T, 2 * L) + 3 * pe + 4 * (size_t)T +
              SP_WARPS + 2 + 3 * halfz;
   size_t b = d * sizeof(double) + sizeof(int) * (2 * halfz + 2 * (size_t)S) +
@@ -691,6 +692,7 @@ int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit
   PLSB_TRY(h->H.ensure(sizeof(double) * per * count));
   PLSB_TRY(h->M.ensure(sizeof(double) * per * count));
   PLSB_TRY(h->lam.ensure(sizeof(double) * per * count));
+  PLSB_TRY(h->S1.ensure(sizeof(double) * (size_t)l.S * l.T * count));
   PLSB_TRY(h->S2.ensure(sizeof(double) * (size_t)l.S * l.T * count));
   SimplsParams p;
   p.S = l.S; p.T = l.T; p.L = l.L;
@@ -704,6 +706,7 @@ int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit
   p.idx = idx;
   p.Wcoef = h->G.as<double>(); p.Bs = h->H.as<double>(); p.Gs = h->M.as<double>();
   p.Tm = h->lam.as<double>();
+  p.Abuf = h->S1.as<double>();
   p.KAbuf = h->S2.as<double>();
   p.pct = pct; p.D = h->A.as<double>(); p.distrib = distrib;
   PLSB_CHECK(l.T <= SP_PROBES || omega != nullptr, PLSB_ERR_ARG, "SIMPLS: missing Omega table");
