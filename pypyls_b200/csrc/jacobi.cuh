@@ -103,16 +103,32 @@ static __device__ void jacobi_sym_t(double *A, double *V, int n, int ld, const J
         A[pb * ld + qa] = z10;
         A[qb * ld + qa] = z11;
       }
-      // phase 1b: V <- V J, one (pair, row) item per thread
-      for (int e = tid; e < half * n; e += nthreads) {
-        const int pi = e / n, i = e - pi * n;
-        const double s = sc.cst[3 * pi + 1];
-        if (s == 0.0) continue;
-        const double c = sc.cst[3 * pi];
-        const int p = sc.pq[2 * pi], q = sc.pq[2 * pi + 1];
-        const double vx = V[i * ld + p], vy = V[i * ld + q];
-        V[i * ld + p] = c * vx - s * vy;
-        V[i * ld + q] = s * vx + c * vy;
+      // phase 1b: V <- V J.  CTA: a warp per pair, lanes over the rows (conflict-free
+      // columns); single warp: one (pair, row) item per lane
+      if (WARP) {
+        for (int e = tid; e < half * n; e += 32) {
+          const int pi = e / n, i = e - pi * n;
+          const double s = sc.cst[3 * pi + 1];
+          if (s == 0.0) continue;
+          const double c = sc.cst[3 * pi];
+          const int p = sc.pq[2 * pi], q = sc.pq[2 * pi + 1];
+          const double vx = V[i * ld + p], vy = V[i * ld + q];
+          V[i * ld + p] = c * vx - s * vy;
+          V[i * ld + q] = s * vx + c * vy;
+        }
+      } else {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
+        for (int pi = warp; pi < half; pi += nwarps) {
+          const double s = sc.cst[3 * pi + 1];
+          if (s == 0.0) continue;
+          const double c = sc.cst[3 * pi];
+          const int p = sc.pq[2 * pi], q = sc.pq[2 * pi + 1];
+          for (int i = lane; i < n; i += 32) {
+            const double vx = V[i * ld + p], vy = V[i * ld + q];
+            V[i * ld + p] = c * vx - s * vy;
+            V[i * ld + q] = s * vx + c * vy;
+          }
+        }
       }
       if (WARP) __syncwarp(); else __syncthreads();
     }

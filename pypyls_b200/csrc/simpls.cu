@@ -60,18 +60,6 @@ __device__ double block_sum(double v, double *red) {
   return t;
 }
 
-// out[t] = sum_i x[i] * M[i*T + t]  (t < T), a warp per column; then barrier
-__device__ void colvec(const double *x, const double *M, int S, int T, double *out) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int t = warp; t < T; t += SP_WARPS) {
-    double v = 0.0;
-    for (int i = lane; i < S; i += 32) v += x[i] * M[i * T + t];
-    v = warp_sum(v);
-    if (lane == 0) out[t] = v;
-  }
-  __syncthreads();
-}
-
 // Upper Cholesky factor of the symmetric P x P matrix G (upper triangle used), in
 // place, by ONE warp: G = Rc^T Rc.  A pivot at or below rel * max(diag) is dropped
 // (its row of Rc is zero): a rank-deficient Gram matrix keeps the span of its
@@ -228,8 +216,10 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
   double *ysum = qv + T;           // T
   double *csum = ysum + T;         // T
   double *red = csum + T;          // SP_WARPS + 2
+  double *cg = red + SP_WARPS + 2; // L: G_prev^T b
+  double *part = cg + L;           // 8 * SP_THREADS: partial sums of the deflation sweep
   JacobiScratch sc;
-  sc.cst = red + SP_WARPS + 2;                                  // 3*halfz
+  sc.cst = part + 8 * SP_THREADS;                               // 3*halfz
   sc.pq = reinterpret_cast<int *>(sc.cst + 3 * halfz);          // 2*halfz
   int *pix = sc.pq + 2 * halfz;                                 // S
   int *piy = pix + S;                                           // S
@@ -272,17 +262,17 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
   ssy = block_sum(ssy, red);
 
   gram_apply<TT>(p, pix, A, KA, csum);
+  // C = A^T KA (upper triangle, mirrored); the deflation keeps it current
+  for (int e = tid; e < T * T; e += SP_THREADS) {
+    const int t1 = e / T, t2 = e - t1 * T;
+    if (t2 < t1) continue;
+    double v = 0.0;
+    for (int s = 0; s < S; ++s) v += A[s * T + t1] * KA[s * T + t2];
+    C[t1 * T + t2] = v;
+    C[t2 * T + t1] = v;
+  }
+  __syncthreads();
   for (int comp = 0; comp < L; ++comp) {
-    // C = A^T KA (upper triangle, mirrored)
-    for (int e = tid; e < T * T; e += SP_THREADS) {
-      const int t1 = e / T, t2 = e - t1 * T;
-      if (t2 < t1) continue;
-      double v = 0.0;
-      for (int s = 0; s < S; ++s) v += A[s * T + t1] * KA[s * T + t2];
-      C[t1 * T + t2] = v;
-      C[t2 * T + t1] = v;
-    }
-    __syncthreads();
     // ---- randomized range finder: W = orth(C^n_iter Omega) ----
     if (T <= SP_PROBES) {
       for (int e = tid; e < T * P; e += SP_THREADS) W[e] = (e / P == e % P) ? 1.0 : 0.0;
@@ -463,36 +453,71 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
       __syncthreads();
     }
     if (comp + 1 == L) break;
-    // deflation:  A -= b (g^T A);  A -= B_prev (G_prev^T A); the same rank-one terms
-    // keep KA = Kx A current (Kx b = g, Kx B_prev = G_prev): no second Kx A product
-    colvec(gv, A, S, T, qv);
+    // deflation (pyls/types/regression.py:143-147):  A' = A - b q^T with q = A^T g, then
+    // A'' = A' - B_prev Z with Z = G_prev^T A' = G_prev^T A - (G_prev^T b) q^T.  One sweep
+    // over A gives q and G_prev^T A, one read-modify-write sweep applies both terms; the
+    // same terms keep KA = Kx A (Kx b = g, Kx B_prev = G_prev) and C = A^T Kx A
+    // (b^T g = 1, B_prev^T Kx B_prev = I:  C'' = C - q q^T - Z^T Z) current.
+    {
+      const int ngrp = SP_THREADS / T, t = tid % T, grp = tid / T;
+      for (int c0 = -1; c0 < comp; c0 += 8) {    // vectors c0 .. c0+7; -1 is the current g
+        double acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+        if (grp < ngrp)
+          for (int i = grp; i < S; i += ngrp) {
+            const double a = A[i * T + t];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int j = c0 + k;
+              if (j < comp) acc[k] += (j < 0 ? gv[i] : Gs[(size_t)i * L + j]) * a;
+            }
+          }
+        if (grp < ngrp) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) part[(grp * 8 + k) * T + t] = acc[k];
+        }
+        __syncthreads();
+        for (int o = tid; o < 8 * T; o += SP_THREADS) {
+          const int k = o / T, tt = o - k * T, j = c0 + k;
+          if (j >= comp) continue;
+          double v = 0.0;
+          for (int g2 = 0; g2 < ngrp; ++g2) v += part[(g2 * 8 + k) * T + tt];
+          if (j < 0) qv[tt] = v; else Z[j * T + tt] = v;
+        }
+        __syncthreads();
+      }
+    }
+    if (comp > 0) {
+      for (int j = warp; j < comp; j += SP_WARPS) {
+        double v = 0.0;
+        for (int i = lane; i < S; i += 32) v += Gs[(size_t)i * L + j] * bv[i];
+        v = warp_sum(v);
+        if (lane == 0) cg[j] = v;
+      }
+      __syncthreads();
+      for (int o = tid; o < comp * T; o += SP_THREADS) Z[o] -= cg[o / T] * qv[o % T];
+      __syncthreads();
+    }
     for (int e = tid; e < S * T; e += SP_THREADS) {
-      const double q_ = qv[e % T];
-      A[e] -= bv[e / T] * q_;
-      KA[e] -= gv[e / T] * q_;
+      const int i = e / T, t = e - i * T;
+      const double q_ = qv[t];
+      double v = bv[i] * q_, w = gv[i] * q_;
+      for (int j = 0; j < comp; ++j) {
+        const double z = Z[j * T + t];
+        v += Bs[(size_t)i * L + j] * z;
+        w += Gs[(size_t)i * L + j] * z;
+      }
+      A[e] -= v;
+      KA[e] -= w;
+    }
+    for (int e = tid; e < T * T; e += SP_THREADS) {
+      const int t1 = e / T, t2 = e - t1 * T;
+      double v = qv[t1] * qv[t2];
+      for (int j = 0; j < comp; ++j) v += Z[j * T + t1] * Z[j * T + t2];
+      C[e] -= v;
     }
     __syncthreads();
-    if (comp > 0) {
-      for (int o = warp; o < comp * T; o += SP_WARPS) {
-        const int j = o / T, t = o - j * T;
-        double v = 0.0;
-        for (int i = lane; i < S; i += 32) v += Gs[(size_t)i * L + j] * A[i * T + t];
-        v = warp_sum(v);
-        if (lane == 0) Z[o] = v;
-      }
-      __syncthreads();
-      for (int e = tid; e < S * T; e += SP_THREADS) {
-        const int i = e / T, t = e - i * T;
-        double v = 0.0, w = 0.0;
-        for (int j = 0; j < comp; ++j) {
-          v += Bs[(size_t)i * L + j] * Z[j * T + t];
-          w += Gs[(size_t)i * L + j] * Z[j * T + t];
-        }
-        A[e] -= v;
-        KA[e] -= w;
-      }
-      __syncthreads();
-    }
   }
   __syncthreads();
   if (!p.emit_ops) return;
@@ -550,7 +575,7 @@ size_t simpls_smem(int S, int T, int L) {
   const int P = std::min(T, SP_PROBES), pe = P + (P & 1), ldz = pe | 1, halfz = pe / 2;
   size_t d = 3 * (size_t)S + (size_t)T * T + 4 * (size_t)T * P +
              3 * (size_t)pe * ldz + (size_t)std::max(L * T, 2 * L) + 3 * pe + 4 * (size_t)T +
-             SP_WARPS + 2 + 3 * halfz;
+             SP_WARPS + 2 + (size_t)L + 8 * SP_THREADS + 3 * halfz;
   size_t b = d * sizeof(double) + sizeof(int) * (2 * halfz + 2 * (size_t)S) +
              sizeof(short2) * (halfz * (halfz + 1) / 2) + 16;
   return b;

@@ -393,6 +393,74 @@ def test_config2_properties_full_size():
     close(yb[..., :4], refd)
 
 
+def test_config3_properties_full_size():
+    """BASELINE config 3 at full size (mean-centred, X 320 x 20000, groups
+    [40]*4 x 2 conditions -- the 320-row reading of the inconsistent spec,
+    SURVEY.md section 0.8 -- 10000 permutations + 10000 bootstraps)."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(1234)
+    X = rs.rand(320, 20000)
+    kw = dict(groups=[40, 40, 40, 40], n_cond=2, mean_centering=0,
+              n_perm=10000, n_boot=10000, seed=1234, verbose=False)
+    out = pyls.meancentered_pls(X, **kw)
+    L = 8
+    ps, cb = out.permres.perm_singval, out.bootres.contrast_boot
+    assert ps.shape == (L, 10000) and cb.shape == (L, L, 10000)
+    assert np.all(np.isfinite(ps)) and np.all(np.isfinite(cb))
+    # every permutation column is a permutation of the rows; no column twice
+    tab = out.permres.permsamples
+    assert np.all(np.sort(tab, axis=0) == np.arange(320)[:, None])
+    assert len({c.tobytes() for c in tab.T}) == 10000
+    cnt = out.permres.pvals * 10001 - 1
+    assert np.allclose(cnt, np.round(cnt)) and np.all(cnt >= 0)
+    ci = out.bootres.contrast_ci
+    keep = out.singvals > 1e-8 * out.singvals.max()
+    assert keep.sum() == 4          # mean_centering=0, 4 groups: rank J - n_groups
+    inside = ((cb >= ci[..., :1]) & (cb <= ci[..., 1:])).mean(axis=-1)
+    assert np.all(np.abs(inside[:, keep] - 0.95) < 0.002)
+    again = pyls.meancentered_pls(X, **kw)
+    assert np.array_equal(again.permres.pvals, out.permres.pvals)
+    assert np.array_equal(again.bootres.bootsamples, out.bootres.bootsamples)
+    # the CPU oracle on the first resamples of the same tables
+    spec = po._Spec('meancentered', kw['groups'], 2, mean_centering=0)
+    ref = po.run_perms(spec, X, spec.dummy, tab[:, :6], out.y_weights)
+    close(ps[keep, :6], ref[keep])
+    refd, _, _ = po.run_boots(spec, X, spec.dummy,
+                              out.bootres.bootsamples[:, :3], out.x_weights)
+    close(cb[:, keep, :3], refd[:, keep])
+
+
+def test_config5_properties_full_size():
+    """BASELINE config 5 at full size on one GPU (behavioural, X 200 x 100000,
+    Y 200 x 10, 10000 permutations + 10000 bootstraps; the multi-GPU run shards
+    exactly this over ranks)."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(1234)
+    X, Y = rs.rand(200, 100000), rs.rand(200, 10)
+    kw = dict(n_perm=10000, n_boot=10000, seed=1234, verbose=False)
+    out = pyls.behavioral_pls(X, Y, **kw)
+    L = 10
+    ps, yb = out.permres.perm_singval, out.bootres.y_loadings_boot
+    assert ps.shape == (L, 10000) and yb.shape == (L, L, 10000)
+    assert np.all(np.isfinite(ps))
+    tot = (ps ** 2).sum(axis=0)
+    assert np.all(tot > 0) and np.all(tot <= 10 * 100000)
+    cnt = out.permres.pvals * 10001 - 1
+    assert np.allclose(cnt, np.round(cnt)) and np.all(cnt >= 0)
+    assert np.all(np.abs(yb) <= 1 + 1e-12)
+    ci = out.bootres.y_loadings_ci
+    inside = ((yb >= ci[..., :1]) & (yb <= ci[..., 1:])).mean(axis=-1)
+    assert np.all(np.abs(inside - 0.95) < 0.002)
+    assert np.all(np.isfinite(out.bootres.x_weights_normed))
+    spec = po._Spec('behavioral', [200], 1)
+    ref = po.run_perms(spec, X, Y, out.permres.permsamples[:, :3],
+                       out.y_weights)
+    close(ps[:, :3], ref)
+    refd, _, _ = po.run_boots(spec, X, Y, out.bootres.bootsamples[:, :2],
+                              out.x_weights)
+    close(yb[..., :2], refd)
+
+
 def test_workspace_chunking_is_invisible():
     """A tiny workspace forces many chunks; results must not change."""
     import pypyls_b200 as pyls
