@@ -278,6 +278,14 @@ int plsb_split_half(plsb_handle_t h, const int32_t *d_idx, const double *d_yperm
  *   (:323-325); d_pctvar (count,L). */
 int plsb_simpls_set_original(plsb_handle_t h, const double *d_xweights,
                              void *stream);
+/* Rows the reference's get_mask drops (pyls/types/regression.py:48-53: a row of X or
+ * of Y that is all NaN): d_valid_x, d_valid_y (S) int32, 0 = that row of X / of Y is
+ * missing; both NULL clears the masks.  Upload X / Y with those rows zero-filled.  Every
+ * decomposition then runs on the rows of the RESAMPLED matrices whose X source and Y
+ * source are both present (regression.py:271-272, 322-323; permutations move the rows of
+ * Y only).  Call after plsb_set_data and before plsb_simpls_decompose. */
+int plsb_simpls_set_row_mask(plsb_handle_t h, const int32_t *d_valid_x,
+                             const int32_t *d_valid_y, void *stream);
 int plsb_simpls_decompose(plsb_handle_t h, const double *d_omega,
                           double *d_xweights, double *d_pctvar, void *stream);
 int plsb_simpls_run_perms(plsb_handle_t h, const int32_t *d_idx, int count,

@@ -55,6 +55,7 @@ PROTOTYPES = {
     'plsb_timing_classes': (_i, []),
     'plsb_timing_class_name': (C.c_char_p, [_i]),
     'plsb_timing_read': (_i, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
+    'plsb_simpls_set_row_mask': (_i, [_vp, _vp, _vp, _vp]),
     'plsb_simpls_set_original': (_i, [_vp, _vp, _vp]),
     'plsb_simpls_decompose': (_i, [_vp, _vp, _vp, _vp, _vp]),
     'plsb_simpls_run_perms': (_i, [_vp, _vp, _i, _vp, _vp, _vp]),

@@ -191,7 +191,7 @@ int plsb_destroy(plsb_handle_t h) {
   DevBuf *bufs[] = {&h->tables, &h->Xraw, &h->Xcell, &h->Xglob, &h->Y,    &h->Cmat,  &h->Uo,
                     &h->Vo,     &h->dorig, &h->Sx,   &h->norms, &h->A,    &h->Ac,    &h->R,
                     &h->S1,     &h->S2,   &h->G,     &h->H,     &h->M,    &h->lam,   &h->rowsq,
-                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx};
+                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx, &h->rowmask};
   for (DevBuf *b : bufs) b->release();
   delete h;
   return PLSB_OK;
@@ -376,6 +376,7 @@ int plsb_set_data(plsb_handle_t h, const double *d_X, const double *d_Y, void *s
   PLSB_CHECK(!(l.behavioral() || l.simpls()) || d_Y != nullptr, PLSB_ERR_ARG,
              "plsb_set_data: null Y");
   const size_t bytes = sizeof(double) * (size_t)l.S_pad * l.ldx;
+  h->has_rowmask = false;
   if (l.simpls()) {
     // X and Y arrive column-centred (pyls/types/regression.py:395-396).  Kraw = X X^T (S,S)
     // is the only B-sized object the component loops need.
@@ -776,6 +777,26 @@ int plsb_simpls_set_original(plsb_handle_t h, const double *d_xweights, void *st
   PLSB_TRY(launch_xproj(h, h->Xraw.as<double>(), l.ldx, l.S, l.B, h->Uo.as<double>(), l.L, nullptr,
                         h->Sx.as<double>(), st));
   h->has_original = true;
+  return PLSB_OK;
+}
+
+int plsb_simpls_set_row_mask(plsb_handle_t h, const int32_t *d_valid_x, const int32_t *d_valid_y,
+                             void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->lay.simpls(), PLSB_ERR_STATE,
+             "plsb_simpls_set_row_mask needs a SIMPLS handle with data");
+  h->has_rowmask = false;
+  h->has_original = false;
+  if (!d_valid_x && !d_valid_y) return PLSB_OK;
+  PLSB_CHECK(d_valid_x && d_valid_y, PLSB_ERR_ARG,
+             "plsb_simpls_set_row_mask: give both masks or none");
+  const size_t bytes = sizeof(int32_t) * (size_t)h->lay.S;
+  PLSB_TRY(h->rowmask.ensure(2 * bytes));
+  PLSB_CUDA(cudaMemcpyAsync(h->rowmask.p, d_valid_x, bytes, cudaMemcpyDeviceToDevice,
+                            as_stream(stream)));
+  PLSB_CUDA(cudaMemcpyAsync(h->rowmask.as<int32_t>() + h->lay.S, d_valid_y, bytes,
+                            cudaMemcpyDeviceToDevice, as_stream(stream)));
+  h->has_rowmask = true;
   return PLSB_OK;
 }
 

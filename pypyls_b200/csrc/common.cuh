@@ -153,6 +153,8 @@ struct plsb_ctx {
   plsb::DevBuf Xglob;  // X centred (and for corr scaled) with whole-column statistics
   plsb::DevBuf Y;      // Y (S, T)
   plsb::DevBuf Cmat;   // mean-centred: operator C (J, S)
+  plsb::DevBuf rowmask;   // SIMPLS: optional (2, S) int32 (rows of X, rows of Y), 0 = missing
+  bool has_rowmask = false;
   // original decomposition
   plsb::DevBuf Uo;     // (B, L)
   plsb::DevBuf Kx;     // Gram matrix of the permutation data matrix, (S_pad, round_up(S_pad,128))

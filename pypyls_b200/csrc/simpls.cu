@@ -36,6 +36,7 @@ struct SimplsParams {
   int S, T, L, p, n_iter, boot, emit_ops, lda;
   const double *Kraw, *Yc, *omega, *So;
   const int32_t *idx;
+  const int32_t *valid;   // optional (2, S): row 0 = rows of X, row 1 = rows of Y; 0 = missing (all NaN)
   long long om_stride_r, om_stride_c;
   double *Wcoef, *Bs, *Gs, *Tm;   // (n, S, L) each
   double *Abuf, *KAbuf;           // (n, S, T) each: A and Kx A of every resample (L2-resident scratch)
@@ -99,10 +100,10 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 // 8 rows x 4 consecutive columns = whole 32-byte sectors for permutations, nearly so
 // for the sorted bootstrap tables), the A fragments from shared memory.
 template <int TT>
-__device__ void gram_apply(const SimplsParams &p, const int *pix, const double *A, double *KA,
-                           double *csum) {
+__device__ void gram_apply(const SimplsParams &p, int S, const int *pix, const double *A,
+                           double *KA, double *csum) {
   constexpr int NT = TT / 8, MT = 4;
-  const int S = p.S, T = p.T;
+  const int T = p.T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int n_mt = (S + 7) / 8;
   for (int m0 = warp * MT; m0 < n_mt; m0 += SP_WARPS * MT) {
@@ -110,7 +111,7 @@ __device__ void gram_apply(const SimplsParams &p, const int *pix, const double *
     const double *krow[MT];
 #pragma unroll
     for (int mi = 0; mi < MT; ++mi) {
-      krow[mi] = p.Kraw + (size_t)pix[min((m0 + mi) * 8 + g, S - 1)] * S;
+      krow[mi] = p.Kraw + (size_t)pix[min((m0 + mi) * 8 + g, S - 1)] * p.S;
 #pragma unroll
       for (int ni = 0; ni < NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     }
@@ -160,11 +161,12 @@ __device__ void gram_apply(const SimplsParams &p, const int *pix, const double *
 
 // out[i] = sum_j Kraw[pix[i]][pix[j]] x[j]: a warp per pair of rows, lanes along the
 // row (coalesced for permutations, nearly so for sorted bootstrap tables); barrier
-__device__ void kx_matvec(const SimplsParams &p, const int *pix, const double *x, double *out) {
-  const int S = p.S, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ void kx_matvec(const SimplsParams &p, int S, const int *pix, const double *x,
+                          double *out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = warp * 2; i < S; i += SP_WARPS * 2) {
     const int i1 = min(i + 1, S - 1);
-    const double *r0 = p.Kraw + (size_t)pix[i] * S, *r1 = p.Kraw + (size_t)pix[i1] * S;
+    const double *r0 = p.Kraw + (size_t)pix[i] * p.S, *r1 = p.Kraw + (size_t)pix[i1] * p.S;
     double v0 = 0.0, v1 = 0.0;
 #pragma unroll 4
     for (int j = lane; j < S; j += 32) {
@@ -186,7 +188,7 @@ __device__ void kx_matvec(const SimplsParams &p, const int *pix, const double *x
 template <int TT>
 __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsParams p) {
   extern __shared__ __align__(16) double sm[];
-  const int S = p.S, T = p.T, L = p.L, P = p.p;
+  const int Sf = p.S, T = p.T, L = p.L, P = p.p;   // Sf: rows of the data; S below: rows in use
   const int pe = P + (P & 1), ldz = pe | 1, halfz = pe / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = blockIdx.x;
@@ -194,12 +196,12 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
   // A and KA = Kx A live in global memory (streamed, L2 resident): with only the
   // small matrices in shared memory several resamples share an SM, so one's
   // single-warp sections (Cholesky, Jacobi) overlap the others' work
-  double *A = p.Abuf + (size_t)blockIdx.x * S * T;
-  double *KA = p.KAbuf + (size_t)blockIdx.x * S * T;
+  double *A = p.Abuf + (size_t)blockIdx.x * Sf * T;
+  double *KA = p.KAbuf + (size_t)blockIdx.x * Sf * T;
   double *tv = sm;                 // S
-  double *bv = tv + S;             // S
-  double *gv = bv + S;             // S
-  double *C = gv + S;              // T*T
+  double *bv = tv + Sf;            // S
+  double *gv = bv + Sf;            // S
+  double *C = gv + Sf;             // T*T
   double *W = C + T * T;           // T*P
   double *CW = W + T * P;          // T*P
   double *F = CW + T * P;          // P*T
@@ -222,24 +224,45 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
   sc.cst = part + 8 * SP_THREADS;                               // 3*halfz
   sc.pq = reinterpret_cast<int *>(sc.cst + 3 * halfz);          // 2*halfz
   int *pix = sc.pq + 2 * halfz;                                 // S
-  int *piy = pix + S;                                           // S
-  sc.blk = reinterpret_cast<short2 *>(piy + S);                 // halfz*(halfz+1)/2
+  int *piy = pix + Sf;                                          // S
+  sc.blk = reinterpret_cast<short2 *>(piy + Sf);                // halfz*(halfz+1)/2
+  __shared__ int s_rows;
 
-  double *Wc = p.Wcoef + (size_t)r * S * L;
-  double *Bs = p.Bs + (size_t)r * S * L;
-  double *Gs = p.Gs + (size_t)r * S * L;
-  double *Tm = p.Tm + (size_t)r * S * L;
+  double *Wc = p.Wcoef + (size_t)r * Sf * L;
+  double *Bs = p.Bs + (size_t)r * Sf * L;
+  double *Gs = p.Gs + (size_t)r * Sf * L;
+  double *Tm = p.Tm + (size_t)r * Sf * L;
 
   for (int a = tid; a < halfz; a += SP_THREADS) {
     int bi = a * halfz - a * (a - 1) / 2;
     for (int b = a; b < halfz; ++b) sc.blk[bi++] = make_short2((short)a, (short)b);
   }
-  for (int i = tid; i < S; i += SP_THREADS) {
-    const int src = p.idx ? p.idx[(size_t)r * S + i] : i;
-    piy[i] = src;
-    pix[i] = p.boot ? src : i;
+  // source rows of X (pix) and Y (piy) of the rows in use.  The reference masks the rows
+  // of the RESAMPLED matrices that are missing (get_mask, pyls/types/regression.py:48-53,
+  // 271-272): a row is in use when both of its sources are valid; the lists keep the order
+  if (warp == 0) {
+    int count = 0;
+    for (int base = 0; base < Sf; base += 32) {
+      const int i = base + lane;
+      int xs = 0, ys = 0, ok = 0;
+      if (i < Sf) {
+        const int src = p.idx ? p.idx[(size_t)r * Sf + i] : i;
+        ys = src;
+        xs = p.boot ? src : i;
+        ok = !p.valid || (p.valid[xs] != 0 && p.valid[Sf + ys] != 0);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int pos = count + __popc(m & ((1u << lane) - 1u));
+        pix[pos] = xs;
+        piy[pos] = ys;
+      }
+      count += __popc(m);
+    }
+    if (lane == 0) s_rows = count;
   }
   __syncthreads();
+  const int S = s_rows;
   // A = Y0 = Yp - column means;  ysum = column sums of Yp
   for (int e = tid; e < S * T; e += SP_THREADS) {
     const int i = e / T, t = e - i * T;
@@ -261,7 +284,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
   }
   ssy = block_sum(ssy, red);
 
-  gram_apply<TT>(p, pix, A, KA, csum);
+  gram_apply<TT>(p, S, pix, A, KA, csum);
   // C = A^T KA (upper triangle, mirrored); the deflation keeps it current
   for (int e = tid; e < T * T; e += SP_THREADS) {
     const int t1 = e / T, t2 = e - t1 * T;
@@ -419,7 +442,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
     }
     // b = t;  g = Kx b
     for (int i = tid; i < S; i += SP_THREADS) bv[i] = tv[i];
-    kx_matvec(p, pix, tv, gv);
+    kx_matvec(p, S, pix, tv, gv);
     {
       double v = 0.0;
       for (int i = tid; i < S; i += SP_THREADS) v += gv[i];
@@ -538,7 +561,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
       double v[8];
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) v[kk] = 0.0;
-      if (u < S)
+      if (u < Sf)
         for (int i = 0; i < S; ++i)
           if (pix[i] == u) {
 #pragma unroll
@@ -552,7 +575,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
   }
   if (!p.boot || !p.distrib) return;
   // distrib[t][k] = flip_k (Yp^T Tm + ysum (kappa^T Wcoef) / S),  kappa = Kpi 1
-  kx_matvec(p, pix, nullptr, gv);
+  kx_matvec(p, S, pix, nullptr, gv);
   for (int k = warp; k < L; k += SP_WARPS) {
     double v = 0.0;
     for (int i = lane; i < S; i += 32) v += gv[i] * Wc[(size_t)i * L + k];
@@ -729,6 +752,7 @@ int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit
   p.omega = omega; p.om_stride_r = om_stride_r; p.om_stride_c = om_stride_c;
   p.So = h->has_original ? h->Sx.as<double>() : nullptr;
   p.idx = idx;
+  p.valid = h->has_rowmask ? h->rowmask.as<int32_t>() : nullptr;
   p.Wcoef = h->G.as<double>(); p.Bs = h->H.as<double>(); p.Gs = h->M.as<double>();
   p.Tm = h->lam.as<double>();
   p.Abuf = h->S1.as<double>();

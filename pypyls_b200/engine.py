@@ -406,6 +406,23 @@ class ResamplingEngine:
             self._h, _ptr(omega), _ptr(xw), _ptr(pct), self._stream()))
         return xw, pct
 
+    def simpls_set_row_mask(self, valid_x, valid_y):
+        """Marks the rows of X and of Y (False / 0, shape (S,) each) that are
+        missing altogether -- what the reference's get_mask drops
+        (pyls/types/regression.py:48-53); call after set_data (with those rows
+        zero-filled), before simpls_decompose."""
+        dev = []
+        for v in (valid_x, valid_y):
+            v = np.asarray(v).astype(np.int32).ravel()
+            if v.size != self.S:
+                raise ValueError('row masks must have {} entries'
+                                 .format(self.S))
+            dev.append(torch.from_numpy(np.ascontiguousarray(v))
+                       .to(self.device))
+        _cabi.check(self._lib.plsb_simpls_set_row_mask(
+            self._h, _ptr(dev[0]), _ptr(dev[1]), self._stream()))
+        return self
+
     def simpls_set_original(self, x_weights):
         xw = self.to_device(x_weights)
         _cabi.check(self._lib.plsb_simpls_set_original(self._h, _ptr(xw),

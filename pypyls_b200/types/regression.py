@@ -29,6 +29,13 @@ def resid_yscores(x_scores, y_scores):
     return out
 
 
+def get_mask(X, Y):
+    """Rows where neither `X` nor `Y` is missing altogether (all NaN);
+    pyls/types/regression.py:48-53."""
+    return np.logical_not(np.logical_or(np.all(np.isnan(X), axis=1),
+                                        np.all(np.isnan(Y), axis=1)))
+
+
 def gaussian_tables(seeds, T):
     """(len(seeds), T, 11) test matrices: what sklearn's randomized_svd draws
     for ``compute.svd(Cov, n_components=1, seed=i)`` with an integer seed
@@ -61,10 +68,12 @@ class PLSRegression(BasePLS):
             if n_components > max_components:
                 raise ValueError('Provided `n_components` cannot be greater '
                                  'than {}'.format(max_components))
-        if np.isnan(X).any() or np.isnan(Y).any():
-            raise NotImplementedError(
-                'Rows with missing values (NaN) are not supported by the '
-                'accelerated path yet; drop them before the call.')
+        # rows that are missing altogether are masked like the reference does
+        # (get_mask, pyls/types/regression.py:48-53); any other NaN fails there
+        # inside sklearn's input validation with this message
+        mask = get_mask(X, Y)
+        if np.isnan(X[mask]).any() or np.isnan(Y[mask]).any():
+            raise ValueError('Input contains NaN.')
         kwargs.update(n_split=0, test_split=0)
         super().__init__(X=X, Y=Y, n_components=n_components, n_perm=n_perm,
                          n_boot=n_boot, rotate=rotate, ci=ci, aggfunc=aggfunc,
@@ -92,10 +101,20 @@ class PLSRegression(BasePLS):
     def run_pls(self, X, Y):
         """Follows pyls/types/regression.py:375-428 and pyls/base.py:341-371."""
         # the reference centres the caller's arrays in place; copies here
-        X -= np.mean(X, axis=0, keepdims=True)
-        Y -= np.mean(Y, axis=0, keepdims=True)
+        X -= np.nanmean(X, axis=0, keepdims=True)
+        Y -= np.nanmean(Y, axis=0, keepdims=True)
+        mask = get_mask(X, Y)
         self.res = res = structures.PLSResults(inputs=self.inputs)
-        self.engine = eng = self._make_engine(X, Y)
+        if mask.all():
+            self.engine = eng = self._make_engine(X, Y)
+        else:
+            # missing rows travel zero-filled together with the row mask: every
+            # decomposition then uses the rows of the resampled matrices whose X
+            # and Y sources are both present (regression.py:271-272, 322-323)
+            self.engine = eng = self._make_engine(np.nan_to_num(X),
+                                                  np.nan_to_num(Y))
+            eng.simpls_set_row_mask(~np.all(np.isnan(X), axis=1),
+                                    ~np.all(np.isnan(Y), axis=1))
         T, L = Y.shape[1], self.n_components
 
         # the reference draws one (T, 11) Gaussian matrix per component from
@@ -105,6 +124,7 @@ class PLSRegression(BasePLS):
         self._dev = dict(U=xw, d=torch.ones_like(pct), pct=pct)
         res['x_weights'] = to_host(xw)
         res['x_scores'] = to_host(eng.project_scores(xw))
+        res['x_scores'][np.isnan(X).any(axis=1)] = np.nan    # X @ x_weights
         varexp = pct.cpu().numpy()
 
         n_omega = max(self.inputs.n_perm, self.inputs.n_boot)
@@ -119,9 +139,10 @@ class PLSRegression(BasePLS):
             res['permres']['permsamples'] = self.permsamp
             res['permres']['perm_singval'] = d_perm
 
-        res['y_loadings'] = Y.T @ res['x_scores']
-        res['y_scores'] = resid_yscores(res['x_scores'],
-                                        Y @ res['y_loadings'])
+        res['y_loadings'] = Y[mask].T @ res['x_scores'][mask]
+        res['y_scores'] = np.full((len(Y), L), np.nan)
+        res['y_scores'][mask] = resid_yscores(res['x_scores'][mask],
+                                              Y[mask] @ res['y_loadings'])
 
         if self.inputs.n_boot > 0:
             distrib, u_sum, u_square = self.bootstrap(X, Y, self.rs)
@@ -175,8 +196,9 @@ def pls_regression(X, Y, *, n_components=None, n_perm=5000, n_boot=5000,
     PLS regression (SIMPLS) of `Y` (S, T) on `X` (S, B); same call as
     ``pyls.pls_regression`` (pyls/types/regression.py:432-440) with the
     permutation test and bootstrap executed on the GPU.  Unlike the reference
-    the caller's arrays are not centred in place.  Two-dimensional `Y` without
-    missing values only; ``n_proc`` is accepted but unused.
+    the caller's arrays are not centred in place.  Two-dimensional `Y` only;
+    rows of `X` or `Y` that are missing altogether (all NaN) are masked as in
+    the reference; ``n_proc`` is accepted but unused.
 
     Returns
     -------

@@ -205,6 +205,22 @@ def regression_cases():
         save('plsr_' + tag, dict(X=X, Y=Y, **kw), flat(r, 'r'))
 
 
+def regression_missing_rows_case():
+    """Rows of X / Y that are missing altogether (all NaN): masked by get_mask
+    (pyls/types/regression.py:48-53) in the original decomposition and, on the
+    resampled matrices, in every permutation and bootstrap."""
+    rs = np.random.RandomState(3)
+    X, Y = rs.rand(40, 60), rs.rand(40, 5)
+    Y[:, :2] += X[:, :10] @ rs.rand(10, 2) * 0.3
+    X[17, :] = np.nan
+    Y[25, :] = np.nan
+    X[31, :] = np.nan
+    kw = dict(n_components=3, n_perm=12, n_boot=12, seed=5)
+    r = pyls.pls_regression(X.copy(), Y.copy(), permindices=True,
+                            verbose=False, **kw)
+    save('plsr_missing_rows', dict(X=X, Y=Y, **kw), flat(r, 'r'))
+
+
 def index_cases():
     out = {}
     for n, (groups, n_cond, seed, cnt) in enumerate((
@@ -255,11 +271,15 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['splithalf']:
         splithalf_cases()
         sys.exit(0)
+    if sys.argv[1:] == ['missing']:
+        regression_missing_rows_case()
+        sys.exit(0)
     behavioral_cases()
     splithalf_cases()
     prepermuted_case()
     crossval_case()
     meancentered_cases()
     regression_cases()
+    regression_missing_rows_case()
     index_cases()
     matlab_cases()

@@ -499,7 +499,7 @@ def test_argument_errors_match_reference():
 # pls_regression (SIMPLS).  The reference's own tests pin shapes only for this
 # type ("parity unpinned by the reference's tests"); parity rests on the
 # shimmed reference run stored in tests/golden/plsr_*.npz and on the oracle.
-@pytest.mark.parametrize('name', ['plsr_t12', 'plsr_t5'])
+@pytest.mark.parametrize('name', ['plsr_t12', 'plsr_t5', 'plsr_missing_rows'])
 def test_regression_matches_reference_golden(name):
     import pypyls_b200 as pyls
     ins, ref = load_golden(name)
@@ -516,6 +516,38 @@ def test_regression_matches_reference_golden(name):
     close(out.bootres.y_loadings_ci, ref['y_loadings_ci'])
     close(out.bootres.x_weights_normed, ref['x_weights_normed'], rtol=1e-7)
     close(out.bootres.x_weights_stderr, ref['x_weights_stderr'], rtol=1e-7)
+
+
+def test_regression_missing_rows_match_oracle():
+    """Rows of X / Y that are missing altogether (get_mask,
+    pyls/types/regression.py:48-53) with T > 11 (Gaussian test matrices in use)
+    and user tables: every permutation / bootstrap drops the rows of the
+    RESAMPLED matrices whose sources are missing."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(21)
+    S, B, T, L = 64, 150, 13, 4
+    X, Y = rs.rand(S, B), rs.rand(S, T)
+    Y[:, :3] += X[:, :12] @ rs.rand(12, 3) * 0.3
+    X[[5, 40]] = np.nan
+    Y[[12, 40, 63]] = np.nan
+    ps = po.gen_permsamp([S], 1, 14, seed=1)
+    bs = po.gen_bootsamp([S], 1, 14, seed=2)
+    kw = dict(n_components=L, n_perm=14, n_boot=14, permsamples=ps,
+              bootsamples=bs, seed=8)
+    ref = po.pls_regression(X, Y, **kw)
+    out = pyls.pls_regression(X, Y, verbose=False, **kw)
+    for k in ('x_weights', 'x_scores', 'y_scores', 'y_loadings', 'varexp'):
+        close(out[k], ref[k])
+    assert np.isnan(out.x_scores).any(axis=1).sum() == 2
+    assert np.isnan(out.y_scores).any(axis=1).sum() == 4
+    close(out.permres.perm_singval, ref['perm_singval'])
+    assert np.array_equal(out.permres.pvals, ref['pvals'])
+    close(out.bootres.y_loadings_boot, ref['distrib'])
+    close(out.bootres.x_weights_normed, ref['x_weights_normed'], rtol=1e-7)
+    with pytest.raises(ValueError, match='NaN'):
+        Xp = X.copy()
+        Xp[7, 3] = np.nan
+        pyls.pls_regression(Xp, Y, verbose=False, **kw)
 
 
 @pytest.mark.parametrize('S,B,T,L', [(60, 300, 12, 4), (50, 200, 20, 9),

@@ -177,9 +177,11 @@ def test_regression_front_end_argument_errors():
         pyls.pls_regression(X, Y, n_components=25, n_perm=0, n_boot=0)
     with pytest.raises(NotImplementedError):
         pyls.pls_regression(X, rs.rand(20, 4, 3), n_perm=0, n_boot=0)
+    # rows that are missing altogether are masked (on the GPU); any other NaN
+    # fails like it does inside the reference's randomized_svd
     Xn = X.copy()
-    Xn[3] = np.nan
-    with pytest.raises(NotImplementedError):
+    Xn[3, 5] = np.nan
+    with pytest.raises(ValueError, match='NaN'):
         pyls.pls_regression(Xn, Y, n_perm=0, n_boot=0)
 
 
