@@ -7,7 +7,8 @@ loops run as batched CUDA launches through ``libplsb200.so``.
 """
 
 __all__ = ['behavioral_pls', 'meancentered_pls', 'pls_regression', 'PLSResults', 'PLSInputs',
-           'ResamplingEngine', 'release_workspaces', 'gen_permsamp', 'gen_bootsamp', '__version__']
+           'ResamplingEngine', 'release_workspaces', 'gen_permsamp', 'gen_bootsamp', 'save_results',
+           'load_results', '__version__']
 
 __version__ = '0.1.0'
 
@@ -15,3 +16,4 @@ from .structures import PLSInputs, PLSResults
 from .resample import gen_bootsamp, gen_permsamp
 from .engine import ResamplingEngine, release_workspaces
 from .types import behavioral_pls, meancentered_pls, pls_regression
+from .io import load_results, save_results

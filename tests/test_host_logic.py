@@ -201,3 +201,29 @@ def test_gen_splits_replays_the_reference_stream(groups, n_cond, test_size):
     # conditions follow their subject
     n_subj = sum(groups)
     assert a.sum() % n_cond == 0 and a.shape[0] == n_subj * n_cond
+
+
+def test_results_io_round_trip(tmp_path):
+    """save_results / load_results keep the reference's HDF5 layout
+    (pyls/io.py:12-122; pyls/tests/test_io.py): arrays as datasets, scalars as
+    attributes, None as the string 'None'.  Needs h5py (not in every image)."""
+    h5py = pytest.importorskip('h5py')
+    import pypyls_b200 as pyls
+    from pypyls_b200.structures import PLSResults
+    rs = np.random.RandomState(0)
+    res = PLSResults(x_weights=rs.rand(5, 2), singvals=rs.rand(2),
+                     inputs=dict(X=rs.rand(4, 5), n_perm=3, seed=None,
+                                 groups=[4]),
+                     permres=dict(pvals=rs.rand(2)))
+    fname = pyls.save_results(tmp_path / 'res', res)
+    assert fname.endswith('.hdf5') and h5py.is_hdf5(fname)
+    back = pyls.load_results(fname)
+    np.testing.assert_array_equal(back.x_weights, res.x_weights)
+    np.testing.assert_array_equal(back.permres.pvals, res.permres.pvals)
+    assert back.inputs.n_perm == 3 and back.inputs.seed is None
+    with h5py.File(fname, 'r') as f:
+        assert f['/results/inputs'].attrs['seed'] == 'None'
+        assert isinstance(f['/results/permres/pvals'], h5py.Dataset)
+    with pytest.raises(TypeError):
+        (tmp_path / 'junk.hdf5').write_text('not hdf5')
+        pyls.load_results(tmp_path / 'junk.hdf5')
