@@ -159,27 +159,32 @@ __device__ void gram_apply(const SimplsParams &p, int S, const int *pix, const d
   __syncthreads();
 }
 
-// out[i] = sum_j Kraw[pix[i]][pix[j]] x[j]: a warp per pair of rows, lanes along the
-// row (coalesced for permutations, nearly so for sorted bootstrap tables); barrier
+// out[i] = sum_j Kraw[pix[i]][pix[j]] x[j]: a warp per group of four rows, lanes along the
+// rows (coalesced for permutations, nearly so for sorted bootstrap tables; sixteen
+// independent loads in flight per lane hide the L2 latency); barrier
 __device__ void kx_matvec(const SimplsParams &p, int S, const int *pix, const double *x,
                           double *out) {
+  constexpr int RB = 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = warp * 2; i < S; i += SP_WARPS * 2) {
-    const int i1 = min(i + 1, S - 1);
-    const double *r0 = p.Kraw + (size_t)pix[i] * p.S, *r1 = p.Kraw + (size_t)pix[i1] * p.S;
-    double v0 = 0.0, v1 = 0.0;
+  for (int i = warp * RB; i < S; i += SP_WARPS * RB) {
+    const double *row[RB];
+    double v[RB];
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      row[k] = p.Kraw + (size_t)pix[min(i + k, S - 1)] * p.S;
+      v[k] = 0.0;
+    }
 #pragma unroll 4
     for (int j = lane; j < S; j += 32) {
       const int c = pix[j];
       const double xj = x ? x[j] : 1.0;
-      v0 += __ldg(r0 + c) * xj;
-      v1 += __ldg(r1 + c) * xj;
+#pragma unroll
+      for (int k = 0; k < RB; ++k) v[k] += __ldg(row[k] + c) * xj;
     }
-    v0 = warp_sum(v0);
-    v1 = warp_sum(v1);
-    if (lane == 0) {
-      out[i] = v0;
-      if (i + 1 < S) out[i + 1] = v1;
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      v[k] = warp_sum(v[k]);
+      if (lane == 0 && i + k < S) out[i + k] = v[k];
     }
   }
   __syncthreads();
