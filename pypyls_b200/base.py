@@ -18,7 +18,7 @@ import torch
 
 from . import dist as pdist
 from . import structures
-from .engine import ResamplingEngine, to_host
+from .engine import Download, ResamplingEngine, to_host
 from .resample import (check_random_state, gen_bootsamp, gen_permsamp,
                        gen_splits)
 
@@ -28,6 +28,39 @@ def _device_seed(rs):
     RandomState so that an integer ``seed`` makes runs repeatable."""
     hi, lo = rs.randint(0, 2 ** 31 - 1, size=2)
     return (int(hi) << 32) | int(lo)
+
+
+class _DeviceTable:
+    """A device-generated resampling table, (n, S) int32, on its way to the
+    host.  ``start()`` queues the copy (side stream) behind the kernels already
+    queued; ``get()`` waits for that copy only and gives the (S, n) int array
+    the reference keeps."""
+
+    def __init__(self, full):
+        self.dev, self.dl, self.arr = full, None, None
+
+    def start(self):
+        self.dl = Download(self.dev)
+
+    def get(self):
+        if self.arr is None:
+            if self.dl is None:
+                self.start()
+            self.arr = self.dl.get().T.astype(int)
+            self.dev = self.dl = None
+        return self.arr
+
+
+def _resolve(table):
+    return table.get() if isinstance(table, _DeviceTable) else table
+
+
+def _host_t(t):
+    return None if t is None else to_host(t).T.copy()
+
+
+def _start(t):
+    return None if t is None else Download(t)
 
 
 class BasePLS():
@@ -119,45 +152,69 @@ class BasePLS():
     def run_pls(self, X, Y):
         """
         Original decomposition + permutation test
-        (pyls/base.py:341-399).  Returns the results object; device copies of
-        the decomposition stay in ``self._dev``.
+        (pyls/base.py:341-399).  Only QUEUES the device work and registers the
+        downloads in ``self._later``: the results object is complete after the
+        caller's ``self._finalize()``.  Device copies of the decomposition stay
+        in ``self._dev``.
         """
         self.res = res = structures.PLSResults(inputs=self.inputs)
+        self._later = []
         X = np.asarray(X) if not isinstance(X, torch.Tensor) else X
         self.engine = eng = self._make_engine(X, self._engine_y(Y))
         U, d, V = eng.decompose()
         self._replay_svd_draws()
         self._dev = dict(U=U, d=d, V=V)
-        res['x_weights'] = to_host(U)
-        res['singvals'] = np.diag(to_host(d))
-        res['y_weights'] = to_host(V)
-        res['x_scores'] = to_host(eng.project_scores(U))
+        dl = [Download(t) for t in (U, d, V, eng.project_scores(U))]
+
+        def fill_decomposition():
+            res['x_weights'] = dl[0].get()
+            res['singvals'] = np.diag(dl[1].get())
+            res['y_weights'] = dl[2].get()
+            res['x_scores'] = dl[3].get()
+        self._later.append(fill_decomposition)
 
         if self.inputs.n_perm > 0:
-            d_perm, ucorrs, vcorrs = self.permutation(X, Y, seed=self.rs)
-            res['permres']['pvals'] = eng.perm_pvals(
-                self._dev['d_perm'], d).cpu().numpy()
-            res['permres']['permsamples'] = self.permsamp
-            res['permres']['perm_singval'] = d_perm
-
+            out = self._permutation_device(X, Y, seed=self.rs)
+            pv = eng.perm_pvals(out['d_perm'], d)
+            stats = {}
             if self.inputs.n_split is not None:
                 # split-half reliability of the original singular vectors and
                 # its permutation statistics (pyls/base.py:373-397)
                 ou, ov = self.split_half(X, Y, seed=self.rs)
-                dev = self._dev
                 ci = self.inputs.get('ci')
                 ci = 95 if ci is None else ci
                 low = (100 - ci) / 2
-                out = {}
-                for name, orig, perm in (('ucorr', ou, dev['ucorrs']),
-                                         ('vcorr', ov, dev['vcorrs'])):
+                for name, orig, perm in (('ucorr', ou, out['ucorrs']),
+                                         ('vcorr', ov, out['vcorrs'])):
                     lo, hi = eng.percentile(perm, low, 100 - low)
-                    out[name] = to_host(orig)
-                    out[name + '_pvals'] = to_host(eng.perm_pvals(perm, orig))
-                    out[name + '_lolim'] = to_host(lo)
-                    out[name + '_uplim'] = to_host(hi)
-                res['splitres'].update(out)
+                    stats[name] = orig
+                    stats[name + '_pvals'] = eng.perm_pvals(perm, orig)
+                    stats[name + '_lolim'] = lo
+                    stats[name + '_uplim'] = hi
+            dl_pv, dl_dperm = Download(pv), Download(out['d_perm'])
+            dl_stats = {k: Download(v) for k, v in stats.items()}
+
+            def fill():
+                res['permres']['pvals'] = dl_pv.get()
+                self.permsamp = _resolve(out['table'])
+                res['permres']['permsamples'] = self.permsamp
+                res['permres']['perm_singval'] = dl_dperm.get().T.copy()
+                if dl_stats:
+                    res['splitres'].update({k: v.get()
+                                            for k, v in dl_stats.items()})
+            self._later.append(fill)
         return res
+
+    def _finalize(self):
+        """Everything above only queues device work and starts the downloads
+        (side stream) behind their producers; the host conversions registered
+        on the way run here in queue order, each waiting for its own download
+        only -- the early ones while the later kernels are still running."""
+        later, self._later = self._later, []
+        for fill in later:
+            fill()
+        if self.engine is not None:
+            torch.cuda.current_stream(self.engine.device).synchronize()
 
     def _split_masks(self, first, count):
         """Half / half masks of the permutations [first, first + count):
@@ -202,12 +259,11 @@ class BasePLS():
 
     def _table(self, kind, n, seed):
         """Resampling table for this analysis: user-provided, replayed on the
-        host, or generated on the device.  Returns (host, block, first):
+        host, or generated on the device.  Returns (table, block, first):
         `block` is the device (n_local, S) int32 block of this rank starting at
-        resample id `first`; `host` is a callable that gives the (S, n) int
-        array of the whole table -- for device-generated tables the copy to
-        the host is deferred so that it overlaps the resampling kernels the
-        caller queues first."""
+        resample id `first`; `table` is the (S, n) int array of the whole
+        table or, for device-generated tables, a :class:`_DeviceTable` whose
+        copy to the host the caller starts after queuing its kernels."""
         eng = self.engine
         key = 'permsamples' if kind == 'perm' else 'bootsamples'
         first, count = pdist.my_block(n)
@@ -222,7 +278,7 @@ class BasePLS():
                 raise ValueError('Provided `{}` must have shape ({}, {}); got '
                                  '{}'.format(key, eng.S, n, given.shape))
             block = eng.to_device_indices(given[:, first:first + count])
-            return (lambda: given), block, first
+            return given, block, first
         gen = eng.gen_perm_indices if kind == 'perm' else eng.gen_boot_indices
         block, exhausted = gen(_device_seed(check_random_state(seed)), count,
                                first=first)
@@ -230,7 +286,7 @@ class BasePLS():
             warnings.warn('WARNING: Duplicate {} used.'.format(
                 'permutations' if kind == 'perm' else 'bootstraps'))
         full = pdist.gather_resamples(block, n)
-        return (lambda: to_host(full).T.astype(int)), block, first
+        return _DeviceTable(full), block, first
 
     def permutation(self, X, Y, seed=None):
         """
@@ -242,6 +298,15 @@ class BasePLS():
         ucorrs, vcorrs : (L, P) numpy.ndarray or None
             Split-half correlations of every permutation (``n_split``)
         """
+        out = self._permutation_device(X, Y, seed=seed)
+        self.permsamp = _resolve(out['table'])
+        return (_host_t(out['d_perm']), _host_t(out['ucorrs']),
+                _host_t(out['vcorrs']))
+
+    def _permutation_device(self, X, Y, seed=None):
+        """Queues the permutation test; returns the device results
+        (``d_perm`` (P, L), ``ucorrs`` / ``vcorrs`` (P, L) or None) and the
+        table (array or :class:`_DeviceTable`) without waiting for anything."""
         n = self.inputs.n_perm
         rotate = self.inputs.get('rotate')
         rotate = True if rotate is None else bool(rotate)
@@ -253,31 +318,34 @@ class BasePLS():
         if given is not None and self.inputs.get('permindices') is False:
             # pre-permuted Y matrices, (P, S, T) (pyls/base.py:636-639, 689-692)
             local = self._prepermuted(given, n, rotate)
+            table = given
             first, count = pdist.my_block(n)
             split_of = dict(Yperm=given[first:first + count])
         else:
             path = self.inputs.get('perm_path') or 'gemm'
             if path not in ('gemm', 'gram'):
                 raise ValueError("perm_path must be 'gemm' or 'gram'")
-            host_table, block, first = self._table('perm', n, seed)
+            table, block, first = self._table('perm', n, seed)
             count = int(block.shape[0])
             if path == 'gram' and rotate:
                 local = self.engine.run_perms_gram(block)
             else:
                 local = self.engine.run_perms(block, rotate=rotate)
-            self.permsamp = host_table()     # overlaps the kernels queued above
+            if isinstance(table, _DeviceTable):
+                table.start()            # behind the kernels queued above
             split_of = dict(idx=block)
         d_perm = pdist.gather_resamples(local, n)
         self._dev['d_perm'] = d_perm
+        out = dict(d_perm=d_perm, ucorrs=None, vcorrs=None, table=table)
         if n_split is None:
-            return to_host(d_perm).T.copy(), None, None
+            return out
         # split-half resampling of every permuted data set (pyls/base.py:704-708)
         uc, vc = self.engine.split_half(self._split_masks(first, count),
                                         **split_of)
         uc, vc = pdist.gather_resamples(uc, n), pdist.gather_resamples(vc, n)
         self._dev.update(ucorrs=uc, vcorrs=vc)
-        return (to_host(d_perm).T.copy(), to_host(uc).T.copy(),
-                to_host(vc).T.copy())
+        out.update(ucorrs=uc, vcorrs=vc)
+        return out
 
     def _prepermuted(self, given, n, rotate):
         eng = self.engine
@@ -290,7 +358,6 @@ class BasePLS():
             raise ValueError('Provided pre-permuted `permsamples` must have '
                              'shape ({}, {}, {}); got {}'.format(
                                  n, eng.S, eng.T, shape))
-        self.permsamp = given
         first, count = pdist.my_block(n)
         return eng.run_perms_prepermuted(given[first:first + count],
                                          rotate=rotate)
@@ -304,26 +371,43 @@ class BasePLS():
         distrib : (K, L, R) numpy.ndarray
         u_sum, u_square : (B, L) numpy.ndarray
         """
+        out = self._bootstrap_device(X, Y, seed=seed)
+        us, uq = to_host(out['u_sum']), to_host(out['u_square'])   # waits
+        self.bootsamp = _resolve(out['table'])
+        return self._host_distrib(out), us, uq
+
+    @staticmethod
+    def _host_distrib(out):
+        """(K, L, R) host view of the bootstrap distribution of a
+        :meth:`_bootstrap_device`; waits for its copies."""
+        if out['host'] is not None:
+            out['host_done'].synchronize()
+            return out['host'].numpy().transpose(1, 2, 0)
+        return to_host(out['distrib'].permute(1, 2, 0).contiguous())
+
+    def _bootstrap_device(self, X, Y, seed=None):
+        """Queues the bootstrap; returns device ``distrib`` (R, K, L), ``u_sum``,
+        ``u_square`` (B, L), the pinned host copy of ``distrib`` that is being
+        filled on a side stream (single GPU) and the table, without waiting."""
         n = self.inputs.n_boot
-        host_table, block, _ = self._table('boot', n, seed)
+        table, block, _ = self._table('boot', n, seed)
+        host = host_done = None
         if pdist.world()[1] == 1:
             # single GPU: every internal pass's slice of `distrib` goes to the host
             # on a side stream while the next pass computes
-            distrib, host, u_sum, u_square = \
-                self.engine.run_boots_streamed(block)
-            self.bootsamp = host_table()
-            self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
-            us, uq = to_host(u_sum), to_host(u_square)   # synchronises the stream
-            return host.numpy().transpose(1, 2, 0), us, uq
-        distrib, u_sum, u_square = self.engine.run_boots(block)
-        self.bootsamp = host_table()         # overlaps the kernels queued above
-        distrib = pdist.gather_resamples(distrib, n)
-        pdist.reduce_sum(u_sum, u_square)
+            distrib, host, u_sum, u_square, host_done = \
+                self.engine.run_boots_streamed(block, wait=False)
+        else:
+            distrib, u_sum, u_square = self.engine.run_boots(block)
+            distrib = pdist.gather_resamples(distrib, n)
+            pdist.reduce_sum(u_sum, u_square)
+        if isinstance(table, _DeviceTable):
+            table.start()                # behind the kernels queued above
         self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
-        return (to_host(distrib.permute(1, 2, 0).contiguous()),
-                to_host(u_sum), to_host(u_square))
+        return dict(distrib=distrib, host=host, host_done=host_done,
+                    u_sum=u_sum, u_square=u_square, table=table)
 
-    def _boot_stats(self, add_orig):
+    def _boot_stats(self, add_orig, device=False):
         """Bootstrap ratios, standard errors and percentile intervals from the
         device-resident accumulators (compute.boot_rel / boot_ci,
         pyls/compute.py:184-237)."""
@@ -335,5 +419,5 @@ class BasePLS():
         ci = 95 if ci is None else ci
         low = (100 - ci) / 2
         lo, hi = eng.percentile(dev['distrib'], low, 100 - low)
-        return (to_host(bsr), to_host(se),
-                to_host(torch.stack([lo, hi], dim=-1)))
+        out = (bsr, se, torch.stack([lo, hi], dim=-1))
+        return out if device else tuple(to_host(t) for t in out)

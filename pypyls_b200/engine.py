@@ -46,6 +46,40 @@ _FREE_HANDLES = {}
 _COPY_STREAMS = {}     # device index -> side stream for overlapped device->host copies
 
 
+def copy_stream(device):
+    """The side stream device -> host copies are queued on, so that they do
+    not hold up the kernels queued behind them on the main stream."""
+    index = torch.device(device).index
+    side = _COPY_STREAMS.get(index)
+    if side is None:
+        side = _COPY_STREAMS[index] = torch.cuda.Stream(torch.device(device))
+    return side
+
+
+class Download:
+    """A device tensor on its way to pinned host memory.  Creating it queues
+    the copy on the side stream behind the work queued so far on the current
+    stream; nothing blocks the host until :meth:`get`, which waits for this
+    copy only and returns the NumPy array."""
+
+    def __init__(self, t):
+        self.dev = t                      # keeps the device memory alive
+        self.host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        main, side = torch.cuda.current_stream(t.device), copy_stream(t.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.done = torch.cuda.Event()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            self.host.copy_(t, non_blocking=True)
+            self.done.record(side)
+
+    def get(self):
+        self.done.synchronize()
+        self.dev = None
+        return self.host.numpy()
+
+
 def release_workspaces():
     """Destroys every pooled library handle (frees their device memory)."""
     lib = _cabi.lib()
@@ -340,11 +374,13 @@ class ResamplingEngine:
             self._stream()))
         return distrib, u_sum, u_square
 
-    def run_boots_streamed(self, idx):
+    def run_boots_streamed(self, idx, wait=True):
         """run_boots in blocks of the library's internal pass size; the block's
         slice of `distrib` is copied to pinned host memory on a side stream
         while the next block computes.  Returns (distrib on the device,
-        the same (count, K, L) on the host, u_sum, u_square)."""
+        the same (count, K, L) on the host, u_sum, u_square); with
+        ``wait=False`` the main stream is not made to wait for the copies and
+        the event that marks the last one is returned as a fifth item."""
         idx = self.to_device_indices(idx)
         n = int(idx.shape[0])
         distrib = self._f64(n, self.K, self.L)
@@ -355,9 +391,7 @@ class ResamplingEngine:
         u_square = torch.zeros_like(u_sum)
         chunk = max(1, int(self._lib.plsb_boot_chunk(self._h, n))) if n else 1
         main = torch.cuda.current_stream(self.device)
-        side = _COPY_STREAMS.get(self.device.index)
-        if side is None:
-            side = _COPY_STREAMS[self.device.index] = torch.cuda.Stream(self.device)
+        side = copy_stream(self.device)
         for a in range(0, n, chunk):
             b = min(n, a + chunk)
             _cabi.check(self._lib.plsb_run_boots(
@@ -368,8 +402,12 @@ class ResamplingEngine:
             with torch.cuda.stream(side):
                 side.wait_event(done)
                 host[a:b].copy_(distrib[a:b], non_blocking=True)
-        main.wait_stream(side)
-        return distrib, host, u_sum, u_square
+        if wait:
+            main.wait_stream(side)
+            return distrib, host, u_sum, u_square
+        last = torch.cuda.Event()
+        last.record(side)
+        return distrib, host, u_sum, u_square, last
 
     def crosscov(self, idx=None, bootstrap=False):
         """Cross-covariance matrices (count, K, B) of the given resamples;

@@ -6,8 +6,9 @@ CUDA resampling engine.
 
 import numpy as np
 
-from .. import structures
-from ..base import BasePLS
+from ..base import BasePLS, _resolve
+from ..engine import Download, to_host
+from ..resample import gen_splits
 
 
 class BehavioralPLS(BasePLS):
@@ -42,51 +43,64 @@ class BehavioralPLS(BasePLS):
         -------
         r_scores, r2_scores : (T, C) numpy.ndarray
         """
-        from ..engine import to_host
-        from ..resample import gen_splits
+        r, r2 = self._crossval_device(seed)
+        return to_host(r).T.copy(), to_host(r2).T.copy()
+
+    def _crossval_device(self, seed):
         splits = gen_splits(self.inputs.groups, self.inputs.n_cond,
                             self.inputs.test_split, seed=seed,
                             test_size=self.inputs.test_size)
-        r, r2 = self.engine.crossval(splits)
-        return to_host(r).T.copy(), to_host(r2).T.copy()
+        return self.engine.crossval(splits)
 
     def run_pls(self, X, Y):
-        """Follows pyls/types/behavioral.py:172-227."""
+        """Follows pyls/types/behavioral.py:172-227.  Device work is queued
+        first (decomposition, permutations, bootstraps, cross-validation);
+        downloads and host-side post-processing follow in one go."""
         res = super().run_pls(X, Y)
         eng = self.engine
-
-        # y_scores: every cell's rows of Y times that cell's block of V
-        cells = np.repeat(res['inputs']['groups'], res['inputs']['n_cond'])
-        T = Y.shape[1]
-        res['y_scores'] = np.vstack([
-            y @ res['y_weights'][j * T:(j + 1) * T]
-            for j, y in enumerate(np.split(Y, np.cumsum(cells)[:-1]))])
 
         # y_loadings = per-cell xcorr(x_scores, Y): the bootstrap distribution
         # kernel evaluated on the identity resample (X @ U has unit-norm U)
         ident = np.arange(eng.S)[:, None]
-        y_load, _, _ = eng.run_boots(ident)
-        res['y_loadings'] = y_load[0].cpu().numpy()
+        y_load = Download(eng.run_boots(ident)[0][0])
 
+        boot = stats = None
         if self.inputs.n_boot > 0:
-            distrib, u_sum, u_square = self.bootstrap(X, Y, self.rs)
-            bsrs, uboot_se, corrci = self._boot_stats(add_orig=True)
-            res['bootres'].update(dict(x_weights_normed=bsrs,
-                                       x_weights_stderr=uboot_se,
-                                       y_loadings=res['y_loadings'].copy(),
-                                       y_loadings_boot=distrib,
-                                       y_loadings_ci=corrci,
-                                       bootsamples=self.bootsamp))
+            boot = self._bootstrap_device(X, Y, self.rs)
+            stats = [Download(t) for t in
+                     self._boot_stats(add_orig=True, device=True)]
 
         # cross-validated prediction of Y (pyls/types/behavioral.py:217-219)
+        cv = None
         if self.inputs.get('test_split') is not None and \
                 (self.inputs.get('test_size') or 0) > 0:
-            r, r2 = self.crossval(X, Y, seed=self.rs)
-            res['cvres'].update(dict(pearson_r=r, r_squared=r2))
+            cv = [Download(t) for t in self._crossval_device(self.rs)]
 
-        sq = np.diag(res['singvals']) ** 2
-        res['varexp'] = sq / np.sum(sq)
-        res['singvals'] = np.diag(res['singvals'])
+        def fill():
+            # y_scores: every cell's rows of Y times that cell's block of V
+            cells = np.repeat(res['inputs']['groups'], res['inputs']['n_cond'])
+            T = Y.shape[1]
+            res['y_scores'] = np.vstack([
+                y @ res['y_weights'][j * T:(j + 1) * T]
+                for j, y in enumerate(np.split(Y, np.cumsum(cells)[:-1]))])
+            res['y_loadings'] = y_load.get()
+            if boot is not None:
+                self.bootsamp = _resolve(boot['table'])
+                res['bootres'].update(dict(
+                    x_weights_normed=stats[0].get(),
+                    x_weights_stderr=stats[1].get(),
+                    y_loadings=res['y_loadings'].copy(),
+                    y_loadings_boot=self._host_distrib(boot),
+                    y_loadings_ci=stats[2].get(),
+                    bootsamples=self.bootsamp))
+            if cv is not None:
+                res['cvres'].update(dict(pearson_r=cv[0].get().T.copy(),
+                                         r_squared=cv[1].get().T.copy()))
+            sq = np.diag(res['singvals']) ** 2
+            res['varexp'] = sq / np.sum(sq)
+            res['singvals'] = np.diag(res['singvals'])
+        self._later.append(fill)
+        self._finalize()
         return res
 
 

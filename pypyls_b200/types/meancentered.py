@@ -8,7 +8,8 @@ import warnings
 
 import numpy as np
 
-from ..base import BasePLS
+from ..base import BasePLS, _resolve
+from ..engine import Download
 
 
 def dummy_code(groups, n_cond=1):
@@ -64,29 +65,38 @@ class MeanCenteredPLS(BasePLS):
         return None
 
     def run_pls(self, X, Y):
-        """Follows pyls/types/meancentered.py:127-179."""
+        """Follows pyls/types/meancentered.py:127-179.  Device work is queued
+        first; downloads and host-side post-processing follow in one go."""
         res = super().run_pls(X, Y)
         eng = self.engine
-        res['y_scores'] = Y @ res['y_weights']
 
         # contrast = cell means of the de-meaned rows projected on U: the
         # bootstrap distribution kernel evaluated on the identity resample
         ident = np.arange(eng.S)[:, None]
-        contrast = eng.run_boots(ident)[0][0].cpu().numpy()
+        contrast = Download(eng.run_boots(ident)[0][0])
 
+        boot = stats = None
         if self.inputs.n_boot > 0:
-            distrib, u_sum, u_square = self.bootstrap(X, Y, self.rs)
-            bsrs, uboot_se, corrci = self._boot_stats(add_orig=False)
-            res['bootres'].update(dict(x_weights_normed=bsrs,
-                                       x_weights_stderr=uboot_se,
-                                       bootsamples=self.bootsamp,
-                                       contrast=contrast,
-                                       contrast_boot=distrib,
-                                       contrast_ci=corrci))
+            boot = self._bootstrap_device(X, Y, self.rs)
+            stats = [Download(t) for t in
+                     self._boot_stats(add_orig=False, device=True)]
 
-        sq = np.diag(res['singvals']) ** 2
-        res['varexp'] = sq / np.sum(sq)
-        res['singvals'] = np.diag(res['singvals'])
+        def fill():
+            res['y_scores'] = Y @ res['y_weights']
+            if boot is not None:
+                self.bootsamp = _resolve(boot['table'])
+                res['bootres'].update(dict(
+                    x_weights_normed=stats[0].get(),
+                    x_weights_stderr=stats[1].get(),
+                    bootsamples=self.bootsamp,
+                    contrast=contrast.get(),
+                    contrast_boot=self._host_distrib(boot),
+                    contrast_ci=stats[2].get()))
+            sq = np.diag(res['singvals']) ** 2
+            res['varexp'] = sq / np.sum(sq)
+            res['singvals'] = np.diag(res['singvals'])
+        self._later.append(fill)
+        self._finalize()
         return res
 
 

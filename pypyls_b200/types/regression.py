@@ -9,7 +9,7 @@ import torch
 
 from .. import dist as pdist
 from .. import structures
-from ..base import BasePLS
+from ..base import BasePLS, _DeviceTable, _resolve
 from ..engine import ResamplingEngine, to_host
 
 
@@ -105,6 +105,7 @@ class PLSRegression(BasePLS):
         Y -= np.nanmean(Y, axis=0, keepdims=True)
         mask = get_mask(X, Y)
         self.res = res = structures.PLSResults(inputs=self.inputs)
+        self._later = []
         if mask.all():
             self.engine = eng = self._make_engine(X, Y)
         else:
@@ -165,10 +166,12 @@ class PLSRegression(BasePLS):
         (pyls/types/regression.py:329-373): variance explained in Y per
         component for every permutation of the rows of Y."""
         n = self.inputs.n_perm
-        host_table, block, first = self._table('perm', n, seed)
+        table, block, first = self._table('perm', n, seed)
         local = self.engine.simpls_run_perms(
             block, self._omega_block(first, block.shape[0]))
-        self.permsamp = host_table()
+        if isinstance(table, _DeviceTable):
+            table.start()
+        self.permsamp = _resolve(table)
         d_perm = pdist.gather_resamples(local, n)
         self._dev['d_perm'] = d_perm
         return to_host(d_perm).T.copy(), None, None
@@ -177,10 +180,12 @@ class PLSRegression(BasePLS):
         """Replaces BasePLS.bootstrap + PLSRegression._single_boot
         (pyls/types/regression.py:279-327)."""
         n = self.inputs.n_boot
-        host_table, block, first = self._table('boot', n, seed)
+        table, block, first = self._table('boot', n, seed)
         distrib, u_sum, u_square, _ = self.engine.simpls_run_boots(
             block, self._omega_block(first, block.shape[0]))
-        self.bootsamp = host_table()
+        if isinstance(table, _DeviceTable):
+            table.start()
+        self.bootsamp = _resolve(table)
         distrib = pdist.gather_resamples(distrib, n)
         pdist.reduce_sum(u_sum, u_square)
         self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)

@@ -1,0 +1,36 @@
+"""GPU timeline of one end-to-end front-end call at BASELINE config 2: busy time vs
+span and the largest idle gaps (torch.profiler / CUPTI; run on the GPU box)."""
+import os
+import sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from torch.profiler import profile, ProfilerActivity
+import pypyls_b200 as pyls
+
+rs = np.random.RandomState(1234)
+X, Y = rs.rand(80, 10000), rs.rand(80, 10)
+Xh, Yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(Y).pin_memory()
+kw = dict(groups=[20, 20], n_cond=2, n_perm=5000, n_boot=5000, verbose=False)
+for i in range(3):
+    pyls.behavioral_pls(Xh, Yh, seed=i, **kw)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    pyls.behavioral_pls(Xh, Yh, seed=7, **kw)
+    torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+ev.sort(key=lambda e: e.time_range.start)
+t0, t1 = ev[0].time_range.start, max(e.time_range.end for e in ev)
+busy, cur_end, gaps = 0.0, t0, []
+for e in ev:
+    s, en = e.time_range.start, e.time_range.end
+    if s > cur_end:
+        gaps.append((s - cur_end, prev.name[:60], e.name[:60], (cur_end - t0) / 1e3))
+    busy += max(0.0, en - max(s, cur_end))
+    if en > cur_end:
+        cur_end, prev = en, e
+print('span %.2f ms, busy %.2f ms, idle %.2f ms, %d device events' %
+      ((t1 - t0) / 1e3, busy / 1e3, (t1 - t0 - busy) / 1e3, len(ev)))
+for g in sorted(gaps, reverse=True)[:14]:
+    print('gap %7.1f us at %6.2f ms  after %-60s before %s' % (g[0], g[3], g[1], g[2]))
