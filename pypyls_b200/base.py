@@ -18,7 +18,7 @@ import torch
 
 from . import dist as pdist
 from . import structures
-from .engine import Download, ResamplingEngine, to_host
+from .engine import Download, ResamplingEngine, copy_stream, to_host
 from .resample import (check_random_state, gen_bootsamp, gen_permsamp,
                        gen_splits)
 
@@ -388,24 +388,42 @@ class BasePLS():
     def _bootstrap_device(self, X, Y, seed=None):
         """Queues the bootstrap; returns device ``distrib`` (R, K, L), ``u_sum``,
         ``u_square`` (B, L), the pinned host copy of ``distrib`` that is being
-        filled on a side stream (single GPU) and the table, without waiting."""
+        filled on a side stream (``host_done`` marks its last copy) and the
+        table, without waiting."""
         n = self.inputs.n_boot
-        table, block, _ = self._table('boot', n, seed)
-        host = host_done = None
-        if pdist.world()[1] == 1:
-            # single GPU: every internal pass's slice of `distrib` goes to the host
-            # on a side stream while the next pass computes
-            distrib, host, u_sum, u_square, host_done = \
-                self.engine.run_boots_streamed(block, wait=False)
-        else:
-            distrib, u_sum, u_square = self.engine.run_boots(block)
+        table, block, first = self._table('boot', n, seed)
+        count = int(block.shape[0])
+        size = pdist.world()[1]
+        # every internal pass's slice of `distrib` goes to pinned host memory on a
+        # side stream while the next pass computes: straight into this rank's rows
+        # of the full (R, K, L) host array
+        host = torch.empty((n, self.engine.K, self.engine.L),
+                           dtype=torch.float64, pin_memory=True)
+        distrib, _, u_sum, u_square, host_done = \
+            self.engine.run_boots_streamed(block, wait=False,
+                                           host=host[first:first + count])
+        local = distrib         # stays alive until its side-stream copies are done
+        if size > 1:
+            # the other ranks' rows: all-gather on the device, then only those rows
+            # follow to the host (side stream)
             distrib = pdist.gather_resamples(distrib, n)
             pdist.reduce_sum(u_sum, u_square)
+            main = torch.cuda.current_stream(self.engine.device)
+            side = copy_stream(self.engine.device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            host_done = torch.cuda.Event()
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                for a, b in ((0, first), (first + count, n)):
+                    if b > a:
+                        host[a:b].copy_(distrib[a:b], non_blocking=True)
+                host_done.record(side)
         if isinstance(table, _DeviceTable):
             table.start()                # behind the kernels queued above
         self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
         return dict(distrib=distrib, host=host, host_done=host_done,
-                    u_sum=u_sum, u_square=u_square, table=table)
+                    u_sum=u_sum, u_square=u_square, table=table, keep=local)
 
     def _boot_stats(self, add_orig, device=False):
         """Bootstrap ratios, standard errors and percentile intervals from the

@@ -374,18 +374,21 @@ class ResamplingEngine:
             self._stream()))
         return distrib, u_sum, u_square
 
-    def run_boots_streamed(self, idx, wait=True):
+    def run_boots_streamed(self, idx, wait=True, host=None):
         """run_boots in blocks of the library's internal pass size; the block's
         slice of `distrib` is copied to pinned host memory on a side stream
         while the next block computes.  Returns (distrib on the device,
         the same (count, K, L) on the host, u_sum, u_square); with
         ``wait=False`` the main stream is not made to wait for the copies and
-        the event that marks the last one is returned as a fifth item."""
+        the event that marks the last one is returned as a fifth item.  `host`:
+        optional pinned (count, K, L) tensor (e.g. this rank's slice of a
+        larger buffer) to fill instead of a new one."""
         idx = self.to_device_indices(idx)
         n = int(idx.shape[0])
         distrib = self._f64(n, self.K, self.L)
-        host = torch.empty((n, self.K, self.L), dtype=torch.float64,
-                           pin_memory=True)
+        if host is None:
+            host = torch.empty((n, self.K, self.L), dtype=torch.float64,
+                               pin_memory=True)
         u_sum = torch.zeros((self.B, self.L), dtype=torch.float64,
                             device=self.device)
         u_square = torch.zeros_like(u_sum)
