@@ -43,8 +43,10 @@ constexpr int SM_WARPS = SM_THREADS / 32;
 //   lam_out (K): eigenvalues sorted descending (sqrt_lam: their square roots)
 __global__ void __launch_bounds__(SM_THREADS)
 eigen_kernel(const double *__restrict__ G, int ldg, long long g_stride, int K, int sqrt_lam,
-             double *__restrict__ V_out, double *__restrict__ lam_out) {
+             double *__restrict__ V_out, double *__restrict__ lam_out,
+             const int *__restrict__ todo) {
   extern __shared__ __align__(16) double sm[];
+  if (todo && !todo[blockIdx.x]) return;   // done by the Newton-Schulz fast path
   const int ne = K + (K & 1), ld = ne | 1, half = ne / 2;
   double *bufA = sm;                 // G -> diag(lam)
   double *bufV = bufA + ne * ld;     // V
@@ -121,8 +123,10 @@ __device__ __forceinline__ void small_mm(const double *A, int sam, int sak, cons
 __global__ void __launch_bounds__(SM_THREADS)
 rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
                 const double *__restrict__ lam_in, int K, int L,
-                const double *__restrict__ dorig, double *__restrict__ M_out, int ldm) {
+                const double *__restrict__ dorig, double *__restrict__ M_out, int ldm,
+                const int *__restrict__ todo) {
   extern __shared__ __align__(16) double sm[];
+  if (todo && !todo[blockIdx.x]) return;   // done by the Newton-Schulz fast path
   const int LP = (K + 7) & ~7, ld = LP + 4;
   double *Vs = sm;                // V          [LP][ld]
   double *Hs = Vs + LP * ld;      // H, later the second iterate
@@ -216,8 +220,158 @@ rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
   }
 }
 
+// Fast path of the bootstrap rotation without an eigen-decomposition.
+//
+//   M = V Q  with  Q = polar(H^T V lam^-1/2)^T   is   M = polar(G^-1/2 H)
+//
+// (V polar(Y) = polar(V Y) for orthogonal V), and both factors come out of
+// Newton-Schulz iterations -- DMMA matrix products only:
+//   G^-1/2:  Y_0 = G / c, Z_0 = I;  T = (3 I - Z Y) / 2,  Y <- Y T,  Z <- T Z
+//            (Z -> (G / c)^-1/2; c = |G|_inf >= lam_max, so |I - Y_0| < 1)
+//   polar:   X_0 = Z H;  X <- X (3 I - X^T X) / 2     (sigma(X_0) <= 1: cosines)
+// The first iteration converges in about log_2.25(cond(G)) + 5 steps; a
+// resample whose G does not get there in NS_MAX_IT steps (ill-conditioned or
+// rank-deficient bootstrap samples), or an analysis whose original
+// decomposition has null latent variables (mean-centred PLS), is left to the
+// Jacobi path: todo[r] = 1.
+constexpr int NS_MAX_IT = 24;
+
+__global__ void __launch_bounds__(SM_THREADS)
+ns_rotation_kernel(const double *__restrict__ G, const double *__restrict__ H, int K, int L,
+                   const double *__restrict__ dorig, double *__restrict__ M_out, int ldm,
+                   int *__restrict__ todo) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double s_red[SM_WARPS];
+  __shared__ int s_flag;
+  const int LP = (K + 7) & ~7, ld = LP + 4;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  double *Y = sm, *Z = Y + LP * ld, *T = Z + LP * ld, *S = T + LP * ld, *Hs = S + LP * ld;
+
+  // null ORIGINAL latent variables take the other path (see rotation_kernel)
+  if (tid == 0) {
+    int bad = 0;
+    if (dorig) {
+      double domax = 0.0;
+      for (int i = 0; i < L; ++i) domax = fmax(domax, dorig[i]);
+      for (int i = 0; i < L; ++i) bad |= !(dorig[i] > 1e-10 * domax);
+    }
+    s_flag = bad;
+  }
+  // c = max row sum of |G|
+  double rs = 0.0;
+  if (tid < K)
+    for (int j = 0; j < K; ++j) rs += fabs(G[(size_t)r * K * K + (size_t)tid * K + j]);
+  for (int o = 16; o > 0; o >>= 1) rs = fmax(rs, __shfl_xor_sync(0xffffffffu, rs, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = rs;
+  __syncthreads();
+  double c = 0.0;
+  for (int w = 0; w < SM_WARPS; ++w) c = fmax(c, s_red[w]);
+  if (s_flag || !(c > 0.0)) {
+    if (tid == 0) todo[r] = 1;
+    return;
+  }
+  const double ic = 1.0 / c;
+  for (int e = tid; e < LP * LP; e += SM_THREADS) {
+    const int i = e / LP, j = e - i * LP;
+    const bool in = i < K && j < K;
+    // the padding block is the identity: it stays the identity under the iteration
+    Y[i * ld + j] = in ? 0.5 * ic * (G[(size_t)r * K * K + (size_t)i * K + j] +
+                                     G[(size_t)r * K * K + (size_t)j * K + i])
+                       : (i == j ? 1.0 : 0.0);
+    Z[i * ld + j] = i == j ? 1.0 : 0.0;
+    Hs[i * ld + j] = (in && j < L) ? H[(size_t)r * K * L + (size_t)i * L + j] : 0.0;
+  }
+  __syncthreads();
+  bool ok = false;
+  for (int it = 0; it < NS_MAX_IT; ++it) {
+    double dev = 0.0;
+    small_mm(Z, ld, 1, Y, ld, 1, LP, [&](int i, int j, double v) {
+      const double t = (i == j ? 1.5 : 0.0) - 0.5 * v;
+      T[i * ld + j] = t;
+      dev = fmax(dev, fabs(t - (i == j ? 1.0 : 0.0)));
+    });
+    for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    __syncthreads();                       // s_red is free again, T is complete
+    if ((tid & 31) == 0) s_red[tid >> 5] = dev;
+    __syncthreads();
+    dev = 0.0;
+    for (int w = 0; w < SM_WARPS; ++w) dev = fmax(dev, s_red[w]);
+    // |T - I| = (1 - x) / 2 for the slowest eigenvalue x of Z Y, which grows by 2.25 per
+    // step while it is small and needs ~5 steps from 1/2 to rounding level: give up as
+    // soon as that cannot fit (rank-deficient / ill-conditioned G: x_0 ~ 1e-16 .. 1e-7)
+    const double x = fmax(1.0 - 2.0 * dev, 1e-300);
+    const double need = x < 0.5 ? log(0.5 / x) * (1.0 / 0.8109302162163288) + 5.0 : 0.0;
+    if (!(dev < 0.75) || it + need > NS_MAX_IT) break;
+    small_mm(Y, ld, 1, T, ld, 1, LP, [&](int i, int j, double v) { S[i * ld + j] = v; });
+    __syncthreads();
+    // Z <- T Z into the buffer of the old Y
+    small_mm(T, ld, 1, Z, ld, 1, LP, [&](int i, int j, double v) { Y[i * ld + j] = v; });
+    __syncthreads();
+    double *oldz = Z;
+    Z = Y;
+    Y = S;
+    S = oldz;
+    if (dev <= 1e-10) {
+      ok = true;
+      break;
+    }
+  }
+  if (!ok) {
+    if (tid == 0) todo[r] = 1;
+    return;
+  }
+  if (tid == 0) todo[r] = 0;
+  // X_0 = c^-1/2 Z H = G^-1/2 H
+  double *X = S, *X2 = Y, *Bs = T;
+  const double isc = sqrt(ic);
+  small_mm(Z, ld, 1, Hs, ld, 1, LP, [&](int i, int j, double v) { X[i * ld + j] = v * isc; });
+  __syncthreads();
+  for (int it = 0; it < 100; ++it) {
+    small_mm(X, 1, ld, X, ld, 1, LP, [&](int i, int j, double v) {
+      Bs[i * ld + j] = (i == j ? 1.5 : 0.0) - 0.5 * v;
+    });
+    __syncthreads();
+    if (it == 0) {
+      // |X^T X|_inf bounds sigma_max^2; the iteration needs sigma_max < sqrt(3)
+      double q = 0.0;
+      if (tid < LP)
+        for (int j = 0; j < LP; ++j) q += fabs((tid == j ? 3.0 : 0.0) - 2.0 * Bs[tid * ld + j]);
+      for (int o = 16; o > 0; o >>= 1) q = fmax(q, __shfl_xor_sync(0xffffffffu, q, o));
+      if ((tid & 31) == 0) s_red[tid >> 5] = q;
+      __syncthreads();
+      double s = 0.0;
+      for (int w = 0; w < SM_WARPS; ++w) s = fmax(s, s_red[w]);
+      if (s > 2.8) {
+        const double f2 = 2.8 / s, f = sqrt(f2);
+        for (int e = tid; e < LP * LP; e += SM_THREADS) {
+          const int i = e / LP, j = e - i * LP;
+          X[i * ld + j] *= f;
+          const double xtx = (i == j ? 3.0 : 0.0) - 2.0 * Bs[i * ld + j];
+          Bs[i * ld + j] = (i == j ? 1.5 : 0.0) - 0.5 * f2 * xtx;
+        }
+      }
+      __syncthreads();
+    }
+    int changed = 0;
+    small_mm(X, ld, 1, Bs, ld, 1, LP, [&](int i, int j, double v) {
+      X2[i * ld + j] = v;
+      changed |= fabs(v - X[i * ld + j]) > 1e-14;
+    });
+    const int more = __syncthreads_or(changed);
+    double *t = X;
+    X = X2;
+    X2 = t;
+    if (!more) break;
+  }
+  for (int e = tid; e < K * ldm; e += SM_THREADS) {
+    const int a = e / ldm, j = e - a * ldm;
+    M_out[((size_t)r * K + a) * ldm + j] = j < L ? X[a * ld + j] : 0.0;
+  }
+}
+
 int launch_eigen(plsb_ctx *h, const double *G, int count, int K, int sqrt_lam, double *V,
-                 double *lam, cudaStream_t st, int ldg = 0, long long g_stride = 0) {
+                 double *lam, cudaStream_t st, int ldg = 0, long long g_stride = 0,
+                 const int *todo = nullptr) {
   KernelTimer kt(h, KC_SMALL, st);
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(K >= 1 && K <= MAX_K, PLSB_ERR_ARG, "small decomposition: K=%d outside [1,%d]", K,
@@ -233,13 +387,14 @@ int launch_eigen(plsb_ctx *h, const double *G, int count, int K, int sqrt_lam, d
       tune_int("PLSB_EIGEN_THREADS", nb), 32)));
   if (ldg <= 0) ldg = K;
   if (g_stride <= 0) g_stride = (long long)K * K;
-  eigen_kernel<<<count, threads, smem, st>>>(G, ldg, g_stride, K, sqrt_lam, V, lam);
+  eigen_kernel<<<count, threads, smem, st>>>(G, ldg, g_stride, K, sqrt_lam, V, lam, todo);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
 
 int launch_rotation(plsb_ctx *h, const double *H, const double *V, const double *lam, int count,
-                    int K, int L, const double *dorig, double *M, int ldm, cudaStream_t st) {
+                    int K, int L, const double *dorig, double *M, int ldm, cudaStream_t st,
+                    const int *todo = nullptr) {
   KernelTimer kt(h, KC_SMALL, st);
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(L == K, PLSB_ERR_ARG, "small decomposition: L=%d must equal K=%d", L, K);
@@ -247,7 +402,7 @@ int launch_rotation(plsb_ctx *h, const double *H, const double *V, const double 
   const size_t smem = sizeof(double) * (4 * (size_t)LP * ld + 2 * LP);
   PLSB_CUDA(cudaFuncSetAttribute(rotation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-  rotation_kernel<<<count, SM_THREADS, smem, st>>>(H, V, lam, K, L, dorig, M, ldm);
+  rotation_kernel<<<count, SM_THREADS, smem, st>>>(H, V, lam, K, L, dorig, M, ldm, todo);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
@@ -259,10 +414,23 @@ int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(ldm >= L, PLSB_ERR_ARG, "small decomposition: output pitch %d < L=%d", ldm, L);
   const size_t kk = (size_t)K * K;
-  PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)count * (kk + K)));
+  PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)count * (kk + K) + sizeof(int) * (size_t)count));
   double *V = h->misc.as<double>(), *lam_s = V + (size_t)count * kk;
-  PLSB_TRY(launch_eigen(h, G, count, K, 0, V, lam_s, st));
-  PLSB_TRY(launch_rotation(h, H, V, lam_s, count, K, L, dorig, M, ldm, st));
+  // Newton-Schulz fast path (no eigen-decomposition); what it leaves -- and every
+  // resample when the caller wants the eigenvalues -- takes the Jacobi path
+  int *todo = nullptr;
+  const int LP = round_up(K, 8);
+  const size_t ns_smem = sizeof(double) * 5 * (size_t)LP * (LP + 4);
+  if (!lam && L == K && ns_smem <= 200 * 1024 && tune_int("PLSB_NS_ROTATION", 1)) {
+    KernelTimer kt(h, KC_SMALL, st);
+    todo = reinterpret_cast<int *>(lam_s + (size_t)count * K);
+    PLSB_CUDA(cudaFuncSetAttribute(ns_rotation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)ns_smem));
+    ns_rotation_kernel<<<count, SM_THREADS, ns_smem, st>>>(G, H, K, L, dorig, M, ldm, todo);
+    PLSB_LAUNCHED(h);
+  }
+  PLSB_TRY(launch_eigen(h, G, count, K, 0, V, lam_s, st, 0, 0, todo));
+  PLSB_TRY(launch_rotation(h, H, V, lam_s, count, K, L, dorig, M, ldm, st, todo));
   if (lam)
     PLSB_CUDA(cudaMemcpyAsync(lam, lam_s, sizeof(double) * (size_t)count * K,
                               cudaMemcpyDeviceToDevice, st));
