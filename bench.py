@@ -295,6 +295,8 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-fast-path', action='store_true',
+                    help='skip the separately reported sample-space permutation leg')
     ap.add_argument('--workspace-gib', type=float, default=None,
                     help='chunk workspace of the engine (default: library default)')
     args = ap.parse_args()
@@ -439,7 +441,7 @@ def main():
 
     # ---- algorithmic fast path (sample-space permutations), timed the same way --
     fast = None
-    if kind != 'regression':
+    if kind != 'regression' and not args.no_fast_path:
         for _ in range(2):
             step_fast()
         barrier()
