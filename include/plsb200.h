@@ -140,12 +140,20 @@ int plsb_run_perms_prepermuted(plsb_handle_t h, const double *d_Yperm, int count
  * (pyls/base.py:439-576), gen_distrib (pyls/types/behavioral.py:54-80,
  * pyls/types/meancentered.py:75-102) and compute.procrustes
  * (pyls/compute.py:240-264).
- *   d_distrib (count,K,L);  d_usum / d_usquare (B,L) are ACCUMULATED into
- *   (zero them first; base.py:475-476, 510-511).
+ *   d_distrib (count,K,L), may be NULL (see plsb_boot_distrib);  d_usum /
+ *   d_usquare (B,L) are ACCUMULATED into (zero them first; base.py:475-476,
+ *   510-511).
  */
 int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count,
                    double *d_distrib, double *d_usum, double *d_usquare,
                    void *stream);
+/* Only the bootstrap distribution of `count` resamples, d_distrib (count,K,L)
+ * (gen_distrib, pyls/types/behavioral.py:54-80, pyls/types/meancentered.py:
+ * 75-102): it needs the original weights alone, so a caller can have it -- and
+ * start moving it to the host -- before the cross-covariance work of
+ * plsb_run_boots (called with d_distrib = NULL) begins. */
+int plsb_boot_distrib(plsb_handle_t h, const int32_t *d_idx, int count,
+                      double *d_distrib, void *stream);
 /* Resamples plsb_run_boots handles per internal pass for the current workspace
  * limit (<= count).  A caller that wants each pass's slice of `distrib` as soon as
  * it is final (to overlap its device->host copy with the next pass) can call

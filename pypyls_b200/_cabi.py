@@ -39,6 +39,7 @@ PROTOTYPES = {
     'plsb_run_perms_gram': (_i, [_vp, _vp, _i, _vp, _vp]),
     'plsb_run_perms_prepermuted': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'plsb_run_boots': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    'plsb_boot_distrib': (_i, [_vp, _vp, _i, _vp, _vp]),
     'plsb_crossval': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     'plsb_gen_split_masks': (_i, [_vp, _u64, _i64, _i, _i, _dbl, _vp, _ip, _vp]),
     'plsb_split_half': (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),

@@ -394,22 +394,29 @@ class BasePLS():
         table, block, first = self._table('boot', n, seed)
         count = int(block.shape[0])
         size = pdist.world()[1]
-        # every internal pass's slice of `distrib` goes to pinned host memory on a
-        # side stream while the next pass computes: straight into this rank's rows
-        # of the full (R, K, L) host array
+        # the bootstrap distribution needs the original weights only: it is computed
+        # first and moves to pinned host memory (side stream, straight into this
+        # rank's rows of the full (R, K, L) host array) under the cross-covariance
+        # work queued behind it
         host = torch.empty((n, self.engine.K, self.engine.L),
                            dtype=torch.float64, pin_memory=True)
-        distrib, _, u_sum, u_square, host_done = \
-            self.engine.run_boots_streamed(block, wait=False,
-                                           host=host[first:first + count])
+        distrib = self.engine.boot_distrib(block)
+        main = torch.cuda.current_stream(self.engine.device)
+        side = copy_stream(self.engine.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        host_done = torch.cuda.Event()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            host[first:first + count].copy_(distrib, non_blocking=True)
+            host_done.record(side)
+        _, u_sum, u_square = self.engine.run_boots(block, want_distrib=False)
         local = distrib         # stays alive until its side-stream copies are done
         if size > 1:
             # the other ranks' rows: all-gather on the device, then only those rows
             # follow to the host (side stream)
             distrib = pdist.gather_resamples(distrib, n)
             pdist.reduce_sum(u_sum, u_square)
-            main = torch.cuda.current_stream(self.engine.device)
-            side = copy_stream(self.engine.device)
             ready = torch.cuda.Event()
             ready.record(main)
             host_done = torch.cuda.Event()

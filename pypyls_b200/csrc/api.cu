@@ -671,7 +671,7 @@ int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, double *d_d
   PLSB_HANDLE(h);
   PLSB_CHECK(h->has_data && h->has_original, PLSB_ERR_STATE,
              "plsb_run_boots before data and original decomposition are set");
-  PLSB_CHECK(d_idx && d_distrib && d_usum && d_usquare && count >= 0, PLSB_ERR_ARG,
+  PLSB_CHECK(d_idx && d_usum && d_usquare && count >= 0, PLSB_ERR_ARG,
              "plsb_run_boots: bad argument");
   const Layout &l = h->lay;
   cudaStream_t st = as_stream(stream);
@@ -679,7 +679,7 @@ int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, double *d_d
   for (int off = 0; off < count; off += chunk) {
     const int n = std::min(chunk, count - off);
     PLSB_TRY(crosscov_chunk(h, d_idx + (size_t)off * l.S, nullptr, n, true,
-                            d_distrib + (size_t)off * l.K * l.L, st));
+                            d_distrib ? d_distrib + (size_t)off * l.K * l.L : nullptr, st));
     PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * l.K * l.K));
     PLSB_TRY(h->H.ensure(sizeof(double) * (size_t)n * l.K * l.L));
     const int ldm = accum_ldm(l.L);
@@ -692,6 +692,16 @@ int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, double *d_d
                             d_usum, d_usquare, st));
   }
   return PLSB_OK;
+}
+
+int plsb_boot_distrib(plsb_handle_t h, const int32_t *d_idx, int count, double *d_distrib,
+                      void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->has_original && !h->lay.simpls(), PLSB_ERR_STATE,
+             "plsb_boot_distrib before data and original decomposition are set");
+  PLSB_CHECK(d_idx && d_distrib && count >= 0, PLSB_ERR_ARG, "plsb_boot_distrib: bad argument");
+  return launch_build(h, BUILD_BOOT, d_idx, nullptr, count, nullptr, nullptr, d_distrib, 0, 0,
+                      as_stream(stream));
 }
 
 int plsb_boot_chunk(plsb_handle_t h, int count) {

@@ -162,8 +162,8 @@ __global__ void build_behavioral_kernel(BuildParams p) {
     return;
   }
 
-  // ---- BUILD_BOOT ----
-  {
+  // ---- BUILD_BOOT ----  (A == nullptr: only the bootstrap distribution is wanted)
+  if (p.A) {
     for (int e = tid; e < K * lda; e += nt) {
       const int row = e / lda, u = e - row * lda;
       const int g = row / T, t = row - g * T;
@@ -298,10 +298,12 @@ __global__ void build_meancentered_kernel(BuildParams p) {
     }
     return;
   }
-  double *Ar = p.A + (size_t)r * J * lda;
-  for (int e = tid; e < J * lda; e += nt) {
-    const int j = e / lda, u = e - j * lda;
-    Ar[e] = u < S ? AR[j * S + u] : 0.0;
+  if (p.A) {
+    double *Ar = p.A + (size_t)r * J * lda;
+    for (int e = tid; e < J * lda; e += nt) {
+      const int j = e / lda, u = e - j * lda;
+      Ar[e] = u < S ? AR[j * S + u] : 0.0;
+    }
   }
   if (p.kind == BUILD_BOOT && p.distrib) {
     double *Dr = p.distrib + (size_t)r * J * L;

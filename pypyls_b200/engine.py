@@ -15,7 +15,9 @@ import torch
 
 from . import _cabi
 
-DEFAULT_WORKSPACE = 8 << 30      # bytes per chunk of stored cross-covariances
+DEFAULT_WORKSPACE = 32 << 30     # bytes per pass of stored cross-covariances, capped at 1/5
+                                 # of the device memory: B200 has 180 GB, and fewer, larger
+                                 # passes keep every kernel's grid full
 
 MODES = {
     'behavioral': _cabi.PLSB_BEHAVIORAL_CORR,
@@ -132,8 +134,11 @@ class ResamplingEngine:
                 _cabi.check(self._lib.plsb_create(C.byref(self._h),
                                                   self.device.index))
         # pooled handles keep their settings: always (re)set them
+        if not workspace_bytes:
+            total = torch.cuda.get_device_properties(self.device).total_memory
+            workspace_bytes = min(DEFAULT_WORKSPACE, total // 5)
         _cabi.check(self._lib.plsb_set_workspace_limit(
-            self._h, int(workspace_bytes or DEFAULT_WORKSPACE)))
+            self._h, int(workspace_bytes)))
         _cabi.check(self._lib.plsb_timing_enable(self._h, 0))
         garr = (C.c_int * len(groups))(*groups)
         _cabi.check(self._lib.plsb_configure(
@@ -359,12 +364,24 @@ class ResamplingEngine:
             int(bool(use_original)), _ptr(uc), _ptr(vc), self._stream()))
         return uc, vc
 
-    def run_boots(self, idx, u_sum=None, u_square=None):
-        """(distrib (count,K,L), u_sum (B,L), u_square (B,L)) on the device
-        (BasePLS.bootstrap, pyls/base.py:439-576)."""
+    def boot_distrib(self, idx):
+        """Bootstrap distribution (count, K, L) alone (gen_distrib needs only
+        the original weights): ready, and on its way to the host, before the
+        cross-covariance work of run_boots(..., want_distrib=False) starts."""
         idx = self.to_device_indices(idx)
         n = int(idx.shape[0])
         distrib = self._f64(n, self.K, self.L)
+        _cabi.check(self._lib.plsb_boot_distrib(
+            self._h, _ptr(idx), n, _ptr(distrib), self._stream()))
+        return distrib
+
+    def run_boots(self, idx, u_sum=None, u_square=None, want_distrib=True):
+        """(distrib (count,K,L), u_sum (B,L), u_square (B,L)) on the device
+        (BasePLS.bootstrap, pyls/base.py:439-576); ``want_distrib=False``
+        leaves the distribution out (None)."""
+        idx = self.to_device_indices(idx)
+        n = int(idx.shape[0])
+        distrib = self._f64(n, self.K, self.L) if want_distrib else None
         if u_sum is None:
             u_sum = torch.zeros((self.B, self.L), dtype=torch.float64,
                                 device=self.device)
