@@ -532,8 +532,9 @@ def main():
     # DRAM traffic of the class per step from the committed `ncu --set full`
     # capture (dram__bytes_read.sum + dram__bytes_write.sum over its launches,
     # profiles/r1_ncu_full_v6_summary.csv: permutation launch 0.14 GB, per full
-    # bootstrap chunk 0.66 + 0.66 + 7.74 GB, last chunk 2.7 GB); only known for
-    # the configuration that was captured
+    # bootstrap chunk 0.66 + 0.66 + 7.74 GB, last chunk 2.7 GB -- the bytes do not
+    # depend on how the bootstraps are split into passes); only known for the
+    # configuration that was captured
     if (args.workload, world, top) == ('cfg2', 1, 'xcov_gemm') and \
             args.workspace_gib is None:
         roofline['traffic'] = 20.9e9
