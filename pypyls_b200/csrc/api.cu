@@ -74,9 +74,15 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, const double *yperm, int n, 
   } else {
     PLSB_TRY(zero_tail(h->A.as<double>(), Mw, Mw_op, l.S_pad, st));
   }
+  // column scales of the resampled X: one dedicated pass (colstats.cu) or, when a cell
+  // does not fit its shared-memory tile, two count-operand GEMMs + colscale
+  bool fused_scale = false;
   if (scaled) {
-    PLSB_TRY(h->Ac.ensure(sizeof(double) * (size_t)Mc_op * l.S_pad));
     PLSB_TRY(h->S1.ensure(sizeof(double) * (size_t)Mc_pad * l.ldx));
+    PLSB_TRY(launch_colstats(h, idx, n, h->S1.as<double>(), &fused_scale, st));
+  }
+  if (scaled && !fused_scale) {
+    PLSB_TRY(h->Ac.ensure(sizeof(double) * (size_t)Mc_op * l.S_pad));
     PLSB_TRY(h->S2.ensure(sizeof(double) * (size_t)Mc_pad * l.ldx));
     if (grouped) {
       PLSB_CUDA(cudaMemsetAsync(h->Ac.p, 0, sizeof(double) * (size_t)Mc_op * l.S_pad, st));
@@ -86,7 +92,8 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, const double *yperm, int n, 
     }
   }
   PLSB_TRY(launch_build(h, boot ? BUILD_BOOT : BUILD_PLAIN, idx, yperm, n, h->A.as<double>(),
-                        scaled ? h->Ac.as<double>() : nullptr, distrib, cellpad_w, cellpad_c, st));
+                        scaled && !fused_scale ? h->Ac.as<double>() : nullptr, distrib, cellpad_w,
+                        cellpad_c, st));
   GemmArgs g;
   g.lda = l.S_pad;
   g.ldx = l.ldx;
@@ -94,7 +101,7 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, const double *yperm, int n, 
   g.Kd = l.S_pad;
   g.ldc = l.ldx;
   if (grouped) g.k_len = l.kr_max;
-  if (scaled) {
+  if (scaled && !fused_scale) {
     g.A = h->Ac.as<double>();
     g.X = h->Xglob.as<double>();
     g.M_pad = (int)Mc_op;
@@ -107,6 +114,8 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, const double *yperm, int n, 
     PLSB_TRY(launch_gemm(h, g, st));
     g.square_b = false;
     PLSB_TRY(launch_colscale(h, h->S1.as<double>(), h->S2.as<double>(), (int)Mc, l.ldx, st));
+  }
+  if (scaled) {
     g.scale = h->S1.as<double>();
     g.scale_div = l.T;
     g.lds = l.ldx;

@@ -257,6 +257,8 @@ int launch_rowdot_sqrt(plsb_ctx *h, const double *T, long long ldt, const double
                        int n_cols, long long n_rows, double *out, cudaStream_t st);
 int launch_colscale(plsb_ctx *h, double *S1, const double *S2, int n_rows, long long ld,
                     cudaStream_t st, int rows_per_resample = 0, const int *nrow = nullptr);
+int launch_colstats(plsb_ctx *h, const int32_t *idx, int n_res, double *scale, bool *done,
+                    cudaStream_t st);
 int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int K,
                      const double *UoT, int L, double *G, double *H, cudaStream_t st,
                      long long uot_stride = 0, int uot_div = 1);
