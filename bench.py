@@ -531,13 +531,12 @@ def main():
                 'launches_per_step': top_n / args.steps}
     # DRAM traffic of the class per step from the committed `ncu --set full`
     # capture (dram__bytes_read.sum + dram__bytes_write.sum over its launches,
-    # profiles/r1_ncu_full_v6_summary.csv: permutation launch 0.14 GB, per full
-    # bootstrap chunk 0.66 + 0.66 + 7.74 GB, last chunk 2.7 GB -- the bytes do not
-    # depend on how the bootstraps are split into passes); only known for the
-    # configuration that was captured
+    # profiles/r1_ncu_full_v11_summary.csv: permutation launch 0.135 + 0.006 GB,
+    # bootstrap launch 1.763 + 16.130 GB -- the stored cross-covariances are 16.2 GB
+    # of it); only known for the configuration that was captured
     if (args.workload, world, top) == ('cfg2', 1, 'xcov_gemm') and \
             args.workspace_gib is None:
-        roofline['traffic'] = 20.9e9
+        roofline['traffic'] = 18.03e9
         roofline['traffic_unit'] = 'bytes per step, all launches of the class'
     roofline['algorithmic_flop_per_step'] = flops
     # flop the launches really execute: rotated permutations contract L rows per
@@ -545,8 +544,12 @@ def main():
     if top == 'xcov_gemm' and kind == 'behavioral':
         J = len(w['groups']) * w['n_cond']
         ng = w['S'] / J
+        # bootstraps: the block-diagonal operand (T rows per cell over the cell's
+        # ng rows); cells too tall for colstats_kernel's shared-memory tile also
+        # run the two count-operand GEMMs of the column statistics
+        extra = 0 if ng * 128 * 8 <= 100 * 1024 else 2
         executed = 2.0 * w['S'] * w['B'] * (J * w['T']) * n_perm + \
-            2.0 * ng * w['B'] * (J * (w['T'] + 2)) * n_boot
+            2.0 * ng * w['B'] * (J * (w['T'] + extra)) * n_boot
         roofline['executed_flop_per_step'] = executed
     if bound == 'tensor' and flops:
         ach = flops * args.steps / (top_ms * 1e-3) / 1e12
