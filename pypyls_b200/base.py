@@ -400,7 +400,7 @@ class BasePLS():
         # work queued behind it
         host = torch.empty((n, self.engine.K, self.engine.L),
                            dtype=torch.float64, pin_memory=True)
-        distrib = self.engine.boot_distrib(block)
+        distrib = local = self.engine.boot_distrib(block)
         main = torch.cuda.current_stream(self.engine.device)
         side = copy_stream(self.engine.device)
         ready = torch.cuda.Event()
@@ -408,24 +408,20 @@ class BasePLS():
         host_done = torch.cuda.Event()
         with torch.cuda.stream(side):
             side.wait_event(ready)
-            host[first:first + count].copy_(distrib, non_blocking=True)
-            host_done.record(side)
-        _, u_sum, u_square = self.engine.run_boots(block, want_distrib=False)
-        local = distrib         # stays alive until its side-stream copies are done
-        if size > 1:
-            # the other ranks' rows: all-gather on the device, then only those rows
-            # follow to the host (side stream)
-            distrib = pdist.gather_resamples(distrib, n)
-            pdist.reduce_sum(u_sum, u_square)
-            ready = torch.cuda.Event()
-            ready.record(main)
-            host_done = torch.cuda.Event()
-            with torch.cuda.stream(side):
-                side.wait_event(ready)
+            host[first:first + count].copy_(local, non_blocking=True)
+            if size > 1:
+                # the other ranks' rows: all-gather on the device and on to the host,
+                # all of it on the side stream -- under the cross-covariance work
+                distrib = pdist.gather_resamples(local, n)
                 for a, b in ((0, first), (first + count, n)):
                     if b > a:
                         host[a:b].copy_(distrib[a:b], non_blocking=True)
-                host_done.record(side)
+            host_done.record(side)
+        _, u_sum, u_square = self.engine.run_boots(block, want_distrib=False)
+        if size > 1:
+            pdist.reduce_sum(u_sum, u_square)
+            main.wait_event(host_done)       # the statistics read the gathered rows
+            distrib.record_stream(main)
         if isinstance(table, _DeviceTable):
             table.start()                # behind the kernels queued above
         self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
