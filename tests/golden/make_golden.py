@@ -176,6 +176,36 @@ def splithalf_cases():
         out = flat(r, 'm')
         out.update({k: np.asarray(r['splitres'][k]) for k in keys})
         save('mpls_split_mc%d' % mc, dict(X=X, **kw), out)
+    splithalf_more_cases(keys)
+
+
+def splithalf_more_cases(keys):
+    """Split-half with pre-permuted Y matrices (permindices=False: the masks
+    split X and the handed-in Y, pyls/base.py:689-692, 704-708) and with
+    uneven groups x three conditions."""
+    rs = np.random.RandomState(4243)
+    X, Y = rs.rand(36, 90), rs.rand(36, 5)
+    Y[:, 0] += X[:, :8].mean(axis=1)
+    groups, n_cond, P = [10, 8], 2, 14
+    Yp = np.stack([Y[rs.permutation(36)] + 0.05 * rs.rand(36, 5)
+                   for _ in range(P)])
+    kw = dict(groups=groups, n_cond=n_cond, n_perm=P, n_boot=0, seed=11,
+              n_split=5, rotate=True)
+    r = pyls.behavioral_pls(X, Y, test_split=0, permsamples=Yp,
+                            permindices=False, verbose=False, **kw)
+    out = flat(r, 'b')
+    out.pop('permsamples', None)
+    out.update({k: np.asarray(r['splitres'][k]) for k in keys})
+    save('bpls_split_prepermuted', dict(X=X, Y=Y, Yperm=Yp, **kw), out)
+
+    X, Y = rs.rand(57, 70), rs.rand(57, 2)
+    kw = dict(groups=[7, 5, 7], n_cond=3, n_perm=12, n_boot=0, seed=3,
+              n_split=4)
+    r = pyls.behavioral_pls(X, Y, test_split=0, permindices=True,
+                            verbose=False, **kw)
+    out = flat(r, 'b')
+    out.update({k: np.asarray(r['splitres'][k]) for k in keys})
+    save('bpls_split_3g3c', dict(X=X, Y=Y, **kw), out)
 
 
 def meancentered_cases():
@@ -270,6 +300,11 @@ def matlab_cases():
 if __name__ == '__main__':
     if sys.argv[1:] == ['splithalf']:
         splithalf_cases()
+        sys.exit(0)
+    if sys.argv[1:] == ['splitmore']:
+        splithalf_more_cases(('ucorr', 'vcorr', 'ucorr_pvals', 'vcorr_pvals',
+                              'ucorr_lolim', 'ucorr_uplim', 'vcorr_lolim',
+                              'vcorr_uplim'))
         sys.exit(0)
     if sys.argv[1:] == ['missing']:
         regression_missing_rows_case()

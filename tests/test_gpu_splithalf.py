@@ -30,19 +30,25 @@ def _non_null(singvals):
 
 
 @pytest.mark.parametrize('name', ['bpls_split_rot', 'bpls_split_cov_norot',
+                                  'bpls_split_3g3c', 'bpls_split_prepermuted',
                                   'mpls_split_mc0', 'mpls_split_mc1',
                                   'mpls_split_mc2'])
 def test_split_half_matches_reference_golden(name):
     import pypyls_b200 as pyls
     ins, ref = load_golden(name)
     X = ins.pop('X')
-    if name.startswith('bpls'):
+    if 'Yperm' in ins:
+        out = pyls.behavioral_pls(X, ins.pop('Y'), permsamples=ins.pop('Yperm'),
+                                  permindices=False, index_backend='reference',
+                                  verbose=False, **ins)
+    elif name.startswith('bpls'):
         out = pyls.behavioral_pls(X, ins.pop('Y'), index_backend='reference',
                                   verbose=False, **ins)
     else:
         out = pyls.meancentered_pls(X, index_backend='reference',
                                     verbose=False, **ins)
-    assert np.array_equal(out.permres.permsamples, ref['permsamples'])
+    if 'permsamples' in ref:
+        assert np.array_equal(out.permres.permsamples, ref['permsamples'])
     keep = _non_null(ref['singvals'])
     np.testing.assert_allclose(out.permres.perm_singval[keep],
                                ref['perm_singval'][keep], rtol=1e-8,
