@@ -19,8 +19,8 @@ import torch
 from . import dist as pdist
 from . import structures
 from .engine import Download, ResamplingEngine, copy_stream, to_host
-from .resample import (check_random_state, gen_bootsamp, gen_permsamp,
-                       gen_splits)
+from .resample import (check_bootsamples, check_random_state, gen_bootsamp,
+                       gen_permsamp, gen_splits)
 
 
 def _device_seed(rs):
@@ -277,6 +277,13 @@ class BasePLS():
             if given.ndim != 2 or given.shape[-1] != n:
                 raise ValueError('Provided `{}` must have shape ({}, {}); got '
                                  '{}'.format(key, eng.S, n, given.shape))
+            # behavioural analyses with several cells contract every cell's operand
+            # rows over that cell's rows of X only
+            if kind == 'boot' and eng.mode.startswith('behavioral') and \
+                    eng.J > 1 and given.shape[0] == eng.S and \
+                    given.size and 0 <= given.min() and given.max() < eng.S:
+                check_bootsamples(given, self.inputs.groups,
+                                  self.inputs.n_cond)
             block = eng.to_device_indices(given[:, first:first + count])
             return given, block, first
         gen = eng.gen_perm_indices if kind == 'perm' else eng.gen_boot_indices

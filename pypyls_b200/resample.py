@@ -173,6 +173,30 @@ def gen_splits(groups, n_cond, n_split, seed=None, test_size=0.5):
     return out
 
 
+def cell_of_rows(groups, n_cond):
+    """Cell (group x condition) of every row: rows are ordered group ->
+    condition -> subject (pyls/structures.py:37-44)."""
+    return np.repeat(np.arange(len(groups) * n_cond),
+                     np.repeat([int(g) for g in groups], n_cond))
+
+
+def check_bootsamples(table, groups, n_cond):
+    """A bootstrap table must draw every row from its own group x condition
+    cell, as gen_bootsamp does (pyls/base.py:134-143): the engine contracts
+    each cell's operand rows over that cell's rows of X only, so rows drawn
+    from another cell would be left out silently."""
+    cells = cell_of_rows(groups, n_cond)
+    table = np.asarray(table)
+    if table.shape[0] != cells.size:
+        return            # the shape check of the caller reports this
+    if not np.array_equal(cells[table], np.broadcast_to(cells[:, None],
+                                                        table.shape)):
+        raise ValueError('Provided `bootsamples` draw rows from other '
+                         'group / condition cells; bootstrap resamples must '
+                         'keep every row inside its cell (as gen_bootsamp '
+                         'does).')
+
+
 def shard_range(n, rank, world_size):
     """Contiguous block [first, first + count) of ``n`` resample ids owned by
     ``rank``; blocks differ in size by at most one."""

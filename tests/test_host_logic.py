@@ -227,3 +227,18 @@ def test_results_io_round_trip(tmp_path):
     with pytest.raises(TypeError):
         (tmp_path / 'junk.hdf5').write_text('not hdf5')
         pyls.load_results(tmp_path / 'junk.hdf5')
+
+
+def test_bootsamples_must_stay_inside_their_cells():
+    """The engine's cell-grouped operands assume what gen_bootsamp guarantees
+    (pyls/base.py:134-143); a table that breaks it is refused, not mangled."""
+    from pypyls_b200.resample import (cell_of_rows, check_bootsamples,
+                                      gen_bootsamp, gen_permsamp)
+    groups, n_cond = [5, 4], 2
+    assert cell_of_rows(groups, n_cond).tolist() == \
+        [0] * 5 + [1] * 5 + [2] * 4 + [3] * 4
+    check_bootsamples(gen_bootsamp(groups, n_cond, 30, seed=1, verbose=False),
+                      groups, n_cond)
+    with pytest.raises(ValueError, match='cells'):
+        check_bootsamples(gen_permsamp(groups, n_cond, 5, seed=1,
+                                       verbose=False), groups, n_cond)
