@@ -171,6 +171,21 @@ int plsb_percentile(plsb_handle_t h, const double *d_distrib, int count,
                     int n_series, double q_lo, double q_hi, double *d_lo,
                     double *d_hi, void *stream);
 
+/* The same percentiles for series-major input: series j is the `count` values
+ * at d_series + j * ld (what a rank holds after the series of the bootstrap
+ * distribution have been dealt over the ranks: each rank selects the order
+ * statistics of its own series over ALL resamples). */
+int plsb_percentile_series(plsb_handle_t h, const double *d_series,
+                           int n_series, int count, int64_t ld, double q_lo,
+                           double q_hi, double *d_lo, double *d_hi,
+                           void *stream);
+
+/* d_out (cols, rows) = d_in (rows, cols)^T, both dense row-major: turns the
+ * resample-major bootstrap distribution (count, K*L) into the series-major
+ * blocks the ranks exchange before plsb_percentile_series. */
+int plsb_transpose(plsb_handle_t h, const double *d_in, int rows, int cols,
+                   double *d_out, void *stream);
+
 /* compute.boot_rel (pyls/compute.py:212-237) incl. the "add the original
  * sample" step of behavioral.py:202-207 when add_orig != 0.
  * d_bs (B,L) = U @ diag(d) flattened to n_elem values; outputs d_bsr, d_se. */

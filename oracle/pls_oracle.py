@@ -7,7 +7,8 @@ netneurolab/pypyls (reference checked out at /root/reference, commit e0ff056).
 It exists so that the CUDA engine in ``pypyls_b200`` can be checked against the
 reference's arithmetic on a box where the reference itself is not present.
 
-Rules (enforced by tests/test_no_oracle_in_product.py):
+Rules (enforced by
+tests/test_host_logic.py::test_product_never_imports_the_oracle):
   * only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
     ``cpu_baseline`` / ``--impl reference`` legs may import this module;
   * the product package ``pypyls_b200`` never imports it and has no CPU
@@ -669,6 +670,99 @@ def _regression_single_boot(spec, X, Y, inds, original, seed):
 # whole analyses (what the reference's front-end functions return, restricted
 # to the keys the hot path feeds).  test_split / n_split are always off.
 # --------------------------------------------------------------------------
+
+# --------------------------------------------------------------------------
+# vectorised "fast oracle" (SURVEY 7.1 step 1 / 8d): the statistics that do NOT
+# need a B-sized product per resample -- permuted singular values (hence
+# p-values) and the bootstrap distribution (hence CIs) -- at full n_perm /
+# n_boot on the CPU in seconds.  It restates the SAME reference functions
+# through two exact identities and is itself held to the per-resample oracle
+# above (tests/test_oracle_golden.py::test_fast_oracle_*):
+#   * X is fixed under a behavioural permutation and the z-score is per cell, so
+#     R = A_pi Zx with Zx the cell-wise standardised X and A_pi (K, S) holding the
+#     standardised permuted Y; the rotated singular values
+#     sqrt(sum(procrustes(V, V_pi, d_pi)**2, 0)) (pyls/base.py:699-700) equal
+#     |R^T v_j| = sqrt(v_j^T A (Zx Zx^T) A^T v_j) whenever K <= B, the un-rotated
+#     ones are sqrt(eig(A (Zx Zx^T) A^T)).  Mean-centred: R = (C P_pi) X.
+#   * gen_distrib only uses the ORIGINAL weights (pyls/base.py:574), and both
+#     variants are linear in X before the projection:
+#     gen_distrib(X[i], Y[i], U) = gen_distrib((X @ normalize(U))[i], Y[i], I).
+# --------------------------------------------------------------------------
+
+def _perm_operator(spec, Y, perminds):
+    """(K, S) left operand A with R = A @ Xfixed for one permutation."""
+    S = len(perminds)
+    if spec.kind == 'meancentered':
+        # R = C X[pi]: scatter the columns of the centring operator through pi
+        C = get_mean_center(np.eye(S), spec.dummy, spec.n_cond,
+                            spec.mean_centering, means=True)
+        A = np.zeros_like(C)
+        np.add.at(A.T, perminds, C.T)
+        return A
+    Yp = Y[perminds]
+    T = Y.shape[1]
+    cells = spec.dummy.T.astype(bool)
+    A = np.zeros((len(cells) * T, S))
+    for g, c in enumerate(cells):
+        y = Yp[c]
+        yn = y - y.mean(axis=0)
+        if not spec.covariance:
+            yn = yn / y.std(axis=0, ddof=1)
+        A[g * T:(g + 1) * T, c] = yn.T / (c.sum() - 1)
+    return A
+
+
+def fixed_gram(spec, X):
+    """S x S Gram matrix of the data matrix the permutations contract with."""
+    if spec.kind == 'meancentered':
+        return X @ X.T
+    Zx = np.zeros_like(X, dtype=float)
+    for c in spec.dummy.T.astype(bool):
+        x = X[c]
+        Zx[c] = x - x.mean(axis=0)
+        if not spec.covariance:
+            Zx[c] /= x.std(axis=0, ddof=1)
+    return Zx @ Zx.T
+
+
+def fast_perm_singvals(spec, X, Y, permsamp, original_v, gram=None):
+    """d_perm (L, P) for index permutations, in sample space (see above).
+    Needs K <= B (true for every benchmark configuration)."""
+    gram = fixed_gram(spec, X) if gram is None else gram
+    out = np.empty((original_v.shape[1], permsamp.shape[1]))
+    for i in range(permsamp.shape[1]):
+        A = _perm_operator(spec, Y, permsamp[:, i])
+        if spec.rotate:
+            W = original_v.T @ A
+            out[:, i] = np.sqrt(np.maximum(np.sum((W @ gram) * W, axis=1), 0))
+        else:
+            lam = np.linalg.eigvalsh(A @ gram @ A.T)[::-1]
+            out[:, i] = np.sqrt(np.maximum(lam, 0))[:out.shape[0]]
+    return out
+
+
+def fast_boot_distrib(spec, X, Y, bootsamp, original_u):
+    """distrib (K, L, R): gen_distrib of every bootstrap evaluated on the
+    projected scores X @ normalize(U_orig) (S x L) instead of on X."""
+    Sx = X @ normalize(original_u)
+    eye = np.eye(Sx.shape[1])
+    out = [gen_distrib(spec, Sx[bootsamp[:, i]],
+                       None if spec.kind == 'meancentered' else
+                       Y[bootsamp[:, i]], eye)
+           for i in range(bootsamp.shape[1])]
+    return np.stack(out, axis=-1)
+
+
+def fast_stats(spec, X, Y, permsamp, bootsamp, U, d, V, ci=95):
+    """p-values and bootstrap percentile intervals at full n from the two
+    functions above -> dict(pvals, perm_singval, distrib, distrib_ci)."""
+    d_perm = fast_perm_singvals(spec, X, Y, permsamp, V)
+    distrib = fast_boot_distrib(spec, X, Y, bootsamp, U)
+    d = np.diag(d) if np.ndim(d) == 1 else d
+    return dict(perm_singval=d_perm, pvals=perm_sig(d, d_perm),
+                distrib=distrib,
+                distrib_ci=np.stack(boot_ci(distrib, ci=ci), -1))
+
 
 def _finish_boot(res, orig_bs, distrib, u_sum, u_square, n, ci, add_orig):
     if add_orig:

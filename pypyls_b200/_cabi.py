@@ -46,6 +46,8 @@ PROTOTYPES = {
     'plsb_boot_chunk': (_i, [_vp, _i]),
     'plsb_perm_pvals': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     'plsb_percentile': (_i, [_vp, _vp, _i, _i, _dbl, _dbl, _vp, _vp, _vp]),
+    'plsb_percentile_series': (_i, [_vp, _vp, _i, _i, _i64, _dbl, _dbl, _vp, _vp, _vp]),
+    'plsb_transpose': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'plsb_boot_ratio': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     'plsb_dgemm': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     'plsb_crosscov': (_i, [_vp, _vp, _i, _i, _vp, _vp]),

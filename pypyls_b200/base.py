@@ -80,7 +80,12 @@ class BasePLS():
         ordinal), ``workspace_bytes`` and ``perm_path`` ('gemm': every
         permutation runs the cross-covariance contraction, default; 'gram':
         rotated permutations are evaluated in sample space through the S x S
-        Gram matrix of the data -- same values, no B-sized work).
+        Gram matrix of the data -- same values, no B-sized work) and
+        ``gather_results`` (multi-process runs only: 'all' -- every rank
+        returns the complete results, default; 'root' -- the per-resample
+        arrays (bootstrap distribution, tables) and the B-sized arrays are
+        moved to the host of rank 0 only, the other ranks return the
+        statistics (p-values, intervals) and ``None`` for those arrays).
     """
 
     engine_mode = None
@@ -107,7 +112,18 @@ class BasePLS():
 
         self.inputs = structures.PLSInputs(X=X, Y=Y, groups=groups,
                                            n_cond=n_cond, **kwargs)
-        self.rs = check_random_state(self.inputs.get('seed'))
+        seed = self.inputs.get('seed')
+        if pdist.world()[1] > 1 and \
+                not isinstance(seed, (int, np.integer)):
+            # every rank must draw the same tables, masks and device keys:
+            # rank 0 fixes an integer seed for all of them
+            seed = pdist.broadcast_seed(check_random_state(seed))
+        self.rs = check_random_state(seed)
+        mode = self.inputs.get('gather_results')
+        if mode is None:
+            self.inputs['gather_results'] = mode = 'all'
+        if mode not in ('all', 'root'):
+            raise ValueError("gather_results must be 'all' or 'root'")
         backend = self.inputs.get('index_backend')
         if backend is None:
             self.inputs['index_backend'] = backend = 'device'
@@ -324,8 +340,11 @@ class BasePLS():
         split_of = None
         if given is not None and self.inputs.get('permindices') is False:
             # pre-permuted Y matrices, (P, S, T) (pyls/base.py:636-639, 689-692)
+            given = np.asarray(given)
             local = self._prepermuted(given, n, rotate)
-            table = given
+            # the reference keeps the stack transposed, (S, T, P)
+            # (pyls/base.py:638-639, 370)
+            table = np.transpose(given, (1, 2, 0))
             first, count = pdist.my_block(n)
             split_of = dict(Yperm=given[first:first + count])
         else:
@@ -390,6 +409,8 @@ class BasePLS():
         if out['host'] is not None:
             out['host_done'].synchronize()
             return out['host'].numpy().transpose(1, 2, 0)
+        if out['distrib'] is None:
+            return None                  # gather_results='root', other ranks
         return to_host(out['distrib'].permute(1, 2, 0).contiguous())
 
     def _bootstrap_device(self, X, Y, seed=None):
@@ -400,13 +421,17 @@ class BasePLS():
         n = self.inputs.n_boot
         table, block, first = self._table('boot', n, seed)
         count = int(block.shape[0])
-        size = pdist.world()[1]
+        rank, size = pdist.world()
+        root_only = size > 1 and self.inputs.gather_results == 'root'
         # the bootstrap distribution needs the original weights only: it is computed
-        # first and moves to pinned host memory (side stream, straight into this
-        # rank's rows of the full (R, K, L) host array) under the cross-covariance
-        # work queued behind it
+        # first and moves to pinned host memory (side stream) under the
+        # cross-covariance work queued behind it.  Several ranks: the blocks are
+        # all-gathered on the device (or gathered to rank 0 alone,
+        # gather_results='root') and every host copies the result ONCE
+        want_host = not root_only or rank == 0
         host = torch.empty((n, self.engine.K, self.engine.L),
-                           dtype=torch.float64, pin_memory=True)
+                           dtype=torch.float64, pin_memory=True) \
+            if want_host else None
         distrib = local = self.engine.boot_distrib(block)
         main = torch.cuda.current_stream(self.engine.device)
         side = copy_stream(self.engine.device)
@@ -415,23 +440,21 @@ class BasePLS():
         host_done = torch.cuda.Event()
         with torch.cuda.stream(side):
             side.wait_event(ready)
-            host[first:first + count].copy_(local, non_blocking=True)
             if size > 1:
-                # the other ranks' rows: all-gather on the device and on to the host,
-                # all of it on the side stream -- under the cross-covariance work
-                distrib = pdist.gather_resamples(local, n)
-                for a, b in ((0, first), (first + count, n)):
-                    if b > a:
-                        host[a:b].copy_(distrib[a:b], non_blocking=True)
+                distrib = pdist.gather_to_root(local, n) if root_only \
+                    else pdist.gather_resamples(local, n)
+            if want_host:
+                host.copy_(distrib, non_blocking=True)
             host_done.record(side)
+        if distrib is not None:
+            distrib.record_stream(side)
         _, u_sum, u_square = self.engine.run_boots(block, want_distrib=False)
         if size > 1:
             pdist.reduce_sum(u_sum, u_square)
-            main.wait_event(host_done)       # the statistics read the gathered rows
-            distrib.record_stream(main)
         if isinstance(table, _DeviceTable):
             table.start()                # behind the kernels queued above
-        self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
+        self._dev.update(distrib=distrib, distrib_local=local, u_sum=u_sum,
+                         u_square=u_square)
         return dict(distrib=distrib, host=host, host_done=host_done,
                     u_sum=u_sum, u_square=u_square, table=table, keep=local)
 
@@ -446,6 +469,9 @@ class BasePLS():
         ci = self.inputs.get('ci')
         ci = 95 if ci is None else ci
         low = (100 - ci) / 2
-        lo, hi = eng.percentile(dev['distrib'], low, 100 - low)
+        # several ranks: every rank selects the order statistics of its share of
+        # the K x L series over all resamples (one all-to-all), not of everything
+        lo, hi = pdist.percentile_sharded(eng, dev['distrib_local'],
+                                          self.inputs.n_boot, low, 100 - low)
         out = (bsr, se, torch.stack([lo, hi], dim=-1))
         return out if device else tuple(to_host(t) for t in out)

@@ -200,7 +200,7 @@ int plsb_destroy(plsb_handle_t h) {
   DevBuf *bufs[] = {&h->tables, &h->Xraw, &h->Xcell, &h->Xglob, &h->Y,    &h->Cmat,  &h->Uo,
                     &h->Vo,     &h->dorig, &h->Sx,   &h->norms, &h->A,    &h->Ac,    &h->R,
                     &h->S1,     &h->S2,   &h->G,     &h->H,     &h->M,    &h->lam,   &h->rowsq,
-                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx, &h->rowmask};
+                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx, &h->rowmask, &h->pctl};
   for (DevBuf *b : bufs) b->release();
   delete h;
   return PLSB_OK;
@@ -732,6 +732,23 @@ int plsb_percentile(plsb_handle_t h, const double *d_distrib, int count, int n_s
   PLSB_CHECK(d_distrib && d_lo && d_hi, PLSB_ERR_ARG, "plsb_percentile: null argument");
   return launch_percentile(h, d_distrib, count, n_series, q_lo, q_hi, d_lo, d_hi,
                            as_stream(stream));
+}
+
+int plsb_percentile_series(plsb_handle_t h, const double *d_series, int n_series, int count,
+                           int64_t ld, double q_lo, double q_hi, double *d_lo, double *d_hi,
+                           void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_series && d_lo && d_hi, PLSB_ERR_ARG, "plsb_percentile_series: null argument");
+  return launch_percentile_series(h, d_series, ld, count, n_series, q_lo, q_hi, d_lo, d_hi,
+                                  as_stream(stream));
+}
+
+int plsb_transpose(plsb_handle_t h, const double *d_in, int rows, int cols, double *d_out,
+                   void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_in && d_out && rows >= 0 && cols >= 0, PLSB_ERR_ARG, "plsb_transpose: bad argument");
+  if (rows == 0 || cols == 0) return PLSB_OK;
+  return launch_transpose(h, d_in, rows, cols, cols, d_out, as_stream(stream));
 }
 
 int plsb_boot_ratio(plsb_handle_t h, const double *d_bs, const double *d_usum,

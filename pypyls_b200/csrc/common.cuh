@@ -165,7 +165,7 @@ struct plsb_ctx {
   plsb::DevBuf Sx;     // Xraw @ normalize(Uo)   (S, L)
   plsb::DevBuf norms;  // (L)
   // per-chunk workspaces
-  plsb::DevBuf A, Ac, R, S1, S2, G, H, M, lam, rowsq, part, misc, idxall, flags, maps;
+  plsb::DevBuf A, Ac, R, S1, S2, G, H, M, lam, rowsq, part, misc, idxall, flags, maps, pctl;
 };
 
 namespace plsb {
@@ -311,6 +311,9 @@ int launch_pvals(plsb_ctx *h, const double *dperm, int count, int L, const doubl
                  double *pvals, cudaStream_t st);
 int launch_percentile(plsb_ctx *h, const double *distrib, int count, int n_series, double qlo,
                       double qhi, double *lo, double *hi, cudaStream_t st);
+int launch_percentile_series(plsb_ctx *h, const double *series, long long ld, int count,
+                             int n_series, double qlo, double qhi, double *lo, double *hi,
+                             cudaStream_t st);
 int launch_boot_ratio(plsb_ctx *h, const double *bs, const double *usum, const double *usq,
                       long long n, int n_boot, int add_orig, double *bsr, double *se,
                       cudaStream_t st);

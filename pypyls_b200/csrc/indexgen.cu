@@ -245,13 +245,11 @@ gen_splits_kernel(uint64_t seed, long long first, int n_split, double frac, int 
                   int *__restrict__ n_exhausted) {
   extern __shared__ unsigned long long sh_hash[];   // n_split hashes, then n_split redo flags
   int *redo = reinterpret_cast<int *>(sh_hash + n_split);
-  __shared__ int s_again;
   const int set = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const uint32_t id = (uint32_t)(first + set);
   int32_t *out = masks + (size_t)set * n_split * S;
   for (int i = tid; i < n_split; i += nt) redo[i] = 1;
   for (int round = 0; round < MAX_TRIES; ++round) {
-    if (tid == 0) s_again = 0;
     __syncthreads();
     for (int i = tid; i < n_split; i += nt) {
       if (!redo[i]) continue;
@@ -273,6 +271,7 @@ gen_splits_kernel(uint64_t seed, long long first, int n_split, double frac, int 
     }
     __syncthreads();
     // a mask that repeats an earlier mask of the set is drawn again
+    int dup_any = 0;
     for (int i = tid; i < n_split; i += nt) {
       bool dup = false;
       const unsigned long long hi = sh_hash[i];
@@ -282,10 +281,10 @@ gen_splits_kernel(uint64_t seed, long long first, int n_split, double frac, int 
         dup = false;
       }
       redo[i] = dup ? 1 : 0;
-      if (dup) s_again = 1;
+      dup_any |= dup;
     }
-    __syncthreads();
-    if (!s_again) break;
+    // one uniform decision for the whole CTA (barrier + reduction in one)
+    if (!__syncthreads_or(dup_any)) break;
   }
 }
 

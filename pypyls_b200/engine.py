@@ -86,7 +86,8 @@ def release_workspaces():
     """Destroys every pooled library handle (frees their device memory)."""
     lib = _cabi.lib()
     for handles in _FREE_HANDLES.values():
-        for h in handles:
+        for h, idle in handles:
+            idle.synchronize()
             lib.plsb_destroy(h)
     _FREE_HANDLES.clear()
 
@@ -127,7 +128,11 @@ class ResamplingEngine:
         self.L = self.K
         pool = _FREE_HANDLES.setdefault(self.device.index, [])
         if pool:
-            self._h = pool.pop()
+            self._h, idle = pool.pop()
+            # the previous borrower's kernels may still be queued (on any
+            # stream); plsb_configure uploads its tables synchronously and the
+            # workspaces are shared, so wait for them here
+            idle.synchronize()
         else:
             self._h = C.c_void_p(0)
             with torch.cuda.device(self.device):
@@ -148,9 +153,12 @@ class ResamplingEngine:
     # -- plumbing ----------------------------------------------------------
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:
-            # stream-ordered reuse: the next borrower enqueues on the same
-            # (current) stream, so no synchronisation is needed here
-            _FREE_HANDLES.setdefault(self.device.index, []).append(self._h)
+            # the next borrower waits for everything queued so far on this
+            # engine's stream before it touches the handle's buffers
+            idle = torch.cuda.Event()
+            idle.record(torch.cuda.current_stream(self.device))
+            _FREE_HANDLES.setdefault(self.device.index, []).append(
+                (self._h, idle))
             self._h = C.c_void_p(0)
 
     def __del__(self):
@@ -532,6 +540,28 @@ class ResamplingEngine:
             self._h, _ptr(distrib), n, series, float(q_lo), float(q_hi),
             _ptr(lo), _ptr(hi), self._stream()))
         return lo, hi
+
+    def percentile_series(self, series, q_lo, q_hi):
+        """The same percentiles for a series-major (n_series, count) tensor
+        (rows may be padded: stride(0) >= count)."""
+        if series.dim() != 2 or series.stride(1) != 1:
+            raise ValueError('series-major input must be 2-D with unit column '
+                             'stride')
+        n_series, n = int(series.shape[0]), int(series.shape[1])
+        lo, hi = self._f64(n_series), self._f64(n_series)
+        _cabi.check(self._lib.plsb_percentile_series(
+            self._h, _ptr(series), n_series, n, int(series.stride(0)),
+            float(q_lo), float(q_hi), _ptr(lo), _ptr(hi), self._stream()))
+        return lo, hi
+
+    def transpose(self, a):
+        """(rows, cols) -> contiguous (cols, rows) on the device."""
+        a = self.to_device(a)
+        rows, cols = int(a.shape[0]), int(a.numel() // max(int(a.shape[0]), 1))
+        out = self._f64(cols, rows)
+        _cabi.check(self._lib.plsb_transpose(self._h, _ptr(a), rows, cols,
+                                             _ptr(out), self._stream()))
+        return out
 
     def boot_ratio(self, bs, u_sum, u_square, n_boot, add_orig):
         bs = self.to_device(bs)

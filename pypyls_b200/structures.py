@@ -90,7 +90,7 @@ class ResDict(dict):
 
 class PLSInputs(ResDict):
     """Inputs of an analysis (pyls/structures.py:146-172).  ``index_backend``,
-    ``device``, ``workspace_bytes`` and ``perm_path`` are additions of this
+    ``device``, ``workspace_bytes``, ``perm_path`` and ``gather_results`` are additions of this
     engine."""
 
     allowed = [
@@ -99,6 +99,7 @@ class PLSInputs(ResDict):
         'ci', 'seed', 'verbose', 'n_proc', 'bootsamples', 'permsamples',
         'method', 'n_components', 'aggfunc', 'permindices',
         'index_backend', 'device', 'workspace_bytes', 'perm_path',
+        'gather_results',
     ]
 
     def __init__(self, **kwargs):

@@ -74,6 +74,42 @@ def test_two_rank_sharding_equals_single_process(tmp_path):
         np.testing.assert_allclose(z['u_square'], want_uq, rtol=1e-10)
 
 
+def _exchange_worker(rank, world, port, n_total, n_series, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from pypyls_b200 import dist as pdist
+    from pypyls_b200.resample import shard_range
+    full = torch.arange(float(n_total * n_series)).reshape(n_total, n_series)
+    first, count = pdist.my_block(n_total)
+    local = full[first:first + count]
+    # series-major blocks dealt over the ranks: rank q ends up with its share
+    # of the series over ALL resamples, in resample-id order
+    mine = pdist.exchange_series(local.t().contiguous(), n_total)
+    s0, sc = shard_range(n_series, rank, world)
+    assert torch.equal(mine, full[:, s0:s0 + sc].t())
+    # per-series results back in series order on every rank
+    got = pdist.gather_series(mine.sum(dim=1), n_series)
+    assert torch.equal(got, full.sum(dim=0))
+    # whole per-resample output on the root only
+    root = pdist.gather_to_root(local, n_total)
+    assert (root is None) == (rank != 0)
+    if rank == 0:
+        assert torch.equal(root, full)
+    assert torch.equal(pdist.gather_resamples(local, n_total), full)
+    open(os.path.join(out_dir, 'ok%d' % rank), 'w').close()
+    dist.destroy_process_group()
+
+
+def test_series_exchange_even_and_ragged(tmp_path):
+    for n_total, n_series in ((8, 6), (9, 7), (5, 3)):
+        out = tmp_path / ('%d_%d' % (n_total, n_series))
+        out.mkdir()
+        mp.spawn(_exchange_worker, args=(2, _free_port(), n_total, n_series,
+                                         str(out)), nprocs=2, join=True)
+        assert (out / 'ok0').exists() and (out / 'ok1').exists()
+
+
 def test_single_process_is_a_no_op():
     from pypyls_b200 import dist as pdist
     t = torch.arange(6.).reshape(3, 2)

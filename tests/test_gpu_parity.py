@@ -110,7 +110,9 @@ def test_prepermuted_y_matches_reference_golden(name):
         close(out[k], ref[k])
     close(out.permres.perm_singval, ref['perm_singval'])
     assert np.array_equal(out.permres.pvals, ref['pvals'])
-    assert out.permres.permsamples.shape == Yp.shape
+    # the reference keeps the stack transposed, (S, T, P) (pyls/base.py:638-639)
+    assert np.array_equal(out.permres.permsamples,
+                          np.transpose(Yp, (1, 2, 0)))
 
 
 @pytest.mark.parametrize('name', ['bpls_crossval_corr', 'bpls_crossval_cov'])

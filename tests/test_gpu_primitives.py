@@ -129,13 +129,58 @@ def test_small_decomp_rank_deficient(torch_cuda):
 
 
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize('count', [1, 2, 3, 100, 1000, 5000, 20001])
+@pytest.mark.parametrize('count', [1, 2, 3, 100, 511, 512, 513, 1000, 5000,
+                                   20001, 40000, 70001])
 def test_percentile_bit_equal_numpy(torch_cuda, count):
+    """Order statistics by selection (register-resident keys up to 32768
+    values per series, the streaming variant beyond) are bit-equal to
+    np.percentile, for every keys-per-thread instantiation."""
     rs = np.random.RandomState(count)
     D = rs.randn(count, 7, 3)
     eng = make_engine('behavioral', 4, 8, 1, [4])
     lo, hi = eng.percentile(D, 2.5, 97.5)
     want = np.percentile(D, [2.5, 97.5], axis=0)
+    assert np.array_equal(lo.cpu().numpy(), want[0])
+    assert np.array_equal(hi.cpu().numpy(), want[1])
+
+
+def test_percentile_ties_signs_nan_and_other_quantiles(torch_cuda):
+    rs = np.random.RandomState(5)
+    eng = make_engine('behavioral', 4, 8, 1, [4])
+    D = rs.randn(999, 6)
+    D[:, 1] = np.round(D[:, 1])                # heavy ties, both signs, +-0
+    D[:, 2] = -np.abs(D[:, 2])                 # all negative
+    D[:, 3] = 7.25                             # constant series
+    D[::3, 4] = 0.0
+    D[1::3, 4] = -0.0
+    for qlo, qhi in ((2.5, 97.5), (0.0, 100.0), (50.0, 99.9), (0.5, 5.0)):
+        lo, hi = eng.percentile(D, qlo, qhi)
+        want = np.percentile(D, [qlo, qhi], axis=0)
+        assert np.array_equal(lo.cpu().numpy(), want[0])
+        assert np.array_equal(hi.cpu().numpy(), want[1])
+    D[17, 5] = np.nan                          # np.percentile propagates NaN
+    lo, hi = eng.percentile(D, 2.5, 97.5)
+    assert np.isnan(lo.cpu().numpy()[5]) and np.isnan(hi.cpu().numpy()[5])
+    assert np.array_equal(lo.cpu().numpy()[:5],
+                          np.percentile(D[:, :5], 2.5, axis=0))
+
+
+def test_percentile_series_major_and_transpose(torch_cuda):
+    """The series-major entry (what a rank holds after the series exchange of
+    a multi-GPU run), padded rows included, and the transpose that feeds it."""
+    import torch
+    rs = np.random.RandomState(6)
+    eng = make_engine('behavioral', 4, 8, 1, [4])
+    D = rs.randn(1234, 37)
+    Dt = eng.transpose(D)
+    assert np.array_equal(Dt.cpu().numpy(), D.T)
+    want = np.percentile(D, [2.5, 97.5], axis=0)
+    lo, hi = eng.percentile_series(Dt, 2.5, 97.5)
+    assert np.array_equal(lo.cpu().numpy(), want[0])
+    assert np.array_equal(hi.cpu().numpy(), want[1])
+    padded = torch.full((37, 1300), 1e300, dtype=torch.float64, device='cuda')
+    padded[:, :1234] = Dt
+    lo, hi = eng.percentile_series(padded[:, :1234], 2.5, 97.5)
     assert np.array_equal(lo.cpu().numpy(), want[0])
     assert np.array_equal(hi.cpu().numpy(), want[1])
 
