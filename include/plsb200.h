@@ -193,6 +193,14 @@ int plsb_boot_ratio(plsb_handle_t h, const double *d_bs, const double *d_usum,
                     const double *d_usquare, int64_t n_elem, int n_boot,
                     int add_orig, double *d_bsr, double *d_se, void *stream);
 
+/* Profiling aid: mean milliseconds per launch of one variant of the
+ * cross-covariance GEMM (compute.xcorr's `Yn.T @ Xn`, pyls/compute.py:92, for a
+ * stack of M operand rows) on synthetic operands.  variant 0 = store,
+ * 1 = store with column scales, 2 = row sums of squares (rotated permutations). */
+int plsb_gemm_probe(plsb_handle_t h, int variant, int M, int N, int Kd,
+                    int k_valid, int scale_div, int iters, double *ms_out,
+                    void *stream);
+
 /* ---- primitives (exposed for unit tests and for callers that want the
  *      compute.py-level operations; pyls/compute.py:55-94, 10-52, 240-264) -- */
 

@@ -50,6 +50,7 @@ PROTOTYPES = {
     'plsb_transpose': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'plsb_boot_ratio': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     'plsb_dgemm': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    'plsb_gemm_probe': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_dbl), _vp]),
     'plsb_crosscov': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'plsb_small_decomp': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'plsb_gram_proj': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),

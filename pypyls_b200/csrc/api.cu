@@ -99,6 +99,7 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, const double *yperm, int n, 
   g.ldx = l.ldx;
   g.N_pad = l.ldx;
   g.Kd = l.S_pad;
+  g.k_valid = l.S;
   g.ldc = l.ldx;
   if (grouped) g.k_len = l.kr_max;
   if (scaled && !fused_scale) {
@@ -567,7 +568,7 @@ static int run_perms_impl(plsb_ctx *h, const int32_t *d_idx, const double *d_ype
                             d_yperm ? d_yperm + off * ystride : nullptr, n, h->A.as<double>(),
                             nullptr, nullptr, 0, 0, st));
       const int n_mtiles = (int)(M_pad / GEMM_BM);
-      const int n_splits = gemm_pick_splits(h, n_mtiles, n_ntiles);
+      const int n_splits = gemm_pick_splits(h, (int)M_pad, n_ntiles, gemm_small_tile(l.S_pad));
       PLSB_TRY(h->rowsq.ensure(sizeof(double) * (size_t)n_splits * M_pad));
       GemmArgs g;
       g.A = h->A.as<double>();
@@ -577,6 +578,7 @@ static int run_perms_impl(plsb_ctx *h, const int32_t *d_idx, const double *d_ype
       g.M_pad = (int)M_pad;
       g.N_pad = l.ldx;
       g.Kd = l.S_pad;
+      g.k_valid = l.S;
       g.rowsq = h->rowsq.as<double>();
       g.n_splits = n_splits;
       PLSB_TRY(launch_gemm(h, g, st));
@@ -655,6 +657,7 @@ int plsb_run_perms_gram(plsb_handle_t h, const int32_t *d_idx, int count, double
     g.M_pad = (int)M_pad;
     g.N_pad = N_pad;
     g.Kd = l.S_pad;
+    g.k_valid = l.S;
     g.k_len = l.S_pad;
     g.C = h->R.as<double>();
     g.ldc = N_pad;
@@ -769,6 +772,63 @@ int plsb_dgemm(plsb_handle_t h, const double *d_A, const double *d_X, int M, int
   return dense_gemm(h, d_A, d_X, M, N, Kd, d_C, as_stream(stream));
 }
 
+// Times one variant of the cross-covariance GEMM on synthetic operands (profiling aid):
+// variant 0 = STORE, 1 = STORE with column scales (scale_div rows share a scale row),
+// 2 = ROWSUMSQ.  Returns the mean milliseconds per launch over `iters` launches.
+int plsb_gemm_probe(plsb_handle_t h, int variant, int M, int N, int Kd, int k_valid, int scale_div,
+                    int iters, double *ms_out, void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(ms_out && M >= 1 && N >= 1 && Kd >= 1 && iters >= 1 && variant >= 0 && variant <= 2,
+             PLSB_ERR_ARG, "plsb_gemm_probe: bad argument");
+  cudaStream_t st = as_stream(stream);
+  const int M_pad = round_up(M, GEMM_BM), N_pad = round_up(N, GEMM_BN), K_pad = round_up(Kd, GEMM_BK);
+  scale_div = std::max(scale_div, 1);
+  PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)M_pad * K_pad));
+  PLSB_TRY(h->misc.ensure(sizeof(double) * (size_t)K_pad * N_pad));
+  PLSB_CUDA(cudaMemsetAsync(h->A.p, 0x3F, sizeof(double) * (size_t)M_pad * K_pad, st));
+  PLSB_CUDA(cudaMemsetAsync(h->misc.p, 0x3F, sizeof(double) * (size_t)K_pad * N_pad, st));
+  GemmArgs g;
+  g.A = h->A.as<double>();
+  g.lda = K_pad;
+  g.X = h->misc.as<double>();
+  g.ldx = N_pad;
+  g.M_pad = M_pad;
+  g.N_pad = N_pad;
+  g.Kd = K_pad;
+  g.k_valid = k_valid > 0 ? k_valid : Kd;
+  if (variant == 2) {
+    g.n_splits = gemm_pick_splits(h, M_pad, N_pad / GEMM_BN, gemm_small_tile(K_pad));
+    PLSB_TRY(h->rowsq.ensure(sizeof(double) * (size_t)g.n_splits * M_pad));
+    g.rowsq = h->rowsq.as<double>();
+  } else {
+    g.ldc = tune_int("PLSB_PROBE_LDC", N_pad);   // small pitch: same stores into few pages
+    PLSB_TRY(h->R.ensure(sizeof(double) * ((size_t)M_pad * g.ldc + N_pad)));
+    g.C = h->R.as<double>();
+    if (variant == 1) {
+      const size_t rows = (size_t)cdiv(M_pad, scale_div);
+      PLSB_TRY(h->S1.ensure(sizeof(double) * rows * N_pad));
+      PLSB_CUDA(cudaMemsetAsync(h->S1.p, 0x3F, sizeof(double) * rows * N_pad, st));
+      g.scale = h->S1.as<double>();
+      g.scale_div = scale_div;
+      g.lds = N_pad;
+    }
+  }
+  PLSB_TRY(launch_gemm(h, g, st));   // warm-up
+  cudaEvent_t e0, e1;
+  PLSB_CUDA(cudaEventCreate(&e0));
+  PLSB_CUDA(cudaEventCreate(&e1));
+  PLSB_CUDA(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) PLSB_TRY(launch_gemm(h, g, st));
+  PLSB_CUDA(cudaEventRecord(e1, st));
+  PLSB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  PLSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = (double)ms / iters;
+  return PLSB_OK;
+}
+
 // ---- SIMPLS (pls_regression) ---------------------------------------------------
 
 // x_weights operand rows D (n*L, S_pad) in h->A  ->  R (n*L, ldx) = D @ X
@@ -785,6 +845,7 @@ static int simpls_weights_gemm(plsb_ctx *h, int n, cudaStream_t st) {
   g.M_pad = (int)M_pad;
   g.N_pad = l.ldx;
   g.Kd = l.S_pad;
+  g.k_valid = l.S;
   g.C = h->R.as<double>();
   g.ldc = l.ldx;
   return launch_gemm(h, g, st);
@@ -947,6 +1008,7 @@ static int crossval_chunk(plsb_ctx *h, const int32_t *mask, int n, int max_test,
   g.ldx = l.ldx;
   g.N_pad = l.ldx;
   g.Kd = l.S_pad;
+  g.k_valid = l.S;
   g.ldc = l.ldx;
   g.k_len = l.kr_max;
   g.X = h->Xglob.as<double>();
@@ -1067,6 +1129,7 @@ static int halves_chunk(plsb_ctx *h, const int32_t *masks, const double *yperm,
   g.ldx = l.ldx;
   g.N_pad = l.ldx;
   g.Kd = l.S_pad;
+  g.k_valid = l.S;
   g.ldc = l.ldx;
   if (grouped) g.k_len = l.kr_max;
   if (scaled) {

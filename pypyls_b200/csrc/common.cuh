@@ -202,6 +202,7 @@ struct GemmArgs {
   int M_pad = 0;               // multiple of GEMM_BM
   int N_pad = 0;               // multiple of GEMM_BN (<= ldx)
   int Kd = 0;                  // contraction length, multiple of GEMM_BK (padding zero)
+  int k_valid = 0;             // rows of X beyond this are zero padding (0: Kd): their k steps are skipped
   const int4 *kranges = nullptr;  // optional per-M-tile [kbeg,kend) (kbeg even) + non-zero k steps [z,w)
   int k_len = 0;               // longest contraction range in kranges (0: Kd); picks the tile
   bool square_b = false;       // use X*X elementwise as the right operand
@@ -217,7 +218,8 @@ struct GemmArgs {
   int n_splits = 1;
 };
 int launch_gemm(plsb_ctx *h, const GemmArgs &a, cudaStream_t st);
-int gemm_pick_splits(const plsb_ctx *h, int n_mtiles, int n_ntiles);
+bool gemm_small_tile(int klen);
+int gemm_pick_splits(const plsb_ctx *h, int M_pad, int n_ntiles, bool small_tile);
 
 // data preparation (prep.cu)
 int launch_pad_copy(plsb_ctx *h, const double *X, int S, int B, double *out, int S_pad, int ldx,

@@ -290,35 +290,375 @@ xcov_gemm_kernel(const double *__restrict__ A, int lda, const double *__restrict
   }
 }
 
+// ---- v2: the same tiling with the producer interleaved into the tensor stream ----------
+// In the kernel above every warp stops at the CTA barrier, then issues its share of the
+// next stage's cp.async (address arithmetic + 8 LDGSTS), then loads fragments, and only
+// then feeds the DMMA pipe again: ~300 of the ~4100 cycles of a k chunk with the tensor
+// pipe idle.  Here the copies of ring step s + STAGES - 1 are issued ONE AT A TIME between
+// the DMMA groups of step s (source pointers advance incrementally, no divisions), so that
+// after the barrier a warp only loads its first fragments before the pipe is busy again.
+// Also skips the k steps beyond `k_valid` (rows of the data matrix that are zero padding).
+template <int EPI, bool SQB, int MF>
+__global__ void __launch_bounds__(NTHREADS, MF == 8 ? 1 : 2)
+xcov_gemm2_kernel(const double *__restrict__ A, int lda, const double *__restrict__ X, int ldx,
+                  int n_mtiles, int n_ntiles, int nt_per_split, const int4 *__restrict__ kranges,
+                  int Kd, int k_valid, double *__restrict__ C, long long ldc,
+                  const int *__restrict__ row_map, const double *__restrict__ scale,
+                  int scale_div, long long lds, double *__restrict__ rowsq, int M_pad, int dbg) {
+  constexpr int TM = 2 * MF * 8;          // rows of the CTA tile
+  constexpr int A_STAGE = TM * LDA_S;     // doubles
+  constexpr int STAGES = stages_of(MF);
+  constexpr int MAXS = max_slots_of(MF);
+  constexpr int NA = TM / 32;             // A copies per thread and stage
+  constexpr int NX = 4;                   // X copies per thread and stage
+  constexpr int NP = NA + NX;
+  extern __shared__ __align__(16) double smem[];
+  double *As = smem;
+  double *Bs = smem + STAGES * A_STAGE;
+  double *Sb = smem + ring_doubles(MF);   // [STAGES][MAXS][LDB_S] staged column scales
+  __shared__ int s_slot[TM];              // tile row -> staged scale row
+  __shared__ int s_srow[MAXS];            // staged scale row -> row of `scale`
+  __shared__ int s_nslot;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+
+  const int split = blockIdx.x / n_mtiles;
+  const int mtile = blockIdx.x - split * n_mtiles;
+  const int nt0 = split * nt_per_split;
+  const int nt1 = min(nt0 + nt_per_split, n_ntiles);
+  if (nt0 >= nt1) return;
+
+  int kbeg = 0, kend = Kd, vbeg = 0, vend = min(Kd, (k_valid + 3) & ~3);
+  if (kranges) {
+    int4 kr = kranges[(mtile * TM) / BM];
+    kbeg = kr.x;
+    kend = kr.y;
+    vbeg = kr.z;
+    vend = kr.w;
+  } else {
+    kend = min(Kd, (vend + BK - 1) / BK * BK);
+  }
+  const int nkc = (kend - kbeg + BK - 1) / BK;     // k chunks per N tile
+  const int total = (nt1 - nt0) * nkc;             // flattened pipeline steps
+
+  const double *Ablk = A + (size_t)mtile * TM * lda;
+
+  int nslot = 0;
+  int orow_i[MF], slot_i[MF];
+  if (EPI == EPI_STORE) {
+    if (scale) {
+      if (tid < TM) {
+        const int m = mtile * TM + tid;
+        const int orow = row_map ? row_map[m] : m;
+        s_slot[tid] = orow >= 0 ? orow / scale_div : -1;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int n = 0, prev = -1;
+        for (int t = 0; t < TM; ++t) {
+          const int sr = s_slot[t];
+          if (sr < 0) {
+            s_slot[t] = 0;
+            continue;
+          }
+          if (sr != prev) {
+            if (n < MAXS) s_srow[n] = sr;
+            ++n;
+            prev = sr;
+          }
+          s_slot[t] = n - 1;
+        }
+        s_nslot = n <= MAXS ? n : 0;
+      }
+      __syncthreads();
+      nslot = s_nslot;
+    }
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+      const int ml = wm * MF * 8 + i * 8 + g;
+      const int m = mtile * TM + ml;
+      orow_i[i] = row_map ? row_map[m] : m;
+      slot_i[i] = nslot > 0 ? s_slot[ml] : 0;
+    }
+  }
+
+  // ---- producer state: one source pointer per copy, advanced per step ----
+  const double *a_src[NA];
+  unsigned a_dst[NA];
+#pragma unroll
+  for (int it = 0; it < NA; ++it) {
+    const int c = tid + it * NTHREADS;
+    const int row = c >> 3, seg = c & 7;
+    a_src[it] = Ablk + (size_t)row * lda + kbeg + seg * 2;
+    a_dst[it] = (unsigned)__cvta_generic_to_shared(As + row * LDA_S + seg * 2);
+  }
+  const double *x_src[NX];
+  unsigned x_dst[NX];
+#pragma unroll
+  for (int it = 0; it < NX; ++it) {
+    const int c = tid + it * NTHREADS;
+    const int row = c >> 6, seg = c & 63;
+    x_src[it] = X + (size_t)(kbeg + row) * ldx + (size_t)nt0 * BN + seg * 2;
+    x_dst[it] = (unsigned)__cvta_generic_to_shared(Bs + row * LDB_S + seg * 2);
+  }
+  const size_t x_step = (size_t)BK * ldx;                       // next k chunk
+  const long long x_wrap = (long long)BN - (long long)nkc * BK * ldx;   // next N tile, first chunk
+  int p_step = 0, p_kc = 0, p_slot = 0, p_tile = 0;   // step being produced, its chunk, ring slot, tile ordinal
+
+  auto copy16 = [](unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+  };
+  // copy number `pi` of the step being produced (A first, then X)
+  auto piece = [&](int pi) {
+    if (p_step >= total) return;
+    if (pi < NA) {
+#pragma unroll
+      for (int it = 0; it < NA; ++it)
+        if (it == pi) copy16(a_dst[it] + p_slot * (A_STAGE * 8), a_src[it] + p_kc * BK);
+    } else {
+#pragma unroll
+      for (int it = 0; it < NX; ++it)
+        if (it == pi - NA) copy16(x_dst[it] + p_slot * (B_STAGE * 8), x_src[it]);
+    }
+  };
+  // all copies of the step issued: commit, advance the producer to the next step
+  auto produced = [&]() {
+    if (p_step < total) {
+      if (EPI == EPI_STORE && p_kc == 0 && nslot > 0) {
+        // scale rows of this N tile; buffer (tile ordinal) % STAGES is free again:
+        // the tile that used it finished its epilogue >= 1 iteration ago
+        double *sb = Sb + (p_tile % STAGES) * MAXS * LDB_S;
+        for (int e = tid; e < nslot * (BN / 2); e += NTHREADS) {
+          const int sl = e / (BN / 2), seg = e - sl * (BN / 2);
+          cp_async16(sb + sl * LDB_S + seg * 2,
+                     scale + (size_t)s_srow[sl] * lds + (size_t)(nt0 + p_tile) * BN + seg * 2);
+        }
+      }
+      ++p_step;
+      p_slot = p_slot + 1 == STAGES ? 0 : p_slot + 1;
+      if (++p_kc == nkc) {
+        p_kc = 0;
+        ++p_tile;
+#pragma unroll
+        for (int it = 0; it < NX; ++it) x_src[it] += x_wrap + (long long)x_step;
+      } else {
+#pragma unroll
+        for (int it = 0; it < NX; ++it) x_src[it] += x_step;
+      }
+    }
+    cp_async_commit();
+  };
+
+  double acc[MF][NF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i)
+#pragma unroll
+    for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double rsq[MF];
+#pragma unroll
+  for (int i = 0; i < MF; ++i) rsq[i] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+#pragma unroll
+    for (int pi = 0; pi < NP; ++pi) piece(pi);
+    produced();
+  }
+
+  int kc = 0, nt = nt0, slot = 0;
+  for (int s = 0; s < total; ++s) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+
+    const double *as = As + slot * A_STAGE + (wm * MF * 8 + g) * LDA_S + q;
+    const double *bs = Bs + slot * B_STAGE + q * LDB_S + wn * 32 + g;
+    const int kabs = kbeg + kc * BK;
+    if (kabs >= vbeg && kabs + BK <= vend) {
+      // whole chunk: one copy of the step being produced after every group of DMMAs
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double af[MF], bf[NF];
+#pragma unroll
+        for (int i = 0; i < MF; ++i) af[i] = as[i * 8 * LDA_S + kk * 4];
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+          double v = bs[kk * 4 * LDB_S + j * 8];
+          bf[j] = SQB ? v * v : v;
+        }
+#pragma unroll
+        for (int i = 0; i < MF; ++i) {
+#pragma unroll
+          for (int j = 0; j < NF; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          if (kk * MF + i < NP) piece(kk * MF + i);
+        }
+      }
+    } else {
+      // chunk with k steps that multiply structural zeros (skipped): copies first
+#pragma unroll
+      for (int pi = 0; pi < NP; ++pi) piece(pi);
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        if (kabs + kk * 4 < vbeg || kabs + kk * 4 >= vend) continue;
+        double af[MF], bf[NF];
+#pragma unroll
+        for (int i = 0; i < MF; ++i) af[i] = as[i * 8 * LDA_S + kk * 4];
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+          double v = bs[kk * 4 * LDB_S + j * 8];
+          bf[j] = SQB ? v * v : v;
+        }
+#pragma unroll
+        for (int i = 0; i < MF; ++i)
+#pragma unroll
+          for (int j = 0; j < NF; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    }
+    produced();
+    slot = slot + 1 == STAGES ? 0 : slot + 1;
+
+    if (++kc == nkc) {
+      // ---- epilogue of N tile `nt` ----
+      if (EPI == EPI_STORE) {
+        const double *sb = Sb + (((nt - nt0) % STAGES) * MAXS) * LDB_S + wn * 32 + 2 * q;
+#pragma unroll
+        for (int i = 0; i < MF; ++i) {
+          const int orow = orow_i[i];
+          if (orow >= 0) {
+            const size_t col = (size_t)nt * BN + wn * 32 + 2 * q;
+            double *crow = C + (size_t)orow * ldc + col;
+            if (scale) {
+              const double *srow = nslot > 0 ? sb + slot_i[i] * LDB_S
+                                             : scale + (size_t)(orow / scale_div) * lds + col;
+#pragma unroll
+              for (int j = 0; j < NF; ++j) {
+                const double2 sc = *reinterpret_cast<const double2 *>(srow + j * 8);
+                *reinterpret_cast<double2 *>(crow + j * 8) =
+                    make_double2(acc[i][j][0] * sc.x, acc[i][j][1] * sc.y);
+              }
+            } else if (dbg == 1) {
+              // timing experiment: same store count, every instruction one contiguous 512 B
+              double *base = C + (size_t)(mtile * TM + (warp * MF + i) % TM) * ldc +
+                             (size_t)nt * BN + lane * 2;
+#pragma unroll
+              for (int j = 0; j < NF; ++j)
+                *reinterpret_cast<double2 *>(base + (j & 1) * 64 + (size_t)(j >> 1) * ldc) =
+                    make_double2(acc[i][j][0], acc[i][j][1]);
+            } else if (dbg == 2) {
+              // timing experiment: a quarter of the stores
+              *reinterpret_cast<double2 *>(crow) = make_double2(
+                  acc[i][0][0] + acc[i][1][0] + acc[i][2][0] + acc[i][3][0],
+                  acc[i][0][1] + acc[i][1][1] + acc[i][2][1] + acc[i][3][1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < NF; ++j)
+                *reinterpret_cast<double2 *>(crow + j * 8) =
+                    make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < MF; ++i)
+#pragma unroll
+          for (int j = 0; j < NF; ++j)
+            rsq[i] += acc[i][j][0] * acc[i][j][0] + acc[i][j][1] * acc[i][j][1];
+      }
+#pragma unroll
+      for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      kc = 0;
+      ++nt;
+    }
+  }
+
+  if (EPI == EPI_ROWSUMSQ) {
+    cp_async_wait<0>();
+    __syncthreads();
+    double *red = smem;  // [4 wn][TM rows]
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+      double v = rsq[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (q == 0) red[wn * TM + wm * MF * 8 + i * 8 + g] = v;
+    }
+    __syncthreads();
+    if (tid < TM) {
+      double v = red[tid] + red[TM + tid] + red[2 * TM + tid] + red[3 * TM + tid];
+      rowsq[(size_t)split * M_pad + (size_t)mtile * TM + tid] = v;
+    }
+  }
+}
+
 template <int EPI, bool SQB, int MF>
 int launch_variant(plsb_ctx *h, const GemmArgs &a, int n_ntiles, int n_splits, cudaStream_t st) {
   KernelTimer kt(h, KC_GEMM, st);
   constexpr int TM = 2 * MF * 8;
-  auto kern = xcov_gemm_kernel<EPI, SQB, MF>;
   const int smem = smem_bytes(MF, EPI == EPI_STORE && a.scale != nullptr);
-  PLSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_mtiles = a.M_pad / TM;
   const int nt_per_split = (n_ntiles + n_splits - 1) / n_splits;
   dim3 grid((unsigned)(n_mtiles * n_splits));
-  kern<<<grid, NTHREADS, smem, st>>>(a.A, a.lda, a.X, a.ldx, n_mtiles, n_ntiles,
-                                               nt_per_split, a.kranges, a.Kd, a.C, a.ldc,
-                                               a.row_map, a.scale, a.scale_div, a.lds, a.rowsq,
-                                               a.M_pad);
+  if (tune_int("PLSB_GEMM_V", 2) == 1) {
+    auto kern = xcov_gemm_kernel<EPI, SQB, MF>;
+    PLSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, NTHREADS, smem, st>>>(a.A, a.lda, a.X, a.ldx, n_mtiles, n_ntiles, nt_per_split,
+                                       a.kranges, a.Kd, a.C, a.ldc, a.row_map, a.scale,
+                                       a.scale_div, a.lds, a.rowsq, a.M_pad);
+  } else {
+    auto kern = xcov_gemm2_kernel<EPI, SQB, MF>;
+    PLSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, NTHREADS, smem, st>>>(a.A, a.lda, a.X, a.ldx, n_mtiles, n_ntiles, nt_per_split,
+                                       a.kranges, a.Kd, a.k_valid > 0 ? a.k_valid : a.Kd, a.C,
+                                       a.ldc, a.row_map, a.scale, a.scale_div, a.lds, a.rowsq,
+                                       a.M_pad, tune_int("PLSB_GEMM_DBG", 0));
+  }
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
 
 }  // namespace
 
-// Splits of the N range per M tile: enough CTAs for >= ~6 waves over the SMs,
-// never more than the N tiles there are.
-int gemm_pick_splits(const plsb_ctx *h, int n_mtiles, int n_ntiles) {
-  int want = (6 * h->sm_count + n_mtiles - 1) / n_mtiles;
-  if (want < 1) want = 1;
-  if (want > n_ntiles) want = n_ntiles;
-  // every split must own at least one N tile (a CTA without tiles writes nothing)
-  const int per = (n_ntiles + want - 1) / want;
-  return (n_ntiles + per - 1) / per;
+// 64-row tiles with two CTAs per SM (one CTA's barrier / refill bubbles are covered by the
+// other's DMMAs) unless the environment says otherwise
+bool gemm_small_tile(int klen) {
+  (void)klen;
+  return tune_int("PLSB_GEMM_SMALL_TILE", 1) != 0;
+}
+
+// Splits of the N range per M tile.  A launch is `n_mtiles x n_splits` equal CTAs that run
+// in waves of (SMs x CTAs per SM): the split count is chosen to minimise the modelled
+// makespan  waves x (N tiles per CTA + pipeline fill)  -- a last wave that is nearly empty
+// costs as much as a full one (measured: 6.2 waves ran as 7, -12 % on the bootstrap launch
+// of config 5), so many short CTAs beat few long ones.
+int gemm_pick_splits(const plsb_ctx *h, int M_pad, int n_ntiles, bool small_tile) {
+  const int forced = tune_int("PLSB_GEMM_SPLITS", 0);
+  const int n_mtiles = M_pad / (small_tile ? 64 : BM);
+  const long long slots = (long long)h->sm_count * (small_tile ? 2 : 1);
+  int best = 1;
+  double best_cost = 1e300;
+  const int max_splits = std::min(n_ntiles, 256);
+  for (int want = 1; want <= max_splits; ++want) {
+    const int per = (n_ntiles + want - 1) / want;       // N tiles per CTA
+    const int ns = (n_ntiles + per - 1) / per;          // every split owns >= 1 tile
+    if (ns != want) continue;
+    const long long ctas = (long long)n_mtiles * ns;
+    const long long waves = (ctas + slots - 1) / slots;
+    // + 0.25 tile per CTA for the pipeline fill / drain and the launch of its first loads
+    const double cost = (double)waves * (per + 0.25);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = ns;
+    }
+  }
+  if (forced > 0) {
+    const int per = (n_ntiles + std::min(forced, n_ntiles) - 1) / std::min(forced, n_ntiles);
+    return (n_ntiles + per - 1) / per;
+  }
+  return best;
 }
 
 int launch_gemm(plsb_ctx *h, const GemmArgs &a, cudaStream_t st) {
@@ -332,19 +672,21 @@ int launch_gemm(plsb_ctx *h, const GemmArgs &a, cudaStream_t st) {
   if (rowsq) {
     PLSB_CHECK(a.n_splits >= 1, PLSB_ERR_ARG, "gemm: n_splits");
     if (a.square_b) return launch_variant<EPI_ROWSUMSQ, true, 8>(h, a, n_ntiles, a.n_splits, st);
+    if (gemm_small_tile(a.k_len > 0 ? a.k_len : a.Kd))
+      return launch_variant<EPI_ROWSUMSQ, false, 4>(h, a, n_ntiles, a.n_splits, st);
     return launch_variant<EPI_ROWSUMSQ, false, 8>(h, a, n_ntiles, a.n_splits, st);
   }
   PLSB_CHECK(a.C != nullptr && a.ldc % 2 == 0, PLSB_ERR_ARG, "gemm: bad output");
   // short contractions (block-diagonal operands: one cell's rows) are bound by the
   // store epilogue: 64-row tiles, two CTAs per SM
   const int klen = a.k_len > 0 ? a.k_len : a.Kd;
-  const bool small_tile = tune_int("PLSB_GEMM_SMALL_TILE", klen <= 64);
+  const bool small_tile = gemm_small_tile(klen);
   if (small_tile) {
-    const int n_splits = gemm_pick_splits(h, a.M_pad / 64, n_ntiles);
+    const int n_splits = gemm_pick_splits(h, a.M_pad, n_ntiles, true);
     if (a.square_b) return launch_variant<EPI_STORE, true, 4>(h, a, n_ntiles, n_splits, st);
     return launch_variant<EPI_STORE, false, 4>(h, a, n_ntiles, n_splits, st);
   }
-  const int n_splits = gemm_pick_splits(h, a.M_pad / BM, n_ntiles);
+  const int n_splits = gemm_pick_splits(h, a.M_pad, n_ntiles, false);
   if (a.square_b) return launch_variant<EPI_STORE, true, 8>(h, a, n_ntiles, n_splits, st);
   return launch_variant<EPI_STORE, false, 8>(h, a, n_ntiles, n_splits, st);
 }

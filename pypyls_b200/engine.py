@@ -583,6 +583,15 @@ class ResamplingEngine:
                                          self._stream()))
         return out
 
+    def gemm_probe(self, variant, M, N, Kd, k_valid=0, scale_div=10, iters=3):
+        """Mean milliseconds per launch of a cross-covariance GEMM variant on
+        synthetic operands (0 store, 1 scaled store, 2 row sums of squares)."""
+        ms = C.c_double(0.0)
+        _cabi.check(self._lib.plsb_gemm_probe(
+            self._h, int(variant), int(M), int(N), int(Kd), int(k_valid),
+            int(scale_div), int(iters), C.byref(ms), self._stream()))
+        return float(ms.value)
+
     def small_decomp(self, G, H, d_orig=None):
         G, H = self.to_device(G), self.to_device(H)
         d_orig = None if d_orig is None else self.to_device(d_orig)

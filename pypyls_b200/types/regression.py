@@ -186,9 +186,11 @@ class PLSRegression(BasePLS):
         if isinstance(table, _DeviceTable):
             table.start()
         self.bootsamp = _resolve(table)
-        distrib = pdist.gather_resamples(distrib, n)
+        local = distrib
+        distrib = pdist.gather_resamples(local, n)
         pdist.reduce_sum(u_sum, u_square)
-        self._dev.update(distrib=distrib, u_sum=u_sum, u_square=u_square)
+        self._dev.update(distrib=distrib, distrib_local=local, u_sum=u_sum,
+                         u_square=u_square)
         return (to_host(distrib.permute(1, 2, 0).contiguous()),
                 to_host(u_sum), to_host(u_square))
 
