@@ -532,6 +532,39 @@ def parity_full_n(w, X, Y, out):
     }
 
 
+def rank_invariance(eng, w, out, world, P, R):
+    """N > 1: rank 0 recomputes, on its own GPU, the first resamples of EVERY
+    rank's block from the tables of the sharded run and compares them with
+    what the owning rank produced: the bootstrap distribution must agree bit
+    for bit, the permuted singular values to 1e-12 (their row sums of squares
+    are reduced over a batch-size dependent number of column splits)."""
+    from pypyls_b200.resample import shard_range
+    if w['kind'] == 'regression':
+        return None
+    boot_key = 'contrast_boot' if w['kind'] == 'meancentered' \
+        else 'y_loadings_boot'
+    n_each, bit_equal, worst = 16, True, 0.0
+    for r in range(world):
+        fp, cp = shard_range(P, r, world)
+        ids = np.arange(fp, fp + min(n_each, cp))
+        mine = eng.run_perms(out.permres.permsamples[:, ids],
+                             rotate=True).cpu().numpy().T
+        theirs = out.permres.perm_singval[:, ids]
+        live = theirs.max(axis=1) > 1e-10 * theirs.max()
+        worst = max(worst, _rel(mine[live], theirs[live]))
+        fb, cb = shard_range(R, r, world)
+        ids = np.arange(fb, fb + min(n_each, cb))
+        mine = eng.boot_distrib(out.bootres.bootsamples[:, ids])
+        mine = mine.cpu().numpy().transpose(1, 2, 0)
+        bit_equal = bit_equal and np.array_equal(mine,
+                                                 out.bootres[boot_key][..., ids])
+    return {'ranks_checked': world, 'resamples_per_rank': n_each,
+            'distrib_bit_equal': bool(bit_equal),
+            'perm_singval_max_rel': worst,
+            'what': 'rank 0 recomputed the first resamples of every rank\'s '
+                    'block from the sharded run\'s tables'}
+
+
 # ---------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -778,6 +811,9 @@ def main():
                     pyls, w, X, Y, ref_file, local_rank)
             if out is not None and P + R <= 40000:
                 parity['full_n_vs_fast_oracle'] = parity_full_n(w, X, Y, out)
+            if out is not None and world > 1:
+                parity['rank_invariance'] = rank_invariance(eng, w, out, world,
+                                                            P, R)
             rels = [v['max_rel'] for k, v in parity.items()
                     if v and 'max_rel' in v]
             parity['max_rel'] = max(rels) if rels else None

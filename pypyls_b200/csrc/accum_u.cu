@@ -258,8 +258,9 @@ int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K
                    const double *M, int L, double *usum, double *usq, cudaStream_t st) {
   KernelTimer kt(h, KC_ACCUM, st);
   if (count <= 0) return PLSB_OK;
-  PLSB_CHECK(L >= 1 && L <= MAX_K && K >= 1 && K <= MAX_K, PLSB_ERR_ARG,
-             "accum_u: K=%d L=%d outside [1,%d]", K, L, MAX_K);
+  PLSB_CHECK(L >= 1 && K >= 1, PLSB_ERR_ARG, "accum_u: K=%d L=%d", K, L);
+  if (K > MAX_K || L > MAX_K)
+    return launch_accum_u_generic(h, R, ldr, count, K, B, M, accum_ldm(L), L, usum, usq, st);
   switch (cdiv(L, 8)) {
     case 1: return launch_au<1, 2>(h, R, ldr, count, K, B, M, L, usum, usq, st);
     case 2: return launch_au<2, 2>(h, R, ldr, count, K, B, M, L, usum, usq, st);

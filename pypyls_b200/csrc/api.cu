@@ -201,7 +201,7 @@ int plsb_destroy(plsb_handle_t h) {
   DevBuf *bufs[] = {&h->tables, &h->Xraw, &h->Xcell, &h->Xglob, &h->Y,    &h->Cmat,  &h->Uo,
                     &h->Vo,     &h->dorig, &h->Sx,   &h->norms, &h->A,    &h->Ac,    &h->R,
                     &h->S1,     &h->S2,   &h->G,     &h->H,     &h->M,    &h->lam,   &h->rowsq,
-                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx, &h->rowmask, &h->pctl};
+                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx, &h->rowmask, &h->pctl, &h->big};
   for (DevBuf *b : bufs) b->release();
   delete h;
   return PLSB_OK;
@@ -300,8 +300,6 @@ int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups,
   PLSB_CHECK(l.K <= B, PLSB_ERR_ARG,
              "plsb_configure: K=%d latent variables exceed the %d features (K <= B required)", l.K,
              B);
-  PLSB_CHECK(l.K <= MAX_K, PLSB_ERR_ARG, "plsb_configure: K=%d exceeds the supported maximum %d",
-             l.K, MAX_K);
   l.S_pad = round_up(S, GEMM_BK);
   l.ldx = round_up(B, GEMM_BN);
 
@@ -1057,9 +1055,6 @@ int plsb_crossval(plsb_handle_t h, const int32_t *d_train, int count, int max_te
              "plsb_crossval: bad argument");
   const Layout &l = h->lay;
   const int stride = l.K + round_up(max_test, l.T);
-  PLSB_CHECK(stride <= MAX_K, PLSB_ERR_ARG,
-             "plsb_crossval: K + test rows = %d exceeds the supported %d rows per split "
-             "(use a smaller test_size)", stride, MAX_K);
   cudaStream_t st = as_stream(stream);
   const size_t per = sizeof(double) * ((size_t)stride * l.ldx + (size_t)(l.K + l.J) * l.S_pad +
                                        2 * (size_t)(stride / l.T) * l.ldx);
@@ -1176,9 +1171,6 @@ int plsb_split_half(plsb_handle_t h, const int32_t *d_idx, const double *d_yperm
              "plsb_split_half: only behavioural analyses have a Y matrix to permute");
   const Layout &l = h->lay;
   const int K = l.K, K2 = 2 * K;
-  PLSB_CHECK(K2 <= MAX_K, PLSB_ERR_ARG,
-             "plsb_split_half: 2 K = %d exceeds the supported %d rows per pair of halves", K2,
-             MAX_K);
   cudaStream_t st = as_stream(stream);
   PLSB_CUDA(cudaMemsetAsync(d_ucorr, 0, sizeof(double) * (size_t)count * K, st));
   PLSB_CUDA(cudaMemsetAsync(d_vcorr, 0, sizeof(double) * (size_t)count * K, st));

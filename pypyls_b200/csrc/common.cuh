@@ -165,7 +165,7 @@ struct plsb_ctx {
   plsb::DevBuf Sx;     // Xraw @ normalize(Uo)   (S, L)
   plsb::DevBuf norms;  // (L)
   // per-chunk workspaces
-  plsb::DevBuf A, Ac, R, S1, S2, G, H, M, lam, rowsq, part, misc, idxall, flags, maps, pctl;
+  plsb::DevBuf A, Ac, R, S1, S2, G, H, M, lam, rowsq, part, misc, idxall, flags, maps, pctl, big;
 };
 
 namespace plsb {
@@ -266,6 +266,14 @@ int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int
                      long long uot_stride = 0, int uot_div = 1);
 int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
                    const double *M, int L, double *usum, double *usq, cudaStream_t st);
+
+// generic (any K, L) versions of the two passes above (large_k.cu)
+int launch_gram_proj_generic(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
+                             const double *UoT, int L, double *G, double *H, cudaStream_t st,
+                             long long uot_stride, int uot_div);
+int launch_accum_u_generic(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
+                           const double *M, int ldm, int L, double *usum, double *usq,
+                           cudaStream_t st);
 
 // small matrices (small_matrix.cu)
 // M is written as (count, K, ldm): ldm == L dense, ldm == accum_ldm(L) for launch_accum_u

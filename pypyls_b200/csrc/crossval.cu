@@ -65,21 +65,19 @@ __global__ void rescale_test_kernel(const int32_t *__restrict__ mask, int S, int
   }
 }
 
-// one CTA per split
-__global__ void cv_score_kernel(const int32_t *__restrict__ mask, int S, int T, int J, int K,
-                                int max_test, const int *__restrict__ cell_of_row,
-                                const double *__restrict__ Y, const double *__restrict__ Gz,
-                                int stride, const double *__restrict__ V,
-                                const double *__restrict__ lam,
-                                const double *__restrict__ ytrain, double *__restrict__ r_out,
-                                double *__restrict__ r2_out) {
-  extern __shared__ __align__(16) double sm[];
+// one split; `sm`: work space (shared memory or a global scratch slice)
+__device__ void cv_score_body(int r, double *sm, const int32_t *__restrict__ mask, int S, int T,
+                              int J, int K, int max_test, const int *__restrict__ cell_of_row,
+                              const double *__restrict__ Y, const double *__restrict__ Gz,
+                              int stride, const double *__restrict__ V,
+                              const double *__restrict__ lam, const double *__restrict__ ytrain,
+                              double *__restrict__ r_out, double *__restrict__ r2_out) {
   double *W = sm;                       // K x K: G^-1/2
   double *pred = W + K * K;             // max_test x T
   double *dinv = pred + max_test * T;   // K
   int *rows = reinterpret_cast<int *>(dinv + K);   // max_test
   __shared__ int s_nte;
-  const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
   const double *Vr = V + (size_t)r * K * K, *lr = lam + (size_t)r * K;
   const double *G = Gz + (size_t)r * stride * stride;
 
@@ -89,12 +87,13 @@ __global__ void cv_score_kernel(const int32_t *__restrict__ mask, int S, int T, 
       if (mask[(size_t)r * S + s] == 0 && n < max_test) rows[n++] = s;
     s_nte = n;
   }
-  if (tid < K) {
-    double lmax = 0.0;
-    for (int i = 0; i < K; ++i) lmax = fmax(lmax, lr[i]);
-    const double l = lr[tid];
-    // numerically null directions carry no prediction (cf. rotation_kernel)
-    dinv[tid] = (l > 1e-14 * lmax && l > 0.0) ? rsqrt(sqrt(l)) : 0.0;   // lam^-1/4
+  {
+    const double lmax = lr[0];   // eigenvalues arrive sorted descending
+    for (int i = tid; i < K; i += nt) {
+      const double l = lr[i];
+      // numerically null directions carry no prediction (cf. rotation_kernel)
+      dinv[i] = (l > 1e-14 * lmax && l > 0.0) ? rsqrt(sqrt(l)) : 0.0;   // lam^-1/4
+    }
   }
   __syncthreads();
   const int nte = s_nte;
@@ -141,6 +140,23 @@ __global__ void cv_score_kernel(const int32_t *__restrict__ mask, int S, int T, 
   }
 }
 
+__global__ void cv_score_kernel(const int32_t *__restrict__ mask, int S, int T, int J, int K,
+                                int max_test, const int *__restrict__ cell_of_row,
+                                const double *__restrict__ Y, const double *__restrict__ Gz,
+                                int stride, const double *__restrict__ V,
+                                const double *__restrict__ lam,
+                                const double *__restrict__ ytrain, double *__restrict__ r_out,
+                                double *__restrict__ r2_out, int count, double *gscratch,
+                                size_t gs_stride) {
+  extern __shared__ __align__(16) double sm_dyn[];
+  double *ws = gscratch ? gscratch + (size_t)blockIdx.x * gs_stride : sm_dyn;
+  for (int r = blockIdx.x; r < count; r += gridDim.x) {
+    __syncthreads();
+    cv_score_body(r, ws, mask, S, T, J, K, max_test, cell_of_row, Y, Gz, stride, V, lam, ytrain,
+                  r_out, r2_out);
+  }
+}
+
 }  // namespace
 
 int launch_rescale_test(plsb_ctx *h, const int32_t *mask, int count, int max_test,
@@ -164,11 +180,20 @@ int launch_cv_score(plsb_ctx *h, const int32_t *mask, int count, int max_test, c
   const Layout &l = h->lay;
   const size_t smem = sizeof(double) * ((size_t)l.K * l.K + (size_t)max_test * l.T + l.K) +
                       sizeof(int) * (size_t)max_test + 16;
-  PLSB_CUDA(cudaFuncSetAttribute(cv_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-  cv_score_kernel<<<count, 256, smem, st>>>(mask, l.S, l.T, l.J, l.K, max_test, h->d_cell_of_row,
-                                            h->Y.as<double>(), Gz, stride, V, lam, ytrain, r_out,
-                                            r2_out);
+  if (smem <= 200 * 1024) {
+    PLSB_CUDA(cudaFuncSetAttribute(cv_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    cv_score_kernel<<<count, 256, smem, st>>>(mask, l.S, l.T, l.J, l.K, max_test, h->d_cell_of_row,
+                                              h->Y.as<double>(), Gz, stride, V, lam, ytrain, r_out,
+                                              r2_out, count, nullptr, 0);
+  } else {
+    const size_t gs = (smem + 7) / 8;
+    const int ctas = std::min(count, 2 * h->sm_count);
+    PLSB_TRY(h->big.ensure(sizeof(double) * gs * ctas));
+    cv_score_kernel<<<ctas, 256, 0, st>>>(mask, l.S, l.T, l.J, l.K, max_test, h->d_cell_of_row,
+                                          h->Y.as<double>(), Gz, stride, V, lam, ytrain, r_out,
+                                          r2_out, count, h->big.as<double>(), gs);
+  }
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }

@@ -387,7 +387,10 @@ int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int
                      long long uot_stride, int uot_div) {
   KernelTimer kt(h, KC_GRAM, st);
   if (count <= 0) return PLSB_OK;
-  PLSB_CHECK(K >= 1 && K <= MAX_K, PLSB_ERR_ARG, "gram_proj: K=%d outside [1,%d]", K, MAX_K);
+  PLSB_CHECK(K >= 1, PLSB_ERR_ARG, "gram_proj: K=%d", K);
+  if (K > MAX_K)   // beyond the fragment tables: the generic tiled kernel (columns >= B are zero)
+    return launch_gram_proj_generic(h, R, ldr, count, K, (int)ldr, UoT, L, G, H, st, uot_stride,
+                                    uot_div);
   const bool proj = UoT && H;
   PLSB_CHECK(!proj || cdiv(L, 8) == cdiv(K, 8), PLSB_ERR_ARG,
              "gram_proj: L=%d and K=%d must span the same number of fragments", L, K);

@@ -41,12 +41,11 @@ constexpr int SM_WARPS = SM_THREADS / 32;
 // eigen-decomposition of the symmetric K x K matrices G[r]:
 //   V_out (K,K): eigenvectors in columns, sorted by descending eigenvalue
 //   lam_out (K): eigenvalues sorted descending (sqrt_lam: their square roots)
-__global__ void __launch_bounds__(SM_THREADS)
-eigen_kernel(const double *__restrict__ G, int ldg, long long g_stride, int K, int sqrt_lam,
-             double *__restrict__ V_out, double *__restrict__ lam_out,
-             const int *__restrict__ todo) {
-  extern __shared__ __align__(16) double sm[];
-  if (todo && !todo[blockIdx.x]) return;   // done by the Newton-Schulz fast path
+// `sm`: the CTA's work space -- shared memory, or (matrices too large for it) a slice of
+// a global scratch buffer that stays L2 resident
+__device__ void eigen_body(int r, double *sm, const double *__restrict__ G, int ldg,
+                           long long g_stride, int K, int sqrt_lam, double *__restrict__ V_out,
+                           double *__restrict__ lam_out) {
   const int ne = K + (K & 1), ld = ne | 1, half = ne / 2;
   double *bufA = sm;                 // G -> diag(lam)
   double *bufV = bufA + ne * ld;     // V
@@ -56,7 +55,7 @@ eigen_kernel(const double *__restrict__ G, int ldg, long long g_stride, int K, i
   sc.pq = reinterpret_cast<int *>(sc.cst + 3 * half);  // 2*half
   int *rank = sc.pq + 2 * half;                        // ne
   sc.blk = reinterpret_cast<short2 *>(rank + ne);      // half*(half+1)/2
-  const int r = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const double *Gr = G + (size_t)r * g_stride;
 
   // block table: bi -> (a, b), a <= b
@@ -92,6 +91,19 @@ eigen_kernel(const double *__restrict__ G, int ldg, long long g_stride, int K, i
     }
 }
 
+__global__ void __launch_bounds__(SM_THREADS)
+eigen_kernel(const double *__restrict__ G, int ldg, long long g_stride, int K, int sqrt_lam,
+             double *__restrict__ V_out, double *__restrict__ lam_out,
+             const int *__restrict__ todo, int count, double *gscratch, size_t gs_stride) {
+  extern __shared__ __align__(16) double sm_dyn[];
+  double *ws = gscratch ? gscratch + (size_t)blockIdx.x * gs_stride : sm_dyn;
+  for (int r = blockIdx.x; r < count; r += gridDim.x) {
+    if (todo && !todo[r]) continue;   // done by the Newton-Schulz fast path
+    __syncthreads();                  // the work space of the previous matrix is free
+    eigen_body(r, ws, G, ldg, g_stride, K, sqrt_lam, V_out, lam_out);
+  }
+}
+
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
   asm volatile(
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -120,13 +132,10 @@ __device__ __forceinline__ void small_mm(const double *A, int sam, int sak, cons
 }
 
 // M[r] (K,L) from V[r] (K,K), lam[r] (K) (eigen_kernel's output) and H[r] (K,L)
-__global__ void __launch_bounds__(SM_THREADS)
-rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
-                const double *__restrict__ lam_in, int K, int L,
-                const double *__restrict__ dorig, double *__restrict__ M_out, int ldm,
-                const int *__restrict__ todo) {
-  extern __shared__ __align__(16) double sm[];
-  if (todo && !todo[blockIdx.x]) return;   // done by the Newton-Schulz fast path
+__device__ void rotation_body(int r, double *sm, const double *__restrict__ H,
+                              const double *__restrict__ V_in, const double *__restrict__ lam_in,
+                              int K, int L, const double *__restrict__ dorig,
+                              double *__restrict__ M_out, int ldm) {
   const int LP = (K + 7) & ~7, ld = LP + 4;
   double *Vs = sm;                // V          [LP][ld]
   double *Hs = Vs + LP * ld;      // H, later the second iterate
@@ -134,7 +143,7 @@ rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
   double *Bs = Xs + LP * ld;      // (3 I - X^T X) / 2
   double *dinv = Bs + LP * ld;    // LP
   double *omask = dinv + LP;      // LP: 1 for non-null original latent variables
-  const int r = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
 
   for (int e = tid; e < LP * LP; e += SM_THREADS) {
     const int i = e / LP, j = e - i * LP;
@@ -142,21 +151,24 @@ rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
     Vs[i * ld + j] = in ? V_in[(size_t)r * K * K + (size_t)i * K + j] : 0.0;
     Hs[i * ld + j] = in ? H[(size_t)r * K * L + (size_t)i * L + j] : 0.0;
   }
-  if (tid < LP) {
-    double lmax = 0.0, domax = 0.0;
-    for (int i = 0; i < K; ++i) lmax = fmax(lmax, lam_in[(size_t)r * K + i]);
+  {
+    // eigenvalues arrive sorted descending: lam[0] is the largest
+    const double lmax = lam_in[(size_t)r * K];
+    double domax = 0.0;
     if (dorig)
       for (int i = 0; i < L; ++i) domax = fmax(domax, dorig[i]);
-    double di = 0.0, om = 0.0;
-    if (tid < K) {
-      const double l = lam_in[(size_t)r * K + tid];
-      // d^-1 with a guard for numerically null directions
-      di = (l > 1e-14 * lmax && l > 0.0) ? rsqrt(l) : 0.0;
-      // a numerically null ORIGINAL latent variable has no direction to rotate onto
-      om = (!dorig || dorig[tid] > 1e-10 * domax) ? 1.0 : 0.0;
+    for (int i = tid; i < LP; i += SM_THREADS) {
+      double di = 0.0, om = 0.0;
+      if (i < K) {
+        const double l = lam_in[(size_t)r * K + i];
+        // d^-1 with a guard for numerically null directions
+        di = (l > 1e-14 * lmax && l > 0.0) ? rsqrt(l) : 0.0;
+        // a numerically null ORIGINAL latent variable has no direction to rotate onto
+        om = (!dorig || dorig[i] > 1e-10 * domax) ? 1.0 : 0.0;
+      }
+      dinv[i] = di;
+      omask[i] = om;
     }
-    dinv[tid] = di;
-    omask[tid] = om;
   }
   __syncthreads();
   // temp[i][j] = omask_i * sum_k H[k][i] V[k][j] * dinv_j
@@ -177,8 +189,11 @@ rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
       // |X^T X|_inf bounds sigma_max^2; the iteration needs sigma_max < sqrt(3).
       // (The polar factor does not depend on a positive scale of X.)
       double rs = 0.0;
-      if (tid < LP)
-        for (int j = 0; j < LP; ++j) rs += fabs((tid == j ? 3.0 : 0.0) - 2.0 * Bs[tid * ld + j]);
+      for (int i = tid; i < LP; i += SM_THREADS) {
+        double t = 0.0;
+        for (int j = 0; j < LP; ++j) t += fabs((i == j ? 3.0 : 0.0) - 2.0 * Bs[i * ld + j]);
+        rs = fmax(rs, t);
+      }
       // max over the CTA through an integer OR of the comparison is not enough:
       // reduce the maximum with shuffles + shared memory
       for (int o = 16; o > 0; o >>= 1) rs = fmax(rs, __shfl_xor_sync(0xffffffffu, rs, o));
@@ -217,6 +232,20 @@ rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
   for (int e = tid; e < K * (ldm - L); e += SM_THREADS) {
     const int a = e / (ldm - L), j = L + e - a * (ldm - L);
     M_out[((size_t)r * K + a) * ldm + j] = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(SM_THREADS)
+rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
+                const double *__restrict__ lam_in, int K, int L,
+                const double *__restrict__ dorig, double *__restrict__ M_out, int ldm,
+                const int *__restrict__ todo, int count, double *gscratch, size_t gs_stride) {
+  extern __shared__ __align__(16) double sm_dyn[];
+  double *ws = gscratch ? gscratch + (size_t)blockIdx.x * gs_stride : sm_dyn;
+  for (int r = blockIdx.x; r < count; r += gridDim.x) {
+    if (todo && !todo[r]) continue;   // done by the Newton-Schulz fast path
+    __syncthreads();
+    rotation_body(r, ws, H, V_in, lam_in, K, L, dorig, M_out, ldm);
   }
 }
 
@@ -369,25 +398,37 @@ ns_rotation_kernel(const double *__restrict__ G, const double *__restrict__ H, i
   }
 }
 
+// matrices whose work space exceeds this run out of a global (L2 resident) scratch slice
+// per CTA instead of shared memory: any K, at global-memory speed
+constexpr size_t SMALL_SMEM_MAX = 220 * 1024;
+
 int launch_eigen(plsb_ctx *h, const double *G, int count, int K, int sqrt_lam, double *V,
                  double *lam, cudaStream_t st, int ldg = 0, long long g_stride = 0,
                  const int *todo = nullptr) {
   KernelTimer kt(h, KC_SMALL, st);
   if (count <= 0) return PLSB_OK;
-  PLSB_CHECK(K >= 1 && K <= MAX_K, PLSB_ERR_ARG, "small decomposition: K=%d outside [1,%d]", K,
-             MAX_K);
+  PLSB_CHECK(K >= 1 && K <= 16384, PLSB_ERR_ARG, "small decomposition: K=%d", K);
   const int ne = K + (K & 1), ld = ne | 1, half = ne / 2;
   const int nb = half * (half + 1) / 2;
   const size_t smem = sizeof(double) * (2 * (size_t)ne * ld + ne + 3 * half) +
                       sizeof(int) * (2 * half + ne) + sizeof(short2) * nb + 16;
-  PLSB_CUDA(cudaFuncSetAttribute(eigen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
   // one thread per 2 x 2 block of a Jacobi round (measured: fewer, busier threads lose)
   const int threads = std::min(SM_THREADS, std::max(32, round_up(
       tune_int("PLSB_EIGEN_THREADS", nb), 32)));
   if (ldg <= 0) ldg = K;
   if (g_stride <= 0) g_stride = (long long)K * K;
-  eigen_kernel<<<count, threads, smem, st>>>(G, ldg, g_stride, K, sqrt_lam, V, lam, todo);
+  if (smem <= SMALL_SMEM_MAX) {
+    PLSB_CUDA(cudaFuncSetAttribute(eigen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    eigen_kernel<<<count, threads, smem, st>>>(G, ldg, g_stride, K, sqrt_lam, V, lam, todo, count,
+                                               nullptr, 0);
+  } else {
+    const size_t stride = (smem + 7) / 8;   // doubles
+    const int ctas = std::min(count, 2 * h->sm_count);
+    PLSB_TRY(h->big.ensure(sizeof(double) * stride * ctas));
+    eigen_kernel<<<ctas, threads, 0, st>>>(G, ldg, g_stride, K, sqrt_lam, V, lam, todo, count,
+                                           h->big.as<double>(), stride);
+  }
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
@@ -400,9 +441,18 @@ int launch_rotation(plsb_ctx *h, const double *H, const double *V, const double 
   PLSB_CHECK(L == K, PLSB_ERR_ARG, "small decomposition: L=%d must equal K=%d", L, K);
   const int LP = round_up(K, 8), ld = LP + 4;
   const size_t smem = sizeof(double) * (4 * (size_t)LP * ld + 2 * LP);
-  PLSB_CUDA(cudaFuncSetAttribute(rotation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-  rotation_kernel<<<count, SM_THREADS, smem, st>>>(H, V, lam, K, L, dorig, M, ldm, todo);
+  if (smem <= SMALL_SMEM_MAX) {
+    PLSB_CUDA(cudaFuncSetAttribute(rotation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    rotation_kernel<<<count, SM_THREADS, smem, st>>>(H, V, lam, K, L, dorig, M, ldm, todo, count,
+                                                     nullptr, 0);
+  } else {
+    const size_t stride = smem / 8;
+    const int ctas = std::min(count, 2 * h->sm_count);
+    PLSB_TRY(h->big.ensure(sizeof(double) * stride * ctas));
+    rotation_kernel<<<ctas, SM_THREADS, 0, st>>>(H, V, lam, K, L, dorig, M, ldm, todo, count,
+                                                 h->big.as<double>(), stride);
+  }
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }

@@ -47,13 +47,15 @@ __global__ void projblock_kernel(const double *__restrict__ R, int K, int B, lon
 
 // G, H: (n_perm * ns, 2K, 2K) from gram_proj; V (K,K) eigenvectors in columns and d (K)
 // singular values per permutation (v_stride / d_stride 0: shared by all)
-__global__ void __launch_bounds__(256)
-splithalf_score_kernel(const double *__restrict__ G, const double *__restrict__ H, int K, int B,
-                       int ns, const double *__restrict__ V, long long v_stride,
-                       const double *__restrict__ d, long long d_stride, double inv_nsplit,
-                       double *__restrict__ ucorr, double *__restrict__ vcorr) {
-  extern __shared__ __align__(16) double sm[];
-  const int K2 = 2 * K, tid = threadIdx.x, nt = blockDim.x, p = blockIdx.x;
+// `sm`: the CTA's work space (shared memory, or a slice of a global scratch buffer when
+// 11 K^2 doubles do not fit); thread loops run over the latent variables, so any K works
+__device__ void splithalf_score_body(int p, double *sm, const double *__restrict__ G,
+                                     const double *__restrict__ H, int K, int B, int ns,
+                                     const double *__restrict__ V, long long v_stride,
+                                     const double *__restrict__ d, long long d_stride,
+                                     double inv_nsplit, double *__restrict__ ucorr,
+                                     double *__restrict__ vcorr) {
+  const int K2 = 2 * K, tid = threadIdx.x, nt = blockDim.x;
   double *vd = sm;                    // K*K   V d^-1
   double *w = vd + K * K;             // K*K   V d^-2
   double *Gs = w + K * K;             // K2*K2
@@ -74,7 +76,7 @@ splithalf_score_kernel(const double *__restrict__ G, const double *__restrict__ 
     vd[e] = Vp[e] * di;
     w[e] = Vp[e] * di * di;
   }
-  double acc_u = 0.0, acc_v = 0.0;    // thread j < K owns latent variable j
+  double *uc_all = Q + 3 * (size_t)K * K;   // K: ucorr of the current split
   for (int i = 0; i < ns; ++i) {
     const double *Gp = G + ((size_t)p * ns + i) * K2 * K2;
     const double *Hp = H + ((size_t)p * ns + i) * K2 * K2;
@@ -101,9 +103,7 @@ splithalf_score_kernel(const double *__restrict__ G, const double *__restrict__ 
       Q[2 * K * K + e] = va * p3;
     }
     __syncthreads();
-    double uc = 0.0;
-    if (tid < K) {
-      const int j = tid;
+    for (int j = tid; j < K; j += nt) {
       double q11 = 0.0, q12 = 0.0, q22 = 0.0, s1 = 0.0, s2 = 0.0;
       for (int a = 0; a < K; ++a) {
         q11 += Q[a * K + j];
@@ -113,7 +113,7 @@ splithalf_score_kernel(const double *__restrict__ G, const double *__restrict__ 
         s2 += vd[a * K + j] * Hs[(K + a) * (K + 1) + K];
       }
       const double c11 = q11 - s1 * s1 / B, c22 = q22 - s2 * s2 / B, c12 = q12 - s1 * s2 / B;
-      uc = c12 / sqrt(c11 * c22);
+      uc_all[j] = c12 / sqrt(c11 * c22);
     }
     __syncthreads();
     // b1 = H1 w, b2 = H2 w   (K x K each), stored in Q
@@ -124,8 +124,7 @@ splithalf_score_kernel(const double *__restrict__ G, const double *__restrict__ 
       Q[e] = v;
     }
     __syncthreads();
-    if (tid < K) {
-      const int j = tid;
+    for (int j = tid; j < K; j += nt) {
       double m1 = 0.0, m2 = 0.0;
       for (int a = 0; a < K; ++a) {
         m1 += Q[a * K + j];
@@ -142,14 +141,30 @@ splithalf_score_kernel(const double *__restrict__ G, const double *__restrict__ 
       }
       const bool null_lv = !(dp[j] > 1e-7 * s_dmax && dp[j] > 0.0);
       const double vc = s12 / sqrt(s11 * s22);
-      // compute.efficient_corr clips rounding overshoot (pyls/compute.py:389)
-      acc_u += null_lv ? 0.0 : fmin(1.0, fmax(-1.0, uc));
-      acc_v += null_lv ? 0.0 : fmin(1.0, fmax(-1.0, vc));
+      // compute.efficient_corr clips rounding overshoot (pyls/compute.py:389); splits are
+      // added in order, one owner thread per latent variable: deterministic
+      if (!null_lv) {
+        ucorr[(size_t)p * K + j] += fmin(1.0, fmax(-1.0, uc_all[j])) * inv_nsplit;
+        vcorr[(size_t)p * K + j] += fmin(1.0, fmax(-1.0, vc)) * inv_nsplit;
+      }
     }
   }
-  if (tid < K) {
-    ucorr[(size_t)p * K + tid] += acc_u * inv_nsplit;
-    vcorr[(size_t)p * K + tid] += acc_v * inv_nsplit;
+}
+
+// G, H: (n_perm * ns, 2K, 2K) from gram_proj; V (K,K) eigenvectors in columns and d (K)
+// singular values per permutation (v_stride / d_stride 0: shared by all)
+__global__ void __launch_bounds__(256)
+splithalf_score_kernel(const double *__restrict__ G, const double *__restrict__ H, int K, int B,
+                       int ns, const double *__restrict__ V, long long v_stride,
+                       const double *__restrict__ d, long long d_stride, double inv_nsplit,
+                       double *__restrict__ ucorr, double *__restrict__ vcorr, int n_perm,
+                       double *gscratch, size_t gs_stride) {
+  extern __shared__ __align__(16) double sm_dyn[];
+  double *ws = gscratch ? gscratch + (size_t)blockIdx.x * gs_stride : sm_dyn;
+  for (int p = blockIdx.x; p < n_perm; p += gridDim.x) {
+    __syncthreads();
+    splithalf_score_body(p, ws, G, H, K, B, ns, V, v_stride, d, d_stride, inv_nsplit, ucorr,
+                         vcorr);
   }
 }
 
@@ -174,14 +189,23 @@ int launch_splithalf_score(plsb_ctx *h, const double *G, const double *H, int n_
   if (n_perm <= 0 || ns <= 0) return PLSB_OK;
   const Layout &l = h->lay;
   const int K = l.K, K2 = 2 * K;
-  const size_t smem =
-      sizeof(double) * (2 * (size_t)K * K + (size_t)K2 * K2 + (size_t)K2 * (K + 1) + 3 * (size_t)K * K);
-  PLSB_CHECK(smem <= 200 * 1024, PLSB_ERR_ARG, "split-half scoring needs %zu bytes of shared memory",
-             smem);
-  PLSB_CUDA(cudaFuncSetAttribute(splithalf_score_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  splithalf_score_kernel<<<n_perm, 256, smem, st>>>(G, H, K, l.B, ns, V, v_stride, d, d_stride,
-                                                    1.0 / n_split, ucorr, vcorr);
+  const size_t smem = sizeof(double) * (2 * (size_t)K * K + (size_t)K2 * K2 +
+                                       (size_t)K2 * (K + 1) + 3 * (size_t)K * K + K);
+  if (smem <= 200 * 1024) {
+    PLSB_CUDA(cudaFuncSetAttribute(splithalf_score_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    splithalf_score_kernel<<<n_perm, 256, smem, st>>>(G, H, K, l.B, ns, V, v_stride, d, d_stride,
+                                                      1.0 / n_split, ucorr, vcorr, n_perm,
+                                                      nullptr, 0);
+  } else {
+    // beyond shared memory: a global (L2 resident) work space per CTA
+    const size_t stride = smem / sizeof(double);
+    const int ctas = std::min(n_perm, 2 * h->sm_count);
+    PLSB_TRY(h->big.ensure(sizeof(double) * stride * ctas));
+    splithalf_score_kernel<<<ctas, 256, 0, st>>>(G, H, K, l.B, ns, V, v_stride, d, d_stride,
+                                                 1.0 / n_split, ucorr, vcorr, n_perm,
+                                                 h->big.as<double>(), stride);
+  }
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }

@@ -117,7 +117,10 @@ def behavioral_pls(X, Y, *, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
     Differences from the reference front-end: ``test_split`` defaults to 0
     (the reference's default is 100; pass it to get ``cvres``) and ``n_proc``
     is accepted but unused (resamples run as one batched launch).  ``n_split``
-    runs the split-half resampling on the device (needs 2 K <= 80).
+    runs the split-half resampling on the device.  Analyses with more than 80
+    latent variables (K = cells x behaviours), more than 80 rows per pair of
+    split halves or per stacked train / test split run through generic
+    (slower) kernels; K must not exceed the number of features.
     Extra keywords: ``index_backend``, ``device``, ``workspace_bytes``.
 
     Returns

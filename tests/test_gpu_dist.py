@@ -50,9 +50,23 @@ def _worker(rank, world, port, out_dir):
     kwm = {k: v for k, v in kw.items() if k != 'n_split'}
     outm = pyls.meancentered_pls(X, verbose=False, device=rank,
                                  mean_centering=0, **kwm)
+    # per-resample arrays on the host of rank 0 only; the statistics (p-values,
+    # intervals from the series-sharded percentile exchange) everywhere
+    outr = pyls.behavioral_pls(X, Y, index_backend='reference', verbose=False,
+                               device=rank, gather_results='root',
+                               **{k: v for k, v in kw.items()
+                                  if k != 'n_split'})
+    assert (outr.bootres.y_loadings_boot is None) == (rank != 0)
+    if rank == 0:
+        assert np.array_equal(outr.bootres.y_loadings_boot,
+                              out.bootres.y_loadings_boot)
+    assert np.array_equal(outr.bootres.y_loadings_ci,
+                          out.bootres.y_loadings_ci)
+    assert np.array_equal(outr.permres.pvals, out.permres.pvals)
     np.savez(os.path.join(out_dir, 'rank%d.npz' % rank),
              perm=out.permres.perm_singval, pvals=out.permres.pvals,
              boot=out.bootres.y_loadings_boot, bsr=out.bootres.x_weights_normed,
+             ci=out.bootres.y_loadings_ci, mci=outm.bootres.contrast_ci,
              ucorr_pvals=out.splitres.ucorr_pvals,
              ucorr_uplim=out.splitres.ucorr_uplim,
              mperm=outm.permres.perm_singval, mboot=outm.bootres.contrast_boot,
@@ -81,6 +95,12 @@ def test_two_gpu_front_end_matches_oracle(tmp_path):
                                    atol=1e-11)
         np.testing.assert_allclose(z['bsr'], ref['x_weights_normed'],
                                    rtol=1e-6)
+        # percentile limits: every rank selected its share of the series
+        np.testing.assert_allclose(z['ci'], ref['distrib_ci'], rtol=1e-8,
+                                   atol=1e-11)
+        np.testing.assert_allclose(z['mci'][:, keep],
+                                   refm['distrib_ci'][:, keep], rtol=1e-8,
+                                   atol=1e-11)
         assert np.array_equal(z['ucorr_pvals'], ref['ucorr_pvals'])
         np.testing.assert_allclose(z['ucorr_uplim'], ref['ucorr_uplim'],
                                    rtol=0, atol=1e-7)

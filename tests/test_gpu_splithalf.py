@@ -65,6 +65,7 @@ def test_split_half_matches_reference_golden(name):
     ([15], 1, 6, True),
     ([9, 11, 8], 2, 2, False),
     ([12], 3, 1, False),
+    ([25, 25], 1, 50, False),       # K = 100: generic passes, global work space
 ])
 def test_split_half_behavioral_matches_oracle(groups, n_cond, T, cov):
     """Engine level: permutations given as an index table, masks from the
