@@ -464,7 +464,8 @@ def parity_vs_reference(pyls, w, X, Y, ref_file, device):
                         seed=1234, verbose=False, device=device,
                         permsamples=ref['permsamples'],
                         bootsamples=ref['bootsamples'])
-    sv_ref = np.asarray(ref['singvals'])
+    sv_key = 'singvals' if 'singvals' in ref else 'varexp'   # regression: pctvar
+    sv_ref = np.asarray(ref[sv_key])
     sv_ref = np.diag(sv_ref) if sv_ref.ndim == 2 else sv_ref
     live = sv_ref > 1e-10 * sv_ref.max()      # numerically null LVs: noise
     boot_key = 'contrast_boot' if w['kind'] == 'meancentered' \
@@ -472,7 +473,7 @@ def parity_vs_reference(pyls, w, X, Y, ref_file, device):
     ci_key = 'contrast_ci' if w['kind'] == 'meancentered' else 'y_loadings_ci'
     res = {
         'n_perm': n, 'n_boot': n,
-        'singvals_max_rel': _rel(out.singvals[live], sv_ref[live]),
+        'singvals_max_rel': _rel(np.asarray(out[sv_key])[live], sv_ref[live]),
         'perm_singval_max_rel': _rel(out.permres.perm_singval[live],
                                      ref['perm_singval'][live]),
         'pvals_max_abs_diff': float(np.max(np.abs(

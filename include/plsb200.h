@@ -306,9 +306,23 @@ int plsb_split_half(plsb_handle_t h, const int32_t *d_idx, const double *d_yperm
  *   (regression.py:279-327): X and Y rows follow d_idx; x_weights are sign
  *   aligned with the original (efficient_corr, :317-320) and ACCUMULATED into
  *   d_usum / d_usquare (B,L); d_distrib (count,T,L) = Yi^T (Xi x_weights)
- *   (:323-325); d_pctvar (count,L). */
+ *   (:323-325); d_pctvar (count,L).
+ * plsb_simpls_run_boots_yres: the same for a three-dimensional Y (S,T,C): the
+ *   reference aggregates a bootstrap sample of the third axis into a fresh (S,T)
+ *   behaviour matrix for every bootstrap (`aggfunc(Y[..., cboot], axis=-1)`,
+ *   regression.py:207-235, 308-310); d_yres (count,S,T) holds those matrices
+ *   (uncentred, as the reference uses them) and resample r draws its rows from
+ *   d_yres[r] through d_idx[r]. */
 int plsb_simpls_set_original(plsb_handle_t h, const double *d_xweights,
                              void *stream);
+/* The (T, 11) Gaussian test matrices of resamples [first, first + count) on the
+ * device: table i is RandomState(i).normal(size=(T, 11)) of NumPy's legacy
+ * generator (what compute.svd(..., seed=i) makes sklearn's randomized_svd draw,
+ * pyls/types/regression.py:103, pyls/base.py:646-648, 502-507), replayed by an
+ * MT19937 + polar-method kernel -- so that only the seed crosses PCIe.
+ * d_omega (count, T, 11). */
+int plsb_gen_gaussian_tables(plsb_handle_t h, int64_t first, int count, int T,
+                             double *d_omega, void *stream);
 /* Rows the reference's get_mask drops (pyls/types/regression.py:48-53: a row of X or
  * of Y that is all NaN): d_valid_x, d_valid_y (S) int32, 0 = that row of X / of Y is
  * missing; both NULL clears the masks.  Upload X / Y with those rows zero-filled.  Every
@@ -326,6 +340,10 @@ int plsb_simpls_run_boots(plsb_handle_t h, const int32_t *d_idx, int count,
                           const double *d_omega, double *d_pctvar,
                           double *d_distrib, double *d_usum, double *d_usquare,
                           void *stream);
+int plsb_simpls_run_boots_yres(plsb_handle_t h, const int32_t *d_idx, int count,
+                               const double *d_omega, const double *d_yres,
+                               double *d_pctvar, double *d_distrib,
+                               double *d_usum, double *d_usquare, void *stream);
 
 /* Counters for bench / tests: kernels launched by this handle so far. */
 int64_t plsb_launch_count(plsb_handle_t h);

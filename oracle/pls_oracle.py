@@ -882,12 +882,22 @@ def meancentered_pls(X, groups=None, n_cond=1, mean_centering=0, n_perm=5000,
     return res
 
 
+AGGFUNCS = dict(mean=np.mean, median=np.median, sum=np.sum)
+
+
 def pls_regression(X, Y, n_components=None, n_perm=5000, n_boot=5000,
                    rotate=True, ci=95, permsamples=None, bootsamples=None,
-                   seed=None):
-    """pyls.pls_regression for 2-D Y.  Follows
-    pyls/types/regression.py:190-246 and :375-428.  Unlike the reference the
-    caller's arrays are not centred in place (the oracle works on copies)."""
+                   seed=None, aggfunc='mean'):
+    """pyls.pls_regression.  Follows pyls/types/regression.py:190-246 and
+    :375-428.  Unlike the reference the caller's arrays are not centred in
+    place (the oracle works on copies).
+
+    Three-dimensional Y (S, T, C) (regression.py:207-235, 308-310, 391-399):
+    the decomposition and the permutations run on ``aggfunc(Y, axis=-1)``;
+    bootstrap i draws rows ``s[:, i]`` AND a bootstrap sample ``c[:, i]`` of
+    the third axis, aggregating a fresh, un-centred behaviour matrix
+    ``aggfunc(Y[..., c[:, i]], axis=-1)[s[:, i]]``.  `bootsamples` is then the
+    pair of tables ``(s (S, n_boot), c (C, n_boot))``."""
     X, Y = np.array(X, dtype=float), np.array(Y, dtype=float)
     max_comp = min(len(X) - 1, X.shape[1])
     n_components = max_comp if n_components is None else int(n_components)
@@ -898,6 +908,13 @@ def pls_regression(X, Y, n_components=None, n_perm=5000, n_boot=5000,
     spec = _Spec('regression', groups, 1, rotate=rotate,
                  n_components=n_components)
     rs = check_random_state(seed)
+    Y3 = None
+    if Y.ndim == 3:
+        agg = AGGFUNCS.get(aggfunc, aggfunc)
+        Y3, Y = Y, agg(Y, axis=-1)
+        if n_boot > 0 and bootsamples is None:
+            bootsamples = (gen_bootsamp([Y3.shape[0]], 1, n_boot, seed=seed),
+                           gen_bootsamp([Y3.shape[-1]], 1, n_boot, seed=seed))
     X -= np.nanmean(X, axis=0, keepdims=True)
     Y -= np.nanmean(Y, axis=0, keepdims=True)
     mask = get_mask(X, Y)
@@ -916,7 +933,20 @@ def pls_regression(X, Y, n_components=None, n_perm=5000, n_boot=5000,
     res['y_scores'] = np.full((len(Y), n_components), np.nan)
     res['y_scores'][mask] = resid_yscores(res['x_scores'][mask],
                                           Y[mask] @ res['y_loadings'])
-    if n_boot > 0:
+    if n_boot > 0 and Y3 is not None:
+        srows, third = bootsamples
+        u_sum, u_square, distrib = np.zeros_like(W), np.zeros_like(W), []
+        for i in range(n_boot):
+            # regression.py:308-310: the aggregated matrix is used as it is
+            Yi = agg(Y3[..., third[:, i]], axis=-1)
+            d, u = _regression_single_boot(spec, X, Yi, srows[:, i], W, i)
+            u_sum += u
+            u_square += u ** 2
+            distrib.append(d)
+        res['bootsamples'] = bootsamples
+        _finish_boot(res, W, np.stack(distrib, axis=-1), u_sum, u_square,
+                     n_boot + 1, ci, add_orig=True)
+    elif n_boot > 0:
         if bootsamples is None:
             bootsamples = gen_bootsamp(groups, 1, n_boot, seed=rs)
         distrib, u_sum, u_square = run_boots(spec, X, Y, bootsamples, W)

@@ -125,7 +125,7 @@ def call(pyls, w, X, Y, n_each, n_proc, seed, **extra):
 
 def flatten(res):
     out = {}
-    for k in ('x_weights', 'y_weights', 'singvals'):
+    for k in ('x_weights', 'y_weights', 'singvals', 'varexp'):
         v = res.get(k)
         if isinstance(v, np.ndarray):
             out[k] = v

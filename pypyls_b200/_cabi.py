@@ -64,6 +64,8 @@ PROTOTYPES = {
     'plsb_simpls_decompose': (_i, [_vp, _vp, _vp, _vp, _vp]),
     'plsb_simpls_run_perms': (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     'plsb_simpls_run_boots': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'plsb_simpls_run_boots_yres': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'plsb_gen_gaussian_tables': (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     'plsb_launch_count': (_i64, [_vp]),
 }
 

@@ -32,22 +32,22 @@ def _device_seed(rs):
 
 class _DeviceTable:
     """A device-generated resampling table, (n, S) int32, on its way to the
-    host.  ``start()`` queues the copy (side stream) behind the kernels already
-    queued; ``get()`` waits for that copy only and gives the (S, n) int array
-    the reference keeps."""
+    host.  The copy (side stream) is queued as soon as the table exists --
+    transposed and widened on the device to the (S, n) int64 array the
+    reference keeps, so the host does no conversion -- and ``get()`` waits for
+    that copy only."""
 
     def __init__(self, full):
-        self.dev, self.dl, self.arr = full, None, None
+        self.dl = Download(full.t().contiguous().to(torch.int64))
+        self.arr = None
 
     def start(self):
-        self.dl = Download(self.dev)
+        """Kept for callers that used to trigger the copy themselves."""
 
     def get(self):
         if self.arr is None:
-            if self.dl is None:
-                self.start()
-            self.arr = self.dl.get().T.astype(int)
-            self.dev = self.dl = None
+            self.arr = self.dl.get()
+            self.dl = None
         return self.arr
 
 

@@ -522,6 +522,13 @@ int plsb_gen_split_masks(plsb_handle_t h, uint64_t seed, int64_t first, int coun
                          as_stream(stream));
 }
 
+int plsb_gen_gaussian_tables(plsb_handle_t h, int64_t first, int count, int T, double *d_omega,
+                             void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(d_omega && T >= 1, PLSB_ERR_ARG, "plsb_gen_gaussian_tables: bad argument");
+  return gen_gaussian_tables(h, first, count, T * 11, d_omega, as_stream(stream));
+}
+
 int plsb_crosscov(plsb_handle_t h, const int32_t *d_idx, int count, int bootstrap, double *d_R,
                   void *stream) {
   PLSB_HANDLE(h);
@@ -931,25 +938,21 @@ int plsb_simpls_run_perms(plsb_handle_t h, const int32_t *d_idx, int count, cons
   return PLSB_OK;
 }
 
-int plsb_simpls_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, const double *d_omega,
-                          double *d_pctvar, double *d_distrib, double *d_usum, double *d_usquare,
-                          void *stream) {
-  PLSB_HANDLE(h);
-  PLSB_CHECK(h->has_data && h->has_original && h->lay.simpls(), PLSB_ERR_STATE,
-             "plsb_simpls_run_boots needs a SIMPLS handle with data and the original weights");
-  PLSB_CHECK(d_idx && d_pctvar && d_distrib && d_usum && d_usquare && count >= 0, PLSB_ERR_ARG,
-             "plsb_simpls_run_boots: bad argument");
+static int simpls_boots_impl(plsb_ctx *h, const int32_t *d_idx, int count, const double *d_omega,
+                             const double *d_yres, double *d_pctvar, double *d_distrib,
+                             double *d_usum, double *d_usquare, cudaStream_t st) {
   const Layout &l = h->lay;
-  cudaStream_t st = as_stream(stream);
   const int chunk = simpls_chunk(h, count, true);
   const long long om = (long long)l.T * 11;
+  const size_t ystride = (size_t)l.S * l.T;
   for (int off = 0; off < count; off += chunk) {
     const int n = std::min(chunk, count - off);
     const long long M_pad = round_up_ll((long long)n * l.L, GEMM_BM);
     PLSB_TRY(h->A.ensure(sizeof(double) * (size_t)M_pad * l.S_pad));
     PLSB_TRY(launch_simpls(h, d_idx + (size_t)off * l.S, n, 1, 1,
                            d_omega ? d_omega + (size_t)off * om : nullptr, om, 0,
-                           d_pctvar + (size_t)off * l.L, d_distrib + (size_t)off * l.T * l.L, st));
+                           d_pctvar + (size_t)off * l.L, d_distrib + (size_t)off * l.T * l.L, st,
+                           d_yres ? d_yres + (size_t)off * ystride : nullptr));
     PLSB_TRY(simpls_weights_gemm(h, n, st));
     // u_sum += x_weights_r, u_square += x_weights_r^2 (pyls/base.py:510-511): the shared
     // accumulation kernel with identity rotations
@@ -959,6 +962,34 @@ int plsb_simpls_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, cons
                             d_usum, d_usquare, st));
   }
   return PLSB_OK;
+}
+
+int plsb_simpls_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, const double *d_omega,
+                          double *d_pctvar, double *d_distrib, double *d_usum, double *d_usquare,
+                          void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->has_original && h->lay.simpls(), PLSB_ERR_STATE,
+             "plsb_simpls_run_boots needs a SIMPLS handle with data and the original weights");
+  PLSB_CHECK(d_idx && d_pctvar && d_distrib && d_usum && d_usquare && count >= 0, PLSB_ERR_ARG,
+             "plsb_simpls_run_boots: bad argument");
+  return simpls_boots_impl(h, d_idx, count, d_omega, nullptr, d_pctvar, d_distrib, d_usum,
+                           d_usquare, as_stream(stream));
+}
+
+int plsb_simpls_run_boots_yres(plsb_handle_t h, const int32_t *d_idx, int count,
+                               const double *d_omega, const double *d_yres, double *d_pctvar,
+                               double *d_distrib, double *d_usum, double *d_usquare,
+                               void *stream) {
+  PLSB_HANDLE(h);
+  PLSB_CHECK(h->has_data && h->has_original && h->lay.simpls(), PLSB_ERR_STATE,
+             "plsb_simpls_run_boots_yres needs a SIMPLS handle with data and the original "
+             "weights");
+  PLSB_CHECK(d_idx && d_yres && d_pctvar && d_distrib && d_usum && d_usquare && count >= 0,
+             PLSB_ERR_ARG, "plsb_simpls_run_boots_yres: bad argument");
+  PLSB_CHECK(!h->has_rowmask, PLSB_ERR_ARG,
+             "plsb_simpls_run_boots_yres: missing rows are not supported with per-resample Y");
+  return simpls_boots_impl(h, d_idx, count, d_omega, d_yres, d_pctvar, d_distrib, d_usum,
+                           d_usquare, as_stream(stream));
 }
 
 int plsb_small_decomp(plsb_handle_t h, const double *d_G, const double *d_H, int count, int K,

@@ -286,7 +286,7 @@ int launch_sym_eig(plsb_ctx *h, const double *G, int count, int K, double *V, do
 // SIMPLS (simpls.cu)
 int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit_ops,
                   const double *omega, long long om_stride_r, long long om_stride_c, double *pct,
-                  double *distrib, cudaStream_t st);
+                  double *distrib, cudaStream_t st, const double *yres = nullptr);
 int launch_transpose(plsb_ctx *h, const double *in, int rows, int cols, int ld_in, double *out,
                      cudaStream_t st);
 // out (cols, ld_out) = in (rows, cols)^T, columns >= rows of out zeroed
@@ -315,6 +315,8 @@ int launch_splithalf_score(plsb_ctx *h, const double *G, const double *H, int n_
 // index generation (indexgen.cu), statistics (stats.cu)
 int gen_indices(plsb_ctx *h, bool boot, uint64_t seed, int64_t first, int count, int32_t *d_idx,
                 int *h_n_exhausted, cudaStream_t st);
+int gen_gaussian_tables(plsb_ctx *h, int64_t first, int count, int per, double *d_out,
+                        cudaStream_t st);
 int gen_split_masks(plsb_ctx *h, uint64_t seed, int64_t first, int count, int n_split, double frac,
                     int32_t *d_masks, int *h_n_exhausted, cudaStream_t st);
 int launch_pvals(plsb_ctx *h, const double *dperm, int count, int L, const double *dorig,

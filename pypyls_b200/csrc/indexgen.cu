@@ -288,6 +288,81 @@ gen_splits_kernel(uint64_t seed, long long first, int n_split, double frac, int 
   }
 }
 
+// ---- Gaussian test matrices of the randomized range finder ---------------------------
+// SIMPLS resample i takes its (T, 11) test matrix from RandomState(i).normal(size=(T, 11))
+// (compute.svd(Cov, n_components=1, seed=i), pyls/types/regression.py:103 ->
+// sklearn randomized_svd): NumPy's legacy stream, i.e. MT19937 seeded by init_genrand(i),
+// 53-bit doubles from two outputs, and the Marsaglia polar method with its cached second
+// deviate.  One thread replays one stream (624 words of state in local memory): the
+// uniforms are bit-exact, the deviates equal NumPy's up to the last bit of log / sqrt.
+struct MT19937 {
+  uint32_t key[624];
+  int pos;
+  __device__ void seed(uint32_t s) {
+    for (int i = 0; i < 624; ++i) {
+      key[i] = s;
+      s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+    }
+    pos = 624;
+  }
+  __device__ void twist() {
+    const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MAT = 0x9908b0dfu;
+    int i = 0;
+    for (; i < 624 - 397; ++i) {
+      const uint32_t y = (key[i] & UPPER) | (key[i + 1] & LOWER);
+      key[i] = key[i + 397] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
+    }
+    for (; i < 623; ++i) {
+      const uint32_t y = (key[i] & UPPER) | (key[i + 1] & LOWER);
+      key[i] = key[i + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
+    }
+    const uint32_t y = (key[623] & UPPER) | (key[0] & LOWER);
+    key[623] = key[396] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
+    pos = 0;
+  }
+  __device__ uint32_t next() {
+    if (pos == 624) twist();
+    uint32_t y = key[pos++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+  __device__ double next_double() {
+    const uint32_t a = next() >> 5, b = next() >> 6;
+    return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+  }
+};
+
+__global__ void __launch_bounds__(64)
+gaussian_tables_kernel(long long first, int count, int per, double *__restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= count) return;
+  MT19937 mt;
+  mt.seed((uint32_t)(first + r));
+  double *o = out + (size_t)r * per;
+  bool has = false;
+  double cached = 0.0;
+  for (int e = 0; e < per; ++e) {
+    if (has) {
+      o[e] = cached;
+      has = false;
+      continue;
+    }
+    double x1, x2, r2;
+    do {
+      x1 = __dsub_rn(__dmul_rn(2.0, mt.next_double()), 1.0);
+      x2 = __dsub_rn(__dmul_rn(2.0, mt.next_double()), 1.0);
+      r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+    } while (r2 >= 1.0 || r2 == 0.0);
+    const double f = sqrt(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
+    cached = __dmul_rn(f, x1);
+    has = true;
+    o[e] = __dmul_rn(f, x2);
+  }
+}
+
 __global__ void fill_int_kernel(int *p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -388,6 +463,17 @@ int gen_indices(plsb_ctx *h, bool boot, uint64_t seed, int64_t first, int count,
   PLSB_CUDA(cudaMemcpyAsync(d_idx, h->idxall.as<int32_t>() + (size_t)first * l.S,
                             sizeof(int32_t) * (size_t)count * l.S, cudaMemcpyDeviceToDevice, st));
   PLSB_CUDA(cudaStreamSynchronize(st));
+  return PLSB_OK;
+}
+
+int gen_gaussian_tables(plsb_ctx *h, int64_t first, int count, int per, double *d_out,
+                        cudaStream_t st) {
+  KernelTimer kt(h, KC_INDEX, st);
+  PLSB_CHECK(first >= 0 && count >= 0 && first + count <= 0xffffffffll && per >= 1, PLSB_ERR_ARG,
+             "Gaussian tables: seeds must lie in [0, 2^32)");
+  if (count == 0) return PLSB_OK;
+  gaussian_tables_kernel<<<cdiv(count, 64), 64, 0, st>>>(first, count, per, d_out);
+  PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
 

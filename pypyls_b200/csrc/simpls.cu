@@ -35,6 +35,7 @@ constexpr int SP_PROBES = 11;   // n_components (1) + n_oversamples (10) of rand
 struct SimplsParams {
   int S, T, L, p, n_iter, boot, emit_ops, lda;
   const double *Kraw, *Yc, *omega, *So;
+  const double *Yres;     // optional (n, S, T): resample r draws its rows from Yres[r] instead of Yc
   const int32_t *idx;
   const int32_t *valid;   // optional (2, S): row 0 = rows of X, row 1 = rows of Y; 0 = missing (all NaN)
   long long om_stride_r, om_stride_c;
@@ -233,6 +234,8 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
   sc.blk = reinterpret_cast<short2 *>(piy + Sf);                // halfz*(halfz+1)/2
   __shared__ int s_rows;
 
+  // behaviour matrix this resample draws its rows from (3-D Y: aggregated per bootstrap)
+  const double *Yr = p.Yres ? p.Yres + (size_t)r * Sf * T : p.Yc;
   double *Wc = p.Wcoef + (size_t)r * Sf * L;
   double *Bs = p.Bs + (size_t)r * Sf * L;
   double *Gs = p.Gs + (size_t)r * Sf * L;
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
   // A = Y0 = Yp - column means;  ysum = column sums of Yp
   for (int e = tid; e < S * T; e += SP_THREADS) {
     const int i = e / T, t = e - i * T;
-    A[e] = p.Yc[(size_t)piy[i] * T + t];
+    A[e] = Yr[(size_t)piy[i] * T + t];
   }
   __syncthreads();
   for (int t = warp; t < T; t += SP_WARPS) {
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
     // pctvar in Y:  q = Yp^T t  (t is centred, so Y0^T t = Yp^T t)
     for (int t = warp; t < T; t += SP_WARPS) {
       double v = 0.0;
-      for (int i = lane; i < S; i += 32) v += p.Yc[(size_t)piy[i] * T + t] * tv[i];
+      for (int i = lane; i < S; i += 32) v += Yr[(size_t)piy[i] * T + t] * tv[i];
       v = warp_sum(v);
       if (lane == 0) qv[t] = v;
     }
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_MIN_CTAS) simpls_kernel(SimplsP
     const int t = o / L, k = o - t * L;
     double v = 0.0;
     for (int i = lane; i < S; i += 32)
-      v += p.Yc[(size_t)piy[i] * T + t] * Tm[(size_t)i * L + k];
+      v += Yr[(size_t)piy[i] * T + t] * Tm[(size_t)i * L + k];
     v = warp_sum(v);
     if (lane == 0)
       p.distrib[(size_t)r * T * L + o] = flip[k] * (v + ysum[t] * flip[L + k]);
@@ -732,7 +735,7 @@ int launch_xweights_flip(plsb_ctx *h, const double *Rw, long long ldr, int B, in
 // in h->A when emit_ops.
 int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit_ops,
                   const double *omega, long long om_stride_r, long long om_stride_c, double *pct,
-                  double *distrib, cudaStream_t st) {
+                  double *distrib, cudaStream_t st, const double *yres) {
   KernelTimer kt(h, KC_SMALL, st);
   const Layout &l = h->lay;
   if (count <= 0) return PLSB_OK;
@@ -754,6 +757,7 @@ int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit
   p.boot = boot; p.emit_ops = emit_ops; p.lda = l.S_pad;
   p.Kraw = h->Cmat.as<double>();
   p.Yc = h->Y.as<double>();
+  p.Yres = yres;
   p.omega = omega; p.om_stride_r = om_stride_r; p.om_stride_c = om_stride_c;
   p.So = h->has_original ? h->Sx.as<double>() : nullptr;
   p.idx = idx;

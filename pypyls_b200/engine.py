@@ -463,6 +463,16 @@ class ResamplingEngine:
                              .format(n, self.T))
         return omega
 
+    def gen_gaussian_tables(self, first, count):
+        """(count, T, 11) Gaussian test matrices of resamples
+        [first, first + count) on the device (NumPy's legacy
+        ``RandomState(i).normal(size=(T, 11))`` replayed per resample)."""
+        out = self._f64(count, self.T, 11)
+        _cabi.check(self._lib.plsb_gen_gaussian_tables(
+            self._h, int(first), int(count), self.T, _ptr(out),
+            self._stream()))
+        return out
+
     def simpls_decompose(self, omega=None):
         """Original SIMPLS decomposition -> (x_weights (B,L), pctvar_y (L,)).
         `omega` (L, T, 11): one Gaussian test matrix per component."""
@@ -505,20 +515,33 @@ class ResamplingEngine:
             self._h, _ptr(idx), n, _ptr(omega), _ptr(out), self._stream()))
         return out
 
-    def simpls_run_boots(self, idx, omega=None):
+    def simpls_run_boots(self, idx, omega=None, yres=None, u_sum=None,
+                         u_square=None):
         """(distrib (count,T,L), u_sum (B,L), u_square (B,L), pctvar
-        (count,L)) of the bootstraps, on the device."""
+        (count,L)) of the bootstraps, on the device.  `yres` (count, S, T):
+        a behaviour matrix of its own for every bootstrap (three-dimensional Y
+        aggregated per bootstrap, pyls/types/regression.py:308-310)."""
         idx = self.to_device_indices(idx)
         n = int(idx.shape[0])
         omega = self._omega(omega, n)
         pct = self._f64(n, self.L)
         distrib = self._f64(n, self.T, self.L)
-        u_sum = torch.zeros((self.B, self.L), dtype=torch.float64,
-                            device=self.device)
-        u_square = torch.zeros_like(u_sum)
-        _cabi.check(self._lib.plsb_simpls_run_boots(
-            self._h, _ptr(idx), n, _ptr(omega), _ptr(pct), _ptr(distrib),
-            _ptr(u_sum), _ptr(u_square), self._stream()))
+        if u_sum is None:
+            u_sum = torch.zeros((self.B, self.L), dtype=torch.float64,
+                                device=self.device)
+            u_square = torch.zeros_like(u_sum)
+        if yres is None:
+            _cabi.check(self._lib.plsb_simpls_run_boots(
+                self._h, _ptr(idx), n, _ptr(omega), _ptr(pct), _ptr(distrib),
+                _ptr(u_sum), _ptr(u_square), self._stream()))
+        else:
+            yres = self.to_device(yres)
+            if tuple(yres.shape) != (n, self.S, self.T):
+                raise ValueError('per-bootstrap Y must have shape ({}, {}, {})'
+                                 .format(n, self.S, self.T))
+            _cabi.check(self._lib.plsb_simpls_run_boots_yres(
+                self._h, _ptr(idx), n, _ptr(omega), _ptr(yres), _ptr(pct),
+                _ptr(distrib), _ptr(u_sum), _ptr(u_square), self._stream()))
         return distrib, u_sum, u_square, pct
 
     # -- statistics -----------------------------------------------------------

@@ -251,6 +251,33 @@ def regression_missing_rows_case():
     save('plsr_missing_rows', dict(X=X, Y=Y, **kw), flat(r, 'r'))
 
 
+def regression_3d_cases():
+    """Three-dimensional Y (S, T, C) with `aggfunc` (pyls/types/regression.py:
+    207-235, 308-310): every bootstrap aggregates a bootstrap sample of the
+    third axis into its own behaviour matrix.  The reference's own table
+    generation for this case does not run under NumPy 2 (inhomogeneous
+    np.array, regression.py:215), so the (2, n_boot) object table is built
+    here from its two gen_bootsamp draws and handed in, which is the
+    reference's documented alternative (regression.py:217-228)."""
+    rs = np.random.RandomState(77)
+    S, B, T, C, n_boot = 40, 120, 5, 6, 12
+    X, Y = rs.rand(S, B), rs.rand(S, T, C)
+    s = pyls.base.gen_bootsamp([S], 1, n_boot, seed=5, verbose=False)
+    c = pyls.base.gen_bootsamp([C], 1, n_boot, seed=6, verbose=False)
+    bs = np.empty((2, n_boot), dtype=object)
+    for i in range(n_boot):
+        bs[0, i], bs[1, i] = s[:, i], c[:, i]
+    for agg in ('mean', 'median'):
+        kw = dict(n_components=4, n_perm=8, n_boot=n_boot, seed=11)
+        r = pyls.pls_regression(X.copy(), Y.copy(), permindices=True,
+                                verbose=False, bootsamples=bs, aggfunc=agg,
+                                **kw)
+        out = flat(r, 'r')
+        out.pop('bootsamples', None)          # object array: kept as two tables
+        save('plsr_3d_' + agg, dict(X=X, Y=Y, boot_rows=s, boot_third=c, **kw),
+             out)
+
+
 def index_cases():
     out = {}
     for n, (groups, n_cond, seed, cnt) in enumerate((
@@ -309,6 +336,9 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['missing']:
         regression_missing_rows_case()
         sys.exit(0)
+    if sys.argv[1:] == ['regression3d']:
+        regression_3d_cases()
+        sys.exit(0)
     behavioral_cases()
     splithalf_cases()
     prepermuted_case()
@@ -316,5 +346,6 @@ if __name__ == '__main__':
     meancentered_cases()
     regression_cases()
     regression_missing_rows_case()
+    regression_3d_cases()
     index_cases()
     matlab_cases()

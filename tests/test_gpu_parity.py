@@ -533,6 +533,43 @@ def test_regression_matches_reference_golden(name):
     close(out.bootres.x_weights_stderr, ref['x_weights_stderr'], rtol=1e-7)
 
 
+@pytest.mark.parametrize('name', ['plsr_3d_mean', 'plsr_3d_median'])
+def test_regression_3d_y_matches_reference_golden(name):
+    """Three-dimensional Y (S, T, C) with aggfunc: every bootstrap aggregates
+    its own sample of the third axis (pyls/types/regression.py:207-235,
+    308-310) -- against vectors made by the reference itself."""
+    import pypyls_b200 as pyls
+    ins, ref = load_golden(name)
+    n_boot = ins['n_boot']
+    table = np.empty((2, n_boot), dtype=object)
+    for i in range(n_boot):
+        table[0, i] = ins['boot_rows'][:, i]
+        table[1, i] = ins['boot_third'][:, i]
+    out = pyls.pls_regression(ins['X'], ins['Y'], index_backend='reference',
+                              verbose=False, n_components=ins['n_components'],
+                              n_perm=ins['n_perm'], n_boot=n_boot,
+                              seed=ins['seed'], aggfunc=name.split('_')[-1],
+                              bootsamples=table)
+    assert np.array_equal(out.permres.permsamples, ref['permsamples'])
+    assert out.bootres.bootsamples.shape == (2, n_boot)
+    for k in ('x_weights', 'x_scores', 'y_scores', 'y_loadings', 'varexp'):
+        close(out[k], ref[k])
+    close(out.permres.perm_singval, ref['perm_singval'])
+    assert np.array_equal(out.permres.pvals, ref['pvals'])
+    close(out.bootres.y_loadings_boot, ref['y_loadings_boot'])
+    close(out.bootres.y_loadings_ci, ref['y_loadings_ci'])
+    close(out.bootres.x_weights_normed, ref['x_weights_normed'], rtol=1e-7)
+    close(out.bootres.x_weights_stderr, ref['x_weights_stderr'], rtol=1e-7)
+    # tables generated by the front-end (the reference's own generation for
+    # this case does not run under NumPy 2): same two gen_bootsamp draws
+    again = pyls.pls_regression(ins['X'], ins['Y'], verbose=False,
+                                n_components=ins['n_components'], n_perm=0,
+                                n_boot=n_boot, seed=5, aggfunc='sum')
+    rows = np.stack(list(again.bootres.bootsamples[0]), axis=-1)
+    assert np.array_equal(rows, po.gen_bootsamp([len(ins['X'])], 1, n_boot,
+                                                seed=5))
+
+
 def test_regression_missing_rows_match_oracle():
     """Rows of X / Y that are missing altogether (get_mask,
     pyls/types/regression.py:48-53) with T > 11 (Gaussian test matrices in use)

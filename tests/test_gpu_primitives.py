@@ -185,6 +185,20 @@ def test_percentile_series_major_and_transpose(torch_cuda):
     assert np.array_equal(hi.cpu().numpy(), want[1])
 
 
+def test_device_gaussian_tables_replay_numpy_legacy_stream(torch_cuda):
+    """Table i = RandomState(i).normal(size=(T, 11)) (what the reference's
+    compute.svd(..., seed=i) makes sklearn draw): the MT19937 uniforms are
+    replayed bit for bit, the polar-method deviates up to the last bit of the
+    device's log / sqrt."""
+    from pypyls_b200.types.regression import gaussian_tables
+    eng = make_engine('regression', 30, 40, 20, [30], n_components=3)
+    for first, count in ((0, 70), (4999, 33), (2 ** 31 + 5, 4)):
+        got = eng.gen_gaussian_tables(first, count).cpu().numpy()
+        want = gaussian_tables(range(first, first + count), 20)
+        np.testing.assert_allclose(got, want, rtol=4e-16, atol=0)
+        assert np.mean(got == want) > 0.9
+
+
 def test_pvals_and_boot_ratio(torch_cuda):
     rs = np.random.RandomState(11)
     eng = make_engine('behavioral', 4, 8, 1, [4])
