@@ -694,8 +694,11 @@ def _perm_operator(spec, Y, perminds):
     S = len(perminds)
     if spec.kind == 'meancentered':
         # R = C X[pi]: scatter the columns of the centring operator through pi
-        C = get_mean_center(np.eye(S), spec.dummy, spec.n_cond,
-                            spec.mean_centering, means=True)
+        C = getattr(spec, '_centring_operator', None)
+        if C is None:
+            C = spec._centring_operator = get_mean_center(
+                np.eye(S), spec.dummy, spec.n_cond, spec.mean_centering,
+                means=True)
         A = np.zeros_like(C)
         np.add.at(A.T, perminds, C.T)
         return A

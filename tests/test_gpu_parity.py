@@ -683,15 +683,17 @@ def test_single_resample_and_ragged_layout():
     close(out.bootres.y_loadings_boot, ref['distrib'])
 
 
-def test_largest_supported_decomposition():
-    """K = 80 latent variables (the documented maximum): 2 cells x T = 40."""
+def test_largest_fragment_table_decomposition():
+    """K = 80 latent variables (the last size the fragment-table kernels are
+    instantiated for; beyond it the generic passes take over): 2 cells x
+    T = 40."""
     import pypyls_b200 as pyls
     rs = np.random.RandomState(6)
     groups, n_cond, T = [50, 50], 1, 40
     X, Y = rs.rand(100, 400), rs.rand(100, T)
     ps = po.gen_permsamp(groups, n_cond, 3, seed=1)
-    bs = po.gen_bootsamp(groups, n_cond, 3, seed=2)
-    kw = dict(groups=groups, n_cond=n_cond, n_perm=3, n_boot=3, seed=3,
+    bs = po.gen_bootsamp(groups, n_cond, 40, seed=2)
+    kw = dict(groups=groups, n_cond=n_cond, n_perm=3, n_boot=40, seed=3,
               permsamples=ps, bootsamples=bs)
     out = pyls.behavioral_pls(X, Y, verbose=False, **kw)
     ref = po.behavioral_pls(X, Y, **kw)
@@ -699,11 +701,12 @@ def test_largest_supported_decomposition():
     close(out.permres.perm_singval, ref['perm_singval'])
     close(out.bootres.y_loadings_boot, ref['distrib'])
     # a bootstrap of 50 subjects has ~32 distinct ones < T = 40: every resampled
-    # cell block is rank deficient, so the ratios follow the null-safe rule
-    # (three bootstraps are too few to compare with the reference's noise)
+    # cell block is rank deficient, so the ratios follow the null-safe rule and
+    # stay within the reference's own noise of the reference (column
+    # correlation >= 0.999; with EVERY resample rank deficient the largest
+    # single deviation measured is 6 % of the largest ratio)
     check_rank_deficient_bsr(out, X, Y, ref['x_weights_normed'],
-                             np.ones(80, dtype=bool), min_corr=-1.0,
-                             max_dev=np.inf)
+                             np.ones(80, dtype=bool), max_dev=0.1)
 
 
 def test_unsupported_shapes_fail_loudly():
