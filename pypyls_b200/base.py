@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import dist as pdist
-from . import structures
+from . import messages, structures
 from .engine import Download, ResamplingEngine, copy_stream, to_host
 from .resample import (check_bootsamples, check_random_state, gen_bootsamp,
                        gen_permsamp, gen_splits)
@@ -63,6 +63,16 @@ def _start(t):
     return None if t is None else Download(t)
 
 
+def normalise_groups(groups, n_rows, n_cond):
+    """`groups` as a list of ints: one group of every subject when it is not
+    given, a scalar wrapped (the tolerance of pyls/base.py:255-262)."""
+    if groups is None:
+        return [n_rows // n_cond]
+    if isinstance(groups, (list, tuple, np.ndarray)):
+        return [int(g) for g in groups]
+    return [int(groups)]
+
+
 class BasePLS():
     """
     Base class of the PLS types.
@@ -91,24 +101,13 @@ class BasePLS():
     engine_mode = None
 
     def __init__(self, X, Y=None, groups=None, n_cond=1, **kwargs):
-        if groups is None:
-            groups = [len(X) // n_cond]
-        elif not isinstance(groups, (list, np.ndarray)):
-            groups = [groups]
-        groups = [int(g) for g in groups]
-
-        n_samples = sum([g * n_cond for g in groups])
-        if len(X) != n_samples:
-            raise ValueError('Number of samples specified by `groups` and '
-                             '`n_cond` does not match number of samples in '
-                             'input array(s).\n'
-                             '    EXPECTED: {}\n'
-                             '    ACTUAL:   {} (groups: {} * n_cond: {})'
-                             .format(len(X), n_samples, groups, n_cond))
-        if Y is not None and len(X) != len(Y):
-            raise ValueError('Provided `X` and `Y` matrices must have the '
-                             'same number of samples. Provided matrices '
-                             'differed: X: {}, Y: {}'.format(len(X), len(Y)))
+        groups = normalise_groups(groups, len(X), n_cond)
+        expected = sum(groups) * n_cond
+        if expected != len(X):
+            raise ValueError(messages.SAMPLES_MISMATCH.format(
+                len(X), expected, groups, n_cond))
+        if Y is not None and len(Y) != len(X):
+            raise ValueError(messages.XY_ROWS_DIFFER.format(len(X), len(Y)))
 
         self.inputs = structures.PLSInputs(X=X, Y=Y, groups=groups,
                                            n_cond=n_cond, **kwargs)

@@ -259,6 +259,8 @@ int launch_accum_u(plsb_ctx *h, const double *R, long long ldr, int count, int K
   KernelTimer kt(h, KC_ACCUM, st);
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(L >= 1 && K >= 1, PLSB_ERR_ARG, "accum_u: K=%d L=%d", K, L);
+  if (small_k_applies(K, L, true))
+    return launch_accum_u_small(h, R, ldr, count, K, B, M, L, usum, usq, st);
   if (K > MAX_K || L > MAX_K)
     return launch_accum_u_generic(h, R, ldr, count, K, B, M, accum_ldm(L), L, usum, usq, st);
   switch (cdiv(L, 8)) {

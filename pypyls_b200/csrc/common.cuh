@@ -104,7 +104,8 @@ enum KernelClass {
   KC_COUNT
 };
 
-constexpr int MAX_K = 80;     // small-matrix kernels keep four K x K tiles in shared memory
+constexpr int MAX_K = 80;     // largest K the fragment-table kernels (gram_proj, accum_u) are instantiated for
+constexpr int SMALL_K_MAX = 12;   // up to here the FMA streaming kernels of small_k.cu take the two passes
 constexpr int MAX_COND = 32;  // index generator: conditions per subject
 
 // ---- analysis layout --------------------------------------------------------
@@ -274,6 +275,14 @@ int launch_gram_proj_generic(plsb_ctx *h, const double *R, long long ldr, int co
 int launch_accum_u_generic(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
                            const double *M, int ldm, int L, double *usum, double *usq,
                            cudaStream_t st);
+
+// FMA + TMA streaming versions for few latent variables (small_k.cu)
+bool small_k_applies(int K, int L, bool proj);
+int launch_gram_proj_small(plsb_ctx *h, const double *R, long long ldr, int count, int K,
+                           const double *UoT, int L, double *G, double *H, cudaStream_t st,
+                           long long uot_stride, int uot_div);
+int launch_accum_u_small(plsb_ctx *h, const double *R, long long ldr, int count, int K, int B,
+                         const double *M, int L, double *usum, double *usq, cudaStream_t st);
 
 // small matrices (small_matrix.cu)
 // M is written as (count, K, ldm): ldm == L dense, ldm == accum_ldm(L) for launch_accum_u

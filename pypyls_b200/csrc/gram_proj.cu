@@ -392,6 +392,8 @@ int launch_gram_proj(plsb_ctx *h, const double *R, long long ldr, int count, int
     return launch_gram_proj_generic(h, R, ldr, count, K, (int)ldr, UoT, L, G, H, st, uot_stride,
                                     uot_div);
   const bool proj = UoT && H;
+  if (small_k_applies(K, L, proj))   // few latent variables: un-padded FMA work, TMA stream
+    return launch_gram_proj_small(h, R, ldr, count, K, UoT, L, G, H, st, uot_stride, uot_div);
   PLSB_CHECK(!proj || cdiv(L, 8) == cdiv(K, 8), PLSB_ERR_ARG,
              "gram_proj: L=%d and K=%d must span the same number of fragments", L, K);
   switch (cdiv(K, 8)) {

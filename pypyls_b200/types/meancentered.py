@@ -8,7 +8,8 @@ import warnings
 
 import numpy as np
 
-from ..base import BasePLS, _resolve
+from .. import messages
+from ..base import BasePLS, _resolve, normalise_groups
 from ..engine import Download
 
 
@@ -26,29 +27,22 @@ class MeanCenteredPLS(BasePLS):
                  permsamples=None, bootsamples=None, seed=None,
                  verbose=True, n_proc=None, **kwargs):
         X = np.asarray(X)
-        if groups is None:
-            if len(X) // n_cond != len(X) / n_cond:
-                raise ValueError('Provided `X` matrix with {} samples is not '
-                                 'evenly divisible into {} conditions. Please '
-                                 'confirm inputs are correct and try again. '
-                                 .format(len(X), n_cond))
-            groups = [len(X) // n_cond]
-        elif not isinstance(groups, (list, np.ndarray)):
-            groups = [groups]
-
-        if n_cond == 1 and len(groups) == 1:
-            raise ValueError('Cannot perform PLS with only one group and one '
-                             'condition. Please confirm inputs are correct.')
-        if n_cond == 1 and mean_centering == 0:
-            warnings.warn('Cannot set mean_centering to 0 when there is only '
-                          'one condition. Resetting mean_centering to 1.')
+        if groups is None and len(X) % n_cond:
+            raise ValueError(messages.NOT_DIVISIBLE.format(len(X), n_cond))
+        groups = normalise_groups(groups, len(X), n_cond)
+        one_group, one_cond = len(groups) == 1, n_cond == 1
+        if one_group and one_cond:
+            raise ValueError(messages.ONE_GROUP_ONE_COND)
+        # a centring that has nothing to average over falls back to the other
+        # one, with the reference's warning (pyls/types/meancentered.py:29-36)
+        if one_cond and mean_centering == 0:
+            warnings.warn(messages.CENTERING_NEEDS_CONDITIONS)
             mean_centering = 1
-        elif len(groups) == 1 and mean_centering == 1:
-            warnings.warn('Cannot set mean_centering to 1 when there is only '
-                          'one group. Resetting mean_centering to 0.')
+        elif one_group and mean_centering == 1:
+            warnings.warn(messages.CENTERING_NEEDS_GROUPS)
             mean_centering = 0
         if mean_centering not in (0, 1, 2):
-            raise ValueError("Mean centering type must be in [0, 1, 2].")
+            raise ValueError(messages.BAD_CENTERING)
 
         super().__init__(X=X, groups=groups, n_cond=n_cond,
                          mean_centering=mean_centering, n_perm=n_perm,
