@@ -304,7 +304,7 @@ xcov_gemm2_kernel(const double *__restrict__ A, int lda, const double *__restric
                   int n_mtiles, int n_ntiles, int nt_per_split, const int4 *__restrict__ kranges,
                   int Kd, int k_valid, double *__restrict__ C, long long ldc,
                   const int *__restrict__ row_map, const double *__restrict__ scale,
-                  int scale_div, long long lds, double *__restrict__ rowsq, int M_pad, int dbg) {
+                  int scale_div, long long lds, double *__restrict__ rowsq, int M_pad) {
   constexpr int TM = 2 * MF * 8;          // rows of the CTA tile
   constexpr int A_STAGE = TM * LDA_S;     // doubles
   constexpr int STAGES = stages_of(MF);
@@ -330,7 +330,6 @@ xcov_gemm2_kernel(const double *__restrict__ A, int lda, const double *__restric
   const int nt0 = split * nt_per_split;
   const int nt1 = min(nt0 + nt_per_split, n_ntiles);
   if (nt0 >= nt1) return;
-
   int kbeg = 0, kend = Kd, vbeg = 0, vend = min(Kd, (k_valid + 3) & ~3);
   if (kranges) {
     int4 kr = kranges[(mtile * TM) / BM];
@@ -538,19 +537,6 @@ xcov_gemm2_kernel(const double *__restrict__ A, int lda, const double *__restric
                 *reinterpret_cast<double2 *>(crow + j * 8) =
                     make_double2(acc[i][j][0] * sc.x, acc[i][j][1] * sc.y);
               }
-            } else if (dbg == 1) {
-              // timing experiment: same store count, every instruction one contiguous 512 B
-              double *base = C + (size_t)(mtile * TM + (warp * MF + i) % TM) * ldc +
-                             (size_t)nt * BN + lane * 2;
-#pragma unroll
-              for (int j = 0; j < NF; ++j)
-                *reinterpret_cast<double2 *>(base + (j & 1) * 64 + (size_t)(j >> 1) * ldc) =
-                    make_double2(acc[i][j][0], acc[i][j][1]);
-            } else if (dbg == 2) {
-              // timing experiment: a quarter of the stores
-              *reinterpret_cast<double2 *>(crow) = make_double2(
-                  acc[i][0][0] + acc[i][1][0] + acc[i][2][0] + acc[i][3][0],
-                  acc[i][0][1] + acc[i][1][1] + acc[i][2][1] + acc[i][3][1]);
             } else {
 #pragma unroll
               for (int j = 0; j < NF; ++j)
@@ -614,7 +600,7 @@ int launch_variant(plsb_ctx *h, const GemmArgs &a, int n_ntiles, int n_splits, c
     kern<<<grid, NTHREADS, smem, st>>>(a.A, a.lda, a.X, a.ldx, n_mtiles, n_ntiles, nt_per_split,
                                        a.kranges, a.Kd, a.k_valid > 0 ? a.k_valid : a.Kd, a.C,
                                        a.ldc, a.row_map, a.scale, a.scale_div, a.lds, a.rowsq,
-                                       a.M_pad, tune_int("PLSB_GEMM_DBG", 0));
+                                       a.M_pad);
   }
   PLSB_LAUNCHED(h);
   return PLSB_OK;
