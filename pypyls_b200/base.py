@@ -160,8 +160,8 @@ class BasePLS():
         (pyls/base.py:362-363 -> pyls/compute.py:44-45) before any resampling
         table is generated; consume the same draws so that
         index_backend='reference' reproduces the reference's tables."""
-        K = self.engine.K
-        self.rs.normal(size=(K, K + 10))
+        L = self.engine.L          # min(K, B): the short side of the matrix
+        self.rs.normal(size=(L, L + 10))
 
     # -- analysis ------------------------------------------------------------
     def run_pls(self, X, Y):

@@ -201,7 +201,7 @@ int plsb_destroy(plsb_handle_t h) {
   DevBuf *bufs[] = {&h->tables, &h->Xraw, &h->Xcell, &h->Xglob, &h->Y,    &h->Cmat,  &h->Uo,
                     &h->Vo,     &h->dorig, &h->Sx,   &h->norms, &h->A,    &h->Ac,    &h->R,
                     &h->S1,     &h->S2,   &h->G,     &h->H,     &h->M,    &h->lam,   &h->rowsq,
-                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx, &h->rowmask, &h->pctl, &h->big};
+                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx, &h->rowmask, &h->pctl, &h->big, &h->VoT};
   for (DevBuf *b : bufs) b->release();
   delete h;
   return PLSB_OK;
@@ -296,10 +296,8 @@ int plsb_configure(plsb_handle_t h, int mode, int S, int B, int T, int n_groups,
     l.T = 1;
     l.K = l.J;
   }
-  l.L = l.K;
-  PLSB_CHECK(l.K <= B, PLSB_ERR_ARG,
-             "plsb_configure: K=%d latent variables exceed the %d features (K <= B required)", l.K,
-             B);
+  // compute.svd keeps min(K, B) latent variables (pyls/compute.py:36-50)
+  l.L = std::min(l.K, B);
   l.S_pad = round_up(S, GEMM_BK);
   l.ldx = round_up(B, GEMM_BN);
 
@@ -444,11 +442,128 @@ int plsb_set_original(plsb_handle_t h, const double *d_U, const double *d_d, con
   // transposed zero-padded copy (L, ldx) for gram_proj's TMA row copies
   PLSB_TRY(h->UoT.ensure(sizeof(double) * (size_t)l.L * l.ldx));
   PLSB_TRY(launch_transpose_pad(h, h->Uo.as<double>(), l.B, l.L, h->UoT.as<double>(), l.ldx, st));
+  if (l.tall()) {
+    // V_orig^T (L, ldk) zero padded: projection block of the feature-side passes
+    const long long ldk = round_up(l.K, GEMM_BN);
+    PLSB_TRY(h->VoT.ensure(sizeof(double) * (size_t)l.L * ldk));
+    PLSB_TRY(launch_transpose_pad(h, h->Vo.as<double>(), l.K, l.L, h->VoT.as<double>(), ldk, st));
+  }
   // Sx = X @ normalize(U_orig)   (pyls/types/behavioral.py:78, meancentered.py:98)
   PLSB_TRY(launch_colnorm(h, h->Uo.as<double>(), l.B, l.L, h->norms.as<double>(), st));
   PLSB_TRY(launch_xproj(h, h->Xraw.as<double>(), l.ldx, l.S, l.B, h->Uo.as<double>(), l.L,
                         h->norms.as<double>(), h->Sx.as<double>(), st));
   h->has_original = true;
+  return PLSB_OK;
+}
+
+// ---- tall analyses (K > B): see tall.cu ---------------------------------------------
+
+// R' = R^T of the n resamples whose cross-covariances sit in h->R: (n * B rows, ldk) in h->S2
+static int tall_transpose(plsb_ctx *h, int n, long long *ldk_out, cudaStream_t st) {
+  const Layout &l = h->lay;
+  const long long ldk = round_up(l.K, GEMM_BN);
+  PLSB_TRY(h->S2.ensure(sizeof(double) * (size_t)n * l.B * ldk));
+  *ldk_out = ldk;
+  return launch_transpose_batch(h, h->R.as<double>(), l.K, l.B, l.ldx, (long long)l.K * l.ldx,
+                                h->S2.as<double>(), ldk, (long long)l.B * ldk, n, st);
+}
+
+static int tall_chunk(const plsb_ctx *h, bool boot, int count) {
+  const Layout &l = h->lay;
+  const size_t ldk = round_up(l.K, GEMM_BN);
+  size_t per = sizeof(double) * ((size_t)l.K * l.ldx + (size_t)l.K * l.S_pad + (size_t)l.B * ldk +
+                                 4 * (size_t)l.B * l.B);
+  if (boot && l.corr()) per += sizeof(double) * (2 * (size_t)l.J * l.ldx + (size_t)l.J * l.S_pad);
+  long long n = (long long)(h->ws_limit / per);
+  n = std::min<long long>(n, ((1ll << 31) - 1024) / std::max(l.K, 1));
+  return (int)std::max<long long>(1, std::min<long long>(n, count));
+}
+
+static int tall_decompose(plsb_ctx *h, double *d_U, double *d_d, double *d_V, cudaStream_t st) {
+  const Layout &l = h->lay;
+  const int Bf = l.B, L = l.L;   // L == Bf
+  PLSB_TRY(crosscov_chunk(h, nullptr, nullptr, 1, false, nullptr, st));
+  long long ldk = 0;
+  PLSB_TRY(tall_transpose(h, 1, &ldk, st));
+  const double *Rt = h->S2.as<double>();
+  const size_t bb = (size_t)Bf * Bf, kl = (size_t)l.K * L;
+  PLSB_TRY(h->G.ensure(sizeof(double) * 2 * bb));
+  PLSB_TRY(h->lam.ensure(sizeof(double) * Bf));
+  PLSB_TRY(h->misc.ensure(sizeof(double) * 2 * kl));
+  double *Gp = h->G.as<double>(), *W = Gp + bb, *lam = h->lam.as<double>();
+  double *vraw = h->misc.as<double>(), *vsq = vraw + kl;
+  PLSB_TRY(launch_gram_proj(h, Rt, ldk, 1, Bf, nullptr, 0, Gp, nullptr, st));
+  PLSB_TRY(launch_sym_eig(h, Gp, 1, Bf, W, lam, 0, st));
+  // V d = R U = R'^T W  (K x L), then column norms / signs: sklearn's svd_flip decides on
+  // the FIRST factor randomized_svd returns, which is the K-side one in this orientation
+  PLSB_CUDA(cudaMemsetAsync(vraw, 0, sizeof(double) * 2 * kl, st));
+  const int ldm = accum_ldm(L);
+  PLSB_TRY(h->M.ensure(sizeof(double) * (size_t)Bf * ldm));
+  PLSB_TRY(launch_pad_copy(h, W, Bf, L, h->M.as<double>(), Bf, ldm, st));
+  PLSB_TRY(launch_accum_u(h, Rt, ldk, 1, Bf, l.K, h->M.as<double>(), L, vraw, vsq, st));
+  PLSB_CUDA(cudaMemcpyAsync(d_U, W, sizeof(double) * bb, cudaMemcpyDeviceToDevice, st));
+  PLSB_TRY(launch_normalize_flip(h, vraw, l.K, L, lam, d_V, d_U, Bf, d_d, st));
+  return PLSB_OK;
+}
+
+// permutations of a tall analysis: d_dperm (count, L)
+static int tall_run_perms(plsb_ctx *h, const int32_t *d_idx, const double *d_yperm, int count,
+                          int rotate, double *d_dperm, cudaStream_t st) {
+  const Layout &l = h->lay;
+  const int Bf = l.B, L = l.L;
+  const size_t ystride = (size_t)l.S * l.T, bb = (size_t)Bf * Bf;
+  const int chunk = tall_chunk(h, false, count);
+  for (int off = 0; off < count; off += chunk) {
+    const int n = std::min(chunk, count - off);
+    PLSB_TRY(crosscov_chunk(h, d_idx ? d_idx + (size_t)off * l.S : nullptr,
+                            d_yperm ? d_yperm + off * ystride : nullptr, n, false, nullptr, st));
+    long long ldk = 0;
+    PLSB_TRY(tall_transpose(h, n, &ldk, st));
+    PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * bb));
+    if (!rotate) {
+      PLSB_TRY(launch_gram_proj(h, h->S2.as<double>(), ldk, n, Bf, nullptr, 0, h->G.as<double>(),
+                                nullptr, st));
+      PLSB_TRY(launch_sym_eig(h, h->G.as<double>(), n, Bf, nullptr, d_dperm + (size_t)off * L, 1,
+                              st));
+      continue;
+    }
+    PLSB_TRY(h->H.ensure(sizeof(double) * (size_t)n * Bf * L));
+    PLSB_TRY(h->M.ensure(sizeof(double) * (size_t)n * Bf * L));
+    PLSB_TRY(launch_gram_proj(h, h->S2.as<double>(), ldk, n, Bf, h->VoT.as<double>(), L,
+                              h->G.as<double>(), h->H.as<double>(), st));
+    PLSB_TRY(launch_small_decomp(h, h->G.as<double>(), h->H.as<double>(), n, Bf, L,
+                                 h->dorig.as<double>(), h->M.as<double>(), L, nullptr, st));
+    PLSB_TRY(launch_quadform_sqrt(h, h->G.as<double>(), h->M.as<double>(), n, Bf, L,
+                                  d_dperm + (size_t)off * L, st));
+  }
+  return PLSB_OK;
+}
+
+static int tall_run_boots(plsb_ctx *h, const int32_t *d_idx, int count, double *d_distrib,
+                          double *d_usum, double *d_usquare, cudaStream_t st) {
+  const Layout &l = h->lay;
+  const int Bf = l.B, L = l.L;
+  const size_t bb = (size_t)Bf * Bf;
+  const int chunk = tall_chunk(h, true, count);
+  for (int off = 0; off < count; off += chunk) {
+    const int n = std::min(chunk, count - off);
+    PLSB_TRY(crosscov_chunk(h, d_idx + (size_t)off * l.S, nullptr, n, true,
+                            d_distrib ? d_distrib + (size_t)off * l.K * L : nullptr, st));
+    long long ldk = 0;
+    PLSB_TRY(tall_transpose(h, n, &ldk, st));
+    PLSB_TRY(h->G.ensure(sizeof(double) * (size_t)n * bb));
+    PLSB_TRY(h->H.ensure(sizeof(double) * (size_t)n * bb));
+    PLSB_TRY(h->M.ensure(sizeof(double) * (size_t)n * bb));
+    PLSB_TRY(h->lam.ensure(sizeof(double) * (size_t)n * Bf));
+    PLSB_TRY(launch_gram_proj(h, h->S2.as<double>(), ldk, n, Bf, nullptr, 0, h->G.as<double>(),
+                              nullptr, st));
+    // U_boot (eigenvectors), d^2; then compute.procrustes(U_orig, U_boot, d) = U_boot d Q
+    PLSB_TRY(launch_sym_eig(h, h->G.as<double>(), n, Bf, h->H.as<double>(), h->lam.as<double>(),
+                            0, st));
+    PLSB_TRY(launch_rotation_tall(h, h->Uo.as<double>(), h->H.as<double>(), h->lam.as<double>(),
+                                  n, Bf, h->dorig.as<double>(), h->M.as<double>(), st));
+    PLSB_TRY(launch_accum_small(h, h->M.as<double>(), n, (long long)bb, d_usum, d_usquare, st));
+  }
   return PLSB_OK;
 }
 
@@ -458,6 +573,10 @@ int plsb_decompose(plsb_handle_t h, double *d_U, double *d_d, double *d_V, void 
   const Layout &l = h->lay;
   cudaStream_t st = as_stream(stream);
   PLSB_CHECK(d_U && d_d && d_V, PLSB_ERR_ARG, "plsb_decompose: null output");
+  if (l.tall()) {
+    PLSB_TRY(tall_decompose(h, d_U, d_d, d_V, st));
+    return plsb_set_original(h, d_U, d_d, d_V, stream);
+  }
   PLSB_TRY(crosscov_chunk(h, nullptr, nullptr, 1, false, nullptr, st));
   const size_t kk = (size_t)l.K * l.K, bl = (size_t)l.B * l.L;
   PLSB_TRY(h->G.ensure(sizeof(double) * 4 * kk));
@@ -557,6 +676,7 @@ static int run_perms_impl(plsb_ctx *h, const int32_t *d_idx, const double *d_ype
              "plsb_run_perms(rotate) before the original decomposition is set");
   const Layout &l = h->lay;
   const size_t ystride = (size_t)l.S * l.T;
+  if (l.tall()) return tall_run_perms(h, d_idx, d_yperm, count, rotate, d_dperm, st);
   if (rotate) {
     // |R^T v_j| for every original y-weight v_j: A = V^T-weighted operand, row sums of squares
     const size_t per = sizeof(double) * (size_t)l.L * l.S_pad;
@@ -637,6 +757,8 @@ int plsb_run_perms_gram(plsb_handle_t h, const int32_t *d_idx, int count, double
   PLSB_HANDLE(h);
   PLSB_CHECK(h->has_data && h->has_original && !h->lay.simpls(), PLSB_ERR_STATE,
              "plsb_run_perms_gram needs data and the original decomposition");
+  PLSB_CHECK(!h->lay.tall(), PLSB_ERR_ARG,
+             "plsb_run_perms_gram: the sample-space identity needs K <= B");
   PLSB_CHECK(d_idx && d_dperm && count >= 0, PLSB_ERR_ARG, "plsb_run_perms_gram: bad argument");
   const Layout &l = h->lay;
   cudaStream_t st = as_stream(stream);
@@ -692,6 +814,7 @@ int plsb_run_boots(plsb_handle_t h, const int32_t *d_idx, int count, double *d_d
              "plsb_run_boots: bad argument");
   const Layout &l = h->lay;
   cudaStream_t st = as_stream(stream);
+  if (l.tall()) return tall_run_boots(h, d_idx, count, d_distrib, d_usum, d_usquare, st);
   const int chunk = chunk_size(h, true, count);
   for (int off = 0; off < count; off += chunk) {
     const int n = std::min(chunk, count - off);
@@ -1084,6 +1207,9 @@ int plsb_crossval(plsb_handle_t h, const int32_t *d_train, int count, int max_te
              "plsb_crossval needs a behavioural handle with data");
   PLSB_CHECK(d_train && d_r && d_r2 && count >= 0 && max_test >= 1, PLSB_ERR_ARG,
              "plsb_crossval: bad argument");
+  PLSB_CHECK(!h->lay.tall(), PLSB_ERR_ARG,
+             "plsb_crossval: not available when the latent rows (K=%d) exceed the features (B=%d)",
+             h->lay.K, h->lay.B);
   const Layout &l = h->lay;
   const int stride = l.K + round_up(max_test, l.T);
   cudaStream_t st = as_stream(stream);
@@ -1198,6 +1324,9 @@ int plsb_split_half(plsb_handle_t h, const int32_t *d_idx, const double *d_yperm
              "plsb_split_half: bad argument");
   PLSB_CHECK(!(d_idx && d_yperm), PLSB_ERR_ARG,
              "plsb_split_half: give a permutation table or pre-permuted Y matrices, not both");
+  PLSB_CHECK(!h->lay.tall(), PLSB_ERR_ARG,
+             "plsb_split_half: not available when the latent rows (K=%d) exceed the features "
+             "(B=%d)", h->lay.K, h->lay.B);
   PLSB_CHECK(!d_yperm || h->lay.behavioral(), PLSB_ERR_ARG,
              "plsb_split_half: only behavioural analyses have a Y matrix to permute");
   const Layout &l = h->lay;

@@ -122,6 +122,8 @@ struct Layout {
   bool behavioral() const { return mode == PLSB_BEHAVIORAL_CORR || mode == PLSB_BEHAVIORAL_COV; }
   bool corr() const { return mode == PLSB_BEHAVIORAL_CORR; }
   bool simpls() const { return mode == PLSB_SIMPLS; }
+  // more latent rows than features: the small problem is the B x B feature-side Gram matrix
+  bool tall() const { return !simpls() && K > B; }
 };
 
 }  // namespace plsb
@@ -161,6 +163,7 @@ struct plsb_ctx {
   plsb::DevBuf Kx;     // Gram matrix of the permutation data matrix, (S_pad, round_up(S_pad,128))
   bool has_kx = false;
   plsb::DevBuf UoT;    // Uo transposed, (L, ldx) zero padded: gram_proj's TMA row copies
+  plsb::DevBuf VoT;    // tall analyses: Vo transposed, (L, ldk) zero padded, ldk = round_up(K, 128)
   plsb::DevBuf Vo;     // (K, L)
   plsb::DevBuf dorig;  // (L)
   plsb::DevBuf Sx;     // Xraw @ normalize(Uo)   (S, L)
@@ -291,6 +294,16 @@ int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count
 // G[r] is read at G + r * g_stride with row pitch ldg (0, 0: dense K x K blocks)
 int launch_sym_eig(plsb_ctx *h, const double *G, int count, int K, double *V, double *lam,
                    int sqrt_lam, cudaStream_t st, int ldg = 0, long long g_stride = 0);
+int launch_rotation_tall(plsb_ctx *h, const double *Uorig, const double *V, const double *lam,
+                         int count, int K, const double *dorig, double *M, cudaStream_t st);
+// tall analyses (tall.cu): batched transpose, quadratic forms, accumulation of small matrices
+int launch_transpose_batch(plsb_ctx *h, const double *in, int rows, int cols, long long ld_in,
+                           long long in_stride, double *out, long long ld_out,
+                           long long out_stride, int count, cudaStream_t st);
+int launch_quadform_sqrt(plsb_ctx *h, const double *G, const double *M, int count, int n, int L,
+                         double *out, cudaStream_t st);
+int launch_accum_small(plsb_ctx *h, const double *M, int count, long long n_elem, double *usum,
+                       double *usq, cudaStream_t st);
 
 // SIMPLS (simpls.cu)
 int launch_simpls(plsb_ctx *h, const int32_t *idx, int count, int boot, int emit_ops,

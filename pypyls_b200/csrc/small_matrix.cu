@@ -132,10 +132,14 @@ __device__ __forceinline__ void small_mm(const double *A, int sam, int sak, cons
 }
 
 // M[r] (K,L) from V[r] (K,K), lam[r] (K) (eigen_kernel's output) and H[r] (K,L)
+// tall != 0 (more latent rows than features, the K x K problem is the FEATURE-side Gram
+// matrix): H holds U_orig itself (shared by all resamples, h_stride = 0), temp = U_orig^T V
+// without the d^-1 factor and M = V diag(sqrt(lam)) Q, i.e. compute.procrustes(U_orig,
+// U_boot, d) = U_boot d Q itself (pyls/compute.py:260-262)
 __device__ void rotation_body(int r, double *sm, const double *__restrict__ H,
                               const double *__restrict__ V_in, const double *__restrict__ lam_in,
                               int K, int L, const double *__restrict__ dorig,
-                              double *__restrict__ M_out, int ldm) {
+                              double *__restrict__ M_out, int ldm, int tall, long long h_stride) {
   const int LP = (K + 7) & ~7, ld = LP + 4;
   double *Vs = sm;                // V          [LP][ld]
   double *Hs = Vs + LP * ld;      // H, later the second iterate
@@ -143,13 +147,14 @@ __device__ void rotation_body(int r, double *sm, const double *__restrict__ H,
   double *Bs = Xs + LP * ld;      // (3 I - X^T X) / 2
   double *dinv = Bs + LP * ld;    // LP
   double *omask = dinv + LP;      // LP: 1 for non-null original latent variables
+  double *dsc = omask + LP;       // LP: sqrt(lam) (tall mode), 0 for null directions
   const int tid = threadIdx.x;
 
   for (int e = tid; e < LP * LP; e += SM_THREADS) {
     const int i = e / LP, j = e - i * LP;
     const bool in = i < K && j < K;
     Vs[i * ld + j] = in ? V_in[(size_t)r * K * K + (size_t)i * K + j] : 0.0;
-    Hs[i * ld + j] = in ? H[(size_t)r * K * L + (size_t)i * L + j] : 0.0;
+    Hs[i * ld + j] = in ? H[(size_t)r * h_stride + (size_t)i * L + j] : 0.0;
   }
   {
     // eigenvalues arrive sorted descending: lam[0] is the largest
@@ -162,9 +167,13 @@ __device__ void rotation_body(int r, double *sm, const double *__restrict__ H,
       if (i < K) {
         const double l = lam_in[(size_t)r * K + i];
         // d^-1 with a guard for numerically null directions
-        di = (l > 1e-14 * lmax && l > 0.0) ? rsqrt(l) : 0.0;
+        const bool live = l > 1e-14 * lmax && l > 0.0;
+        di = live ? (tall ? 1.0 : rsqrt(l)) : 0.0;
         // a numerically null ORIGINAL latent variable has no direction to rotate onto
         om = (!dorig || dorig[i] > 1e-10 * domax) ? 1.0 : 0.0;
+        dsc[i] = live ? sqrt(l) : 0.0;
+      } else {
+        dsc[i] = 0.0;
       }
       dinv[i] = di;
       omask[i] = om;
@@ -224,6 +233,15 @@ __device__ void rotation_body(int r, double *sm, const double *__restrict__ H,
     Y = t;
     if (!more) break;
   }
+  if (tall) {
+    // M = V diag(d) Q: scale column i of X (= row i of Q) by d_i first
+    __syncthreads();
+    for (int e = tid; e < LP * LP; e += SM_THREADS) {
+      const int j = e / LP, i = e - j * LP;
+      X[j * ld + i] *= dsc[i];
+    }
+    __syncthreads();
+  }
   // Q = polar(temp)^T;  M[a][j] = sum_i V[a][i] X[j][i]
   small_mm(Vs, ld, 1, X, 1, ld, LP, [&](int a, int j, double v) {
     if (a < K && j < L) M_out[((size_t)r * K + a) * ldm + j] = v;
@@ -239,13 +257,14 @@ __global__ void __launch_bounds__(SM_THREADS)
 rotation_kernel(const double *__restrict__ H, const double *__restrict__ V_in,
                 const double *__restrict__ lam_in, int K, int L,
                 const double *__restrict__ dorig, double *__restrict__ M_out, int ldm,
-                const int *__restrict__ todo, int count, double *gscratch, size_t gs_stride) {
+                const int *__restrict__ todo, int count, double *gscratch, size_t gs_stride,
+                int tall, long long h_stride) {
   extern __shared__ __align__(16) double sm_dyn[];
   double *ws = gscratch ? gscratch + (size_t)blockIdx.x * gs_stride : sm_dyn;
   for (int r = blockIdx.x; r < count; r += gridDim.x) {
     if (todo && !todo[r]) continue;   // done by the Newton-Schulz fast path
     __syncthreads();
-    rotation_body(r, ws, H, V_in, lam_in, K, L, dorig, M_out, ldm);
+    rotation_body(r, ws, H, V_in, lam_in, K, L, dorig, M_out, ldm, tall, h_stride);
   }
 }
 
@@ -435,23 +454,24 @@ int launch_eigen(plsb_ctx *h, const double *G, int count, int K, int sqrt_lam, d
 
 int launch_rotation(plsb_ctx *h, const double *H, const double *V, const double *lam, int count,
                     int K, int L, const double *dorig, double *M, int ldm, cudaStream_t st,
-                    const int *todo = nullptr) {
+                    const int *todo = nullptr, int tall = 0) {
   KernelTimer kt(h, KC_SMALL, st);
   if (count <= 0) return PLSB_OK;
   PLSB_CHECK(L == K, PLSB_ERR_ARG, "small decomposition: L=%d must equal K=%d", L, K);
   const int LP = round_up(K, 8), ld = LP + 4;
-  const size_t smem = sizeof(double) * (4 * (size_t)LP * ld + 2 * LP);
+  const size_t smem = sizeof(double) * (4 * (size_t)LP * ld + 3 * LP);
+  const long long h_stride = tall ? 0 : (long long)K * L;
   if (smem <= SMALL_SMEM_MAX) {
     PLSB_CUDA(cudaFuncSetAttribute(rotation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     rotation_kernel<<<count, SM_THREADS, smem, st>>>(H, V, lam, K, L, dorig, M, ldm, todo, count,
-                                                     nullptr, 0);
+                                                     nullptr, 0, tall, h_stride);
   } else {
     const size_t stride = smem / 8;
     const int ctas = std::min(count, 2 * h->sm_count);
     PLSB_TRY(h->big.ensure(sizeof(double) * stride * ctas));
     rotation_kernel<<<ctas, SM_THREADS, 0, st>>>(H, V, lam, K, L, dorig, M, ldm, todo, count,
-                                                 h->big.as<double>(), stride);
+                                                 h->big.as<double>(), stride, tall, h_stride);
   }
   PLSB_LAUNCHED(h);
   return PLSB_OK;
@@ -485,6 +505,13 @@ int launch_small_decomp(plsb_ctx *h, const double *G, const double *H, int count
     PLSB_CUDA(cudaMemcpyAsync(lam, lam_s, sizeof(double) * (size_t)count * K,
                               cudaMemcpyDeviceToDevice, st));
   return PLSB_OK;
+}
+
+// M[r] = V[r] diag(sqrt(lam[r])) polar(U_orig^T V[r])^T for the feature-side decomposition of
+// analyses with more latent rows than features (K here = number of features = L)
+int launch_rotation_tall(plsb_ctx *h, const double *Uorig, const double *V, const double *lam,
+                         int count, int K, const double *dorig, double *M, cudaStream_t st) {
+  return launch_rotation(h, Uorig, V, lam, count, K, K, dorig, M, K, st, nullptr, 1);
 }
 
 int launch_sym_eig(plsb_ctx *h, const double *G, int count, int K, double *V, double *lam,

@@ -125,7 +125,8 @@ class ResamplingEngine:
         self.K = self.J * self.T if mode != 'meancentered' else self.J
         if mode == 'regression':
             self.K = int(n_components)
-        self.L = self.K
+        # compute.svd keeps min(K, B) latent variables (pyls/compute.py:36-50)
+        self.L = self.K if mode == 'regression' else min(self.K, self.B)
         pool = _FREE_HANDLES.setdefault(self.device.index, [])
         if pool:
             self._h, idle = pool.pop()

@@ -120,7 +120,10 @@ def behavioral_pls(X, Y, *, groups=None, n_cond=1, n_perm=5000, n_boot=5000,
     runs the split-half resampling on the device.  Analyses with more than 80
     latent variables (K = cells x behaviours), more than 80 rows per pair of
     split halves or per stacked train / test split run through generic
-    (slower) kernels; K must not exceed the number of features.
+    (slower) kernels.  With more latent rows than features (K > B) the
+    decomposition keeps L = B latent variables like ``compute.svd`` does and
+    every resample is solved on the feature side; ``n_split`` / ``test_split``
+    are not available in that orientation.
     Extra keywords: ``index_backend``, ``device``, ``workspace_bytes``.
 
     Returns

@@ -709,13 +709,85 @@ def test_largest_fragment_table_decomposition():
                              np.ones(80, dtype=bool), max_dev=0.1)
 
 
-def test_unsupported_shapes_fail_loudly():
+@pytest.mark.parametrize('groups,n_cond,T,B,rotate', [
+    ([40], 1, 10, 6, True),           # K = 10 latent rows, 6 features
+    ([40], 1, 10, 6, False),
+    ([12, 10], 2, 3, 8, True),        # K = 12 > B = 8, several cells
+    ([15, 15], 1, 40, 25, True),      # K = 80 > B = 25
+])
+def test_more_latent_rows_than_features(groups, n_cond, T, B, rotate):
+    """K = cells x behaviours > B: compute.svd decomposes the cross-covariance
+    the other way round (pyls/compute.py:46-50) and keeps L = B latent
+    variables; the engine then solves every resample on the feature side
+    (csrc/tall.cu)."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(31)
+    S = sum(groups) * n_cond
+    X, Y = rs.rand(S, B), rs.rand(S, T)
+    Y[:, 0] += X[:, 0] * 2
+    ps = po.gen_permsamp(groups, n_cond, 12, seed=1)
+    bs = po.gen_bootsamp(groups, n_cond, 12, seed=2)
+    kw = dict(groups=groups, n_cond=n_cond, n_perm=12, n_boot=12, seed=5,
+              rotate=rotate, permsamples=ps, bootsamples=bs)
+    out = pyls.behavioral_pls(X, Y, verbose=False, **kw)
+    ref = po.behavioral_pls(X, Y, **kw)
+    K = len(groups) * n_cond * T
+    assert out.x_weights.shape == (B, B) and out.y_weights.shape == (K, B)
+    assert out.permres.perm_singval.shape == (B, 12)
+    assert out.bootres.y_loadings_boot.shape == (K, B, 12)
+    for k in ('singvals', 'x_weights', 'y_weights', 'x_scores', 'y_scores',
+              'y_loadings', 'varexp'):
+        close(out[k], ref[k], rtol=1e-7, atol=1e-10)
+    close(out.permres.perm_singval, ref['perm_singval'], rtol=1e-7)
+    assert np.array_equal(out.permres.pvals, ref['pvals'])
+    close(out.bootres.y_loadings_boot, ref['distrib'], rtol=1e-7, atol=1e-10)
+    close(out.bootres.y_loadings_ci, ref['distrib_ci'], rtol=1e-7, atol=1e-10)
+    close(out.bootres.x_weights_normed, ref['x_weights_normed'], rtol=1e-6,
+          atol=1e-8)
+    # the same analysis with seed replay only (tables drawn after the (L, L + 10)
+    # normal draw of the original randomized SVD)
+    again = pyls.behavioral_pls(X, Y, groups=groups, n_cond=n_cond, n_perm=6,
+                                n_boot=6, seed=5, rotate=rotate, verbose=False,
+                                index_backend='reference')
+    want = po.behavioral_pls(X, Y, groups=groups, n_cond=n_cond, n_perm=6,
+                             n_boot=6, seed=5, rotate=rotate)
+    assert np.array_equal(again.permres.permsamples, want['permsamples'])
+    close(again.permres.perm_singval, want['perm_singval'], rtol=1e-7)
+
+
+def test_meancentered_more_cells_than_features():
+    """Mean-centred PLS with J = 6 cells and only 4 features (K > B)."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(41)
+    groups, n_cond = [6, 5, 7], 2
+    X = rs.rand(sum(groups) * n_cond, 4)
+    ps = po.gen_permsamp(groups, n_cond, 10, seed=1)
+    bs = po.gen_bootsamp(groups, n_cond, 10, seed=2)
+    kw = dict(groups=groups, n_cond=n_cond, mean_centering=2, n_perm=10,
+              n_boot=10, seed=5, permsamples=ps, bootsamples=bs)
+    out = pyls.meancentered_pls(X, verbose=False, **kw)
+    ref = po.meancentered_pls(X, **kw)
+    keep = ref['singvals'] > 1e-8 * ref['singvals'].max()
+    assert out.x_weights.shape == (4, 4) and out.y_weights.shape == (6, 4)
+    close(out.singvals[keep], ref['singvals'][keep], rtol=1e-7)
+    close(out.permres.perm_singval[keep], ref['perm_singval'][keep],
+          rtol=1e-7)
+    assert np.array_equal(out.permres.pvals[keep], ref['pvals'][keep])
+    close(out.bootres.contrast_boot[:, keep], ref['distrib'][:, keep],
+          rtol=1e-7, atol=1e-10)
+    check_rank_deficient_bsr(out, X, None, ref['x_weights_normed'], keep,
+                             min_corr=0.99, max_dev=0.2)
+
+
+def test_tall_analysis_refuses_what_needs_the_wide_orientation():
     import pypyls_b200 as pyls
     rs = np.random.RandomState(7)
-    # K = 12 latent variables but only 8 features
-    with pytest.raises(ValueError, match='features'):
-        pyls.behavioral_pls(rs.rand(40, 8), rs.rand(40, 12), n_perm=2,
-                            n_boot=2)
+    X, Y = rs.rand(40, 8), rs.rand(40, 12)
+    with pytest.raises(ValueError, match='latent rows'):
+        pyls.behavioral_pls(X, Y, n_perm=2, n_boot=0, n_split=3, verbose=False)
+    with pytest.raises(ValueError, match='latent rows'):
+        pyls.behavioral_pls(X, Y, n_perm=0, n_boot=0, test_split=4,
+                            verbose=False)
 
 
 def test_bad_resampling_tables_are_rejected():
