@@ -57,7 +57,10 @@ const char *plsb_last_error(void);
 /* Handle life cycle.  `device` is the CUDA ordinal. */
 int plsb_create(plsb_handle_t *out, int device);
 int plsb_destroy(plsb_handle_t h);
-/* Upper bound (bytes) for the per-chunk resample workspace (default 8 GiB). */
+/* Upper bound (bytes) for the per-chunk resample workspace: the stored
+ * cross-covariances of one pass.  The library's own default is 8 GiB; the Python
+ * front-end (pypyls_b200/engine.py) sets min(32 GiB, device memory / 5) -- fewer,
+ * larger passes keep every grid full on a 180 GB part. */
 int plsb_set_workspace_limit(plsb_handle_t h, uint64_t bytes);
 
 /*

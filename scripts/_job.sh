@@ -1,4 +1,3 @@
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r2_cfg5_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-fast-path > gpurun_out/ncu_ll.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"xcov_gemm2|gram_proj_small|accum_u_small" -s 0 -c 9 -o gpurun_out/r2_cfg5_full python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-parity --no-fast-path --workspace-gib 8 > gpurun_out/ncu_full.log 2>&1
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_cfg5_n1_final.json 2> gpurun_out/r2_bench_cfg5_n1_final.err
-python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_bench_reference_final.json 2> gpurun_out/r2_bench_reference_final.err
+python bench.py --workload cfg2 --steps 10 --warmup 3 --quick-cpu > gpurun_out/r2_bench_cfg2_n1.json 2> gpurun_out/r2_bench_cfg2_n1.err
+python bench.py --workload cfg3 --steps 10 --warmup 3 --quick-cpu --n-cpu 100 > gpurun_out/r2_bench_cfg3_n1.json 2> gpurun_out/r2_bench_cfg3_n1.err
+python bench.py --workload cfg4 --steps 5 --warmup 3 --quick-cpu --n-cpu 100 > gpurun_out/r2_bench_cfg4_n1.json 2> gpurun_out/r2_bench_cfg4_n1.err
