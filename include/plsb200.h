@@ -62,6 +62,16 @@ int plsb_destroy(plsb_handle_t h);
  * front-end (pypyls_b200/engine.py) sets min(32 GiB, device memory / 5) -- fewer,
  * larger passes keep every grid full on a 180 GB part. */
 int plsb_set_workspace_limit(plsb_handle_t h, uint64_t bytes);
+/* Kernel behind the cross-covariance contraction (compute.xcorr's `Yn.T @ Xn`,
+ * pyls/compute.py:92).  PLSB_GEMM_AUTO (default): the int8 slice GEMM on the
+ * tcgen05 tensor cores (csrc/gemm_i8.cu: FP64 operands cut into `n_slices` signed
+ * base-256 digit planes, exact int32 products in tensor memory, FP64 recombination)
+ * wherever it applies -- dense operands, contraction over at most 224 rows --
+ * and the FP64 DMMA kernel elsewhere; PLSB_GEMM_DMMA: always the DMMA kernel.
+ * n_slices 5 / 6 / 7 (0 keeps the current value; default 6: entries within
+ * ~1e-13 |a||x| of the FP64 product, 7: ~1e-15). */
+enum { PLSB_GEMM_AUTO = 0, PLSB_GEMM_DMMA = 1 };
+int plsb_set_gemm_backend(plsb_handle_t h, int backend, int n_slices);
 
 /*
  * Analysis layout.  Replaces BasePLS.__init__ validation + utils.dummy_code

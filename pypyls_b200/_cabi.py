@@ -18,6 +18,9 @@ PLSB_BEHAVIORAL_COV = 1
 PLSB_MEANCENTERED = 2
 PLSB_SIMPLS = 3
 
+PLSB_GEMM_AUTO = 0
+PLSB_GEMM_DMMA = 1
+
 _vp, _i, _i64, _u64, _dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
 _ip = C.POINTER(C.c_int)
 
@@ -28,6 +31,7 @@ PROTOTYPES = {
     'plsb_create': (_i, [C.POINTER(_vp), _i]),
     'plsb_destroy': (_i, [_vp]),
     'plsb_set_workspace_limit': (_i, [_vp, _u64]),
+    'plsb_set_gemm_backend': (_i, [_vp, _i, _i]),
     'plsb_configure': (_i, [_vp, _i, _i, _i, _i, _i, _ip, _i, _i, _i]),
     'plsb_set_data': (_i, [_vp, _vp, _vp, _vp]),
     'plsb_decompose': (_i, [_vp, _vp, _vp, _vp, _vp]),

@@ -101,6 +101,7 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, const double *yperm, int n, 
   g.Kd = l.S_pad;
   g.k_valid = l.S;
   g.ldc = l.ldx;
+  g.x_persistent = true;
   if (grouped) g.k_len = l.kr_max;
   if (scaled && !fused_scale) {
     g.A = h->Ac.as<double>();
@@ -123,6 +124,7 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, const double *yperm, int n, 
   }
   g.A = h->A.as<double>();
   g.X = boot ? h->Xglob.as<double>() : perm_data(h);
+  g.x_persistent = true;
   g.M_pad = (int)Mw_op;
   g.row_map = map_w;
   g.kranges = kr_w;
@@ -201,7 +203,11 @@ int plsb_destroy(plsb_handle_t h) {
   DevBuf *bufs[] = {&h->tables, &h->Xraw, &h->Xcell, &h->Xglob, &h->Y,    &h->Cmat,  &h->Uo,
                     &h->Vo,     &h->dorig, &h->Sx,   &h->norms, &h->A,    &h->Ac,    &h->R,
                     &h->S1,     &h->S2,   &h->G,     &h->H,     &h->M,    &h->lam,   &h->rowsq,
-                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx, &h->rowmask, &h->pctl, &h->big, &h->VoT};
+                    &h->part,   &h->misc, &h->idxall, &h->flags, &h->maps,  &h->UoT, &h->Kx, &h->rowmask, &h->pctl, &h->big, &h->VoT,
+                    &h->aplanes, &h->ascale, &h->xplanes[0].img, &h->xplanes[0].scale,
+                    &h->xplanes[1].img, &h->xplanes[1].scale, &h->xplanes[2].img,
+                    &h->xplanes[2].scale, &h->xplanes_tmp.img,
+                    &h->xplanes_tmp.scale};
   for (DevBuf *b : bufs) b->release();
   delete h;
   return PLSB_OK;
@@ -211,6 +217,17 @@ int plsb_set_workspace_limit(plsb_handle_t h, uint64_t bytes) {
   PLSB_CHECK(h != nullptr, PLSB_ERR_ARG, "null handle");
   PLSB_CHECK(bytes >= (1ull << 20), PLSB_ERR_ARG, "workspace limit below 1 MiB");
   h->ws_limit = bytes;
+  return PLSB_OK;
+}
+
+int plsb_set_gemm_backend(plsb_handle_t h, int backend, int n_slices) {
+  PLSB_CHECK(h != nullptr, PLSB_ERR_ARG, "null handle");
+  PLSB_CHECK(backend == PLSB_GEMM_AUTO || backend == PLSB_GEMM_DMMA, PLSB_ERR_ARG,
+             "plsb_set_gemm_backend: unknown backend %d", backend);
+  PLSB_CHECK(n_slices == 0 || (n_slices >= 5 && n_slices <= 7), PLSB_ERR_ARG,
+             "plsb_set_gemm_backend: n_slices must be 0, 5, 6 or 7");
+  h->gemm_backend = backend;
+  if (n_slices) h->gemm_slices = n_slices;
   return PLSB_OK;
 }
 
@@ -383,6 +400,7 @@ int plsb_set_data(plsb_handle_t h, const double *d_X, const double *d_Y, void *s
              "plsb_set_data: null Y");
   const size_t bytes = sizeof(double) * (size_t)l.S_pad * l.ldx;
   h->has_rowmask = false;
+  ++h->data_epoch;   // cached digit planes of the data matrices are stale
   if (l.simpls()) {
     // X and Y arrive column-centred (pyls/types/regression.py:395-396).  Kraw = X X^T (S,S)
     // is the only B-sized object the component loops need.
@@ -683,7 +701,6 @@ static int run_perms_impl(plsb_ctx *h, const int32_t *d_idx, const double *d_ype
     int chunk = (int)std::min<long long>(
         count, std::max<long long>(1, (long long)(h->ws_limit / per)));
     chunk = (int)std::min<long long>(chunk, ((1ll << 31) - 1024) / l.L);
-    const int n_ntiles = l.ldx / GEMM_BN;
     for (int off = 0; off < count; off += chunk) {
       const int n = std::min(chunk, count - off);
       const long long M = (long long)n * l.L, M_pad = round_up_ll(M, GEMM_BM);
@@ -692,18 +709,18 @@ static int run_perms_impl(plsb_ctx *h, const int32_t *d_idx, const double *d_ype
       PLSB_TRY(launch_build(h, BUILD_ROT, d_idx ? d_idx + (size_t)off * l.S : nullptr,
                             d_yperm ? d_yperm + off * ystride : nullptr, n, h->A.as<double>(),
                             nullptr, nullptr, 0, 0, st));
-      const int n_mtiles = (int)(M_pad / GEMM_BM);
-      const int n_splits = gemm_pick_splits(h, (int)M_pad, n_ntiles, gemm_small_tile(l.S_pad));
-      PLSB_TRY(h->rowsq.ensure(sizeof(double) * (size_t)n_splits * M_pad));
       GemmArgs g;
       g.A = h->A.as<double>();
       g.lda = l.S_pad;
       g.X = perm_data(h);
+      g.x_persistent = true;
       g.ldx = l.ldx;
       g.M_pad = (int)M_pad;
       g.N_pad = l.ldx;
       g.Kd = l.S_pad;
       g.k_valid = l.S;
+      const int n_splits = gemm_rowsq_splits(h, g);
+      PLSB_TRY(h->rowsq.ensure(sizeof(double) * (size_t)n_splits * M_pad));
       g.rowsq = h->rowsq.as<double>();
       g.n_splits = n_splits;
       PLSB_TRY(launch_gemm(h, g, st));
@@ -924,8 +941,9 @@ int plsb_gemm_probe(plsb_handle_t h, int variant, int M, int N, int Kd, int k_va
   g.N_pad = N_pad;
   g.Kd = K_pad;
   g.k_valid = k_valid > 0 ? k_valid : Kd;
+  g.x_persistent = true;   // synthetic right operand, constant while probing
   if (variant == 2) {
-    g.n_splits = gemm_pick_splits(h, M_pad, N_pad / GEMM_BN, gemm_small_tile(K_pad));
+    g.n_splits = gemm_rowsq_splits(h, g);
     PLSB_TRY(h->rowsq.ensure(sizeof(double) * (size_t)g.n_splits * M_pad));
     g.rowsq = h->rowsq.as<double>();
   } else {
@@ -969,6 +987,7 @@ static int simpls_weights_gemm(plsb_ctx *h, int n, cudaStream_t st) {
   g.A = h->A.as<double>();
   g.lda = l.S_pad;
   g.X = h->Xraw.as<double>();
+  g.x_persistent = true;
   g.ldx = l.ldx;
   g.M_pad = (int)M_pad;
   g.N_pad = l.ldx;
@@ -1283,6 +1302,7 @@ static int halves_chunk(plsb_ctx *h, const int32_t *masks, const double *yperm,
   g.Kd = l.S_pad;
   g.k_valid = l.S;
   g.ldc = l.ldx;
+  g.x_persistent = true;
   if (grouped) g.k_len = l.kr_max;
   if (scaled) {
     g.A = h->Ac.as<double>();

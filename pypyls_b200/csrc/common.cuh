@@ -168,6 +168,20 @@ struct plsb_ctx {
   plsb::DevBuf dorig;  // (L)
   plsb::DevBuf Sx;     // Xraw @ normalize(Uo)   (S, L)
   plsb::DevBuf norms;  // (L)
+  // int8 digit planes of the slice GEMM (gemm_i8.cu): planes of the fixed right operands
+  // (the data matrices) are cached until the data changes, planes of A are per launch
+  struct PlaneCache {
+    const double *src = nullptr;
+    uint64_t epoch = 0, stamp = 0;
+    int S = 0, ldx = 0, N_pad = 0, k_valid = 0;
+    bool square = false;
+    plsb::DevBuf img, scale;
+  };
+  PlaneCache xplanes[3], xplanes_tmp;
+  uint64_t data_epoch = 1, plane_stamp = 0;
+  plsb::DevBuf aplanes, ascale;
+  int gemm_backend = PLSB_GEMM_AUTO;
+  int gemm_slices = 6;
   // per-chunk workspaces
   plsb::DevBuf A, Ac, R, S1, S2, G, H, M, lam, rowsq, part, misc, idxall, flags, maps, pctl, big;
 };
@@ -209,6 +223,7 @@ struct GemmArgs {
   int k_valid = 0;             // rows of X beyond this are zero padding (0: Kd): their k steps are skipped
   const int4 *kranges = nullptr;  // optional per-M-tile [kbeg,kend) (kbeg even) + non-zero k steps [z,w)
   int k_len = 0;               // longest contraction range in kranges (0: Kd); picks the tile
+  bool x_persistent = false;   // X is a data matrix of the handle (its digit planes are cached)
   bool square_b = false;       // use X*X elementwise as the right operand
   // STORE epilogue
   double *C = nullptr;
@@ -224,6 +239,13 @@ struct GemmArgs {
 int launch_gemm(plsb_ctx *h, const GemmArgs &a, cudaStream_t st);
 bool gemm_small_tile(int klen);
 int gemm_pick_splits(const plsb_ctx *h, int M_pad, int n_ntiles, bool small_tile);
+// splits of the ROWSUMSQ epilogue for the kernel launch_gemm will pick for `a`
+int gemm_rowsq_splits(const plsb_ctx *h, const GemmArgs &a);
+// int8 slice GEMM on the tcgen05 tensor cores (gemm_i8.cu)
+bool gemm_i8_applies(const plsb_ctx *h, const GemmArgs &a);
+int gemm_i8_pick_splits(const plsb_ctx *h, int M_pad, int n_ntiles);
+int gemm_i8_slices(const plsb_ctx *h);
+int launch_gemm_i8(plsb_ctx *h, const GemmArgs &a, cudaStream_t st);
 
 // data preparation (prep.cu)
 int launch_pad_copy(plsb_ctx *h, const double *X, int S, int B, double *out, int S_pad, int ldx,

@@ -647,6 +647,12 @@ int gemm_pick_splits(const plsb_ctx *h, int M_pad, int n_ntiles, bool small_tile
   return best;
 }
 
+int gemm_rowsq_splits(const plsb_ctx *h, const GemmArgs &a) {
+  const int n_ntiles = a.N_pad / BN;
+  if (gemm_i8_applies(h, a)) return gemm_i8_pick_splits(h, a.M_pad, n_ntiles);
+  return gemm_pick_splits(h, a.M_pad, n_ntiles, gemm_small_tile(a.k_len > 0 ? a.k_len : a.Kd));
+}
+
 int launch_gemm(plsb_ctx *h, const GemmArgs &a, cudaStream_t st) {
   PLSB_CHECK(a.M_pad % BM == 0 && a.N_pad % BN == 0 && a.Kd % BK == 0, PLSB_ERR_ARG,
              "gemm: M_pad=%d N_pad=%d Kd=%d must be multiples of %d/%d/%d", a.M_pad, a.N_pad, a.Kd,
@@ -655,8 +661,10 @@ int launch_gemm(plsb_ctx *h, const GemmArgs &a, cudaStream_t st) {
   if (a.M_pad == 0 || a.N_pad == 0) return PLSB_OK;
   const int n_ntiles = a.N_pad / BN;
   const bool rowsq = a.rowsq != nullptr;
+  if (rowsq) PLSB_CHECK(a.n_splits >= 1, PLSB_ERR_ARG, "gemm: n_splits");
+  else PLSB_CHECK(a.C != nullptr && a.ldc % 2 == 0, PLSB_ERR_ARG, "gemm: bad output");
+  if (gemm_i8_applies(h, a)) return launch_gemm_i8(h, a, st);
   if (rowsq) {
-    PLSB_CHECK(a.n_splits >= 1, PLSB_ERR_ARG, "gemm: n_splits");
     if (a.square_b) return launch_variant<EPI_ROWSUMSQ, true, 8>(h, a, n_ntiles, a.n_splits, st);
     if (gemm_small_tile(a.k_len > 0 ? a.k_len : a.Kd))
       return launch_variant<EPI_ROWSUMSQ, false, 4>(h, a, n_ntiles, a.n_splits, st);

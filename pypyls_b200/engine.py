@@ -111,7 +111,8 @@ class ResamplingEngine:
     """
 
     def __init__(self, mode, S, B, T, groups, n_cond=1, mean_centering=0,
-                 device=0, workspace_bytes=None, n_components=0):
+                 device=0, workspace_bytes=None, n_components=0,
+                 gemm_backend='auto', gemm_slices=6):
         if not torch.cuda.is_available():
             raise RuntimeError('pypyls_b200 needs a CUDA device (B200, '
                                'sm_100a); there is no CPU fallback.')
@@ -146,12 +147,22 @@ class ResamplingEngine:
         _cabi.check(self._lib.plsb_set_workspace_limit(
             self._h, int(workspace_bytes)))
         _cabi.check(self._lib.plsb_timing_enable(self._h, 0))
+        self.set_gemm_backend(gemm_backend, gemm_slices)
         garr = (C.c_int * len(groups))(*groups)
         _cabi.check(self._lib.plsb_configure(
             self._h, MODES[mode], self.S, self.B, self.T, len(groups), garr,
             self.n_cond, int(mean_centering), int(n_components)))
 
     # -- plumbing ----------------------------------------------------------
+    def set_gemm_backend(self, backend='auto', n_slices=6):
+        """Kernel of the cross-covariance contraction: 'auto' = int8 slice
+        GEMM on the tcgen05 tensor cores where it applies (``n_slices`` digit
+        planes per operand: 6 -> ~1e-13, 7 -> ~1e-15 of |a||x| per entry),
+        'dmma' = FP64 DMMA kernel everywhere."""
+        code = {'auto': _cabi.PLSB_GEMM_AUTO, 'dmma': _cabi.PLSB_GEMM_DMMA}[backend]
+        _cabi.check(self._lib.plsb_set_gemm_backend(self._h, code,
+                                                    int(n_slices)))
+
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:
             # the next borrower waits for everything queued so far on this

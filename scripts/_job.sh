@@ -1,3 +1,1 @@
-python bench.py --workload cfg2 --steps 10 --warmup 3 --quick-cpu > gpurun_out/r2_bench_cfg2_n1.json 2> gpurun_out/r2_bench_cfg2_n1.err
-python bench.py --workload cfg3 --steps 10 --warmup 3 --quick-cpu --n-cpu 100 > gpurun_out/r2_bench_cfg3_n1.json 2> gpurun_out/r2_bench_cfg3_n1.err
-python bench.py --workload cfg4 --steps 5 --warmup 3 --quick-cpu --n-cpu 100 > gpurun_out/r2_bench_cfg4_n1.json 2> gpurun_out/r2_bench_cfg4_n1.err
+timeout 150 python scripts/i8_gemm_check.py quick > gpurun_out/r2_i8_check.txt 2>&1; echo "rc=$?" >> gpurun_out/r2_i8_check.txt
