@@ -31,6 +31,8 @@
 // [16 B]), so a stage is one contiguous bulk copy and no tensor map is needed.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace plsb {
 
 namespace {
@@ -40,37 +42,53 @@ constexpr int MAX_KS = 7;                 // k steps of 32 -> contraction length
 constexpr int KSTEP_BYTES = 128 * 32;     // one k step of one 128-row plane
 constexpr int NSLOT = 4;                  // 128-column accumulators in tensor memory
 constexpr int NSTAGE = 3;
+constexpr int NACC = 4;                   // "pass complete" barriers in flight
 constexpr int N_EPI_WARPS = 16;
-constexpr int THREADS = (2 + N_EPI_WARPS) * 32;
+// warps 0-3: control warpgroup (producer, MMA issuer, two idle), warps 4-19: epilogue
+constexpr int THREADS = (4 + N_EPI_WARPS) * 32;
 
 enum { EPI_STORE = 0, EPI_ROWSUMSQ = 1 };
 
-template <int S> struct Plan {
-  static constexpr int NPASS = S > NSLOT ? 2 : 1;
+// NP0: diagonals of the first pass (the second pass takes the remaining S - NP0 <= NSLOT)
+template <int S, int NP0> struct Plan {
+  static constexpr int NPASS = S > NP0 ? 2 : 1;
   static constexpr int STAGE_KS = S >= 7 ? 2 : 4;   // k steps per ring stage
   static constexpr int STAGE_BYTES = STAGE_KS * KSTEP_BYTES;
   static constexpr int A_BYTES = S * MAX_KS * KSTEP_BYTES;
   static constexpr int RING_OFF = A_BYTES;
   static constexpr int BAR_OFF = RING_OFF + NSTAGE * STAGE_BYTES;
   static constexpr int RED_OFF = BAR_OFF + 128;
-  static constexpr int SMEM = RED_OFF + N_EPI_WARPS * 32 * 8;
-  __host__ __device__ static constexpr int dlo(int p) { return p == 0 ? (S > NSLOT ? S - NSLOT : 0) : 0; }
-  __host__ __device__ static constexpr int dhi(int p) { return p == 0 ? S - 1 : S - NSLOT - 1; }
+  static constexpr int SMEM = RED_OFF + 4 * 128 * 8;
+  __host__ __device__ static constexpr int dhi(int p) { return p == 0 ? S - 1 : S - NP0 - 1; }
+  __host__ __device__ static constexpr int dlo(int p) { return p == 0 ? (S > NP0 ? S - NP0 : 0) : 0; }
 };
 
 struct TcParams {
-  const int8_t *Aimg, *Ximg;
-  const double *rscale, *cscale;
-  int KS, n_mtiles, n_ntiles, n_splits, nt_per_split;
+  const int8_t *res_img, *str_img;   // planes of the resident / the streamed operand
+  const double *rscale, *cscale;     // powers of two of the rows of A / the columns of X
+  int KS, n_rtiles, n_stiles, n_splits, st_per_split;
   double *C;
   long long ldc;
-  const int *row_map;
   const double *scale;
   int scale_div;
   long long lds;
   double *rowsq;
   int M_pad;
+  long long *prof;   // optional per-CTA wait-cycle counters (PLSB_I8_PROF), 8 per CTA
+  int dbg;           // experiments (PLSB_I8_DBG): 8 = STORE epilogue without the stores
 };
+
+// mbarrier wait that adds its duration to `acc` when profiling
+#define TIMED_WAIT(bar, par, acc)            \
+  do {                                       \
+    if (p.prof) {                            \
+      const long long _t = clock64();        \
+      mbar_wait(bar, par);                   \
+      acc += clock64() - _t;                 \
+    } else {                                 \
+      mbar_wait(bar, par);                   \
+    }                                        \
+  } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -106,19 +124,23 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 }
-// shared-memory matrix descriptor: no swizzle, K-major; core matrices adjacent in K 128 B
-// apart, 8-row groups 256 B apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) |
-         ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
-}
-__device__ __forceinline__ void mma_i8(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc,
+// Shared-memory matrix descriptors: no swizzle, K-major; core matrices adjacent in K 128 B
+// apart (LBO), 8-row groups 256 B apart (SBO).
+// a_lo / b_lo: low words of the descriptors; the high word (SBO 256 B, version 1) is constant
+__device__ __forceinline__ void mma_i8(uint32_t tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
                                        uint32_t acc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
-      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(0x4010u)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+               : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mma_commit(uint64_t *b) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::
@@ -133,6 +155,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
@@ -259,34 +283,43 @@ __global__ void __launch_bounds__(128 * MAX_KS) quant_cols_kernel(const double *
 }
 
 // ---- the GEMM ---------------------------------------------------------------------------
-template <int S, int EPI>
+// Per unit of work one operand's planes stay resident in shared memory (128 of its rows /
+// columns: the M side of the MMAs = the 128 TMEM lanes, so an epilogue thread owns one
+// resident row and 32 streamed ones per tile), the other operand's tiles stream past:
+//   ROWSUMSQ: resident = 128 rows of A, streamed = column tiles of X; a thread owns one row of
+//             C and sums its squares over the whole streamed column range in one register;
+//   STORE:    resident = 128 columns of X, streamed = row tiles of A (C^T = X^T A^T); a thread
+//             owns one COLUMN of C, so the 32 lanes of a warp write 32 consecutive doubles of
+//             a row of C (and read the column scales the same way).
+// The MMAs of a product (its k steps) are issued back to back into the same accumulator.
+template <int S, int EPI, int NP0>
 __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams p) {
-  using P = Plan<S>;
+  using P = Plan<S, NP0>;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t *As = smem;
-  uint8_t *Bs = smem + P::RING_OFF;
+  uint8_t *Rs = smem;                        // resident planes [S][KS][128 x 32 B]
+  uint8_t *Ss = smem + P::RING_OFF;          // ring of streamed stages
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + P::BAR_OFF);
   uint64_t *full_b = bars, *empty_b = bars + NSTAGE;
-  uint64_t *a_full = bars + 2 * NSTAGE, *a_empty = a_full + 1;
-  uint64_t *acc_full = a_empty + 1;          // [2]
-  uint64_t *slot_empty = acc_full + 2;       // [NSLOT]
-  double *red = reinterpret_cast<double *>(smem + P::RED_OFF);
+  uint64_t *r_full = bars + 2 * NSTAGE, *r_empty = r_full + 1;
+  uint64_t *acc_full = r_empty + 1;          // [NACC]
+  uint64_t *slot_empty = acc_full + NACC;    // [NSLOT]
+  double *red = reinterpret_cast<double *>(smem + P::RED_OFF);   // [4][128]
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KS = p.KS;
   const uint32_t slice_bytes = (uint32_t)KS * KSTEP_BYTES;
-  const int n_units = p.n_mtiles * p.n_splits;
+  const int n_units = p.n_rtiles * p.n_splits;
+  constexpr int NCHUNK = (MAX_KS + P::STAGE_KS - 1) / P::STAGE_KS;
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full_b[s], 1);
       mbar_init(&empty_b[s], 1);
     }
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
-    mbar_init(&acc_full[0], 1);
-    mbar_init(&acc_full[1], 1);
+    mbar_init(r_full, 1);
+    mbar_init(r_empty, 1);
+    for (int s = 0; s < NACC; ++s) mbar_init(&acc_full[s], 1);
     for (int s = 0; s < NSLOT; ++s) mbar_init(&slot_empty[s], N_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -300,32 +333,43 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
+  // Producer and issuer warps run their loops with all 32 lanes (every value is
+  // warp-uniform, so it lives in uniform registers) and one elected lane issues.
   if (warp == 0) {
     // ===== producer =====
-    if (lane == 0) {
-      uint32_t st = 0, st_phase = 0, a_phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int split = u / p.n_mtiles, mt = u - split * p.n_mtiles;
-        const int nt0 = split * p.nt_per_split, nt1 = min(nt0 + p.nt_per_split, p.n_ntiles);
-        mbar_wait(a_empty, a_phase ^ 1);
-        mbar_expect_tx(a_full, S * slice_bytes);
-        const int8_t *a_src = p.Aimg + (size_t)mt * S * slice_bytes;
+    const bool leader = elect_one();
+    uint32_t st = 0, st_phase = 0, r_phase = 0;
+    long long w_empty = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int split = u / p.n_rtiles, rt = u - split * p.n_rtiles;
+      const int t0 = split * p.st_per_split, t1 = min(t0 + p.st_per_split, p.n_stiles);
+      mbar_wait(r_empty, r_phase ^ 1);
+      if (leader) {
+        mbar_expect_tx(r_full, S * slice_bytes);
+        const int8_t *r_src = p.res_img + (size_t)rt * S * slice_bytes;
 #pragma unroll
         for (int i = 0; i < S; ++i)
-          bulk_g2s(As + (size_t)i * slice_bytes, a_src + (size_t)i * slice_bytes, slice_bytes, a_full);
-        a_phase ^= 1;
-        for (int nt = nt0; nt < nt1; ++nt) {
-          const int8_t *x_tile = p.Ximg + (size_t)nt * S * slice_bytes;
+          bulk_g2s(Rs + (size_t)i * slice_bytes, r_src + (size_t)i * slice_bytes, slice_bytes, r_full);
+      }
+      r_phase ^= 1;
+      for (int t = t0; t < t1; ++t) {
+        const int8_t *s_tile = p.str_img + (size_t)t * S * slice_bytes;
 #pragma unroll
-          for (int ps = 0; ps < P::NPASS; ++ps) {
-            for (int j = P::dhi(ps); j >= 0; --j) {
-              for (int k0 = 0; k0 < KS; k0 += P::STAGE_KS) {
+        for (int ps = 0; ps < P::NPASS; ++ps) {
+#pragma unroll
+          for (int j = P::dhi(ps); j >= 0; --j) {
+#pragma unroll
+            for (int kc = 0; kc < NCHUNK; ++kc) {
+              const int k0 = kc * P::STAGE_KS;
+              if (k0 < KS) {
                 const uint32_t bytes = (uint32_t)min(P::STAGE_KS, KS - k0) * KSTEP_BYTES;
-                mbar_wait(&empty_b[st], st_phase ^ 1);
-                mbar_expect_tx(&full_b[st], bytes);
-                bulk_g2s(Bs + (size_t)st * P::STAGE_BYTES,
-                         x_tile + (size_t)j * slice_bytes + (size_t)k0 * KSTEP_BYTES, bytes,
-                         &full_b[st]);
+                TIMED_WAIT(&empty_b[st], st_phase ^ 1, w_empty);
+                if (leader) {
+                  mbar_expect_tx(&full_b[st], bytes);
+                  bulk_g2s(Ss + (size_t)st * P::STAGE_BYTES,
+                           s_tile + (size_t)j * slice_bytes + (size_t)k0 * KSTEP_BYTES, bytes,
+                           &full_b[st]);
+                }
                 if (++st == NSTAGE) {
                   st = 0;
                   st_phase ^= 1;
@@ -336,100 +380,126 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
         }
       }
     }
+    if (p.prof && leader) p.prof[blockIdx.x * 8 + 4] = w_empty;
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      // instruction descriptor: D = s32, A = B = s8, both K-major, N >> 3, M >> 4
-      constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) |
-                                 ((uint32_t)(TM >> 4) << 24);
-      const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
-      uint32_t st = 0, st_phase = 0, a_phase = 0, slot_ctr = 0, pass_ctr = 0, units_done = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int split = u / p.n_mtiles;
-        const int nt0 = split * p.nt_per_split, nt1 = min(nt0 + p.nt_per_split, p.n_ntiles);
-        mbar_wait(a_full, a_phase);
-        tc_fence_after();
-        a_phase ^= 1;
-        for (int nt = nt0; nt < nt1; ++nt) {
+    const bool leader = elect_one();
+    // instruction descriptor: D = s32, A = B = s8, both K-major, N >> 3, M >> 4
+    constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) |
+                               ((uint32_t)(TM >> 4) << 24);
+    // low words of the shared-memory descriptors (address >> 4 | LBO 128 B); a k step is 256 units on
+    const uint32_t r_lo0 = ((smem_u32(Rs) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
+    const uint32_t s_lo0 = ((smem_u32(Ss) >> 4) & 0x3FFF) | ((128u >> 4) << 16);
+    const uint32_t slice16 = slice_bytes >> 4;
+    uint32_t st = 0, st_phase = 0, r_phase = 0, slot_ctr = 0, pass_ctr = 0, units_done = 0;
+    long long w_full = 0, w_slot = 0, w_a = 0;
+    const long long t_begin = clock64();
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int split = u / p.n_rtiles;
+      const int t0 = split * p.st_per_split, t1 = min(t0 + p.st_per_split, p.n_stiles);
+      TIMED_WAIT(r_full, r_phase, w_a);
+      tc_fence_after();
+      r_phase ^= 1;
+      for (int t = t0; t < t1; ++t) {
 #pragma unroll
-          for (int ps = 0; ps < P::NPASS; ++ps) {
-            const int dlo = P::dlo(ps), dhi = P::dhi(ps);
-            for (int j = dhi; j >= 0; --j) {
-              for (int k0 = 0; k0 < KS; k0 += P::STAGE_KS) {
-                const int ks = min(P::STAGE_KS, KS - k0);
-                mbar_wait(&full_b[st], st_phase);
+        for (int ps = 0; ps < P::NPASS; ++ps) {
+#pragma unroll
+          for (int j = P::dhi(ps); j >= 0; --j) {
+#pragma unroll
+            for (int kc = 0; kc < NCHUNK; ++kc) {
+              const int k0 = kc * P::STAGE_KS;
+              if (k0 < KS) {
+                TIMED_WAIT(&full_b[st], st_phase, w_full);
                 tc_fence_after();
-                const uint32_t b_st = b_base + st * P::STAGE_BYTES;
-                for (int d = max(dlo, j); d <= dhi; ++d) {
-                  const int i = d - j;
-                  const uint32_t c = slot_ctr + (uint32_t)(dhi - d);
-                  const uint32_t slot = c % NSLOT;
-                  const bool first = (i == 0 && k0 == 0);
-                  if (first) {
-                    // the accumulator slot must have been drained by every epilogue warp
-                    mbar_wait(&slot_empty[slot], ((c / NSLOT) & 1) ^ 1);
-                    tc_fence_after();
-                  }
-                  const uint32_t a_sl = a_base + (uint32_t)i * slice_bytes + (uint32_t)k0 * KSTEP_BYTES;
-                  for (int k = 0; k < ks; ++k)
-                    mma_i8(tmem + slot * TN, make_desc(a_sl + k * KSTEP_BYTES),
-                           make_desc(b_st + k * KSTEP_BYTES), idesc, (first && k == 0) ? 0u : 1u);
+                if (kc == 0 && j >= P::dlo(ps)) {
+                  // diagonal j is touched for the first time: its slot must have been drained
+                  const uint32_t c = slot_ctr + (uint32_t)(P::dhi(ps) - j);
+                  TIMED_WAIT(&slot_empty[c % NSLOT], ((c / NSLOT) & 1) ^ 1, w_slot);
+                  tc_fence_after();
                 }
-                mma_commit(&empty_b[st]);     // stage free once these MMAs have read it
+                const uint32_t s_lo = s_lo0 + st * (P::STAGE_BYTES >> 4);
+#pragma unroll
+                for (int d = (P::dlo(ps) > j ? P::dlo(ps) : j); d <= P::dhi(ps); ++d) {
+                  const int i = d - j;
+                  const uint32_t c = slot_ctr + (uint32_t)(P::dhi(ps) - d);
+                  const uint32_t taddr = tmem + (c % NSLOT) * TN;
+                  const uint32_t r_lo = r_lo0 + (uint32_t)i * slice16 + (uint32_t)k0 * (KSTEP_BYTES >> 4);
+#pragma unroll
+                  for (int k = 0; k < P::STAGE_KS; ++k) {
+                    if (k0 + k < KS && leader)
+                      mma_i8(taddr, r_lo + k * (KSTEP_BYTES >> 4), s_lo + k * (KSTEP_BYTES >> 4), idesc,
+                             (i == 0 && kc == 0 && k == 0) ? 0u : 1u);
+                  }
+                }
+                if (leader) mma_commit(&empty_b[st]);   // stage free once these MMAs have read it
                 if (++st == NSTAGE) {
                   st = 0;
                   st_phase ^= 1;
                 }
               }
             }
-            mma_commit(&acc_full[pass_ctr & 1]);
-            ++pass_ctr;
-            slot_ctr += (uint32_t)(dhi - dlo + 1);
           }
+          if (leader) mma_commit(&acc_full[pass_ctr % NACC]);
+          ++pass_ctr;
+          slot_ctr += (uint32_t)(P::dhi(ps) - P::dlo(ps) + 1);
         }
-        mma_commit(a_empty);                  // resident planes of A may be replaced
-        ++units_done;
       }
-      // every asynchronous arrive has landed before the CTA retires
-      if (units_done) mbar_wait(a_empty, (units_done - 1) & 1);
+      if (leader) mma_commit(r_empty);                  // resident planes may be replaced
+      ++units_done;
     }
-  } else {
-    // ===== epilogue: thread = one row of the tile x 32 columns =====
+    // every asynchronous arrive has landed before the CTA retires
+    if (units_done) mbar_wait(r_empty, (units_done - 1) & 1);
+    if (p.prof && leader) {
+      p.prof[blockIdx.x * 8 + 0] = clock64() - t_begin;
+      p.prof[blockIdx.x * 8 + 1] = w_full;
+      p.prof[blockIdx.x * 8 + 2] = w_slot;
+      p.prof[blockIdx.x * 8 + 3] = w_a;
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread = one TMEM lane (resident row) x 32 accumulator columns =====
     const int quarter = warp & 3;             // TMEM lanes a warp may read: 32 * (warp id % 4)
-    const int colq = (warp - 2) >> 2;
+    const int colq = (warp - 4) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colq * 32);
     uint32_t slot_ctr = 0, pass_ctr = 0;
+    long long w_acc = 0;
+    const long long t_begin = clock64();
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int split = u / p.n_mtiles, mt = u - split * p.n_mtiles;
-      const int nt0 = split * p.nt_per_split, nt1 = min(nt0 + p.nt_per_split, p.n_ntiles);
-      const int m = mt * TM + row;
-      const double rs = p.rscale[m];
-      int orow = m;
-      if (EPI == EPI_STORE && p.row_map) orow = p.row_map[m];
+      const int split = u / p.n_rtiles, rt = u - split * p.n_rtiles;
+      const int t0 = split * p.st_per_split, t1 = min(t0 + p.st_per_split, p.n_stiles);
+      const size_t r_idx = (size_t)rt * TM + row;      // resident index of this thread
+      // ROWSUMSQ: resident = rows of A; STORE: resident = columns of X
+      const double r_scale = __ldg((EPI == EPI_ROWSUMSQ ? p.rscale : p.cscale) + r_idx);
       double rsq = 0.0;
-      for (int nt = nt0; nt < nt1; ++nt) {
+      for (int t = t0; t < t1; ++t) {
         double T[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) T[e] = 0.0;
-#pragma unroll
-        for (int ps = 0; ps < P::NPASS; ++ps) {
-          mbar_wait(&acc_full[pass_ctr & 1], (pass_ctr >> 1) & 1);
+        // the 32 streamed indices of this thread: s0 + e; lane e fetches the power of two of
+        // index s0 + e, handed round by shuffles when the tile is finished
+        const size_t s0 = (size_t)t * TN + colq * 32;
+        // (a power of two, zero or NaN: the low word is zero, one 32-bit shuffle moves it)
+        const int s_hi = __double2hiint(__ldg((EPI == EPI_ROWSUMSQ ? p.cscale : p.rscale) + s0 + lane));
+        auto drain_pass = [&](auto ps_c) {
+          constexpr int ps = decltype(ps_c)::value;
+          TIMED_WAIT(&acc_full[pass_ctr % NACC], (pass_ctr / NACC) & 1, w_acc);
           tc_fence_after();
+          constexpr int ND = P::dhi(ps) - P::dlo(ps) + 1;
 #pragma unroll
-          for (int d = P::dhi(ps); d >= P::dlo(ps); --d) {
-            const uint32_t c = slot_ctr + (uint32_t)(P::dhi(ps) - d);
-            const uint32_t slot = c % NSLOT;
+          for (int dd = 0; dd < ND; ++dd) {
+            const uint32_t slot = (slot_ctr + (uint32_t)dd) % NSLOT;
             // int32 -> double through the exponent trick, already weighted by 256^(S-1-d):
             // bits (0x433 + sh) << 52 | (v ^ 2^31)  ==  (2^52 + 2^31 + v) * 2^sh
-            const int sh = 8 * (S - 1 - d);
+            const int sh = 8 * (S - 1 - (P::dhi(ps) - dd));
             const int hi = 0x43300000 + (sh << 20);
             const double magic = __hiloint2double(hi, (int)0x80000000);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               uint32_t v[16];
               tmem_ld16(t_lane + slot * TN + hh * 16, v);
+              tmem_wait_ld();
               if (hh == 1) {
+                // the slot is in registers: hand it back to the MMA issuer
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&slot_empty[slot]);
@@ -441,35 +511,51 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
               }
             }
           }
-          slot_ctr += (uint32_t)(P::dhi(ps) - P::dlo(ps) + 1);
+          slot_ctr += (uint32_t)ND;
           ++pass_ctr;
-        }
+        };
+        drain_pass(std::integral_constant<int, 0>{});
+        if constexpr (P::NPASS > 1) drain_pass(std::integral_constant<int, 1>{});
         // ---- finish the tile ----
-        const size_t col0 = (size_t)nt * TN + colq * 32;
-        const double *cs = p.cscale + col0;
         if (EPI == EPI_ROWSUMSQ) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const double val = T[e] * __ldg(cs + e);
+            const double val = T[e] * __hiloint2double(__shfl_sync(0xffffffffu, s_hi, e), 0);
             rsq = fma(val, val, rsq);
           }
-        } else if (orow >= 0) {
-          double *crow = p.C + (size_t)orow * p.ldc + col0;
+        } else {
+          // thread = column r_idx of C, T[e] = row s0 + e: a warp writes 32 consecutive doubles.
+          // Rows that share a scale row (scale_div consecutive ones) reuse one load; the (at
+          // most NQ) scale rows of the tile's 32 rows are fetched up front.
+          constexpr int NQ = 6;
+          double *cptr = p.C + s0 * (size_t)p.ldc + r_idx;
+          double sc[NQ];
+          int rem = 0, k = 0;
+          bool pre = true;
+          const double *sptr = nullptr;
           if (p.scale) {
-            const double *srow = p.scale + (size_t)(orow / p.scale_div) * p.lds + col0;
+            const int q = (int)(s0 / (size_t)p.scale_div);
+            rem = (int)(s0 - (size_t)q * p.scale_div);
+            const int nq = (int)((s0 + 31) / (size_t)p.scale_div) - q + 1;
+            sptr = p.scale + (size_t)q * p.lds + r_idx;
+            pre = nq <= NQ;
+            if (pre) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              const double2 sc = __ldg(reinterpret_cast<const double2 *>(srow + e));
-              const double2 cc = __ldg(reinterpret_cast<const double2 *>(cs + e));
-              __stcs(reinterpret_cast<double2 *>(crow + e),
-                     make_double2(T[e] * rs * cc.x * sc.x, T[e + 1] * rs * cc.y * sc.y));
+              for (int i = 0; i < NQ; ++i) sc[i] = i < nq ? __ldg(sptr + (size_t)i * p.lds) : 0.0;
             }
-          } else {
+          }
+          double f = p.scale ? r_scale * (pre ? sc[0] : __ldg(sptr)) : r_scale;
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              const double2 cc = __ldg(reinterpret_cast<const double2 *>(cs + e));
-              __stcs(reinterpret_cast<double2 *>(crow + e),
-                     make_double2(T[e] * rs * cc.x, T[e + 1] * rs * cc.y));
+          for (int e = 0; e < 32; ++e) {
+            const double sv = __hiloint2double(__shfl_sync(0xffffffffu, s_hi, e), 0);
+            if (!(p.dbg & 8)) __stcs(cptr, T[e] * f * sv);
+            cptr += p.ldc;
+            if (p.scale && ++rem == p.scale_div) {     // warp-uniform
+              rem = 0;
+              ++k;
+              const double nx = !pre ? __ldg(sptr + (size_t)k * p.lds)
+                                : k == 1 ? sc[1] : k == 2 ? sc[2] : k == 3 ? sc[3] : k == 4 ? sc[4] : sc[5];
+              f = r_scale * nx;
             }
           }
         }
@@ -480,10 +566,14 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
         asm volatile("bar.sync 1, %0;\n" ::"n"(N_EPI_WARPS * 32) : "memory");
         if (colq == 0) {
           const double v = red[row] + red[TM + row] + red[2 * TM + row] + red[3 * TM + row];
-          p.rowsq[(size_t)split * p.M_pad + m] = v * rs * rs;
+          p.rowsq[(size_t)split * p.M_pad + r_idx] = v * r_scale * r_scale;
         }
         asm volatile("bar.sync 1, %0;\n" ::"n"(N_EPI_WARPS * 32) : "memory");
       }
+    }
+    if (p.prof && warp == 4 && lane == 0) {
+      p.prof[blockIdx.x * 8 + 5] = w_acc;
+      p.prof[blockIdx.x * 8 + 6] = clock64() - t_begin;
     }
   }
 
@@ -513,13 +603,37 @@ template <int S> int quantize_cols(plsb_ctx *h, const double *X, int ldx, int N_
   return PLSB_OK;
 }
 
-template <int S, int EPI> int launch_kernel(plsb_ctx *h, const TcParams &p, cudaStream_t st) {
+template <int S, int EPI, int NP0> int launch_kernel(plsb_ctx *h, const TcParams &p, cudaStream_t st) {
   KernelTimer kt(h, KC_GEMM, st);
-  auto kern = xcov_gemm_i8_kernel<S, EPI>;
-  PLSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<S>::SMEM));
-  const int units = p.n_mtiles * p.n_splits;
-  kern<<<std::min(units, h->sm_count), THREADS, Plan<S>::SMEM, st>>>(p);
+  auto kern = xcov_gemm_i8_kernel<S, EPI, NP0>;
+  constexpr int SMEM = Plan<S, NP0>::SMEM;
+  PLSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  const int units = p.n_rtiles * p.n_splits;
+  const int grid = std::min(units, h->sm_count);
+  if (!tune_int("PLSB_I8_PROF", 0)) {
+    kern<<<grid, THREADS, SMEM, st>>>(p);
+    PLSB_LAUNCHED(h);
+    return PLSB_OK;
+  }
+  // profiling aid: where the roles of the kernel wait (cycles, mean over the CTAs)
+  TcParams q = p;
+  PLSB_CUDA(cudaMalloc(&q.prof, sizeof(long long) * 8 * grid));
+  PLSB_CUDA(cudaMemsetAsync(q.prof, 0, sizeof(long long) * 8 * grid, st));
+  kern<<<grid, THREADS, SMEM, st>>>(q);
   PLSB_LAUNCHED(h);
+  std::vector<long long> hp(8 * (size_t)grid);
+  PLSB_CUDA(cudaMemcpyAsync(hp.data(), q.prof, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost, st));
+  PLSB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(q.prof);
+  double m[8] = {0};
+  for (int c = 0; c < grid; ++c)
+    for (int k = 0; k < 8; ++k) m[k] += (double)hp[8 * c + k] / grid;
+  const double tiles = (double)p.n_rtiles * p.n_stiles / grid;
+  fprintf(stderr,
+          "[i8 prof] S=%d epi=%d grid=%d tiles/CTA=%.0f: cycles/tile %.0f | mma waits: stage %.0f "
+          "slot %.0f A %.0f | producer waits empty %.0f | epilogue waits acc %.0f of %.0f\n",
+          S, EPI, grid, tiles, m[0] / tiles, m[1] / tiles, m[2] / tiles, m[3] / tiles, m[4] / tiles,
+          m[5] / tiles, m[6] / tiles);
   return PLSB_OK;
 }
 
@@ -563,38 +677,50 @@ template <int S> int run_i8(plsb_ctx *h, const GemmArgs &a, int KS, int k_valid,
   PLSB_TRY(quantize_rows<S>(h, a.A, a.lda, a.M_pad, a.M_pad, k_valid, KS, h->aplanes.as<int8_t>(),
                             h->ascale.as<double>(), st));
   TcParams p;
-  p.Aimg = h->aplanes.as<int8_t>();
-  p.Ximg = xc->img.as<int8_t>();
   p.rscale = h->ascale.as<double>();
   p.cscale = xc->scale.as<double>();
   p.KS = KS;
-  p.n_mtiles = n_mtiles;
-  p.n_ntiles = n_ntiles;
+  if (a.rowsq) {
+    // rows of A resident, column tiles of X streamed
+    p.res_img = h->aplanes.as<int8_t>();
+    p.str_img = xc->img.as<int8_t>();
+    p.n_rtiles = n_mtiles;
+    p.n_stiles = n_ntiles;
+    p.n_splits = a.n_splits;
+  } else {
+    // columns of X resident, row tiles of A streamed
+    p.res_img = xc->img.as<int8_t>();
+    p.str_img = h->aplanes.as<int8_t>();
+    p.n_rtiles = n_ntiles;
+    p.n_stiles = n_mtiles;
+    p.n_splits = gemm_i8_pick_splits(h, a.N_pad, n_mtiles);
+  }
+  p.st_per_split = (p.n_stiles + p.n_splits - 1) / p.n_splits;
   p.C = a.C;
   p.ldc = a.ldc;
-  p.row_map = a.row_map;
   p.scale = a.scale;
   p.scale_div = a.scale_div;
   p.lds = a.lds;
   p.rowsq = a.rowsq;
   p.M_pad = a.M_pad;
-  if (a.rowsq) {
-    p.n_splits = a.n_splits;
-  } else {
-    p.n_splits = gemm_i8_pick_splits(h, a.M_pad, n_ntiles);
+  p.prof = nullptr;
+  p.dbg = tune_int("PLSB_I8_DBG", 0);
+  if (S == 6 && tune_int("PLSB_I8_NP0", 4) == 3) {
+    if (a.rowsq) return launch_kernel<S, EPI_ROWSUMSQ, 3>(h, p, st);
+    return launch_kernel<S, EPI_STORE, 3>(h, p, st);
   }
-  p.nt_per_split = (n_ntiles + p.n_splits - 1) / p.n_splits;
-  if (a.rowsq) return launch_kernel<S, EPI_ROWSUMSQ>(h, p, st);
-  return launch_kernel<S, EPI_STORE>(h, p, st);
+  if (a.rowsq) return launch_kernel<S, EPI_ROWSUMSQ, 4>(h, p, st);
+  return launch_kernel<S, EPI_STORE, 4>(h, p, st);
 }
 
 }  // namespace
 
-// Splits of the N range per M tile for the persistent kernel: units (M tile, split) are
-// dealt round-robin to one CTA per SM; a unit costs its N tiles plus ~0.6 tile for loading
-// the resident planes of A and filling / draining the pipeline.
-int gemm_i8_pick_splits(const plsb_ctx *h, int M_pad, int n_ntiles) {
-  const int n_mtiles = M_pad / TM;
+// Splits of the streamed range per resident tile for the persistent kernel: units (resident
+// tile, split) are dealt round-robin to one CTA per SM; a unit costs its streamed tiles plus
+// ~0.6 tile for loading the resident planes and filling / draining the pipeline.
+// (res_pad: padded extent of the resident operand, n_ntiles: tiles of the streamed one.)
+int gemm_i8_pick_splits(const plsb_ctx *h, int res_pad, int n_ntiles) {
+  const int n_mtiles = res_pad / TM;
   int best = 1;
   double best_cost = 1e300;
   for (int want = 1; want <= std::min(n_ntiles, 128); ++want) {
@@ -617,7 +743,7 @@ int gemm_i8_pick_splits(const plsb_ctx *h, int M_pad, int n_ntiles) {
 bool gemm_i8_applies(const plsb_ctx *h, const GemmArgs &a) {
   if (h->gemm_backend == PLSB_GEMM_DMMA) return false;
   if (tune_int("PLSB_GEMM_BACKEND", 1) == 0) return false;
-  if (a.kranges) return false;
+  if (a.kranges || a.row_map) return false;
   const int k_valid = a.k_valid > 0 ? a.k_valid : a.Kd;
   if ((k_valid + 31) / 32 > MAX_KS) return false;
   if (a.M_pad % TM || a.N_pad % TN) return false;
