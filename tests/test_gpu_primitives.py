@@ -36,11 +36,63 @@ def rel_err(a, b):
                                     (300, 1000, 80), (129, 257, 33),
                                     (1000, 130, 200)])
 def test_dgemm_matches_numpy(torch_cuda, M, N, Kd):
+    """The FP64 DMMA kernel against NumPy."""
     rs = np.random.RandomState(M * 7 + N)
     A, X = rs.randn(M, Kd), rs.randn(Kd, N)
-    eng = make_engine('behavioral', 4, 8, 1, [4])
+    eng = make_engine('behavioral', 4, 8, 1, [4], gemm_backend='dmma')
     C = eng.dgemm(A, X).cpu().numpy()
     np.testing.assert_allclose(C, A @ X, rtol=1e-12, atol=1e-12)
+
+
+# tolerance per number of int8 digit planes, relative to |a_row| |x_col| per entry
+SLICE_TOL = {5: 2e-10, 6: 1e-12, 7: 8e-15}
+
+
+@pytest.mark.parametrize('slices', [5, 6, 7])
+@pytest.mark.parametrize('M,N,Kd', [(1, 1, 1), (7, 5, 3), (128, 128, 32),
+                                    (300, 1000, 80), (129, 257, 33),
+                                    (1000, 130, 200), (513, 300, 224)])
+def test_slice_gemm_matches_numpy(torch_cuda, M, N, Kd, slices):
+    """The int8 slice GEMM on the tcgen05 tensor cores (csrc/gemm_i8.cu) against
+    NumPy: entry-wise error bounded relative to the norms of the row of A and the
+    column of X it contracts (the bound of a floating-point dot product)."""
+    rs = np.random.RandomState(M * 7 + N + slices)
+    # rows of A / columns of X on very different scales: every row and column
+    # carries its own power of two
+    A = rs.randn(M, Kd) * 10.0 ** rs.randint(-6, 7, size=(M, 1))
+    X = rs.randn(Kd, N) * 10.0 ** rs.randint(-6, 7, size=(1, N))
+    eng = make_engine('behavioral', 4, 8, 1, [4], gemm_backend='auto',
+                      gemm_slices=slices)
+    C = eng.dgemm(A, X).cpu().numpy()
+    norm = np.sqrt((A ** 2).sum(1))[:, None] * np.sqrt((X ** 2).sum(0))[None, :]
+    err = np.abs(C - A @ X) / norm
+    assert err.max() < SLICE_TOL[slices], err.max()
+
+
+def test_slice_gemm_special_values(torch_cuda):
+    """Zero rows / columns stay exactly zero, NaN and Inf poison exactly the rows /
+    columns a product would, contractions beyond 224 rows take the DMMA kernel."""
+    rs = np.random.RandomState(11)
+    eng = make_engine('behavioral', 4, 8, 1, [4], gemm_backend='auto')
+    A, X = rs.randn(200, 100), rs.randn(100, 300)
+    A[5] = 0.0
+    X[:, 7] = 0.0
+    A[3, 5] = np.nan
+    X[7, 9] = np.inf
+    C = eng.dgemm(A, X).cpu().numpy()
+    assert np.all(C[5, np.arange(300) != 9] == 0.0)
+    assert np.all(C[np.arange(200) != 3, 7] == 0.0)
+    assert np.isnan(C[3]).all() and not np.isfinite(C[:, 9]).any()
+    rest = np.delete(np.delete(C, 3, 0), 9, 1)
+    ref = np.delete(np.delete(A, 3, 0) @ np.delete(X, 9, 1), [], 0)
+    assert np.isfinite(rest).all()
+    assert rel_err(rest, ref) < 1e-11
+    A, X = rs.randn(64, 300), rs.randn(300, 200)      # Kd > 224
+    np.testing.assert_allclose(eng.dgemm(A, X).cpu().numpy(), A @ X,
+                               rtol=1e-12, atol=1e-12)
+    # tiny and huge magnitudes: the powers of two carry them
+    A, X = rs.randn(130, 64) * 1e-150, rs.randn(64, 140) * 1e140
+    assert rel_err(eng.dgemm(A, X).cpu().numpy(), A @ X) < 1e-11
 
 
 def test_dgemm_linearity_large(torch_cuda):
@@ -48,10 +100,11 @@ def test_dgemm_linearity_large(torch_cuda):
     (aA1 + bA2) X == a(A1 X) + b(A2 X)."""
     rs = np.random.RandomState(5)
     A1, A2, X = rs.randn(2000, 80), rs.randn(2000, 80), rs.randn(80, 10000)
-    eng = make_engine('behavioral', 4, 8, 1, [4])
-    lhs = eng.dgemm(2.0 * A1 - 3.0 * A2, X)
-    rhs = 2.0 * eng.dgemm(A1, X) - 3.0 * eng.dgemm(A2, X)
-    assert rel_err(lhs.cpu().numpy(), rhs.cpu().numpy()) < 1e-12
+    for backend, tol in (('dmma', 1e-12), ('auto', 1e-11)):
+        eng = make_engine('behavioral', 4, 8, 1, [4], gemm_backend=backend)
+        lhs = eng.dgemm(2.0 * A1 - 3.0 * A2, X)
+        rhs = 2.0 * eng.dgemm(A1, X) - 3.0 * eng.dgemm(A2, X)
+        assert rel_err(lhs.cpu().numpy(), rhs.cpu().numpy()) < tol
 
 
 # ---------------------------------------------------------------------------
