@@ -587,6 +587,12 @@ def main():
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--no-fast-path', action='store_true',
                     help='skip the separately reported sample-space permutation leg')
+    ap.add_argument('--gemm-backend', default='auto', choices=['auto', 'dmma'],
+                    help="cross-covariance contraction: 'auto' = int8 slice GEMM "
+                         "on the tcgen05 tensor cores where it applies, 'dmma' = "
+                         "FP64 DMMA everywhere")
+    ap.add_argument('--gemm-slices', type=int, default=6, choices=[5, 6, 7],
+                    help='int8 digit planes per operand of the slice GEMM')
     ap.add_argument('--workspace-gib', type=float, default=None,
                     help='chunk workspace of the engine (default: library default)')
     args = ap.parse_args()
@@ -641,7 +647,9 @@ def main():
         from pypyls_b200.types.regression import gaussian_tables
         eng = ResamplingEngine('regression', w['S'], w['B'], w['T'], [w['S']],
                                1, device=local_rank, n_components=w['L'],
-                               workspace_bytes=ws_bytes)
+                               workspace_bytes=ws_bytes,
+                               gemm_backend=args.gemm_backend,
+                               gemm_slices=args.gemm_slices)
         eng.set_data(Xh - Xh.mean(0, keepdim=True),
                      Yh - Yh.mean(0, keepdim=True))
         rs0 = np.random.RandomState(1234)
@@ -657,7 +665,9 @@ def main():
     else:
         eng = ResamplingEngine(kind, w['S'], w['B'], w['T'], w['groups'],
                                w['n_cond'], device=local_rank,
-                               workspace_bytes=ws_bytes)
+                               workspace_bytes=ws_bytes,
+                               gemm_backend=args.gemm_backend,
+                               gemm_slices=args.gemm_slices)
         eng.set_data(Xh, Yh if kind == 'behavioral' else None)
         U, d, V = eng.decompose()
         bs, add_orig = (U * d[None, :]).contiguous(), kind == 'behavioral'
@@ -727,10 +737,12 @@ def main():
     sampler = ClockSampler(local_rank)
     eng.timing_enable(True)
     eng.timing_read()
+    eng.gemm_work(reset=True)
     launches0 = eng.launch_count
     ms = timed(step, args.steps)
     launches = eng.launch_count - launches0
     classes = eng.timing_read()
+    i8_macs, dmma_flops = eng.gemm_work(reset=True)
     eng.timing_enable(False)
     value = (P + R) * args.steps / (ms * 1e-3)
 
@@ -754,7 +766,8 @@ def main():
         def call(seed, Xa=Xh, Ya=Yh):
             kw = dict(n_perm=P, n_boot=R, seed=seed, verbose=False,
                       device=local_rank, workspace_bytes=ws_bytes,
-                      gather_results='root')
+                      gather_results='root', gemm_backend=args.gemm_backend,
+                      gemm_slices=args.gemm_slices)
             return frontend_call(pyls, w, Xa, Ya, **kw)
         # warm-up holds on to the previous result like the timed loop does, so that
         # the pinned host blocks of two live results exist before timing starts
@@ -853,7 +866,34 @@ def main():
         executed = 2.0 * w['S'] * w['B'] * (J * w['T']) * n_perm + \
             2.0 * ng * w['B'] * (J * w['T']) * n_boot
         roofline['executed_flop_per_step'] = executed
-    if bound == 'tensor' and flops:
+    if bound == 'tensor' and flops and top == 'xcov_gemm' and i8_macs > 0:
+        # The class ran (mostly) as int8 digit-plane products on the tcgen05
+        # tensor cores: its ceiling is the int8 tensor rate.  achieved = int8
+        # operations the launches executed (padded tiles x plane products, from the
+        # library's own counter) / summed launch time; the FP64 flop the DMMA
+        # kernel still executed in the class (squared-operand statistics of grouped
+        # layouts, ...) are not counted, so the fraction is a lower bound.
+        ach = 2.0 * i8_macs / (top_ms * 1e-3) / 1e12
+        if peaks.get('bf16_tflops'):
+            peak, src = 2.0 * peaks['bf16_tflops'], \
+                '2 x MEASURED_PEAKS.json bf16_tflops (dense int8 issues at twice ' \
+                'the bf16 rate on sm_100a; scripts/probes/tc_rate_probe.cu ' \
+                'measured 4.2-4.4 POP/s of back-to-back int8 MMAs on this pool)'
+        else:
+            peak, src = 4500.0, 'fallback: nominal dense int8 4.5 POP/s'
+        fp64_eq = flops * args.steps / (top_ms * 1e-3) / 1e12
+        roofline.update(achieved=ach, peak=peak, unit='TOP/s (int8)',
+                        frac=ach / peak, peak_source=src,
+                        gemm_backend='int8 slice GEMM, %d digit planes (%d plane '
+                                     'products per FP64 product)' % (
+                                         args.gemm_slices, args.gemm_slices *
+                                         (args.gemm_slices + 1) // 2),
+                        int8_ops_per_step=2.0 * i8_macs / args.steps,
+                        dmma_flop_per_step=dmma_flops / args.steps,
+                        fp64_equivalent_tflops=fp64_eq,
+                        fp64_dgemm_peak_tflops=peak_tf,
+                        fp64_equivalent_over_dgemm_peak=fp64_eq / peak_tf)
+    elif bound == 'tensor' and flops:
         ach = flops * args.steps / (top_ms * 1e-3) / 1e12
         if roofline.get('executed_flop_per_step'):
             roofline['frac_executed'] = roofline['executed_flop_per_step'] * \

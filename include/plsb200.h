@@ -72,6 +72,10 @@ int plsb_set_workspace_limit(plsb_handle_t h, uint64_t bytes);
  * ~1e-13 |a||x| of the FP64 product, 7: ~1e-15). */
 enum { PLSB_GEMM_AUTO = 0, PLSB_GEMM_DMMA = 1 };
 int plsb_set_gemm_backend(plsb_handle_t h, int backend, int n_slices);
+/* Work the contraction kernels have executed since the last reset: int8
+ * multiply-accumulates of the slice GEMM (padded tiles x digit-plane products)
+ * and FP64 flop of the DMMA kernel.  For roofline accounting (bench.py). */
+int plsb_gemm_work(plsb_handle_t h, double *i8_macs, double *dmma_flops, int reset);
 
 /*
  * Analysis layout.  Replaces BasePLS.__init__ validation + utils.dummy_code

@@ -32,6 +32,7 @@ PROTOTYPES = {
     'plsb_destroy': (_i, [_vp]),
     'plsb_set_workspace_limit': (_i, [_vp, _u64]),
     'plsb_set_gemm_backend': (_i, [_vp, _i, _i]),
+    'plsb_gemm_work': (_i, [_vp, C.POINTER(_dbl), C.POINTER(_dbl), _i]),
     'plsb_configure': (_i, [_vp, _i, _i, _i, _i, _i, _ip, _i, _i, _i]),
     'plsb_set_data': (_i, [_vp, _vp, _vp, _vp]),
     'plsb_decompose': (_i, [_vp, _vp, _vp, _vp, _vp]),

@@ -95,7 +95,12 @@ class BasePLS():
         returns the complete results, default; 'root' -- the per-resample
         arrays (bootstrap distribution, tables) and the B-sized arrays are
         moved to the host of rank 0 only, the other ranks return the
-        statistics (p-values, intervals) and ``None`` for those arrays).
+        statistics (p-values, intervals) and ``None`` for those arrays),
+        ``gemm_backend`` ('auto', default: the cross-covariance contraction
+        runs as int8 digit-plane products on the tcgen05 tensor cores where
+        that kernel applies; 'dmma': FP64 DMMA everywhere) and ``gemm_slices``
+        (digit planes per operand, 5 / 6 / 7; default 6: entries within 1e-13
+        of the FP64 product relative to the norms they contract).
     """
 
     engine_mode = None
@@ -144,7 +149,11 @@ class BasePLS():
                                    'mean_centering') or 0,
                                device=device,
                                workspace_bytes=self.inputs.get(
-                                   'workspace_bytes'))
+                                   'workspace_bytes'),
+                               gemm_backend=self.inputs.get(
+                                   'gemm_backend') or 'auto',
+                               gemm_slices=self.inputs.get(
+                                   'gemm_slices') or 6)
         eng.set_data(X, Y)
         return eng
 

@@ -231,6 +231,14 @@ int plsb_set_gemm_backend(plsb_handle_t h, int backend, int n_slices) {
   return PLSB_OK;
 }
 
+int plsb_gemm_work(plsb_handle_t h, double *i8_macs, double *dmma_flops, int reset) {
+  PLSB_CHECK(h != nullptr, PLSB_ERR_ARG, "null handle");
+  if (i8_macs) *i8_macs = h->i8_macs;
+  if (dmma_flops) *dmma_flops = h->dmma_flops;
+  if (reset) h->i8_macs = h->dmma_flops = 0.0;
+  return PLSB_OK;
+}
+
 int64_t plsb_launch_count(plsb_handle_t h) { return h ? h->launches : 0; }
 
 int plsb_timing_enable(plsb_handle_t h, int on) {

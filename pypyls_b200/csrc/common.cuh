@@ -182,6 +182,8 @@ struct plsb_ctx {
   plsb::DevBuf aplanes, ascale;
   int gemm_backend = PLSB_GEMM_AUTO;
   int gemm_slices = 6;
+  // work counters of the contraction kernels since the last plsb_gemm_work(reset)
+  double i8_macs = 0.0, dmma_flops = 0.0;
   // per-chunk workspaces
   plsb::DevBuf A, Ac, R, S1, S2, G, H, M, lam, rowsq, part, misc, idxall, flags, maps, pctl, big;
 };

@@ -603,6 +603,7 @@ int launch_variant(plsb_ctx *h, const GemmArgs &a, int n_ntiles, int n_splits, c
                                        a.M_pad);
   }
   PLSB_LAUNCHED(h);
+  h->dmma_flops += 2.0 * a.M_pad * a.N_pad * (a.k_len > 0 ? a.k_len : (a.k_valid > 0 ? a.k_valid : a.Kd));
   return PLSB_OK;
 }
 

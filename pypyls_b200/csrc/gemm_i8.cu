@@ -705,6 +705,7 @@ template <int S> int run_i8(plsb_ctx *h, const GemmArgs &a, int KS, int k_valid,
   p.M_pad = a.M_pad;
   p.prof = nullptr;
   p.dbg = tune_int("PLSB_I8_DBG", 0);
+  h->i8_macs += (double)a.M_pad * a.N_pad * (KS * 32.0) * (S * (S + 1) / 2);
   if (S == 6 && tune_int("PLSB_I8_NP0", 4) == 3) {
     if (a.rowsq) return launch_kernel<S, EPI_ROWSUMSQ, 3>(h, p, st);
     return launch_kernel<S, EPI_STORE, 3>(h, p, st);

@@ -163,6 +163,14 @@ class ResamplingEngine:
         _cabi.check(self._lib.plsb_set_gemm_backend(self._h, code,
                                                     int(n_slices)))
 
+    def gemm_work(self, reset=True):
+        """(int8 multiply-accumulates of the slice GEMM, FP64 flop of the DMMA
+        kernel) executed since the last reset."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        _cabi.check(self._lib.plsb_gemm_work(self._h, C.byref(a), C.byref(b),
+                                             int(bool(reset))))
+        return float(a.value), float(b.value)
+
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:
             # the next borrower waits for everything queued so far on this

@@ -146,7 +146,11 @@ class PLSRegression(BasePLS):
                                Y.shape[1], [X.shape[0]], 1, device=device,
                                workspace_bytes=self.inputs.get(
                                    'workspace_bytes'),
-                               n_components=self.n_components)
+                               n_components=self.n_components,
+                               gemm_backend=self.inputs.get(
+                                   'gemm_backend') or 'auto',
+                               gemm_slices=self.inputs.get(
+                                   'gemm_slices') or 6)
         eng.set_data(X, Y)
         return eng
 
