@@ -120,6 +120,7 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, const double *yperm, int n, 
   if (scaled) {
     g.scale = h->S1.as<double>();
     g.scale_div = l.T;
+    g.scale_rows = (int)Mc_pad;
     g.lds = l.ldx;
   }
   g.A = h->A.as<double>();
@@ -1208,6 +1209,7 @@ static int crossval_chunk(plsb_ctx *h, const int32_t *mask, int n, int max_test,
                              ntrain));
     g.scale = h->S1.as<double>();
     g.scale_div = l.T;
+    g.scale_rows = (int)S_rows;
     g.lds = l.ldx;
   }
   g.A = h->A.as<double>();
@@ -1328,6 +1330,7 @@ static int halves_chunk(plsb_ctx *h, const int32_t *masks, const double *yperm,
                              ncell));
     g.scale = h->S1.as<double>();
     g.scale_div = l.T;
+    g.scale_rows = (int)Mc_pad;
     g.lds = l.ldx;
   }
   g.A = h->A.as<double>();

@@ -233,6 +233,7 @@ struct GemmArgs {
   const int *row_map = nullptr;   // optional: output row of operand row m, <0 = skip
   const double *scale = nullptr;  // optional: C[m,n] *= scale[(m / scale_div) * lds + n]
   int scale_div = 1;
+  int scale_rows = 0;             // rows of `scale` (0: ceil(M_pad / scale_div))
   long long lds = 0;
   // ROWSUMSQ epilogue: rowsq[split * M_pad + m] = sum_n C[m,n]^2 over the split
   double *rowsq = nullptr;

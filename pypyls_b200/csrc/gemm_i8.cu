@@ -70,7 +70,7 @@ struct TcParams {
   double *C;
   long long ldc;
   const double *scale;
-  int scale_div;
+  int scale_div, scale_rows;
   long long lds;
   double *rowsq;
   int M_pad;
@@ -462,8 +462,6 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colq * 32);
     uint32_t slot_ctr = 0, pass_ctr = 0;
-    long long w_acc = 0;
-    const long long t_begin = clock64();
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int split = u / p.n_rtiles, rt = u - split * p.n_rtiles;
       const int t0 = split * p.st_per_split, t1 = min(t0 + p.st_per_split, p.n_stiles);
@@ -482,16 +480,17 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
         const int s_hi = __double2hiint(__ldg((EPI == EPI_ROWSUMSQ ? p.cscale : p.rscale) + s0 + lane));
         auto drain_pass = [&](auto ps_c) {
           constexpr int ps = decltype(ps_c)::value;
-          TIMED_WAIT(&acc_full[pass_ctr % NACC], (pass_ctr / NACC) & 1, w_acc);
+          mbar_wait(&acc_full[pass_ctr % NACC], (pass_ctr / NACC) & 1);
           tc_fence_after();
           constexpr int ND = P::dhi(ps) - P::dlo(ps) + 1;
-#pragma unroll
+          // (not unrolled over the diagonals: the instruction footprint of the three roles
+          // has to stay in the instruction cache)
+#pragma unroll 1
           for (int dd = 0; dd < ND; ++dd) {
             const uint32_t slot = (slot_ctr + (uint32_t)dd) % NSLOT;
             // int32 -> double through the exponent trick, already weighted by 256^(S-1-d):
             // bits (0x433 + sh) << 52 | (v ^ 2^31)  ==  (2^52 + 2^31 + v) * 2^sh
-            const int sh = 8 * (S - 1 - (P::dhi(ps) - dd));
-            const int hi = 0x43300000 + (sh << 20);
+            const int hi = 0x43300000 + ((8 * (S - 1 - P::dhi(ps)) + 8 * dd) << 20);
             const double magic = __hiloint2double(hi, (int)0x80000000);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -525,26 +524,23 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
           }
         } else {
           // thread = column r_idx of C, T[e] = row s0 + e: a warp writes 32 consecutive doubles.
-          // Rows that share a scale row (scale_div consecutive ones) reuse one load; the (at
-          // most NQ) scale rows of the tile's 32 rows are fetched up front.
-          constexpr int NQ = 6;
+          // Rows that share a scale row (scale_div consecutive ones) reuse one load, and the
+          // next scale row is fetched while the rows of the current one are written.
           double *cptr = p.C + s0 * (size_t)p.ldc + r_idx;
-          double sc[NQ];
-          int rem = 0, k = 0;
-          bool pre = true;
+          double f = r_scale, nxt = 0.0;
           const double *sptr = nullptr;
+          int rem = 0;
+          int q_left = 0;    // scale rows after the current one (rows beyond the table reuse the last)
           if (p.scale) {
-            const int q = (int)(s0 / (size_t)p.scale_div);
+            int q = (int)(s0 / (size_t)p.scale_div);
             rem = (int)(s0 - (size_t)q * p.scale_div);
-            const int nq = (int)((s0 + 31) / (size_t)p.scale_div) - q + 1;
+            q = min(q, p.scale_rows - 1);
+            q_left = p.scale_rows - 1 - q;
             sptr = p.scale + (size_t)q * p.lds + r_idx;
-            pre = nq <= NQ;
-            if (pre) {
-#pragma unroll
-              for (int i = 0; i < NQ; ++i) sc[i] = i < nq ? __ldg(sptr + (size_t)i * p.lds) : 0.0;
-            }
+            f = r_scale * __ldg(sptr);
+            if (q_left > 0) sptr += p.lds;
+            nxt = __ldg(sptr);
           }
-          double f = p.scale ? r_scale * (pre ? sc[0] : __ldg(sptr)) : r_scale;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const double sv = __hiloint2double(__shfl_sync(0xffffffffu, s_hi, e), 0);
@@ -552,10 +548,9 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
             cptr += p.ldc;
             if (p.scale && ++rem == p.scale_div) {     // warp-uniform
               rem = 0;
-              ++k;
-              const double nx = !pre ? __ldg(sptr + (size_t)k * p.lds)
-                                : k == 1 ? sc[1] : k == 2 ? sc[2] : k == 3 ? sc[3] : k == 4 ? sc[4] : sc[5];
-              f = r_scale * nx;
+              f = r_scale * nxt;
+              if (--q_left > 0) sptr += p.lds;
+              nxt = __ldg(sptr);
             }
           }
         }
@@ -570,10 +565,6 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
         }
         asm volatile("bar.sync 1, %0;\n" ::"n"(N_EPI_WARPS * 32) : "memory");
       }
-    }
-    if (p.prof && warp == 4 && lane == 0) {
-      p.prof[blockIdx.x * 8 + 5] = w_acc;
-      p.prof[blockIdx.x * 8 + 6] = clock64() - t_begin;
     }
   }
 
@@ -631,9 +622,8 @@ template <int S, int EPI, int NP0> int launch_kernel(plsb_ctx *h, const TcParams
   const double tiles = (double)p.n_rtiles * p.n_stiles / grid;
   fprintf(stderr,
           "[i8 prof] S=%d epi=%d grid=%d tiles/CTA=%.0f: cycles/tile %.0f | mma waits: stage %.0f "
-          "slot %.0f A %.0f | producer waits empty %.0f | epilogue waits acc %.0f of %.0f\n",
-          S, EPI, grid, tiles, m[0] / tiles, m[1] / tiles, m[2] / tiles, m[3] / tiles, m[4] / tiles,
-          m[5] / tiles, m[6] / tiles);
+          "slot %.0f resident %.0f | producer waits empty %.0f\n",
+          S, EPI, grid, tiles, m[0] / tiles, m[1] / tiles, m[2] / tiles, m[3] / tiles, m[4] / tiles);
   return PLSB_OK;
 }
 
@@ -700,6 +690,7 @@ template <int S> int run_i8(plsb_ctx *h, const GemmArgs &a, int KS, int k_valid,
   p.ldc = a.ldc;
   p.scale = a.scale;
   p.scale_div = a.scale_div;
+  p.scale_rows = a.scale_rows > 0 ? a.scale_rows : (a.M_pad + a.scale_div - 1) / a.scale_div;
   p.lds = a.lds;
   p.rowsq = a.rowsq;
   p.M_pad = a.M_pad;

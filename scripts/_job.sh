@@ -1,1 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gputest_i8_v1.log 2>&1; echo "rc=$?" >> gpurun_out/r2_gputest_i8_v1.log
+timeout 200 python scripts/i8_gemm_check.py quick > gpurun_out/r2_i8_check9.txt 2>&1; echo "rc=$?" >> gpurun_out/r2_i8_check9.txt
+timeout 300 python scripts/i8_prof.py 25000 100000 6 0 > gpurun_out/r2_i8_prof8.txt 2>&1; echo "rc=$?" >> gpurun_out/r2_i8_prof8.txt
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_primitives.py -m gpu -x -q > gpurun_out/r2_gputest_i8_v2.log 2>&1; echo "rc=$?" >> gpurun_out/r2_gputest_i8_v2.log

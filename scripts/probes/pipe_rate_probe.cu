@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(512) rate(long long *cycles, double *sink, int
     for (int i = 0; i < 8; ++i) {
       if (OP == 0) a[i] = a[i] + seed;                     // DADD
       if (OP == 1) a[i] = fma(a[i], seed, seed);           // DFMA
-      if (OP == 2) w[i] = (long long)x * 256 + w[i];       // IMAD.WIDE
+      if (OP == 2) w[i] = (long long)(int)w[(i + 1) & 7] * 256 + w[i];   // IMAD.WIDE
+      if (OP == 6) w[i] = w[i] + (long long)(int)w[(i + 1) & 7];         // 64-bit add of a sign-extended int
       if (OP == 3) a[i] = __hiloint2double(0x43300000, __double2loint(a[i]) ^ 0x80000000);  // LOP3
       if (OP == 4) a[i] = __shfl_sync(0xffffffffu, a[i], (i + it) & 31);                    // 2 SHFL
       if (OP == 5) w[i] = __shfl_sync(0xffffffffu, (int)w[i], (i + it) & 31);               // 1 SHFL
@@ -54,6 +55,7 @@ int main() {
   run<1>("DFMA", 1);
   run<1>("DFMA", 148);
   run<2>("IMAD.WIDE", 1);
+  run<6>("IADD64", 1);
   run<3>("LOP3", 1);
   run<4>("SHFL x2", 1);
   run<5>("SHFL", 1);
