@@ -15,17 +15,17 @@
 // column scales, or row sums of squares).  With S = 6 (21 integer products) the result
 // differs from the FP64 product by ~1e-13 of |a||x| per entry; S = 7 gives ~1e-15.
 //
-// Kernel layout (one persistent CTA per SM, 18 warps):
-//   warp 0      producer: cp.async.bulk (TMA bulk copies) of pre-tiled digit planes; the planes
-//               of the CTA's 128 rows of A stay resident in shared memory (S x 28 KB), the
-//               planes of X stream through a ring of 16 KB stages
-//   warp 1      one thread issues tcgen05.mma (128 x 128 x 32 per instruction); owns TMEM
-//   warps 2-17  epilogue: tcgen05.ld, FP64 combination, stores
+// Kernel layout (one persistent CTA per SM, 20 warps):
+//   warp 0       producer: cp.async.bulk (TMA bulk copies) of pre-tiled digit planes; the planes
+//                of 128 rows of one operand stay resident in shared memory (S x 28 KB), the
+//                planes of the other stream through a ring of 16 KB stages
+//   warp 1       one elected lane issues tcgen05.mma (128 x 128 x 32 per instruction); owns TMEM
+//   warps 4-19   epilogue: tcgen05.ld, FP64 combination, stores / row sums of squares
 // Tensor memory holds four 128 x 128 int32 accumulators, fewer than the S diagonals, so a
 // tile is evaluated in two passes (diagonals S-4 .. S-1, then 0 .. S-5) over a ring of
-// accumulator slots; the planes of X are streamed from the lowest digit up so that a pass
-// touches its accumulators one after the other and the next pass starts while the
-// epilogue still drains the previous one.
+// accumulator slots; the streamed planes come lowest digit first so that a pass touches its
+// accumulators one after the other and the next pass starts while the epilogue still
+// drains the previous one.
 // Operand planes are stored in global memory exactly as the tensor core reads them from
 // shared memory (no-swizzle K-major core matrices: [k step of 32][8-row group][2][8 rows]
 // [16 B]), so a stage is one contiguous bulk copy and no tensor map is needed.

@@ -1,2 +1,1 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --quick-cpu > gpurun_out/r2_bench_cfg5_n2_i8.json 2> gpurun_out/r2_bench_cfg5_n2_i8.err; echo "rc=$?" >> gpurun_out/r2_bench_cfg5_n2_i8.err
-timeout 300 python -m pytest tests/test_gpu_dist.py -m gpu -x -q > gpurun_out/r2_gpudist_i8.log 2>&1; echo "rc=$?" >> gpurun_out/r2_gpudist_i8.log
+timeout 300 python scripts/i8_prof.py 25000 100000 6 0 > gpurun_out/r2_i8_prof9.txt 2>&1; echo "rc=$?" >> gpurun_out/r2_i8_prof9.txt
