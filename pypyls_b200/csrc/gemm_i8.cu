@@ -71,11 +71,12 @@ struct TcParams {
   long long ldc;
   const double *scale;
   int scale_div, scale_rows;
+  uint32_t scale_div_magic;          // ceil(2^32 / scale_div): x / scale_div == umulhi(x, magic) for small x
   long long lds;
   double *rowsq;
   int M_pad;
   long long *prof;   // optional per-CTA wait-cycle counters (PLSB_I8_PROF), 8 per CTA
-  int dbg;           // experiments (PLSB_I8_DBG): 8 = STORE epilogue without the stores
+  int dbg;           // experiments (PLSB_I8_DBG), unused at present
 };
 
 // mbarrier wait that adds its duration to `acc` when profiling
@@ -515,43 +516,39 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
         };
         drain_pass(std::integral_constant<int, 0>{});
         if constexpr (P::NPASS > 1) drain_pass(std::integral_constant<int, 1>{});
-        // ---- finish the tile ----
+        // ---- finish the tile ----  (branch-free: the shuffles need a converged warp)
         if (EPI == EPI_ROWSUMSQ) {
+          double part[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const double val = T[e] * __hiloint2double(__shfl_sync(0xffffffffu, s_hi, e), 0);
-            rsq = fma(val, val, rsq);
+            part[e & 3] = fma(val, val, part[e & 3]);
           }
+          rsq += (part[0] + part[1]) + (part[2] + part[3]);
         } else {
-          // thread = column r_idx of C, T[e] = row s0 + e: a warp writes 32 consecutive doubles.
-          // Rows that share a scale row (scale_div consecutive ones) reuse one load, and the
-          // next scale row is fetched while the rows of the current one are written.
-          double *cptr = p.C + s0 * (size_t)p.ldc + r_idx;
-          double f = r_scale, nxt = 0.0;
-          const double *sptr = nullptr;
-          int rem = 0;
-          int q_left = 0;    // scale rows after the current one (rows beyond the table reuse the last)
-          if (p.scale) {
-            int q = (int)(s0 / (size_t)p.scale_div);
-            rem = (int)(s0 - (size_t)q * p.scale_div);
-            q = min(q, p.scale_rows - 1);
-            q_left = p.scale_rows - 1 - q;
-            sptr = p.scale + (size_t)q * p.lds + r_idx;
-            f = r_scale * __ldg(sptr);
-            if (q_left > 0) sptr += p.lds;
-            nxt = __ldg(sptr);
-          }
+          // thread = column r_idx of C, T[e] = row s0 + e: a warp writes 32 consecutive doubles
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const double sv = __hiloint2double(__shfl_sync(0xffffffffu, s_hi, e), 0);
-            if (!(p.dbg & 8)) __stcs(cptr, T[e] * f * sv);
-            cptr += p.ldc;
-            if (p.scale && ++rem == p.scale_div) {     // warp-uniform
-              rem = 0;
-              f = r_scale * nxt;
-              if (--q_left > 0) sptr += p.lds;
-              nxt = __ldg(sptr);
+          for (int e = 0; e < 32; ++e)
+            T[e] *= r_scale * __hiloint2double(__shfl_sync(0xffffffffu, s_hi, e), 0);
+          double *cptr = p.C + s0 * (size_t)p.ldc + r_idx;
+          if (p.scale) {
+            // row s0 + e takes scale row (s0 + e) / scale_div; the quotient by multiply-shift,
+            // exact for the values it sees.  Rows beyond the table (padding) reuse its last
+            // row.  (Loading only the <= 5 distinct rows and selecting, a one-ahead software
+            // prefetch and an L2 prefetch at the start of the tile were all measured: not faster.)
+            const uint32_t q0 = (uint32_t)(s0 / (size_t)p.scale_div);
+            const uint32_t rem0 = (uint32_t)(s0 - (size_t)q0 * p.scale_div);
+            const uint32_t kmax = (uint32_t)max(p.scale_rows - 1 - (int)q0, 0);
+            const double *sptr = p.scale + (size_t)min(q0, (uint32_t)(p.scale_rows - 1)) * p.lds + r_idx;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const uint32_t x = rem0 + (uint32_t)e;
+              const uint32_t k = min(p.scale_div == 1 ? x : __umulhi(x, p.scale_div_magic), kmax);
+              __stcs(cptr + (size_t)e * p.ldc, T[e] * __ldg(sptr + (size_t)k * p.lds));
             }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) __stcs(cptr + (size_t)e * p.ldc, T[e]);
           }
         }
       }
@@ -691,6 +688,7 @@ template <int S> int run_i8(plsb_ctx *h, const GemmArgs &a, int KS, int k_valid,
   p.scale = a.scale;
   p.scale_div = a.scale_div;
   p.scale_rows = a.scale_rows > 0 ? a.scale_rows : (a.M_pad + a.scale_div - 1) / a.scale_div;
+  p.scale_div_magic = a.scale_div > 1 ? (uint32_t)(((1ull << 32) + a.scale_div - 1) / a.scale_div) : 0u;
   p.lds = a.lds;
   p.rowsq = a.rowsq;
   p.M_pad = a.M_pad;

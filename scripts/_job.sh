@@ -1,6 +1,1 @@
-mkdir -p gpurun_out/sanitize_i8; rm -f gpurun_out/sanitize_i8/*
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitize_i8/memcheck_slice_gemm.log python -m pytest tests/test_gpu_primitives.py -x -q -m gpu -k "slice_gemm" > gpurun_out/sanitize_i8/memcheck_slice_gemm.pytest 2>&1; echo "memcheck slice gemm rc=$?" >> gpurun_out/sanitize_i8/summary.txt
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitize_i8/memcheck_frontend.log python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitize_i8/memcheck_frontend.out 2>&1; echo "memcheck smoke (front-end, both layouts) rc=$?" >> gpurun_out/sanitize_i8/summary.txt
-timeout 600 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 1 --log-file gpurun_out/sanitize_i8/racecheck_slice_gemm.log python -m pytest tests/test_gpu_primitives.py -x -q -m gpu -k "slice_gemm_matches_numpy and 300-1000-80-6" > gpurun_out/sanitize_i8/racecheck_slice_gemm.pytest 2>&1; echo "racecheck slice gemm rc=$?" >> gpurun_out/sanitize_i8/summary.txt
-for f in gpurun_out/sanitize_i8/*.log; do echo "== $f"; tail -4 "$f"; done >> gpurun_out/sanitize_i8/summary.txt
-for f in gpurun_out/sanitize_i8/*.pytest gpurun_out/sanitize_i8/*.out; do echo "== $f"; tail -2 "$f"; done >> gpurun_out/sanitize_i8/summary.txt
+timeout 300 python scripts/i8_prof.py 25000 100000 6 0 > gpurun_out/r2_i8_prof15.txt 2>&1; echo "rc=$?" >> gpurun_out/r2_i8_prof15.txt
