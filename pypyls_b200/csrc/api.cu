@@ -965,7 +965,7 @@ int plsb_gemm_probe(plsb_handle_t h, int variant, int M, int N, int Kd, int k_va
       PLSB_CUDA(cudaMemsetAsync(h->S1.p, 0x3F, sizeof(double) * rows * N_pad, st));
       g.scale = h->S1.as<double>();
       g.scale_div = scale_div;
-      g.lds = N_pad;
+      g.lds = tune_int("PLSB_PROBE_LDS", N_pad);   // 0: every scale row aliases the first (L2 resident)
     }
   }
   PLSB_TRY(launch_gemm(h, g, st));   // warm-up

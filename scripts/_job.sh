@@ -1,2 +1,2 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 --quick-cpu > gpurun_out/r2_bench_cfg5_n8_i8.json 2> gpurun_out/r2_bench_cfg5_n8_i8.err; echo "rc=$?" >> gpurun_out/r2_bench_cfg5_n8_i8.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_cfg5_n4_i8.json 2> gpurun_out/r2_bench_cfg5_n4_i8.err; echo "rc=$?" >> gpurun_out/r2_bench_cfg5_n4_i8.err
+timeout 300 python scripts/i8_prof.py 25000 100000 6 0 > gpurun_out/r2_i8_prof17.txt 2>&1; echo "rc=$?" >> gpurun_out/r2_i8_prof17.txt
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/r2_gputest_i8_v6.log 2>&1; echo "rc=$?" >> gpurun_out/r2_gputest_i8_v6.log
