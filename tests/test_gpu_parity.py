@@ -818,3 +818,46 @@ def test_constant_column_propagates_nan_like_the_reference():
     assert np.all(np.isnan(R[:, 5])) and np.all(np.isnan(want[:, 5]))
     keep = np.arange(40) != 5
     close(R[:, keep], want[:, keep])
+
+
+@pytest.mark.parametrize('kind', ['behavioral', 'behavioral_cov', 'meancentered',
+                                  'regression'])
+def test_contraction_backends_agree(kind):
+    """The same analysis with the cross-covariance contraction on the int8 slice
+    GEMM (tcgen05, 6 and 7 digit planes) and on the FP64 DMMA kernel: one-cell /
+    un-grouped layouts, where every contraction of the analysis takes the slice
+    kernel."""
+    import pypyls_b200 as pyls
+    rs = np.random.RandomState(77)
+    S, B = 60, 1500
+    X = rs.rand(S, B)
+    kw = dict(n_perm=40, n_boot=40, seed=5, verbose=False)
+    if kind == 'meancentered':
+        def run(**o):
+            return pyls.meancentered_pls(X, groups=[20, 20, 20], **kw, **o)
+    elif kind == 'regression':
+        Y = rs.rand(S, 6)
+
+        def run(**o):
+            return pyls.pls_regression(X, Y, n_components=4, **kw, **o)
+    else:
+        Y = rs.rand(S, 5)
+
+        def run(**o):
+            return pyls.behavioral_pls(X, Y, covariance=kind.endswith('cov'),
+                                       **kw, **o)
+    ref = run(gemm_backend='dmma')
+    for slices, tol in ((6, 1e-9), (7, 1e-11)):
+        out = run(gemm_backend='auto', gemm_slices=slices)
+        if kind != 'regression':
+            # (the last latent variable of a mean-centred analysis is numerically
+            # null: rounding noise in either run)
+            keep = ref.singvals > 1e-8 * ref.singvals.max()
+            np.testing.assert_allclose(out.permres.perm_singval[keep],
+                                       ref.permres.perm_singval[keep], rtol=tol)
+            assert np.array_equal(out.permres.pvals[keep], ref.permres.pvals[keep])
+        cols = slice(None) if kind == 'regression' else \
+            ref.singvals > 1e-8 * ref.singvals.max()
+        a = out.bootres.x_weights_normed[:, cols]
+        b = ref.bootres.x_weights_normed[:, cols]
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e3 * tol * np.abs(b).max())

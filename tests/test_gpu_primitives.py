@@ -69,6 +69,23 @@ def test_slice_gemm_matches_numpy(torch_cuda, M, N, Kd, slices):
     assert err.max() < SLICE_TOL[slices], err.max()
 
 
+@pytest.mark.parametrize('slices', [5, 6, 7])
+@pytest.mark.parametrize('M,N,Kd', [(7, 5, 3), (129, 257, 33), (300, 1000, 200)])
+def test_slice_gemm_bit_equal_to_restatement(torch_cuda, M, N, Kd, slices):
+    """Integer work is exact and the FP64 recombination has a fixed order: the CUDA
+    kernel equals the NumPy restatement of its arithmetic (oracle/slice_gemm.py)
+    bit for bit."""
+    from oracle.slice_gemm import slice_gemm
+    rs = np.random.RandomState(M + N + slices)
+    A = rs.randn(M, Kd) * 10.0 ** rs.randint(-3, 4, size=(M, 1))
+    X = rs.randn(Kd, N) * 10.0 ** rs.randint(-3, 4, size=(1, N))
+    A[M // 2] = 0.0
+    eng = make_engine('behavioral', 4, 8, 1, [4], gemm_backend='auto',
+                      gemm_slices=slices)
+    C = eng.dgemm(A, X).cpu().numpy()
+    assert np.array_equal(C, slice_gemm(A, X, slices))
+
+
 def test_slice_gemm_special_values(torch_cuda):
     """Zero rows / columns stay exactly zero, NaN and Inf poison exactly the rows /
     columns a product would, contractions beyond 224 rows take the DMMA kernel."""
