@@ -76,7 +76,6 @@ struct TcParams {
   double *rowsq;
   int M_pad;
   long long *prof;   // optional per-CTA wait-cycle counters (PLSB_I8_PROF), 8 per CTA
-  int dbg;           // experiments (PLSB_I8_DBG), unused at present
 };
 
 // mbarrier wait that adds its duration to `acc` when profiling
@@ -693,12 +692,8 @@ template <int S> int run_i8(plsb_ctx *h, const GemmArgs &a, int KS, int k_valid,
   p.rowsq = a.rowsq;
   p.M_pad = a.M_pad;
   p.prof = nullptr;
-  p.dbg = tune_int("PLSB_I8_DBG", 0);
   h->i8_macs += (double)a.M_pad * a.N_pad * (KS * 32.0) * (S * (S + 1) / 2);
-  if (S == 6 && tune_int("PLSB_I8_NP0", 4) == 3) {
-    if (a.rowsq) return launch_kernel<S, EPI_ROWSUMSQ, 3>(h, p, st);
-    return launch_kernel<S, EPI_STORE, 3>(h, p, st);
-  }
+  // (a 3 + 3 split of the diagonals, Plan<S, 3>, and passes of two were measured: not faster)
   if (a.rowsq) return launch_kernel<S, EPI_ROWSUMSQ, 4>(h, p, st);
   return launch_kernel<S, EPI_STORE, 4>(h, p, st);
 }

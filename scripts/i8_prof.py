@@ -1,4 +1,5 @@
-"""Wait-cycle profile of the int8 slice GEMM (PLSB_I8_PROF=1): python scripts/i8_prof.py [M] [N] [slices,..] [dbg,..]"""
+"""Wait-cycle profile of the int8 slice GEMM (PLSB_I8_PROF=1): python scripts/i8_prof.py [M] [N] [slices,..]
+(build with PLSB_NVCC_EXTRA=-DPLSB_I8_EPI_PROF for the phases of the epilogue as well)"""
 import os
 import sys
 
@@ -10,14 +11,11 @@ from pypyls_b200.engine import ResamplingEngine  # noqa: E402
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
 slices = [int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [6, 5, 7]
-dbgs = [int(v) for v in sys.argv[4].split(',')] if len(sys.argv) > 4 else [0]
 eng = ResamplingEngine('behavioral', 16, 64, 2, [16], 1, device=0)
-for dbg in dbgs:
-    os.environ['PLSB_I8_DBG'] = str(dbg)
-    for s in slices:
-        eng.set_gemm_backend('auto', s)
-        for variant in (2, 1, 0):
-            if variant < 2 and M > 30000:
-                continue
-            ms = eng.gemm_probe(variant, M, N, 208, k_valid=200, iters=1)
-            print('dbg %d slices %d variant %d: %.2f ms' % (dbg, s, variant, ms), flush=True)
+for s in slices:
+    eng.set_gemm_backend('auto', s)
+    for variant in (2, 1, 0):
+        if variant < 2 and M > 30000:
+            continue
+        ms = eng.gemm_probe(variant, M, N, 208, k_valid=200, iters=1)
+        print('slices %d variant %d: %.2f ms' % (s, variant, ms), flush=True)
