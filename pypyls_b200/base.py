@@ -96,7 +96,10 @@ class BasePLS():
         arrays (bootstrap distribution, tables) and the B-sized arrays are
         moved to the host of rank 0 only, the other ranks return the
         statistics (p-values, intervals) and ``None`` for those arrays),
-        ``gemm_backend`` ('auto', default: the cross-covariance contraction
+        ``input_source`` (multi-process runs only: 'local', default -- every rank
+        uploads the arrays it was given; 'root' -- rank 0 uploads its arrays and
+        the other ranks receive them over NCCL, their own copies only give the
+        shapes), ``gemm_backend`` ('auto', default: the cross-covariance contraction
         runs as int8 digit-plane products on the tcgen05 tensor cores where
         that kernel applies; 'dmma': FP64 DMMA everywhere) and ``gemm_slices``
         (digit planes per operand, 5 / 6 / 7; default 6: entries within 1e-13
@@ -133,6 +136,8 @@ class BasePLS():
             self.inputs['index_backend'] = backend = 'device'
         if backend not in ('device', 'reference'):
             raise ValueError("index_backend must be 'device' or 'reference'")
+        if self.inputs.get('input_source') not in (None, 'local', 'root'):
+            raise ValueError("input_source must be 'local' or 'root'")
         self.engine = None
 
     # -- engine ------------------------------------------------------------
@@ -154,6 +159,11 @@ class BasePLS():
                                    'gemm_backend') or 'auto',
                                gemm_slices=self.inputs.get(
                                    'gemm_slices') or 6)
+        if self.inputs.get('input_source') == 'root':
+            # multi-process runs: only rank 0 uploads, the replicas travel over NCCL
+            X = pdist.broadcast_from_root(eng, X, (S, B))
+            if Y is not None:
+                Y = pdist.broadcast_from_root(eng, Y, (S, T))
         eng.set_data(X, Y)
         return eng
 

@@ -22,6 +22,23 @@ def world():
     return 0, 1
 
 
+def broadcast_from_root(eng, a, shape):
+    """Device copy of ``a`` (a host or device array of ``shape``) taken from rank 0:
+    rank 0 uploads its array, the other ranks receive it over NCCL / NVLink instead of
+    pushing their own replicas through the host's memory and PCIe links at the same time."""
+    rank, size = world()
+    if size == 1:
+        return eng.to_device(a)
+    if rank == 0:
+        t = eng.to_device(a)
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError('expected an array of shape {}'.format(tuple(shape)))
+    else:
+        t = torch.empty(tuple(shape), dtype=torch.float64, device=eng.device)
+    dist.broadcast(t, src=0)
+    return t
+
+
 def my_block(n):
     """(first, count) of the resample ids this rank owns."""
     rank, size = world()

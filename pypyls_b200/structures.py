@@ -90,8 +90,8 @@ class ResDict(dict):
 
 class PLSInputs(ResDict):
     """Inputs of an analysis (pyls/structures.py:146-172).  ``index_backend``,
-    ``device``, ``workspace_bytes``, ``perm_path``, ``gather_results``, ``gemm_backend`` and
-    ``gemm_slices`` are additions of this engine."""
+    ``device``, ``workspace_bytes``, ``perm_path``, ``gather_results``, ``gemm_backend``,
+    ``gemm_slices`` and ``input_source`` are additions of this engine."""
 
     allowed = [
         'X', 'Y', 'groups', 'n_cond', 'n_perm', 'n_boot', 'n_split',
@@ -99,7 +99,7 @@ class PLSInputs(ResDict):
         'ci', 'seed', 'verbose', 'n_proc', 'bootsamples', 'permsamples',
         'method', 'n_components', 'aggfunc', 'permindices',
         'index_backend', 'device', 'workspace_bytes', 'perm_path',
-        'gather_results', 'gemm_backend', 'gemm_slices',
+        'gather_results', 'gemm_backend', 'gemm_slices', 'input_source',
     ]
 
     def __init__(self, **kwargs):

@@ -151,6 +151,10 @@ class PLSRegression(BasePLS):
                                    'gemm_backend') or 'auto',
                                gemm_slices=self.inputs.get(
                                    'gemm_slices') or 6)
+        if self.inputs.get('input_source') == 'root':
+            from .. import dist as pdist
+            X = pdist.broadcast_from_root(eng, X, X.shape)
+            Y = pdist.broadcast_from_root(eng, Y, Y.shape)
         eng.set_data(X, Y)
         return eng
 

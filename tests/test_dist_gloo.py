@@ -117,3 +117,34 @@ def test_single_process_is_a_no_op():
     assert pdist.my_block(10) == (0, 10)
     assert pdist.gather_resamples(t, 3) is t
     assert pdist.reduce_sum(t)[0] is t
+
+
+class _HostEngine:
+    """Stands in for ResamplingEngine in the CPU test of broadcast_from_root."""
+    device = torch.device('cpu')
+
+    @staticmethod
+    def to_device(a):
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64)
+
+
+def _bcast_worker(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from pypyls_b200 import dist as pdist
+    # every rank holds different numbers: only rank 0's may come out
+    X = np.full((5, 7), float(rank + 1)) + np.arange(7)
+    got = pdist.broadcast_from_root(_HostEngine(), X, (5, 7))
+    np.save(os.path.join(out_dir, 'bcast%d.npy' % rank), got.numpy())
+    dist.destroy_process_group()
+
+
+def test_inputs_broadcast_from_root(tmp_path):
+    """input_source='root': rank 0 uploads, the other ranks receive its arrays."""
+    world = 2
+    mp.spawn(_bcast_worker, args=(world, _free_port(), str(tmp_path)),
+             nprocs=world, join=True)
+    want = np.full((5, 7), 1.0) + np.arange(7)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / ('bcast%d.npy' % r)), want)

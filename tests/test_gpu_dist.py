@@ -63,6 +63,14 @@ def _worker(rank, world, port, out_dir):
     assert np.array_equal(outr.bootres.y_loadings_ci,
                           out.bootres.y_loadings_ci)
     assert np.array_equal(outr.permres.pvals, out.permres.pvals)
+    # input_source='root': the other ranks' own arrays only give the shapes
+    Xr, Yr = (X, Y) if rank == 0 else (np.zeros_like(X), np.zeros_like(Y))
+    outb = pyls.behavioral_pls(Xr, Yr, index_backend='reference', verbose=False,
+                               device=rank, input_source='root',
+                               **{k: v for k, v in kw.items()
+                                  if k != 'n_split'})
+    assert np.array_equal(outb.permres.perm_singval, out.permres.perm_singval)
+    assert np.array_equal(outb.bootres.y_loadings_ci, out.bootres.y_loadings_ci)
     np.savez(os.path.join(out_dir, 'rank%d.npz' % rank),
              perm=out.permres.perm_singval, pvals=out.permres.pvals,
              boot=out.bootres.y_loadings_boot, bsr=out.bootres.x_weights_normed,
