@@ -40,11 +40,12 @@ __global__ void rowdot_sqrt_kernel(const double *__restrict__ T, long long ldt,
 __global__ void colscale_kernel(double *__restrict__ S1, const double *__restrict__ S2, int n_rows,
                                 long long ld, int B, int J, int rpr,
                                 const int *__restrict__ cell_n, const int *__restrict__ nrow) {
-  const size_t total = (size_t)n_rows * ld;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
-       e += (size_t)gridDim.x * blockDim.x) {
-    const int row = (int)(e / ld), b = (int)(e % ld);
+  // blockIdx.x: 256 columns, blockIdx.y (grid-stride): rows -- no 64-bit division per element
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ld) return;
+  for (int row = blockIdx.y; row < n_rows; row += gridDim.y) {
     const int cell = row % rpr;
+    const size_t e = (size_t)row * ld + b;
     double out = 0.0;
     if (b < B && cell < J) {
       const double n = nrow ? (double)nrow[(size_t)(row / rpr) * J + cell] : (double)cell_n[cell];
@@ -99,11 +100,13 @@ int launch_colscale(plsb_ctx *h, double *S1, const double *S2, int n_rows, long 
                     cudaStream_t st, int rows_per_resample, const int *nrow) {
   KernelTimer kt(h, KC_STATS, st);
   if (n_rows <= 0) return PLSB_OK;
-  const size_t total = (size_t)n_rows * ld;
-  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 32);
+  const unsigned col_blocks = (unsigned)((ld + 255) / 256);
+  // enough row blocks to fill the machine a few times over, every one striding the rows
+  const unsigned row_blocks = (unsigned)std::min<long long>(
+      n_rows, std::max<long long>(1, (long long)h->sm_count * 32 / col_blocks));
   const int rpr = rows_per_resample > 0 ? rows_per_resample : h->lay.J;
-  colscale_kernel<<<blocks, 256, 0, st>>>(S1, S2, n_rows, ld, h->lay.B, h->lay.J, rpr,
-                                          h->d_cell_n, nrow);
+  colscale_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>(S1, S2, n_rows, ld, h->lay.B,
+                                                                 h->lay.J, rpr, h->d_cell_n, nrow);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
