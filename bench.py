@@ -36,6 +36,16 @@ subset).  Falls back to the NumPy oracle port (`kind: "port"`) where
 oracle/_ref is absent.
 
 `--impl reference` times that same stock reference path on all host cores.
+
+`roofline` describes the dominant kernel class (the cross-covariance contraction).
+By default it runs as int8 digit-plane products on the tcgen05 tensor cores
+(csrc/gemm_i8.cu): `achieved` = int8 operations executed (counted by the library,
+plsb_gemm_work) / summed CUDA-event time of the class, `peak` = 2 x the measured
+bf16 tensor figure of MEASURED_PEAKS.json, plus the FP64-equivalent TFLOP/s against
+the cuBLAS DGEMM peak measured in the same run.  `--gemm-backend dmma` runs and
+accounts the FP64 DMMA kernel instead (algorithmic flop / DGEMM peak).  For N > 1
+the end-to-end call uploads X, Y on rank 0 only and broadcasts them over NCCL
+(`input_source="root"`).
 """
 
 import argparse
