@@ -110,11 +110,13 @@ int crosscov_chunk(plsb_ctx *h, const int32_t *idx, const double *yperm, int n, 
     g.row_map = map_c;
     g.kranges = kr_c;
     g.C = h->S1.as<double>();
+    g.a_counts = true;           // multiplicity rows
     PLSB_TRY(launch_gemm(h, g, st));
     g.C = h->S2.as<double>();
     g.square_b = true;
     PLSB_TRY(launch_gemm(h, g, st));
     g.square_b = false;
+    g.a_counts = false;
     PLSB_TRY(launch_colscale(h, h->S1.as<double>(), h->S2.as<double>(), (int)Mc, l.ldx, st));
   }
   if (scaled) {
@@ -1321,11 +1323,13 @@ static int halves_chunk(plsb_ctx *h, const int32_t *masks, const double *yperm,
     g.row_map = map_c;
     g.kranges = kr_c;
     g.C = h->S1.as<double>();
+    g.a_counts = true;           // multiplicity rows
     PLSB_TRY(launch_gemm(h, g, st));
     g.C = h->S2.as<double>();
     g.square_b = true;
     PLSB_TRY(launch_gemm(h, g, st));
     g.square_b = false;
+    g.a_counts = false;
     PLSB_TRY(launch_colscale(h, h->S1.as<double>(), h->S2.as<double>(), (int)Mc, l.ldx, st, l.J,
                              ncell));
     g.scale = h->S1.as<double>();

@@ -226,6 +226,9 @@ struct GemmArgs {
   const int4 *kranges = nullptr;  // optional per-M-tile [kbeg,kend) (kbeg even) + non-zero k steps [z,w)
   int k_len = 0;               // longest contraction range in kranges (0: Kd); picks the tile
   bool x_persistent = false;   // X is a data matrix of the handle (its digit planes are cached)
+  bool a_counts = false;       // A holds small integers (multiplicities): they fill one digit plane
+                               // (the slice GEMM skips the empty ones, as found on the device);
+                               // only the work accounting uses this hint
   bool square_b = false;       // use X*X elementwise as the right operand
   // STORE epilogue
   double *C = nullptr;

@@ -65,6 +65,8 @@ template <int S, int NP0> struct Plan {
 
 struct TcParams {
   const int8_t *res_img, *str_img;   // planes of the resident / the streamed operand
+  const int *str_nplanes;            // optional: leading planes of the streamed operand that are not all
+                                     // zero (multiplicity operands are exact in one): the rest is skipped
   const double *rscale, *cscale;     // powers of two of the rows of A / the columns of X
   int KS, n_rtiles, n_stiles, n_splits, st_per_split;
   double *C;
@@ -184,7 +186,8 @@ template <int S>
 __global__ void __launch_bounds__(256) quant_rows_kernel(const double *__restrict__ A, int lda,
                                                          long long rows_valid, long long rows_pad,
                                                          int k_valid, int KS, int8_t *__restrict__ img,
-                                                         double *__restrict__ rscale) {
+                                                         double *__restrict__ rscale,
+                                                         int *__restrict__ n_planes) {
   constexpr int Q = 8 * S - 2;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -219,10 +222,15 @@ __global__ void __launch_bounds__(256) quant_rows_kernel(const double *__restric
   const size_t slice_bytes = (size_t)KS * KSTEP_BYTES;
   int8_t *dst = img + (size_t)tile * S * slice_bytes + (size_t)(lane >> 1) * KSTEP_BYTES +
                 (size_t)(r >> 3) * 256 + (size_t)(lane & 1) * 128 + (size_t)(r & 7) * 16;
+  int top = 0;   // planes up to the last one with a non-zero digit (small integers need one)
 #pragma unroll
-  for (int i = 0; i < S; ++i)
+  for (int i = 0; i < S; ++i) {
     *reinterpret_cast<uint4 *>(dst + (size_t)i * slice_bytes) =
         make_uint4(pk[i][0], pk[i][1], pk[i][2], pk[i][3]);
+    if (pk[i][0] | pk[i][1] | pk[i][2] | pk[i][3]) top = i + 1;
+  }
+  top = __reduce_max_sync(__activemask(), top);
+  if (lane == 0 && top > 0) atomicMax(n_planes, top);
 }
 
 // One CTA per 128 columns of X (row-major (k, ldx)): thread (x, y) owns column x of the tile
@@ -311,6 +319,8 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
   const uint32_t slice_bytes = (uint32_t)KS * KSTEP_BYTES;
   const int n_units = p.n_rtiles * p.n_splits;
   constexpr int NCHUNK = (MAX_KS + P::STAGE_KS - 1) / P::STAGE_KS;
+  // streamed planes jn .. S-1 hold zeros only: never loaded, never multiplied
+  const int jn = p.str_nplanes ? min(max(__ldg(p.str_nplanes), 1), S) : S;
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -358,6 +368,7 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
         for (int ps = 0; ps < P::NPASS; ++ps) {
 #pragma unroll
           for (int j = P::dhi(ps); j >= 0; --j) {
+            if (j >= jn) continue;
 #pragma unroll
             for (int kc = 0; kc < NCHUNK; ++kc) {
               const int k0 = kc * P::STAGE_KS;
@@ -405,30 +416,32 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
         for (int ps = 0; ps < P::NPASS; ++ps) {
 #pragma unroll
           for (int j = P::dhi(ps); j >= 0; --j) {
+            if (j >= jn) continue;
 #pragma unroll
             for (int kc = 0; kc < NCHUNK; ++kc) {
               const int k0 = kc * P::STAGE_KS;
               if (k0 < KS) {
                 TIMED_WAIT(&full_b[st], st_phase, w_full);
                 tc_fence_after();
-                if (kc == 0 && j >= P::dlo(ps)) {
-                  // diagonal j is touched for the first time: its slot must have been drained
-                  const uint32_t c = slot_ctr + (uint32_t)(P::dhi(ps) - j);
-                  TIMED_WAIT(&slot_empty[c % NSLOT], ((c / NSLOT) & 1) ^ 1, w_slot);
-                  tc_fence_after();
-                }
                 const uint32_t s_lo = s_lo0 + st * (P::STAGE_BYTES >> 4);
 #pragma unroll
                 for (int d = (P::dlo(ps) > j ? P::dlo(ps) : j); d <= P::dhi(ps); ++d) {
                   const int i = d - j;
                   const uint32_t c = slot_ctr + (uint32_t)(P::dhi(ps) - d);
+                  // diagonal d is touched for the first time by its highest streamed plane,
+                  // min(d, jn - 1): its slot must have been drained by every epilogue warp
+                  const bool first = kc == 0 && (i == 0 || j == jn - 1);
+                  if (first) {
+                    TIMED_WAIT(&slot_empty[c % NSLOT], ((c / NSLOT) & 1) ^ 1, w_slot);
+                    tc_fence_after();
+                  }
                   const uint32_t taddr = tmem + (c % NSLOT) * TN;
                   const uint32_t r_lo = r_lo0 + (uint32_t)i * slice16 + (uint32_t)k0 * (KSTEP_BYTES >> 4);
 #pragma unroll
                   for (int k = 0; k < P::STAGE_KS; ++k) {
                     if (k0 + k < KS && leader)
                       mma_i8(taddr, r_lo + k * (KSTEP_BYTES >> 4), s_lo + k * (KSTEP_BYTES >> 4), idesc,
-                             (i == 0 && kc == 0 && k == 0) ? 0u : 1u);
+                             (first && k == 0) ? 0u : 1u);
                   }
                 }
                 if (leader) mma_commit(&empty_b[st]);   // stage free once these MMAs have read it
@@ -572,10 +585,11 @@ __global__ void __launch_bounds__(THREADS, 1) xcov_gemm_i8_kernel(const TcParams
 
 template <int S> int quantize_rows(plsb_ctx *h, const double *A, int lda, long long rows_valid,
                                    long long rows_pad, int k_valid, int KS, int8_t *img,
-                                   double *rscale, cudaStream_t st) {
+                                   double *rscale, int *n_planes, cudaStream_t st) {
   KernelTimer kt(h, KC_GEMM, st);
-  quant_rows_kernel<S><<<(unsigned)((rows_pad + 7) / 8), 256, 0, st>>>(A, lda, rows_valid, rows_pad,
-                                                                        k_valid, KS, img, rscale);
+  PLSB_CUDA(cudaMemsetAsync(n_planes, 0, sizeof(int), st));
+  quant_rows_kernel<S><<<(unsigned)((rows_pad + 7) / 8), 256, 0, st>>>(
+      A, lda, rows_valid, rows_pad, k_valid, KS, img, rscale, n_planes);
   PLSB_LAUNCHED(h);
   return PLSB_OK;
 }
@@ -659,10 +673,12 @@ template <int S> int run_i8(plsb_ctx *h, const GemmArgs &a, int KS, int k_valid,
     xc->stamp = ++h->plane_stamp;
   }
   PLSB_TRY(h->aplanes.ensure((size_t)n_mtiles * S * slice_bytes));
-  PLSB_TRY(h->ascale.ensure(sizeof(double) * (size_t)a.M_pad));
+  PLSB_TRY(h->ascale.ensure(sizeof(double) * ((size_t)a.M_pad + 1)));   // + the plane count
+  int *a_nplanes = reinterpret_cast<int *>(h->ascale.as<double>() + a.M_pad);
   PLSB_TRY(quantize_rows<S>(h, a.A, a.lda, a.M_pad, a.M_pad, k_valid, KS, h->aplanes.as<int8_t>(),
-                            h->ascale.as<double>(), st));
+                            h->ascale.as<double>(), a_nplanes, st));
   TcParams p;
+  p.str_nplanes = nullptr;
   p.rscale = h->ascale.as<double>();
   p.cscale = xc->scale.as<double>();
   p.KS = KS;
@@ -677,6 +693,7 @@ template <int S> int run_i8(plsb_ctx *h, const GemmArgs &a, int KS, int k_valid,
     // columns of X resident, row tiles of A streamed
     p.res_img = xc->img.as<int8_t>();
     p.str_img = h->aplanes.as<int8_t>();
+    p.str_nplanes = a_nplanes;
     p.n_rtiles = n_ntiles;
     p.n_stiles = n_mtiles;
     p.n_splits = gemm_i8_pick_splits(h, a.N_pad, n_mtiles);
@@ -692,7 +709,10 @@ template <int S> int run_i8(plsb_ctx *h, const GemmArgs &a, int KS, int k_valid,
   p.rowsq = a.rowsq;
   p.M_pad = a.M_pad;
   p.prof = nullptr;
-  h->i8_macs += (double)a.M_pad * a.N_pad * (KS * 32.0) * (S * (S + 1) / 2);
+  // plane products executed: all pairs i + j < S -- or, for the multiplicity operands of
+  // the column statistics (one non-empty plane, the kernel skips the rest), S of them
+  h->i8_macs += (double)a.M_pad * a.N_pad * (KS * 32.0) *
+                (a.a_counts && !a.rowsq ? S : S * (S + 1) / 2);
   // (a 3 + 3 split of the diagonals, Plan<S, 3>, and passes of two were measured: not faster)
   if (a.rowsq) return launch_kernel<S, EPI_ROWSUMSQ, 4>(h, p, st);
   return launch_kernel<S, EPI_STORE, 4>(h, p, st);

@@ -86,6 +86,24 @@ def test_slice_gemm_bit_equal_to_restatement(torch_cuda, M, N, Kd, slices):
     assert np.array_equal(C, slice_gemm(A, X, slices))
 
 
+@pytest.mark.parametrize('amax', [1, 7, 63, 64, 300, 70000])
+def test_slice_gemm_skips_empty_planes(torch_cuda, amax):
+    """Operands of small integers (the multiplicity rows of the bootstrap column
+    statistics) fill only their leading digit planes; the kernel skips the planes
+    that are all zero.  Same bits as the restatement, and exact while the product
+    is representable."""
+    from oracle.slice_gemm import slice_gemm
+    rs = np.random.RandomState(amax)
+    A = rs.randint(0, amax + 1, size=(260, 200)).astype(float)
+    A[:, 17] = amax
+    X = rs.randn(200, 400)
+    eng = make_engine('behavioral', 4, 8, 1, [4], gemm_backend='auto')
+    C = eng.dgemm(A, X).cpu().numpy()
+    assert np.array_equal(C, slice_gemm(A, X, 6))
+    Xi = rs.randint(-100, 101, size=(200, 400)).astype(float)
+    assert np.array_equal(eng.dgemm(A, Xi).cpu().numpy(), A @ Xi)
+
+
 def test_slice_gemm_special_values(torch_cuda):
     """Zero rows / columns stay exactly zero, NaN and Inf poison exactly the rows /
     columns a product would, contractions beyond 224 rows take the DMMA kernel."""
