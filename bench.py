@@ -899,7 +899,9 @@ def main():
         else:
             peak, src = 4500.0, 'fallback: nominal dense int8 4.5 POP/s'
         fp64_eq = flops * args.steps / (top_ms * 1e-3) / 1e12
-        roofline.update(achieved=ach, peak=peak, unit='TOP/s (int8)',
+        roofline.update(achieved=ach, peak=peak, unit='TFLOP/s',
+                        unit_detail='int8 tensor operations (TOP/s): achieved and '
+                                    'peak count int8 multiply-adds x 2',
                         frac=ach / peak, peak_source=src,
                         gemm_backend='int8 slice GEMM, %d digit planes (%d plane '
                                      'products per FP64 product)' % (
